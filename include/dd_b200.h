@@ -1,0 +1,178 @@
+/* dd_b200.h -- C ABI of libdd_b200.so: B200-native time stepping for the
+ * nonlinear temperature-enhanced drug-diffusion model.
+ *
+ * The reference (phao/NA-nonlinear-temperature-enhanced-diffusion-model-DD) has
+ * no FFI of its own: its boundary for this path is the Python class API of
+ * src/prob1base.py.  Each entry point below names the reference call(s) it
+ * replaces (file:line relative to the reference root); INTEGRATION.md shows the
+ * ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - plain C: opaque handles, pointers and sizes only.  Every function returns
+ *    0 on success or a negative dd_status; dd_last_error() gives the message.
+ *    Nothing throws across the ABI.
+ *  - fields are float64, C order, shape (nrows, M+1) per member, exactly the
+ *    reference's (N+1, M+1) arrays (src/prob1base.py:242-248) when row0 = 0 and
+ *    nrows = N+1.  Host pointers unless the name says `_dev`.
+ *  - all device work is ordered on the context's stream; one host thread per
+ *    context.  The library owns device memory; the caller owns the handles.
+ *  - a "batch" is B independent trajectories (members) on one grid; B = 1 is a
+ *    single trajectory.  A batch may hold only the row slab [row0, row0+nrows)
+ *    of the global grid (domain decomposition); the caller then fills the
+ *    non-owned rows through the *_dev pointers (halo exchange).
+ */
+#ifndef DD_B200_H
+#define DD_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dd_ctx dd_ctx;
+typedef struct dd_batch dd_batch;
+
+enum dd_status {
+    DD_OK = 0,
+    DD_ERR_INVALID = -1,       /* bad argument (the reference raises AssertionError, e.g. dt <= 0: src/prob1base.py:3118) */
+    DD_ERR_CUDA = -2,          /* CUDA runtime error */
+    DD_ERR_NOT_CONVERGED = -3, /* a Newton linear solve missed its residual bound */
+    DD_ERR_NO_DEVICE = -4      /* no CUDA device: there is no CPU fallback */
+};
+
+enum dd_var { DD_VAR_CP = 0, DD_VAR_T = 1, DD_VAR_CL = 2, DD_VAR_CD = 3, DD_VAR_CS = 4 };
+
+/* forcing (MMS source) modes */
+enum dd_forcing_mode {
+    DD_MODE_NONE = 0,      /* NoForcingTerms, src/prob1base.py:852-869 */
+    DD_MODE_ARRAYS = 1,    /* caller evaluates fcp..fcs and uploads them (any ForcingTermsBase) */
+    DD_MODE_SEPARABLE = 2, /* u_v = phi_v(t) X_v(x) Y_v(y): fused evaluation from 1-D tables */
+    DD_MODE_EXPSIN = 3     /* MMSCaseExpSin closed form, src/prob1_mms_cases.py:296-337 */
+};
+
+/* time profiles phi_v(t) of DD_MODE_SEPARABLE */
+enum dd_phi_kind {
+    DD_PHI_K_INV1PT = 0, /* p0 / (1 + t) */
+    DD_PHI_K_EXP = 1,    /* p0 exp(-p1 t) */
+    DD_PHI_K_LINEAR = 2, /* p0 - p1 t */
+    DD_PHI_K_OSC = 3,    /* p0 (1 + p1 sin(p2 t)) */
+    DD_PHI_K_CONST = 4,  /* p0 */
+    DD_PHI_K_HOST = 5    /* p = phi(t0), phi'(t0), phi(t1), phi'(t1): refreshed by the caller before each step */
+};
+
+/* ModelConsts (src/prob1base.py:28-45) + model kind + eta; one per member */
+typedef struct dd_model {
+    double K1, K2, K3, K4, DT, Dl_max, phi_l, gamma_T, Kd, Sd, Dd_max, phi_d, phi_T, r_sp, T_ref;
+    double eta;   /* regularisation factor of H_eta, src/prob1base.py:3452-3466 */
+    int kind;     /* 1 = DefaultModel01, 2 = DefaultModel02 (Dd uses T + T_ref), src/prob1base.py:71-217 */
+    int _pad;
+} dd_model;
+
+/* options of the predictor-corrector step: the constructor arguments of
+ * P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_RegHCsTriple (src/prob1base.py:3612-3629) */
+typedef struct dd_pc_options {
+    int num_pc_steps;          /* default 1 */
+    int num_newton_steps;      /* default 1 */
+    int num_newton_iterations; /* cs corrector cap, default 5 */
+    int cd_band_swap;          /* 1 reproduces the W/S band exchange of src/prob1base.py:3094-3100 (default) */
+    double consec_xs_rtol;     /* default 1e-6; 0 disables the exit test */
+    double solve_tol;          /* bound on |x - x_exact|_inf / |v_new|_inf per linear solve, default 1e-14 */
+    int max_sweeps;            /* give up (DD_ERR_NOT_CONVERGED) beyond this many SOR sweeps, default 20000 */
+    int fixed_sweeps;          /* > 0: use exactly this many sweeps and skip the adaptive plan */
+} dd_pc_options;
+
+/* what one dd_step_pc call did (worst member of the batch) */
+typedef struct dd_step_stats {
+    int sweeps[3];        /* SOR sweeps used for the T, cl, cd solves (last Newton step) */
+    int passes[3];        /* kernel passes per solve */
+    int retries;          /* how often the step was redone with more sweeps */
+    int cs_newton_iters;  /* iterations of the cs corrector (max over members, last pc step) */
+    double rho[3];        /* Gershgorin ratio of the three matrices */
+    double resid[3];      /* max scaled residual |bb - (I-G)x| */
+    double bound[3];      /* resulting bound on |x - x_exact| / |v_new| */
+} dd_step_stats;
+
+/* ---- context ----------------------------------------------------------- */
+int dd_ctx_create(int device, void* cuda_stream /* cudaStream_t or NULL */, dd_ctx** out);
+int dd_ctx_destroy(dd_ctx* ctx);
+int dd_ctx_synchronize(dd_ctx* ctx);
+const char* dd_last_error(const dd_ctx* ctx);
+const char* dd_version(void);
+
+/* ---- batch: grid + members (replaces Grid / make_uniform_grid, src/prob1base.py:220-490,
+ *      and holds what StateVars holds, 1913-2085) ---------------------------------- */
+int dd_batch_create(dd_ctx* ctx, int N, int M, const double* x /* N+1 */, const double* y /* M+1 */,
+                    int nmembers, int row0, int nrows, int own0, int own1, int nslots, dd_batch** out);
+int dd_batch_destroy(dd_batch* b);
+int dd_batch_set_models(dd_batch* b, int first, int count, const dd_model* models);
+int dd_batch_set_active(dd_batch* b, int first, int count, const int* active);
+
+/* forcing selection (replaces the ForcingTerms_RegHCsTriple object, src/prob1base.py:3468-3551) */
+int dd_forcing_none(dd_batch* b);
+/* u_v = phi_v(t) sum_{r<nterms} X_{v,r}(x) Y_{v,r}(y).  tables: X[v][d] holds nterms rows of N+1 doubles
+ * (d = 0,1,2: value, 1st, 2nd derivative), Y likewise (M+1); XQ[q] (q: cp, T, cl) holds nterms rows of
+ * 3 values per node i (Gauss abscissae of cell i, src/prob1base.py:508-570);
+ * phi_kind[v], phi_p[v][4] select phi_v(t).  per-member phi via dd_forcing_set_phi. */
+int dd_forcing_separable(dd_batch* b, int nterms, const double* const X[5][3], const double* const Y[5][3],
+                         const double* const XQ[3], const double* const YQ[3], const int phi_kind[5],
+                         const double phi_p[5][4]);
+int dd_forcing_set_phi(dd_batch* b, int first, int count, const int* phi_kind /* count*5 */,
+                       const double* phi_p /* count*5*4 */);
+/* sx = sin(pi x), cx = cos(pi x) at the nodes, sxq = sin(pi x) at the abscissae (3 per node) */
+int dd_forcing_expsin(dd_batch* b, const double* sx, const double* cx, const double* sy, const double* cy,
+                      const double* sxq, const double* syq);
+/* host-evaluated sources for the next step: f[v][slot] (slot 0: t0, slot 1: t0+dt), NULL = zero */
+int dd_forcing_arrays(dd_batch* b, int member, const double* const f[5][2]);
+
+/* ---- state slots ------------------------------------------------------- */
+int dd_state_upload(dd_batch* b, int slot, int member, const double* const fields[5] /* NULL entries skipped */);
+int dd_state_download(dd_batch* b, int slot, int member, double* const fields[5]);
+int dd_state_fill_exact(dd_batch* b, int slot, const double* t, int n_t); /* state_from_mms_when, src/prob1base.py:3433-3449 */
+int dd_state_dev_ptr(dd_batch* b, int slot, int var, void** ptr, long long* member_stride, int* ld);
+int dd_work_dev_ptr(dd_batch* b, const char* name, void** ptr); /* "cp1p","cs1p","YT","Ycl","Ycd","bb","aW",... */
+int dd_work_upload(dd_batch* b, const char* name, int member, const double* host);
+int dd_work_download(dd_batch* b, const char* name, int member, double* host);
+
+/* ---- the hot path ------------------------------------------------------ */
+/* ForwardEulerIntegrator.step, src/prob1base.py:2889-2903.  t0/dt: n_t = 1 (broadcast) or nmembers values */
+int dd_step_feuler(dd_batch* b, int slot_in, int slot_out, const double* t0, const double* dt, int n_t);
+/* P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_RegHCsTriple.step, src/prob1base.py:3117-3149 */
+int dd_step_pc(dd_batch* b, int slot_in, int slot_out, const double* t0, const double* dt, int n_t,
+               const dd_pc_options* opt, dd_step_stats* stats /* may be NULL */);
+/* nsteps PC steps with times advanced on the device (current_t += dt, src/mms_trial_utils.py:128);
+ * result ends in slot_a if nsteps is even else slot_b; optional per-step error norms into
+ * norms_out[(nsteps+1)][nmembers][8] (index 0 = initial state) */
+int dd_run_pc(dd_batch* b, int slot_a, int slot_b, const double* t0, const double* dt, int n_t, int nsteps,
+              const dd_pc_options* opt, double* norms_out, dd_step_stats* stats);
+int dd_run_feuler(dd_batch* b, int slot_a, int slot_b, const double* t0, const double* dt, int n_t, int nsteps,
+                  double* norms_out);
+void dd_pc_options_default(dd_pc_options* opt);
+
+/* ---- pieces of the step, for the class-level API and its tests ---------- */
+/* SemiDiscreteField.Fcp/FT/Fcl/Fcd/Fcs(state, t), src/prob1base.py:2599-2672: slot_out[v] = F_v */
+int dd_eval_fields(dd_batch* b, int slot_in, int slot_out, const double* t, int n_t);
+/* initial_cp_pred / initial_cs_pred + Y_T, Y_cl, Y_cd (src/prob1base.py:2953-2965, 3631-3645, 3122-3124)
+ * results in work buffers "cp1p","cs1p","YT","Ycl","Ycd" */
+int dd_pc_predict(dd_batch* b, int slot_in, const double* t0, const double* dt, int n_t);
+/* newton_step_T / _cl / _cd (src/prob1base.py:2998-3115): linearise at slot_star (cp, T, cl, cd, cs all from
+ * that slot), Y from work buffer "YT"/"Ycl"/"Ycd"; T1 / cl1 are read from slot_new for var = CL / CD;
+ * result written to slot_new[var] */
+int dd_pc_newton(dd_batch* b, int var, int slot_star, int slot_new, const double* t0, const double* dt, int n_t,
+                 const dd_pc_options* opt, dd_step_stats* stats);
+/* corrector_cp_step + corrector_cs_step (src/prob1base.py:2967-2996, 3665-3702): reads state0 from slot0 and
+ * T1, cl1, cd1 from slot_new; writes cp, cs of slot_new */
+int dd_pc_correct(dd_batch* b, int slot0, int slot_new, const double* t0, const double* dt, int n_t,
+                  const dd_pc_options* opt, int* cs_iters_out /* nmembers or NULL */);
+/* last_residual[var] = 2 v - dt F_v(state, t1) - Y_v (src/prob1base.py:3041-3043, 3076-3078, 3111-3113) */
+int dd_pc_residual(dd_batch* b, int var, int slot_state, const double* t0, const double* dt, int n_t,
+                   double* out_host /* member 0.. all members, nrows*(M+1) each */);
+
+/* ---- error norms (Grid.norm_H / grad_H / norm_p as used by collect_errors,
+ *      src/prob1base.py:387-433, src/mms_trial_utils.py:81-110) ------------------ */
+/* out[member][8] = H2[cp,T,cl,cd,cs], P2[T,cl,cd] of (state - exact(t)); exact from the forcing tables,
+ * or from slot_exact when >= 0 */
+int dd_error_norms(dd_batch* b, int slot, int slot_exact, const double* t, int n_t, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DD_B200_H */

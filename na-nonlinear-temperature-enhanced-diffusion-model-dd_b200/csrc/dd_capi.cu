@@ -1,0 +1,1074 @@
+// dd_capi.cu -- the C ABI of libdd_b200.so (declared in include/dd_b200.h):
+// context / batch management, forcing tables, state transfer, and the host-side
+// orchestration of the predictor-corrector step.  No Python.h, no torch types.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dd_b200.h"
+#include "dd_kernels.cuh"
+
+#define DD_VERSION_STR "dd_b200 0.1 (sm_100a)"
+
+struct dd_ctx {
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    std::string err;
+    int sm_count;
+};
+
+struct SolveSummary {  // reduced over members on the device
+    double rho, ratio, resid, bound;
+};
+
+struct dd_batch {
+    dd_ctx* ctx;
+    int N, M, B, row0, nrows, own0, own1, nslots;
+    size_t field_elems;  // B * nrows * ld
+    DDGeom g;
+    std::vector<double*> geo_dev;  // owned 1-D arrays
+    DDMember* d_mem;
+    std::vector<DDMember> h_mem;
+    int mode;
+    DDForcing F;
+    std::vector<double*> table_dev;
+    std::vector<std::vector<double*>> slots;  // [slot][var]
+    std::map<std::string, double*> work;
+    double *d_t0, *d_dt;
+    DDSolveStats* d_stats;  // [nsolve_cap][B]
+    int nsolve_cap;
+    SolveSummary* d_summary;  // [nsolve_cap]
+    double *d_itmax, *d_itmin;
+    int* d_used;
+    int cs_cap_alloc;
+    double *d_norm_partial, *d_norm_out;
+    int norm_bpm;
+    int plan_sweeps[3], plan_extra[3];
+    bool is_slab;
+    int cmp0, cmp1;  // local rows with a complete stencil (slabs: everything but the outermost halo row)
+};
+
+// ---------------------------------------------------------------------------
+static int fail(dd_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(ctx, DD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
+    } while (0)
+
+extern "C" const char* dd_version(void) { return DD_VERSION_STR; }
+
+extern "C" const char* dd_last_error(const dd_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int dd_ctx_create(int device, void* cuda_stream, dd_ctx** out) {
+    if (!out) return DD_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return DD_ERR_NO_DEVICE;
+    if (device < 0 || device >= n) return DD_ERR_INVALID;
+    dd_ctx* ctx = new dd_ctx();
+    ctx->device = device;
+    ctx->own_stream = false;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        delete ctx;
+        return DD_ERR_CUDA;
+    }
+    if (cuda_stream) {
+        ctx->stream = (cudaStream_t)cuda_stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return DD_ERR_CUDA;
+        }
+        ctx->own_stream = true;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    ctx->sm_count = prop.multiProcessorCount;
+    if (dd_solver_configure() != cudaSuccess) {
+        cudaGetLastError();
+        delete ctx;
+        return DD_ERR_CUDA;
+    }
+    *out = ctx;
+    return DD_OK;
+}
+
+extern "C" int dd_ctx_destroy(dd_ctx* ctx) {
+    if (!ctx) return DD_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return DD_OK;
+}
+
+extern "C" int dd_ctx_synchronize(dd_ctx* ctx) {
+    if (!ctx) return DD_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DD_OK;
+}
+
+// ---------------------------------------------------------------------------
+static int upload_vec(dd_ctx* ctx, const std::vector<double>& h, double** d, std::vector<double*>& keep) {
+    CK(cudaMalloc((void**)d, h.size() * sizeof(double)));
+    keep.push_back(*d);
+    CK(cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DD_OK;
+}
+
+static int get_work(dd_batch* b, const char* name, double** out) {
+    dd_ctx* ctx = b->ctx;
+    auto it = b->work.find(name);
+    if (it != b->work.end()) {
+        *out = it->second;
+        return DD_OK;
+    }
+    double* p = nullptr;
+    CK(cudaMalloc((void**)&p, b->field_elems * sizeof(double)));
+    CK(cudaMemsetAsync(p, 0, b->field_elems * sizeof(double), ctx->stream));
+    b->work[name] = p;
+    *out = p;
+    return DD_OK;
+}
+
+static void model_to_dev(const dd_model& s, DDModel* d) {
+    d->K1 = s.K1; d->K2 = s.K2; d->K3 = s.K3; d->K4 = s.K4; d->DT = s.DT; d->Dl_max = s.Dl_max;
+    d->phi_l = s.phi_l; d->gamma_T = s.gamma_T; d->Kd = s.Kd; d->Sd = s.Sd; d->Dd_max = s.Dd_max;
+    d->phi_d = s.phi_d; d->phi_T = s.phi_T; d->r_sp = s.r_sp;
+    d->T_shift = (s.kind == 2) ? s.T_ref : 0.0;
+    d->eta = s.eta;
+}
+
+extern "C" int dd_batch_create(dd_ctx* ctx, int N, int M, const double* x, const double* y, int nmembers, int row0,
+                               int nrows, int own0, int own1, int nslots, dd_batch** out) {
+    if (!ctx || !out || !x || !y) return DD_ERR_INVALID;
+    *out = nullptr;
+    if (N < 2 || M < 2 || nmembers < 1 || nslots < 2) return fail(ctx, DD_ERR_INVALID, "need N, M >= 2, members >= 1, slots >= 2");
+    if (row0 < 0 || nrows < 1 || row0 + nrows > N + 1) return fail(ctx, DD_ERR_INVALID, "row slab outside the grid");
+    if (own0 < 0 || own1 > nrows || own0 >= own1) return fail(ctx, DD_ERR_INVALID, "bad owned row range");
+    CK(cudaSetDevice(ctx->device));
+    dd_batch* b = new dd_batch();
+    b->ctx = ctx;
+    b->N = N; b->M = M; b->B = nmembers; b->row0 = row0; b->nrows = nrows; b->own0 = own0; b->own1 = own1;
+    b->nslots = nslots;
+    b->is_slab = !(row0 == 0 && nrows == N + 1);
+    b->cmp0 = (row0 == 0) ? 0 : 1;
+    b->cmp1 = (row0 + nrows == N + 1) ? nrows : nrows - 1;
+    b->plan_extra[0] = b->plan_extra[1] = b->plan_extra[2] = 0;
+    const int ld = M + 1;
+    b->field_elems = (size_t)nmembers * nrows * ld;
+    // geometry (reference Grid.__init__, src/prob1base.py:287-304)
+    std::vector<double> hx(N + 1), hk(M + 1), hp(N + 1), kp(M + 1), rh(N + 1), rk(M + 1), rhp(N + 1), rkp(M + 1);
+    std::vector<double> xs(x, x + N + 1), ys(y, y + M + 1);
+    hx[0] = INFINITY; hk[0] = INFINITY;
+    for (int i = 1; i <= N; ++i) hx[i] = x[i] - x[i - 1];
+    for (int j = 1; j <= M; ++j) hk[j] = y[j] - y[j - 1];
+    for (int i = 0; i < N; ++i) hp[i] = (hx[i] + hx[i + 1]) * 0.5;
+    hp[N] = INFINITY;
+    for (int j = 0; j < M; ++j) kp[j] = (hk[j] + hk[j + 1]) * 0.5;
+    kp[M] = INFINITY;
+    for (int i = 0; i <= N; ++i) { rh[i] = (i == 0) ? 0.0 : 1.0 / hx[i]; rhp[i] = (i == 0 || i == N) ? 0.0 : 1.0 / hp[i]; }
+    for (int j = 0; j <= M; ++j) { rk[j] = (j == 0) ? 0.0 : 1.0 / hk[j]; rkp[j] = (j == 0 || j == M) ? 0.0 : 1.0 / kp[j]; }
+    DDGeom& g = b->g;
+    g.N = N; g.M = M; g.row0 = row0; g.nrows = nrows; g.ld = ld; g.mstride = (long long)nrows * ld;
+    double* d;
+    int rc;
+#define UP(vec, field) if ((rc = upload_vec(ctx, vec, &d, b->geo_dev)) != DD_OK) return rc; g.field = d;
+    UP(xs, x) UP(ys, y) UP(hx, h) UP(hk, k) UP(hp, hp) UP(kp, kp) UP(rh, rh) UP(rk, rk) UP(rhp, rhp) UP(rkp, rkp)
+#undef UP
+    // members
+    b->h_mem.resize(nmembers);
+    memset(b->h_mem.data(), 0, sizeof(DDMember) * nmembers);
+    for (auto& mb : b->h_mem) mb.active = 1;
+    CK(cudaMalloc((void**)&b->d_mem, sizeof(DDMember) * nmembers));
+    CK(cudaMemcpyAsync(b->d_mem, b->h_mem.data(), sizeof(DDMember) * nmembers, cudaMemcpyHostToDevice, ctx->stream));
+    b->mode = DD_FORCING_NONE;
+    memset(&b->F, 0, sizeof(b->F));
+    b->slots.resize(nslots);
+    for (int s = 0; s < nslots; ++s) {
+        b->slots[s].resize(DD_NVAR);
+        for (int v = 0; v < DD_NVAR; ++v) {
+            CK(cudaMalloc((void**)&b->slots[s][v], b->field_elems * sizeof(double)));
+            CK(cudaMemsetAsync(b->slots[s][v], 0, b->field_elems * sizeof(double), ctx->stream));
+        }
+    }
+    CK(cudaMalloc((void**)&b->d_t0, sizeof(double) * nmembers));
+    CK(cudaMalloc((void**)&b->d_dt, sizeof(double) * nmembers));
+    b->nsolve_cap = 0; b->d_stats = nullptr; b->d_summary = nullptr;
+    b->d_itmax = b->d_itmin = nullptr; b->d_used = nullptr; b->cs_cap_alloc = 0;
+    b->norm_bpm = dd_norm_blocks_per_member(g);
+    CK(cudaMalloc((void**)&b->d_norm_partial, sizeof(double) * 8 * (size_t)b->norm_bpm * nmembers));
+    CK(cudaMalloc((void**)&b->d_norm_out, sizeof(double) * 8 * nmembers));
+    b->plan_sweeps[0] = b->plan_sweeps[1] = b->plan_sweeps[2] = 0;
+    CK(cudaStreamSynchronize(ctx->stream));
+    *out = b;
+    return DD_OK;
+}
+
+extern "C" int dd_batch_destroy(dd_batch* b) {
+    if (!b) return DD_OK;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    for (double* p : b->geo_dev) cudaFree(p);
+    for (double* p : b->table_dev) cudaFree(p);
+    for (auto& s : b->slots) for (double* p : s) cudaFree(p);
+    for (auto& kv : b->work) cudaFree(kv.second);
+    cudaFree(b->d_mem); cudaFree(b->d_t0); cudaFree(b->d_dt); cudaFree(b->d_stats); cudaFree(b->d_summary);
+    cudaFree(b->d_itmax); cudaFree(b->d_itmin); cudaFree(b->d_used); cudaFree(b->d_norm_partial);
+    cudaFree(b->d_norm_out);
+    delete b;
+    return DD_OK;
+}
+
+static int push_members(dd_batch* b, int first, int count) {
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(b->d_mem + first, b->h_mem.data() + first, sizeof(DDMember) * count, cudaMemcpyHostToDevice,
+                       ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DD_OK;
+}
+
+// the device copy carries t0/dt/tc written by kernels; refresh the host mirror's
+// static part only (model, phi, active) -- kernels never change those.
+extern "C" int dd_batch_set_models(dd_batch* b, int first, int count, const dd_model* models) {
+    if (!b || !models || first < 0 || count < 1 || first + count > b->B) return DD_ERR_INVALID;
+    for (int k = 0; k < count; ++k) model_to_dev(models[k], &b->h_mem[first + k].m);
+    b->plan_sweeps[0] = b->plan_sweeps[1] = b->plan_sweeps[2] = 0;
+    b->plan_extra[0] = b->plan_extra[1] = b->plan_extra[2] = 0;
+    return push_members(b, first, count);
+}
+
+extern "C" int dd_batch_set_active(dd_batch* b, int first, int count, const int* active) {
+    if (!b || !active || first < 0 || count < 1 || first + count > b->B) return DD_ERR_INVALID;
+    for (int k = 0; k < count; ++k) b->h_mem[first + k].active = active[k] ? 1 : 0;
+    return push_members(b, first, count);
+}
+
+// ---------------------------------------------------------------------------
+// forcing
+// ---------------------------------------------------------------------------
+static void free_tables(dd_batch* b) {
+    for (double* p : b->table_dev) cudaFree(p);
+    b->table_dev.clear();
+    memset(&b->F.tab, 0, sizeof(b->F.tab));
+}
+
+static int up_table(dd_batch* b, const double* h, size_t n, const double** dst) {
+    dd_ctx* ctx = b->ctx;
+    double* d = nullptr;
+    CK(cudaMalloc((void**)&d, n * sizeof(double)));
+    b->table_dev.push_back(d);
+    CK(cudaMemcpyAsync(d, h, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    *dst = d;
+    return DD_OK;
+}
+
+extern "C" int dd_forcing_none(dd_batch* b) {
+    if (!b) return DD_ERR_INVALID;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    free_tables(b);
+    b->mode = DD_FORCING_NONE;
+    return DD_OK;
+}
+
+extern "C" int dd_forcing_separable(dd_batch* b, int nterms, const double* const X[5][3],
+                                    const double* const Y[5][3], const double* const XQ[3],
+                                    const double* const YQ[3], const int phi_kind[5], const double phi_p[5][4]) {
+    if (!b || !X || !Y || !XQ || !YQ || !phi_kind || !phi_p || nterms < 1 || nterms > 16) return DD_ERR_INVALID;
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_tables(b);
+    int rc;
+    for (int v = 0; v < 5; ++v)
+        for (int d = 0; d < 3; ++d) {
+            if (!X[v][d] || !Y[v][d]) return fail(ctx, DD_ERR_INVALID, "null separable table");
+            if ((rc = up_table(b, X[v][d], (size_t)nterms * (b->N + 1), &b->F.tab.X[v][d])) != DD_OK) return rc;
+            if ((rc = up_table(b, Y[v][d], (size_t)nterms * (b->M + 1), &b->F.tab.Y[v][d])) != DD_OK) return rc;
+        }
+    for (int q = 0; q < 3; ++q) {
+        if (!XQ[q] || !YQ[q]) return fail(ctx, DD_ERR_INVALID, "null quadrature table");
+        if ((rc = up_table(b, XQ[q], 3 * (size_t)nterms * (b->N + 1), &b->F.tab.XQ[q])) != DD_OK) return rc;
+        if ((rc = up_table(b, YQ[q], 3 * (size_t)nterms * (b->M + 1), &b->F.tab.YQ[q])) != DD_OK) return rc;
+    }
+    b->F.tab.nterms = nterms;
+    b->F.tab.nx = b->N + 1;
+    b->F.tab.ny = b->M + 1;
+    for (auto& mb : b->h_mem)
+        for (int v = 0; v < 5; ++v) {
+            mb.phi_kind[v] = phi_kind[v];
+            for (int k = 0; k < 4; ++k) mb.phi_p[v][k] = phi_p[v][k];
+        }
+    b->mode = DD_FORCING_SEPARABLE;
+    return push_members(b, 0, b->B);
+}
+
+extern "C" int dd_forcing_set_phi(dd_batch* b, int first, int count, const int* phi_kind, const double* phi_p) {
+    if (!b || !phi_kind || !phi_p || first < 0 || count < 1 || first + count > b->B) return DD_ERR_INVALID;
+    for (int k = 0; k < count; ++k)
+        for (int v = 0; v < 5; ++v) {
+            b->h_mem[first + k].phi_kind[v] = phi_kind[k * 5 + v];
+            for (int q = 0; q < 4; ++q) b->h_mem[first + k].phi_p[v][q] = phi_p[(k * 5 + v) * 4 + q];
+        }
+    return push_members(b, first, count);
+}
+
+extern "C" int dd_forcing_expsin(dd_batch* b, const double* sx, const double* cx, const double* sy, const double* cy,
+                                 const double* sxq, const double* syq) {
+    if (!b || !sx || !cx || !sy || !cy || !sxq || !syq) return DD_ERR_INVALID;
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_tables(b);
+    int rc;
+    if ((rc = up_table(b, sx, b->N + 1, &b->F.tab.X[0][0])) != DD_OK) return rc;
+    if ((rc = up_table(b, cx, b->N + 1, &b->F.tab.X[0][1])) != DD_OK) return rc;
+    if ((rc = up_table(b, sy, b->M + 1, &b->F.tab.Y[0][0])) != DD_OK) return rc;
+    if ((rc = up_table(b, cy, b->M + 1, &b->F.tab.Y[0][1])) != DD_OK) return rc;
+    if ((rc = up_table(b, sxq, 3 * (size_t)(b->N + 1), &b->F.tab.XQ[0])) != DD_OK) return rc;
+    if ((rc = up_table(b, syq, 3 * (size_t)(b->M + 1), &b->F.tab.YQ[0])) != DD_OK) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    b->F.tab.nterms = 1;
+    b->F.tab.nx = b->N + 1;
+    b->F.tab.ny = b->M + 1;
+    b->mode = DD_FORCING_EXPSIN;
+    return DD_OK;
+}
+
+static const char* kForcingNames[5][2] = {{"f_cp0", "f_cp1"}, {"f_T0", "f_T1"}, {"f_cl0", "f_cl1"},
+                                          {"f_cd0", "f_cd1"}, {"f_cs0", "f_cs1"}};
+
+extern "C" int dd_forcing_arrays(dd_batch* b, int member, const double* const f[5][2]) {
+    if (!b || !f || member < 0 || member >= b->B) return DD_ERR_INVALID;
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    if (b->mode != DD_FORCING_ARRAYS) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        free_tables(b);
+        b->mode = DD_FORCING_ARRAYS;
+    }
+    const size_t per = (size_t)b->nrows * b->g.ld;
+    for (int v = 0; v < 5; ++v)
+        for (int s = 0; s < 2; ++s) {
+            double* d;
+            int rc = get_work(b, kForcingNames[v][s], &d);
+            if (rc != DD_OK) return rc;
+            b->F.arr.f[v][s] = d;
+            if (f[v][s])
+                CK(cudaMemcpyAsync(d + member * per, f[v][s], per * sizeof(double), cudaMemcpyHostToDevice,
+                                   ctx->stream));
+            else
+                CK(cudaMemsetAsync(d + member * per, 0, per * sizeof(double), ctx->stream));
+        }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DD_OK;
+}
+
+// ---------------------------------------------------------------------------
+// state
+// ---------------------------------------------------------------------------
+static bool slot_ok(const dd_batch* b, int s) { return s >= 0 && s < b->nslots; }
+
+extern "C" int dd_state_upload(dd_batch* b, int slot, int member, const double* const fields[5]) {
+    if (!b || !fields || !slot_ok(b, slot) || member < 0 || member >= b->B) return DD_ERR_INVALID;
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    const size_t per = (size_t)b->nrows * b->g.ld;
+    for (int v = 0; v < 5; ++v)
+        if (fields[v])
+            CK(cudaMemcpyAsync(b->slots[slot][v] + member * per, fields[v], per * sizeof(double),
+                               cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DD_OK;
+}
+
+extern "C" int dd_state_download(dd_batch* b, int slot, int member, double* const fields[5]) {
+    if (!b || !fields || !slot_ok(b, slot) || member < 0 || member >= b->B) return DD_ERR_INVALID;
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    const size_t per = (size_t)b->nrows * b->g.ld;
+    for (int v = 0; v < 5; ++v)
+        if (fields[v])
+            CK(cudaMemcpyAsync(fields[v], b->slots[slot][v] + member * per, per * sizeof(double),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DD_OK;
+}
+
+extern "C" int dd_state_dev_ptr(dd_batch* b, int slot, int var, void** ptr, long long* member_stride, int* ld) {
+    if (!b || !ptr || !slot_ok(b, slot) || var < 0 || var > 4) return DD_ERR_INVALID;
+    *ptr = b->slots[slot][var];
+    if (member_stride) *member_stride = b->g.mstride;
+    if (ld) *ld = b->g.ld;
+    return DD_OK;
+}
+
+extern "C" int dd_work_dev_ptr(dd_batch* b, const char* name, void** ptr) {
+    if (!b || !name || !ptr) return DD_ERR_INVALID;
+    double* p;
+    int rc = get_work(b, name, &p);
+    if (rc != DD_OK) return rc;
+    *ptr = p;
+    return DD_OK;
+}
+
+extern "C" int dd_work_upload(dd_batch* b, const char* name, int member, const double* host) {
+    if (!b || !name || !host || member < 0 || member >= b->B) return DD_ERR_INVALID;
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    double* p;
+    int rc = get_work(b, name, &p);
+    if (rc != DD_OK) return rc;
+    const size_t per = (size_t)b->nrows * b->g.ld;
+    CK(cudaMemcpyAsync(p + member * per, host, per * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DD_OK;
+}
+
+extern "C" int dd_work_download(dd_batch* b, const char* name, int member, double* host) {
+    if (!b || !name || !host || member < 0 || member >= b->B) return DD_ERR_INVALID;
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    double* p;
+    int rc = get_work(b, name, &p);
+    if (rc != DD_OK) return rc;
+    const size_t per = (size_t)b->nrows * b->g.ld;
+    CK(cudaMemcpyAsync(host, p + member * per, per * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DD_OK;
+}
+
+static DDStateC cstate(const dd_batch* b, int slot) {
+    DDStateC s;
+    for (int v = 0; v < DD_NVAR; ++v) s.v[v] = b->slots[slot][v];
+    return s;
+}
+static DDState mstate(const dd_batch* b, int slot) {
+    DDState s;
+    for (int v = 0; v < DD_NVAR; ++v) s.v[v] = b->slots[slot][v];
+    return s;
+}
+// row ranges: OWNED rows (tile solver), STENCIL rows (every row with a complete stencil: on a slab
+// the halo rows are recomputed redundantly), ALL rows (pointwise work)
+enum RowRange { ROWS_OWNED = 0, ROWS_ALL = 1, ROWS_STENCIL = 2 };
+static DDLaunch launch_of(const dd_batch* b, int range = ROWS_STENCIL) {
+    DDLaunch L;
+    L.stream = b->ctx->stream;
+    L.nmembers = b->B;
+    if (range == ROWS_ALL) { L.own0 = 0; L.own1 = b->nrows; }
+    else if (range == ROWS_STENCIL) { L.own0 = b->cmp0; L.own1 = b->cmp1; }
+    else { L.own0 = b->own0; L.own1 = b->own1; }
+    L.vr0 = b->cmp0;
+    L.vr1 = b->cmp1;
+    return L;
+}
+
+static int set_times(dd_batch* b, const double* t0, const double* dt, int n_t) {
+    dd_ctx* ctx = b->ctx;
+    if (!t0 || !dt || (n_t != 1 && n_t != b->B)) return fail(ctx, DD_ERR_INVALID, "t0/dt: need 1 or nmembers values");
+    for (int k = 0; k < n_t; ++k)
+        if (!(dt[k] > 0.0)) return fail(ctx, DD_ERR_INVALID, "dt must be > 0");
+    CK(cudaMemcpyAsync(b->d_t0, t0, sizeof(double) * n_t, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(b->d_dt, dt, sizeof(double) * n_t, cudaMemcpyHostToDevice, ctx->stream));
+    CK(dd_launch_time_coefs(launch_of(b), b->mode, b->d_mem, b->d_t0, b->d_dt, n_t, 0));
+    return DD_OK;
+}
+
+extern "C" int dd_state_fill_exact(dd_batch* b, int slot, const double* t, int n_t) {
+    if (!b || !slot_ok(b, slot) || !t) return DD_ERR_INVALID;
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<double> one(n_t, 1.0);
+    int rc = set_times(b, t, one.data(), n_t);
+    if (rc != DD_OK) return rc;
+    CK(dd_launch_fill_exact(launch_of(b, ROWS_ALL), b->mode, b->g, b->d_mem, b->F, mstate(b, slot)));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DD_OK;
+}
+
+// ---------------------------------------------------------------------------
+// forward Euler, field evaluation, norms
+// ---------------------------------------------------------------------------
+extern "C" int dd_step_feuler(dd_batch* b, int slot_in, int slot_out, const double* t0, const double* dt, int n_t) {
+    if (!b || !slot_ok(b, slot_in) || !slot_ok(b, slot_out) || slot_in == slot_out) return DD_ERR_INVALID;
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    int rc = set_times(b, t0, dt, n_t);
+    if (rc != DD_OK) return rc;
+    CK(dd_launch_feuler(launch_of(b), b->mode, b->g, b->d_mem, b->F, cstate(b, slot_in), mstate(b, slot_out)));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DD_OK;
+}
+
+extern "C" int dd_eval_fields(dd_batch* b, int slot_in, int slot_out, const double* t, int n_t) {
+    if (!b || !slot_ok(b, slot_in) || !slot_ok(b, slot_out) || slot_in == slot_out || !t) return DD_ERR_INVALID;
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<double> one(n_t, 1.0);
+    int rc = set_times(b, t, one.data(), n_t);
+    if (rc != DD_OK) return rc;
+    CK(dd_launch_fields(launch_of(b), b->mode, b->g, b->d_mem, b->F, cstate(b, slot_in), mstate(b, slot_out), 0));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DD_OK;
+}
+
+static int norms_async(dd_batch* b, int slot, int slot_exact, double* out_host) {
+    dd_ctx* ctx = b->ctx;
+    DDStateC ex;
+    if (slot_exact >= 0) ex = cstate(b, slot_exact);
+    CK(dd_launch_error_norms(launch_of(b), b->mode, b->g, b->d_mem, b->F, cstate(b, slot),
+                             slot_exact >= 0 ? &ex : nullptr, b->d_norm_partial, b->norm_bpm, b->d_norm_out));
+    CK(cudaMemcpyAsync(out_host, b->d_norm_out, sizeof(double) * 8 * b->B, cudaMemcpyDeviceToHost, ctx->stream));
+    return DD_OK;
+}
+
+extern "C" int dd_error_norms(dd_batch* b, int slot, int slot_exact, const double* t, int n_t, double* out) {
+    if (!b || !slot_ok(b, slot) || !out || (slot_exact >= 0 && !slot_ok(b, slot_exact))) return DD_ERR_INVALID;
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    if (slot_exact < 0) {
+        if (!t) return DD_ERR_INVALID;
+        std::vector<double> one(n_t, 1.0);
+        int rc = set_times(b, t, one.data(), n_t);
+        if (rc != DD_OK) return rc;
+    }
+    int rc = norms_async(b, slot, slot_exact, out);
+    if (rc != DD_OK) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DD_OK;
+}
+
+// ---------------------------------------------------------------------------
+// predictor-corrector step
+// ---------------------------------------------------------------------------
+extern "C" void dd_pc_options_default(dd_pc_options* o) {
+    if (!o) return;
+    o->num_pc_steps = 1;
+    o->num_newton_steps = 1;
+    o->num_newton_iterations = 5;
+    o->cd_band_swap = 1;
+    o->consec_xs_rtol = 1e-6;
+    o->solve_tol = 1e-14;
+    o->max_sweeps = 20000;
+    o->fixed_sweeps = 0;
+}
+
+static const size_t kSmemMax = 227 * 1024;
+static const int kSmemArrays = 6;
+
+// SOR sweeps needed for spectral-radius bound rho of the Jacobi matrix
+static int sweeps_for_rho(double rho, int max_sweeps) {
+    if (!(rho >= 0.0)) return max_sweeps;
+    if (rho < 1e-300) return 2;
+    double lam;
+    if (rho < 1.0) {
+        const double om = 2.0 / (1.0 + sqrt(1.0 - rho * rho));
+        lam = om - 1.0;
+    } else {
+        lam = 0.999;  // not diagonally dominant: plain Gauss-Seidel, rely on the residual check
+    }
+    int k = 2;
+    while (k < max_sweeps && (1.0 + k) * pow(lam, k) > 1e-17) ++k;
+    return k;
+}
+
+// choose tile shape and sweeps per pass
+static void plan_pass(const dd_batch* b, int sweeps_left, bool allow_last, DDSolvePlan* P) {
+    const int rows = b->own1 - b->own0, cols = b->M + 1;
+    const size_t cell_bytes = kSmemArrays * sizeof(double);
+    const size_t cells_max = kSmemMax / cell_bytes;
+    // whole member in one tile (no halo needed because every edge is a physical boundary)
+    if (!b->is_slab && (size_t)(rows + 2) * (cols + 2) <= cells_max) {
+        P->sweeps = sweeps_left;
+        P->tile_i = rows;
+        P->tile_j = cols;
+        P->halo = 0;
+        P->last_pass = 1;
+        const size_t cells = (size_t)(rows + 2) * (cols + 2);
+        P->smem_bytes = cells * cell_bytes;
+        P->threads = cells >= 2048 ? 512 : (cells >= 512 ? 256 : 128);
+        return;
+    }
+    const int sm = b->ctx->sm_count > 0 ? b->ctx->sm_count : 148;
+    static const int cand_i[] = {8, 12, 16, 24, 32, 48, 64};
+    static const int cand_j[] = {16, 32, 48, 64, 96, 128};
+    double best = 1e300;
+    DDSolvePlan bp = *P;
+    // sweeps per pass: try everything that fits, cost = (waves * staged cells * sweeps-ish) per sweep done
+    for (int S = sweeps_left; S >= 1; --S) {
+        const int last = (S == sweeps_left) && allow_last;
+        const int H = 2 * S + (last ? 1 : 0);
+        for (int ti : cand_i)
+            for (int tj : cand_j) {
+                const size_t cells = (size_t)(ti + 2 * H + 2) * (tj + 2 * H + 2);
+                if (cells > cells_max) continue;
+                const long long tiles = (long long)((rows + ti - 1) / ti) * ((cols + tj - 1) / tj) * b->B;
+                int per_sm = (int)(kSmemMax / (cells * cell_bytes));
+                if (per_sm > 4) per_sm = 4;
+                const double waves = ceil((double)tiles / ((double)sm * per_sm));
+                // time ~ waves * per-CTA work / concurrency; work = staging + S sweeps over the staged area
+                const double work = (double)cells * (6.0 + 2.0 * S) * (per_sm > 1 ? per_sm * 0.6 : 1.0);
+                const int npass = (sweeps_left + S - 1) / S;
+                const double cost = waves * work * npass;
+                if (cost < best) {
+                    best = cost;
+                    bp.sweeps = S;
+                    bp.tile_i = ti;
+                    bp.tile_j = tj;
+                    bp.halo = H;
+                    bp.last_pass = last;
+                    bp.smem_bytes = cells * cell_bytes;
+                    bp.threads = cells >= 2048 ? 512 : 256;
+                }
+            }
+    }
+    *P = bp;
+}
+
+__global__ void k_summarise(const DDSolveStats* st, int nmem, const DDMember* mem, double tol, SolveSummary* out) {
+    // single block; one summary per solve
+    __shared__ double s_rho[256], s_ratio[256], s_res[256], s_bound[256];
+    double rho = 0.0, ratio = 0.0, res = 0.0, bound = 0.0;
+    for (int m = threadIdx.x; m < nmem; m += blockDim.x) {
+        if (!mem[m].active) continue;
+        const DDSolveStats s = st[m];
+        const double gap = s.rho < 1.0 ? 1.0 - s.rho : 1e-4;
+        // |x - x*|_inf <= resid / (1 - rho); allowed: tol * |v_new| plus the rounding floor of the residual
+        const double eps = 2.220446049250313e-16;
+        const double allowed = tol * gap * s.vmax + 16.0 * eps * (s.bmax + s.xmax);
+        double r = (allowed > 0.0) ? s.resid / allowed : (s.resid > 0.0 ? 1e300 : 0.0);
+        if (s.resid != s.resid || s.rho != s.rho) r = 1e300;
+        rho = fmax(rho, s.rho);
+        if (s.rho != s.rho) rho = s.rho;
+        ratio = fmax(ratio, r);
+        res = fmax(res, s.resid);
+        bound = fmax(bound, s.vmax > 0.0 ? s.resid / (gap * s.vmax) : 0.0);
+    }
+    s_rho[threadIdx.x] = rho; s_ratio[threadIdx.x] = ratio; s_res[threadIdx.x] = res; s_bound[threadIdx.x] = bound;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < blockDim.x; ++k) {
+            if (s_rho[k] != s_rho[k]) rho = s_rho[k]; else rho = fmax(rho, s_rho[k]);
+            ratio = fmax(ratio, s_ratio[k]);
+            res = fmax(res, s_res[k]);
+            bound = fmax(bound, s_bound[k]);
+        }
+        out->rho = rho; out->ratio = ratio; out->resid = res; out->bound = bound;
+    }
+}
+
+static int ensure_solve_slots(dd_batch* b, int n) {
+    dd_ctx* ctx = b->ctx;
+    if (n <= b->nsolve_cap) return DD_OK;
+    cudaFree(b->d_stats);
+    cudaFree(b->d_summary);
+    CK(cudaMalloc((void**)&b->d_stats, sizeof(DDSolveStats) * (size_t)n * b->B));
+    CK(cudaMalloc((void**)&b->d_summary, sizeof(SolveSummary) * n));
+    b->nsolve_cap = n;
+    return DD_OK;
+}
+
+__global__ void k_cs_arm(double* it_max, double* it_min, long long n) {
+    const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    it_max[k] = 0.0;
+    it_min[k] = __longlong_as_double(0x7ff0000000000000LL);
+}
+
+static int ensure_cs_buffers(dd_batch* b, int cap) {
+    dd_ctx* ctx = b->ctx;
+    if (!b->d_used) CK(cudaMalloc((void**)&b->d_used, sizeof(int) * b->B));
+    if (cap <= b->cs_cap_alloc) return DD_OK;
+    cudaFree(b->d_itmax);
+    cudaFree(b->d_itmin);
+    const long long n = (long long)cap * b->B;
+    CK(cudaMalloc((void**)&b->d_itmax, sizeof(double) * n));
+    CK(cudaMalloc((void**)&b->d_itmin, sizeof(double) * n));
+    b->cs_cap_alloc = cap;
+    return DD_OK;
+}
+
+// assemble + solve one Newton system.  `k` indexes the stats slot.
+static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const double* T1, const double* cl1,
+                        const double* Y, double* vnew, const dd_pc_options& opt, int k, int* sweeps_used,
+                        int* passes_used) {
+    dd_ctx* ctx = b->ctx;
+    DDRows R;
+    int rc;
+    if ((rc = get_work(b, "bb", &R.bb)) != DD_OK) return rc;
+    if ((rc = get_work(b, "aW", &R.aW)) != DD_OK) return rc;
+    if ((rc = get_work(b, "aE", &R.aE)) != DD_OK) return rc;
+    if ((rc = get_work(b, "aS", &R.aS)) != DD_OK) return rc;
+    if ((rc = get_work(b, "aN", &R.aN)) != DD_OK) return rc;
+    DDSolveStats* st = b->d_stats + (size_t)k * b->B;
+    // rows are assembled on every local row that has a full stencil (slabs: halo rows included,
+    // so that the tile solver sees valid rows in its halo); tiles cover the owned rows only
+    const DDLaunch L = launch_of(b, ROWS_OWNED);
+    const DDLaunch La = launch_of(b, ROWS_STENCIL);
+    CK(dd_launch_assemble(La, b->mode, var, b->g, b->d_mem, b->F, ustar, T1, cl1, Y, opt.cd_band_swap, R, st));
+    const int vi = var - DD_T;
+    int sweeps = opt.fixed_sweeps > 0 ? opt.fixed_sweeps : b->plan_sweeps[vi];
+    if (sweeps <= 0) {
+        // first use: read the Gershgorin ratio back once to seed the plan
+        CK(cudaMemsetAsync(b->d_summary + k, 0, sizeof(SolveSummary), ctx->stream));
+        k_summarise<<<1, 256, 0, ctx->stream>>>(st, b->B, b->d_mem, opt.solve_tol, b->d_summary + k);
+        SolveSummary s;
+        CK(cudaMemcpyAsync(&s, b->d_summary + k, sizeof(s), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        sweeps = sweeps_for_rho(s.rho, opt.max_sweeps);
+        b->plan_sweeps[vi] = sweeps;
+    }
+    const double* vstar = ustar.v[var];
+    int left = sweeps, passes = 0;
+    double *xa = nullptr, *xb = nullptr;
+    const double* xin = nullptr;
+    while (left > 0) {
+        DDSolvePlan P;
+        memset(&P, 0, sizeof(P));
+        plan_pass(b, left, true, &P);
+        if (P.sweeps <= 0) return fail(ctx, DD_ERR_INVALID, "no feasible solver tile");
+        double* xout = nullptr;
+        if (!P.last_pass) {
+            if (!xa) {
+                if ((rc = get_work(b, "xa", &xa)) != DD_OK) return rc;
+                if ((rc = get_work(b, "xb", &xb)) != DD_OK) return rc;
+            }
+            xout = (xin == xa) ? xb : xa;
+        }
+        if (P.last_pass && P.sweeps < left) return fail(ctx, DD_ERR_INVALID, "solver plan inconsistency");
+        CK(dd_launch_solve_pass(L, b->g, R, xin, xout, vstar, vnew, var == DD_T ? 1 : 0, st, P));
+        left -= P.sweeps;
+        xin = xout;
+        ++passes;
+    }
+    k_summarise<<<1, 256, 0, ctx->stream>>>(st, b->B, b->d_mem, opt.solve_tol, b->d_summary + k);
+    CK(cudaGetLastError());
+    *sweeps_used = sweeps;
+    *passes_used = passes;
+    return DD_OK;
+}
+
+struct StepIO {
+    int slot_in, slot_out;
+};
+
+// one PC step; times must already be on the device (set_times or advance)
+static int pc_step_once(dd_batch* b, int slot_in, int slot_out, const dd_pc_options& opt, dd_step_stats* stats,
+                        bool* converged) {
+    dd_ctx* ctx = b->ctx;
+    int rc;
+    const int P = opt.num_pc_steps, Q = opt.num_newton_steps;
+    if ((rc = ensure_solve_slots(b, 3 * P * Q)) != DD_OK) return rc;
+    DDPredictOut po;
+    if ((rc = get_work(b, "cp1p", &po.cp1p)) != DD_OK) return rc;
+    if ((rc = get_work(b, "cs1p", &po.cs1p)) != DD_OK) return rc;
+    if ((rc = get_work(b, "YT", &po.YT)) != DD_OK) return rc;
+    if ((rc = get_work(b, "Ycl", &po.Ycl)) != DD_OK) return rc;
+    if ((rc = get_work(b, "Ycd", &po.Ycd)) != DD_OK) return rc;
+    const DDLaunch L = launch_of(b, ROWS_STENCIL);
+    const DDLaunch Lall = launch_of(b, ROWS_ALL);
+    const DDStateC s0 = cstate(b, slot_in);
+    const DDState sout = mstate(b, slot_out);
+    CK(dd_launch_predict(L, b->mode, b->g, b->d_mem, b->F, s0, po));
+    DDStateC u;
+    u.v[DD_CP] = po.cp1p; u.v[DD_T] = s0.v[DD_T]; u.v[DD_CL] = s0.v[DD_CL]; u.v[DD_CD] = s0.v[DD_CD];
+    u.v[DD_CS] = po.cs1p;
+    static const char* tmpn[3][2] = {{"T1a", "T1b"}, {"cl1a", "cl1b"}, {"cd1a", "cd1b"}};
+    int pp = 0, k = 0;
+    int sweeps[3] = {0, 0, 0}, passes[3] = {0, 0, 0};
+    for (int pc = 0; pc < P; ++pc) {
+        for (int nw = 0; nw < Q; ++nw) {
+            const bool last = (pc == P - 1) && (nw == Q - 1);
+            double* dst[3];
+            for (int q = 0; q < 3; ++q) {
+                if (last) {
+                    dst[q] = sout.v[DD_T + q];
+                } else if ((rc = get_work(b, tmpn[q][pp], &dst[q])) != DD_OK) {
+                    return rc;
+                }
+            }
+            if ((rc = newton_solve(b, DD_T, u, nullptr, nullptr, po.YT, dst[0], opt, k++, &sweeps[0], &passes[0])) != DD_OK) return rc;
+            if ((rc = newton_solve(b, DD_CL, u, dst[0], nullptr, po.Ycl, dst[1], opt, k++, &sweeps[1], &passes[1])) != DD_OK) return rc;
+            if ((rc = newton_solve(b, DD_CD, u, dst[0], dst[1], po.Ycd, dst[2], opt, k++, &sweeps[2], &passes[2])) != DD_OK) return rc;
+            u.v[DD_T] = dst[0]; u.v[DD_CL] = dst[1]; u.v[DD_CD] = dst[2];
+            pp ^= 1;
+        }
+        const bool lastpc = (pc == P - 1);
+        double* cpd = lastpc ? sout.v[DD_CP] : po.cp1p;
+        double* csd = lastpc ? sout.v[DD_CS] : po.cs1p;
+        const int cap = opt.num_newton_iterations;
+        const bool track = opt.consec_xs_rtol > 0.0 && cap > 0;
+        if (track) {
+            const int had = b->cs_cap_alloc;
+            if ((rc = ensure_cs_buffers(b, cap)) != DD_OK) return rc;
+            if (b->cs_cap_alloc != had) {
+                const long long n = (long long)b->cs_cap_alloc * b->B;
+                k_cs_arm<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(b->d_itmax, b->d_itmin, n);
+            }
+        }
+        CK(dd_launch_correct(Lall, b->mode, b->g, b->d_mem, b->F, s0, u.v[DD_T], u.v[DD_CL], u.v[DD_CD], cpd, csd, cap,
+                             track ? opt.consec_xs_rtol : 0.0, b->d_itmax, b->d_itmin));
+        if (track)
+            CK(dd_launch_cs_finish(Lall, b->mode, b->g, b->d_mem, b->F, s0, u.v[DD_CL], u.v[DD_CD], csd, cap,
+                                   opt.consec_xs_rtol, b->d_itmax, b->d_itmin, b->d_used));
+        u.v[DD_CP] = cpd; u.v[DD_CS] = csd;
+    }
+    // verification of every solve of this step (one small readback)
+    std::vector<SolveSummary> sums(k);
+    CK(cudaMemcpyAsync(sums.data(), b->d_summary, sizeof(SolveSummary) * k, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *converged = true;
+    for (int q = 0; q < k; ++q) {
+        const int vi = q % 3;
+        if (!(sums[q].ratio <= 1.0)) {
+            *converged = false;
+            if (opt.fixed_sweeps <= 0) {
+                // theory said `want`; it was not enough -> keep a growing margin on top of it
+                const int want = sweeps_for_rho(sums[q].rho * 1.02 + 1e-12, opt.max_sweeps);
+                if (b->plan_sweeps[vi] >= want) b->plan_extra[vi] += (b->plan_sweeps[vi] + 1) / 2 + 1;
+                int next = want + b->plan_extra[vi];
+                if (next > opt.max_sweeps) next = opt.max_sweeps;
+                if (next > b->plan_sweeps[vi]) b->plan_sweeps[vi] = next;
+            }
+        } else if (opt.fixed_sweeps <= 0 && q >= k - 3) {
+            // follow rho from step to step (the matrices change slowly)
+            int want = sweeps_for_rho(sums[q].rho * 1.02 + 1e-12, opt.max_sweeps) + b->plan_extra[vi];
+            if (want > opt.max_sweeps) want = opt.max_sweeps;
+            b->plan_sweeps[vi] = want;
+        }
+    }
+    if (stats) {
+        for (int q = 0; q < 3; ++q) {
+            stats->sweeps[q] = sweeps[q];
+            stats->passes[q] = passes[q];
+            stats->rho[q] = sums[k - 3 + q].rho;
+            stats->resid[q] = sums[k - 3 + q].resid;
+            stats->bound[q] = sums[k - 3 + q].bound;
+        }
+        stats->cs_newton_iters = opt.num_newton_iterations;
+        if (opt.consec_xs_rtol > 0.0 && opt.num_newton_iterations > 0) {
+            std::vector<int> used(b->B);
+            CK(cudaMemcpyAsync(used.data(), b->d_used, sizeof(int) * b->B, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            int mx = 0;
+            for (int m = 0; m < b->B; ++m)
+                if (b->h_mem[m].active && used[m] > mx) mx = used[m];
+            stats->cs_newton_iters = mx;
+        }
+    }
+    return DD_OK;
+}
+
+static int check_opts(dd_ctx* ctx, const dd_pc_options& o) {
+    if (o.num_pc_steps < 1 || o.num_newton_steps < 1 || o.num_newton_iterations < 0 || o.max_sweeps < 2)
+        return fail(ctx, DD_ERR_INVALID, "bad dd_pc_options");
+    return DD_OK;
+}
+
+static int pc_step_retry(dd_batch* b, int slot_in, int slot_out, const dd_pc_options& opt, dd_step_stats* stats) {
+    dd_ctx* ctx = b->ctx;
+    int retries = 0;
+    for (;;) {
+        bool ok = false;
+        int rc = pc_step_once(b, slot_in, slot_out, opt, stats, &ok);
+        if (rc != DD_OK) return rc;
+        if (stats) stats->retries = retries;
+        if (ok) return DD_OK;
+        bool can_grow = opt.fixed_sweeps <= 0;
+        if (can_grow) {
+            can_grow = false;
+            for (int q = 0; q < 3; ++q)
+                if (b->plan_sweeps[q] < opt.max_sweeps) can_grow = true;
+        }
+        if (!can_grow || retries >= 40) {
+            char msg[256];
+            snprintf(msg, sizeof(msg), "linear solve did not reach the residual bound (sweeps T/cl/cd = %d/%d/%d)",
+                     b->plan_sweeps[0], b->plan_sweeps[1], b->plan_sweeps[2]);
+            return fail(ctx, DD_ERR_NOT_CONVERGED, msg);
+        }
+        ++retries;
+    }
+}
+
+extern "C" int dd_step_pc(dd_batch* b, int slot_in, int slot_out, const double* t0, const double* dt, int n_t,
+                          const dd_pc_options* opt_in, dd_step_stats* stats) {
+    if (!b || !slot_ok(b, slot_in) || !slot_ok(b, slot_out) || slot_in == slot_out) return DD_ERR_INVALID;
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    dd_pc_options opt;
+    if (opt_in) opt = *opt_in; else dd_pc_options_default(&opt);
+    int rc = check_opts(ctx, opt);
+    if (rc != DD_OK) return rc;
+    if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
+    return pc_step_retry(b, slot_in, slot_out, opt, stats);
+}
+
+extern "C" int dd_run_pc(dd_batch* b, int slot_a, int slot_b, const double* t0, const double* dt, int n_t, int nsteps,
+                         const dd_pc_options* opt_in, double* norms_out, dd_step_stats* stats) {
+    if (!b || !slot_ok(b, slot_a) || !slot_ok(b, slot_b) || slot_a == slot_b || nsteps < 0) return DD_ERR_INVALID;
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    dd_pc_options opt;
+    if (opt_in) opt = *opt_in; else dd_pc_options_default(&opt);
+    int rc = check_opts(ctx, opt);
+    if (rc != DD_OK) return rc;
+    if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
+    int cur = slot_a, nxt = slot_b;
+    const size_t nstride = (size_t)8 * b->B;
+    if (norms_out && (rc = norms_async(b, cur, -1, norms_out)) != DD_OK) return rc;
+    for (int s = 0; s < nsteps; ++s) {
+        if ((rc = pc_step_retry(b, cur, nxt, opt, stats)) != DD_OK) return rc;
+        CK(dd_launch_time_coefs(launch_of(b), b->mode, b->d_mem, b->d_t0, b->d_dt, n_t, 1));
+        if (norms_out && (rc = norms_async(b, nxt, -1, norms_out + (s + 1) * nstride)) != DD_OK) return rc;
+        const int tmp = cur; cur = nxt; nxt = tmp;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DD_OK;
+}
+
+extern "C" int dd_run_feuler(dd_batch* b, int slot_a, int slot_b, const double* t0, const double* dt, int n_t,
+                             int nsteps, double* norms_out) {
+    if (!b || !slot_ok(b, slot_a) || !slot_ok(b, slot_b) || slot_a == slot_b || nsteps < 0) return DD_ERR_INVALID;
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
+    int cur = slot_a, nxt = slot_b;
+    const size_t nstride = (size_t)8 * b->B;
+    if (norms_out && (rc = norms_async(b, cur, -1, norms_out)) != DD_OK) return rc;
+    for (int s = 0; s < nsteps; ++s) {
+        CK(dd_launch_feuler(launch_of(b), b->mode, b->g, b->d_mem, b->F, cstate(b, cur), mstate(b, nxt)));
+        CK(dd_launch_time_coefs(launch_of(b), b->mode, b->d_mem, b->d_t0, b->d_dt, n_t, 1));
+        if (norms_out && (rc = norms_async(b, nxt, -1, norms_out + (s + 1) * nstride)) != DD_OK) return rc;
+        const int tmp = cur; cur = nxt; nxt = tmp;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DD_OK;
+}
+
+// ---------------------------------------------------------------------------
+// pieces of the step (class-level API)
+// ---------------------------------------------------------------------------
+extern "C" int dd_pc_predict(dd_batch* b, int slot_in, const double* t0, const double* dt, int n_t) {
+    if (!b || !slot_ok(b, slot_in)) return DD_ERR_INVALID;
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
+    DDPredictOut po;
+    if ((rc = get_work(b, "cp1p", &po.cp1p)) != DD_OK) return rc;
+    if ((rc = get_work(b, "cs1p", &po.cs1p)) != DD_OK) return rc;
+    if ((rc = get_work(b, "YT", &po.YT)) != DD_OK) return rc;
+    if ((rc = get_work(b, "Ycl", &po.Ycl)) != DD_OK) return rc;
+    if ((rc = get_work(b, "Ycd", &po.Ycd)) != DD_OK) return rc;
+    CK(dd_launch_predict(launch_of(b), b->mode, b->g, b->d_mem, b->F, cstate(b, slot_in), po));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DD_OK;
+}
+
+extern "C" int dd_pc_newton(dd_batch* b, int var, int slot_star, int slot_new, const double* t0, const double* dt,
+                            int n_t, const dd_pc_options* opt_in, dd_step_stats* stats) {
+    if (!b || !slot_ok(b, slot_star) || !slot_ok(b, slot_new) || slot_star == slot_new || var < DD_T || var > DD_CD)
+        return DD_ERR_INVALID;
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    dd_pc_options opt;
+    if (opt_in) opt = *opt_in; else dd_pc_options_default(&opt);
+    int rc = check_opts(ctx, opt);
+    if (rc != DD_OK) return rc;
+    if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
+    if ((rc = ensure_solve_slots(b, 3)) != DD_OK) return rc;
+    static const char* yname[3] = {"YT", "Ycl", "Ycd"};
+    double* Y;
+    if ((rc = get_work(b, yname[var - DD_T], &Y)) != DD_OK) return rc;
+    const DDStateC u = cstate(b, slot_star);
+    const DDState nw = mstate(b, slot_new);
+    for (int attempt = 0;; ++attempt) {
+        int sw = 0, pa = 0;
+        if ((rc = newton_solve(b, var, u, nw.v[DD_T], nw.v[DD_CL], Y, nw.v[var], opt, 0, &sw, &pa)) != DD_OK) return rc;
+        SolveSummary s;
+        CK(cudaMemcpyAsync(&s, b->d_summary, sizeof(s), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const int vi = var - DD_T;
+        if (stats) {
+            stats->sweeps[vi] = sw; stats->passes[vi] = pa; stats->rho[vi] = s.rho; stats->resid[vi] = s.resid;
+            stats->bound[vi] = s.bound; stats->retries = attempt;
+        }
+        if (s.ratio <= 1.0) return DD_OK;
+        if (opt.fixed_sweeps > 0 || b->plan_sweeps[vi] >= opt.max_sweeps || attempt >= 40)
+            return fail(ctx, DD_ERR_NOT_CONVERGED, "linear solve did not reach the residual bound");
+        const int want = sweeps_for_rho(s.rho * 1.02 + 1e-12, opt.max_sweeps);
+        if (b->plan_sweeps[vi] >= want) b->plan_extra[vi] += (b->plan_sweeps[vi] + 1) / 2 + 1;
+        const int next = want + b->plan_extra[vi];
+        b->plan_sweeps[vi] = next > opt.max_sweeps ? opt.max_sweeps : next;
+    }
+}
+
+extern "C" int dd_pc_correct(dd_batch* b, int slot0, int slot_new, const double* t0, const double* dt, int n_t,
+                             const dd_pc_options* opt_in, int* cs_iters_out) {
+    if (!b || !slot_ok(b, slot0) || !slot_ok(b, slot_new) || slot0 == slot_new) return DD_ERR_INVALID;
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    dd_pc_options opt;
+    if (opt_in) opt = *opt_in; else dd_pc_options_default(&opt);
+    int rc = check_opts(ctx, opt);
+    if (rc != DD_OK) return rc;
+    if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
+    const DDLaunch L = launch_of(b, ROWS_ALL);
+    const DDStateC s0 = cstate(b, slot0);
+    const DDState nw = mstate(b, slot_new);
+    const int cap = opt.num_newton_iterations;
+    const bool track = opt.consec_xs_rtol > 0.0 && cap > 0;
+    if (track) {
+        const int had = b->cs_cap_alloc;
+        if ((rc = ensure_cs_buffers(b, cap)) != DD_OK) return rc;
+        if (b->cs_cap_alloc != had) {
+            const long long n = (long long)b->cs_cap_alloc * b->B;
+            k_cs_arm<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(b->d_itmax, b->d_itmin, n);
+        }
+    }
+    CK(dd_launch_correct(L, b->mode, b->g, b->d_mem, b->F, s0, nw.v[DD_T], nw.v[DD_CL], nw.v[DD_CD], nw.v[DD_CP],
+                         nw.v[DD_CS], cap, track ? opt.consec_xs_rtol : 0.0, b->d_itmax, b->d_itmin));
+    if (track)
+        CK(dd_launch_cs_finish(L, b->mode, b->g, b->d_mem, b->F, s0, nw.v[DD_CL], nw.v[DD_CD], nw.v[DD_CS], cap,
+                               opt.consec_xs_rtol, b->d_itmax, b->d_itmin, b->d_used));
+    if (cs_iters_out) {
+        if (track) {
+            CK(cudaMemcpyAsync(cs_iters_out, b->d_used, sizeof(int) * b->B, cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+            for (int m = 0; m < b->B; ++m) cs_iters_out[m] = cap;
+        }
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DD_OK;
+}
+
+extern "C" int dd_pc_residual(dd_batch* b, int var, int slot_state, const double* t0, const double* dt, int n_t,
+                              double* out_host) {
+    if (!b || !slot_ok(b, slot_state) || var < DD_T || var > DD_CD || !out_host) return DD_ERR_INVALID;
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
+    static const char* yname[3] = {"YT", "Ycl", "Ycd"};
+    double *Y, *res;
+    if ((rc = get_work(b, yname[var - DD_T], &Y)) != DD_OK) return rc;
+    if ((rc = get_work(b, "resid", &res)) != DD_OK) return rc;
+    CK(dd_launch_residual(launch_of(b), b->mode, var, b->g, b->d_mem, b->F, cstate(b, slot_state), Y, res));
+    CK(cudaMemcpyAsync(out_host, res, b->field_elems * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DD_OK;
+}

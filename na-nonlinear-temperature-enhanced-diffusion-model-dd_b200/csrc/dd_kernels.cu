@@ -1,0 +1,518 @@
+// dd_kernels.cu -- pointwise / five-point-stencil kernels of the RegHCsTriple
+// step (sm_100a).  Thread mapping: one thread per node, consecutive threads
+// along j (contiguous in memory), blocks aligned to members so that block-wide
+// reductions never mix members.  The arithmetic lives in dd_nodeprog.cuh.
+#include "dd_kernels.cuh"
+
+#define DD_BLOCK 256
+
+struct NodeIdx {
+    int member, r, j;
+    bool valid;
+};
+
+__device__ __forceinline__ NodeIdx node_index(const DDGeom& g, int own0, int own1, int blocks_per_member) {
+    NodeIdx n;
+    n.member = blockIdx.x / blocks_per_member;
+    const int chunk = blockIdx.x - n.member * blocks_per_member;
+    const int ncols = g.M + 1;
+    const long long lin = (long long)chunk * blockDim.x + threadIdx.x;
+    const long long total = (long long)(own1 - own0) * ncols;
+    n.valid = lin < total;
+    const long long rr = lin / ncols;
+    n.r = own0 + (int)rr;
+    n.j = (int)(lin - rr * ncols);
+    return n;
+}
+
+static inline int blocks_per_member(const DDGeom& g, const DDLaunch& L) {
+    const long long total = (long long)(L.own1 - L.own0) * (g.M + 1);
+    return (int)((total + DD_BLOCK - 1) / DD_BLOCK);
+}
+
+// ---- non-negative double max/min via integer atomics (NaN wins the max) ----
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
+    atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(fabs(v)));
+}
+__device__ __forceinline__ void atomic_min_nonneg(double* addr, double v) {
+    atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(fabs(v)));
+}
+
+__device__ __forceinline__ double warp_max_bits(double v) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(fabs(v));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, b, o);
+        b = other > b ? other : b;
+    }
+    return __longlong_as_double((long long)b);
+}
+__device__ __forceinline__ double warp_min_bits(double v) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(fabs(v));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, b, o);
+        b = other < b ? other : b;
+    }
+    return __longlong_as_double((long long)b);
+}
+
+// block-wide max of a non-negative value; result valid in thread 0
+__device__ double block_max_nonneg(double v, double* sh /*[32]*/) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_max_bits(v);
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        double t = lane < nw ? sh[lane] : 0.0;
+        t = warp_max_bits(t);
+        v = t;
+    }
+    return v;
+}
+__device__ double block_min_nonneg(double v, double* sh /*[32]*/) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_min_bits(v);
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        double t = lane < nw ? sh[lane] : __longlong_as_double(0x7ff0000000000000LL);
+        t = warp_min_bits(t);
+        v = t;
+    }
+    return v;
+}
+
+// ---------------------------------------------------------------------------
+// time scalars
+// ---------------------------------------------------------------------------
+__global__ void k_time_coefs(int mode, DDMember* mem, const double* t0, const double* dt, int n_t, int nmem,
+                             int advance) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nmem) return;
+    DDMember& mb = mem[m];
+    if (advance) {
+        if (mb.active) mb.t0 = mb.t0 + mb.dt;
+    } else {
+        mb.t0 = t0[n_t == 1 ? 0 : m];
+        mb.dt = dt[n_t == 1 ? 0 : m];
+    }
+    dd_time_coefs(mode, mb, mb.t0, 0, &mb.tc[0]);
+    dd_time_coefs(mode, mb, mb.t0 + mb.dt, 1, &mb.tc[1]);
+}
+
+cudaError_t dd_launch_time_coefs(const DDLaunch& L, int mode, DDMember* mem, const double* t0_dev,
+                                 const double* dt_dev, int n_t, int advance) {
+    const int nb = (L.nmembers + 127) / 128;
+    k_time_coefs<<<nb, 128, 0, L.stream>>>(mode, mem, t0_dev, dt_dev, n_t, L.nmembers, advance);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// forward Euler / field evaluation / exact fill / residual
+// ---------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(DD_BLOCK) k_feuler(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
+                                                     DDStateC in, DDState out, int own0, int own1, int bpm) {
+    const NodeIdx n = node_index(g, own0, own1, bpm);
+    if (!n.valid) return;
+    const DDMember& mb = mem[n.member];
+    if (!mb.active) return;
+    dd_node_feuler<MODE>(g, mb, F, in, out, n.member * g.mstride, n.r, n.j);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(DD_BLOCK) k_fields(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
+                                                     DDStateC in, DDState out, int slot, int own0, int own1,
+                                                     int bpm) {
+    const NodeIdx n = node_index(g, own0, own1, bpm);
+    if (!n.valid) return;
+    const DDMember& mb = mem[n.member];
+    double Fv[DD_NVAR];
+    const long long mo = n.member * g.mstride;
+    dd_node_F<MODE>(g, mb, F, in, mo, n.r, n.j, slot, Fv);
+    const long long o = mo + (long long)n.r * g.ld + n.j;
+    for (int v = 0; v < DD_NVAR; ++v) out.v[v][o] = Fv[v];
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(DD_BLOCK) k_fill_exact(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
+                                                         DDState out, int own0, int own1, int bpm) {
+    const NodeIdx n = node_index(g, own0, own1, bpm);
+    if (!n.valid) return;
+    const DDMember& mb = mem[n.member];
+    double u[DD_NVAR];
+    dd_exact_values<MODE>(F, mb, 0, g.row0 + n.r, n.j, u);
+    const long long o = n.member * g.mstride + (long long)n.r * g.ld + n.j;
+    for (int v = 0; v < DD_NVAR; ++v) out.v[v][o] = u[v];
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(DD_BLOCK) k_residual(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
+                                                       DDStateC s, const double* __restrict__ Y,
+                                                       double* __restrict__ res, int var, int own0, int own1,
+                                                       int bpm) {
+    const NodeIdx n = node_index(g, own0, own1, bpm);
+    if (!n.valid) return;
+    const DDMember& mb = mem[n.member];
+    double Fv[DD_NVAR];
+    const long long mo = n.member * g.mstride;
+    dd_node_F<MODE>(g, mb, F, s, mo, n.r, n.j, 1, Fv);
+    const long long o = mo + (long long)n.r * g.ld + n.j;
+    res[o] = 2.0 * s.v[var][o] - mb.dt * Fv[var] - Y[o];
+}
+
+#define DD_DISPATCH_MODE(mode, CALL)                               \
+    switch (mode) {                                                \
+        case DD_FORCING_NONE: { constexpr int MODE = DD_FORCING_NONE; CALL; } break;           \
+        case DD_FORCING_ARRAYS: { constexpr int MODE = DD_FORCING_ARRAYS; CALL; } break;       \
+        case DD_FORCING_SEPARABLE: { constexpr int MODE = DD_FORCING_SEPARABLE; CALL; } break; \
+        case DD_FORCING_EXPSIN: { constexpr int MODE = DD_FORCING_EXPSIN; CALL; } break;       \
+        default: return cudaErrorInvalidValue;                     \
+    }
+
+cudaError_t dd_launch_feuler(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem, const DDForcing& F,
+                             const DDStateC& in, const DDState& out) {
+    const int bpm = blocks_per_member(g, L);
+    DD_DISPATCH_MODE(mode, (k_feuler<MODE><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(g, mem, F, in, out, L.own0,
+                                                                                      L.own1, bpm)));
+    return cudaGetLastError();
+}
+
+cudaError_t dd_launch_fields(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem, const DDForcing& F,
+                             const DDStateC& in, const DDState& out, int slot) {
+    const int bpm = blocks_per_member(g, L);
+    DD_DISPATCH_MODE(mode, (k_fields<MODE><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(g, mem, F, in, out, slot,
+                                                                                      L.own0, L.own1, bpm)));
+    return cudaGetLastError();
+}
+
+cudaError_t dd_launch_fill_exact(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,
+                                 const DDForcing& F, const DDState& out) {
+    if (mode != DD_FORCING_SEPARABLE && mode != DD_FORCING_EXPSIN) return cudaErrorInvalidValue;
+    const int bpm = blocks_per_member(g, L);
+    if (mode == DD_FORCING_SEPARABLE)
+        k_fill_exact<DD_FORCING_SEPARABLE><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(g, mem, F, out, L.own0,
+                                                                                        L.own1, bpm);
+    else
+        k_fill_exact<DD_FORCING_EXPSIN><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(g, mem, F, out, L.own0, L.own1,
+                                                                                     bpm);
+    return cudaGetLastError();
+}
+
+cudaError_t dd_launch_residual(const DDLaunch& L, int mode, int var, const DDGeom& g, const DDMember* mem,
+                               const DDForcing& F, const DDStateC& s, const double* Y, double* res) {
+    const int bpm = blocks_per_member(g, L);
+    DD_DISPATCH_MODE(mode, (k_residual<MODE><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(g, mem, F, s, Y, res, var,
+                                                                                        L.own0, L.own1, bpm)));
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// PC phase 1
+// ---------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(DD_BLOCK) k_predict(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
+                                                      DDStateC in, DDPredictOut out, int own0, int own1, int bpm) {
+    const NodeIdx n = node_index(g, own0, own1, bpm);
+    if (!n.valid) return;
+    const DDMember& mb = mem[n.member];
+    if (!mb.active) return;
+    dd_node_predict<MODE>(g, mb, F, in, out, n.member * g.mstride, n.r, n.j);
+}
+
+cudaError_t dd_launch_predict(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,
+                              const DDForcing& F, const DDStateC& in, const DDPredictOut& out) {
+    const int bpm = blocks_per_member(g, L);
+    DD_DISPATCH_MODE(mode, (k_predict<MODE><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(g, mem, F, in, out, L.own0,
+                                                                                       L.own1, bpm)));
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// assemble Newton rows (+ Gershgorin ratio per member)
+// ---------------------------------------------------------------------------
+__global__ void k_reset_stats(DDSolveStats* stats, int nmem) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nmem) return;
+    stats[m].rho = 0.0;
+    stats[m].resid = 0.0;
+    stats[m].xmax = 0.0;
+    stats[m].vmax = 0.0;
+    stats[m].bmax = 0.0;
+}
+
+template <int MODE, int VAR>
+__global__ void __launch_bounds__(DD_BLOCK) k_assemble(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
+                                                       DDStateC u, const double* __restrict__ T1,
+                                                       const double* __restrict__ cl1, const double* __restrict__ Y,
+                                                       int cd_swap, DDRows R, DDSolveStats* stats, int own0,
+                                                       int own1, int bpm) {
+    __shared__ double sh[32];
+    const NodeIdx n = node_index(g, own0, own1, bpm);
+    const DDMember& mb = mem[n.member];
+    if (!mb.active) return;  // whole block belongs to one member
+    double rho = 0.0;
+    if (n.valid) {
+        const long long mo = n.member * g.mstride;
+        if (VAR == DD_T)
+            rho = dd_node_asm_T<MODE>(g, mb, F, u, Y, R, mo, n.r, n.j);
+        else if (VAR == DD_CL)
+            rho = dd_node_asm_cl<MODE>(g, mb, F, u, T1, Y, R, mo, n.r, n.j);
+        else
+            rho = dd_node_asm_cd<MODE>(g, mb, F, u, T1, cl1, Y, cd_swap, R, mo, n.r, n.j);
+    }
+    rho = block_max_nonneg(rho, sh);
+    if (threadIdx.x == 0) atomic_max_nonneg(&stats[n.member].rho, rho);
+}
+
+cudaError_t dd_launch_assemble(const DDLaunch& L, int mode, int var, const DDGeom& g, const DDMember* mem,
+                               const DDForcing& F, const DDStateC& ustar, const double* T1, const double* cl1,
+                               const double* Y, int cd_swap, const DDRows& R, DDSolveStats* stats) {
+    const int bpm = blocks_per_member(g, L);
+    k_reset_stats<<<(L.nmembers + 127) / 128, 128, 0, L.stream>>>(stats, L.nmembers);
+#define DD_ASM(VAR)                                                                                             \
+    DD_DISPATCH_MODE(mode, (k_assemble<MODE, VAR><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(                \
+                               g, mem, F, ustar, T1, cl1, Y, cd_swap, R, stats, L.own0, L.own1, bpm)))
+    if (var == DD_T) {
+        DD_ASM(DD_T);
+    } else if (var == DD_CL) {
+        DD_ASM(DD_CL);
+    } else if (var == DD_CD) {
+        DD_ASM(DD_CD);
+    } else {
+        return cudaErrorInvalidValue;
+    }
+#undef DD_ASM
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// correctors
+// ---------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(DD_BLOCK) k_correct(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
+                                                      DDStateC s0, const double* __restrict__ T1,
+                                                      const double* __restrict__ cl1,
+                                                      const double* __restrict__ cd1, double* __restrict__ cp_out,
+                                                      double* __restrict__ cs_out, int cap, double rtol,
+                                                      double* it_max, double* it_min, int own0, int own1,
+                                                      int bpm) {
+    __shared__ double sh[32];
+    const NodeIdx n = node_index(g, own0, own1, bpm);
+    const DDMember& mb = mem[n.member];
+    if (!mb.active) return;
+    const bool track = rtol > 0.0;
+    double x = 0.0, y = 0.0, a = 0.0, cp1 = 0.0;
+    long long o = 0;
+    bool inter = false;
+    if (n.valid) {
+        const long long mo = n.member * g.mstride;
+        o = mo + (long long)n.r * g.ld + n.j;
+        inter = dd_is_interior(g, g.row0 + n.r, n.j);
+        dd_node_correct_prepare<MODE>(g, mb, F, s0, T1, cl1, cd1, mo, n.r, n.j, &cp1, &y, &a);
+        x = s0.v[DD_CS][o];
+        cp_out[o] = cp1;
+    }
+    const double eta = mb.m.eta;
+    for (int it = 0; it < cap; ++it) {
+        double dx = 0.0;
+        if (n.valid) {
+            dx = dd_cs_newton_dx(x, y, a, eta);
+            x = x + dx;
+        }
+        if (track) {
+            // global exit test of the reference: max_all |dx| < rtol |x| at every node
+            double vmax = block_max_nonneg(n.valid ? dx : 0.0, sh);
+            if (threadIdx.x == 0) atomic_max_nonneg(&it_max[(long long)n.member * cap + it], vmax);
+            double ax = n.valid ? fabs(x) : __longlong_as_double(0x7ff0000000000000LL);
+            if (ax != ax) ax = 0.0;  // NaN |x| fails the test exactly like 0 does
+            double vmin = block_min_nonneg(ax, sh);
+            if (threadIdx.x == 0) atomic_min_nonneg(&it_min[(long long)n.member * cap + it], vmin);
+        }
+    }
+    if (n.valid) cs_out[o] = x * (inter ? 1.0 : 0.0);
+}
+
+cudaError_t dd_launch_correct(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,
+                              const DDForcing& F, const DDStateC& s0, const double* T1, const double* cl1,
+                              const double* cd1, double* cp_out, double* cs_out, int cap, double rtol,
+                              double* it_max, double* it_min) {
+    const int bpm = blocks_per_member(g, L);
+    DD_DISPATCH_MODE(mode, (k_correct<MODE><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(
+                               g, mem, F, s0, T1, cl1, cd1, cp_out, cs_out, cap, rtol, it_max, it_min, L.own0,
+                               L.own1, bpm)));
+    return cudaGetLastError();
+}
+
+// decide the number of iterations the reference would have used, per member
+__global__ void k_cs_decide(const DDMember* __restrict__ mem, int nmem, int cap, double rtol, double* it_max,
+                            double* it_min, int* used) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nmem) return;
+    int u = cap;
+    if (mem[m].active) {
+        for (int it = 0; it < cap; ++it) {
+            const double mx = it_max[(long long)m * cap + it];
+            const double mn = it_min[(long long)m * cap + it];
+            if (mx < rtol * mn) {
+                u = it + 1;
+                break;
+            }
+        }
+    }
+    used[m] = u;
+    // re-arm the accumulators for the next call
+    for (int it = 0; it < cap; ++it) {
+        it_max[(long long)m * cap + it] = 0.0;
+        it_min[(long long)m * cap + it] = __longlong_as_double(0x7ff0000000000000LL);
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(DD_BLOCK) k_cs_redo(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
+                                                      DDStateC s0, const double* __restrict__ cl1,
+                                                      const double* __restrict__ cd1, double* __restrict__ cs_out,
+                                                      int cap, const int* __restrict__ used, int own0, int own1,
+                                                      int bpm) {
+    const NodeIdx n = node_index(g, own0, own1, bpm);
+    if (!n.valid) return;
+    const int u = used[n.member];
+    const DDMember& mb = mem[n.member];
+    if (u >= cap || !mb.active) return;  // the cap-iteration result already stored is the answer
+    const long long mo = n.member * g.mstride;
+    const long long o = mo + (long long)n.r * g.ld + n.j;
+    double cp1, y, a;
+    // T1 is not needed for y, a: pass cl1 as a placeholder for the cp corrector inputs
+    dd_node_correct_prepare<MODE>(g, mb, F, s0, cl1, cl1, cd1, mo, n.r, n.j, &cp1, &y, &a);
+    double x = s0.v[DD_CS][o];
+    for (int it = 0; it < u; ++it) x = x + dd_cs_newton_dx(x, y, a, mb.m.eta);
+    cs_out[o] = x * (dd_is_interior(g, g.row0 + n.r, n.j) ? 1.0 : 0.0);
+}
+
+cudaError_t dd_launch_cs_finish(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,
+                                const DDForcing& F, const DDStateC& s0, const double* cl1, const double* cd1,
+                                double* cs_out, int cap, double rtol, double* it_max, double* it_min,
+                                int* used_out) {
+    k_cs_decide<<<(L.nmembers + 127) / 128, 128, 0, L.stream>>>(mem, L.nmembers, cap, rtol, it_max, it_min,
+                                                                used_out);
+    const int bpm = blocks_per_member(g, L);
+    DD_DISPATCH_MODE(mode, (k_cs_redo<MODE><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(
+                               g, mem, F, s0, cl1, cd1, cs_out, cap, used_out, L.own0, L.own1, bpm)));
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// error norms (reference Grid.norm_H / norm_p / grad_H, src/prob1base.py:387-433,
+// as combined by collect_errors, src/mms_trial_utils.py:81-110)
+// two-stage deterministic reduction: per-block partials, then one block per member
+// ---------------------------------------------------------------------------
+template <int MODE, bool FROM_ARRAY>
+__global__ void __launch_bounds__(DD_BLOCK) k_error_partial(DDGeom g, const DDMember* __restrict__ mem,
+                                                            DDForcing F, DDStateC s, DDStateC ex,
+                                                            double* __restrict__ partial, int own0, int own1,
+                                                            int bpm) {
+    __shared__ double sh[8][DD_BLOCK / 32];
+    const NodeIdx n = node_index(g, own0, own1, bpm);
+    const DDMember& mb = mem[n.member];
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (n.valid) {
+        const int i = g.row0 + n.r, j = n.j;
+        const long long o = n.member * g.mstride + (long long)n.r * g.ld + j;
+        double e[DD_NVAR], ew[DD_NVAR], es[DD_NVAR];
+        const bool need_w = i >= 1 && j >= 1 && j <= g.M - 1;  // D-x at (i,j), i = 1..N, j interior
+        const bool need_s = j >= 1 && i >= 1 && i <= g.N - 1;
+        if (FROM_ARRAY) {
+            for (int v = 0; v < DD_NVAR; ++v) {
+                e[v] = s.v[v][o] - ex.v[v][o];
+                ew[v] = need_w ? s.v[v][o - g.ld] - ex.v[v][o - g.ld] : 0.0;
+                es[v] = need_s ? s.v[v][o - 1] - ex.v[v][o - 1] : 0.0;
+            }
+        } else {
+            double u[DD_NVAR];
+            dd_exact_values<MODE>(F, mb, 0, i, j, u);
+            for (int v = 0; v < DD_NVAR; ++v) e[v] = s.v[v][o] - u[v];
+            if (need_w) {
+                dd_exact_values<MODE>(F, mb, 0, i - 1, j, u);
+                for (int v = 0; v < DD_NVAR; ++v) ew[v] = s.v[v][o - g.ld] - u[v];
+            }
+            if (need_s) {
+                dd_exact_values<MODE>(F, mb, 0, i, j - 1, u);
+                for (int v = 0; v < DD_NVAR; ++v) es[v] = s.v[v][o - 1] - u[v];
+            }
+        }
+        if (dd_is_interior(g, i, j)) {
+            const double wgt = g.hp[i] * g.kp[j];
+            for (int v = 0; v < DD_NVAR; ++v) acc[v] = e[v] * e[v] * wgt;
+        }
+        for (int q = 0; q < 3; ++q) {
+            const int v = DD_T + q;
+            double p = 0.0;
+            if (need_w) {
+                const double d = (e[v] - ew[v]) / g.h[i];
+                p += d * d * g.h[i] * g.kp[j];
+            }
+            if (need_s) {
+                const double d = (e[v] - es[v]) / g.k[j];
+                p += d * d * g.hp[i] * g.k[j];
+            }
+            acc[5 + q] = p;
+        }
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        double v = acc[q];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) sh[q][w] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double t = 0.0;
+        for (int k = 0; k < DD_BLOCK / 32; ++k) t += sh[threadIdx.x][k];
+        partial[(long long)blockIdx.x * 8 + threadIdx.x] = t;
+    }
+}
+
+__global__ void k_error_final(const double* __restrict__ partial, int bpm, double* __restrict__ out) {
+    // one warp per (member, quantity): fixed-order strided accumulation then a shuffle tree
+    const int m = blockIdx.x, q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double t = 0.0;
+    for (int b = lane; b < bpm; b += 32) t += partial[((long long)m * bpm + b) * 8 + q];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+    if (lane == 0) out[(long long)m * 8 + q] = t;
+}
+
+int dd_norm_blocks_per_member(const DDGeom& g) {
+    const long long total = (long long)g.nrows * (g.M + 1);
+    return (int)((total + DD_BLOCK - 1) / DD_BLOCK);
+}
+
+cudaError_t dd_launch_error_norms(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,
+                                  const DDForcing& F, const DDStateC& s, const DDStateC* exact, double* partial,
+                                  int nblocks_per_member, double* out) {
+    const int bpm = blocks_per_member(g, L);
+    if (bpm > nblocks_per_member) return cudaErrorInvalidValue;
+    DDStateC ex = s;
+    if (exact) {
+        ex = *exact;
+        k_error_partial<DD_FORCING_NONE, true><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(g, mem, F, s, ex, partial,
+                                                                                           L.own0, L.own1, bpm);
+    } else if (mode == DD_FORCING_SEPARABLE) {
+        k_error_partial<DD_FORCING_SEPARABLE, false><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(
+            g, mem, F, s, ex, partial, L.own0, L.own1, bpm);
+    } else if (mode == DD_FORCING_EXPSIN) {
+        k_error_partial<DD_FORCING_EXPSIN, false><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(
+            g, mem, F, s, ex, partial, L.own0, L.own1, bpm);
+    } else {
+        return cudaErrorInvalidValue;
+    }
+    k_error_final<<<L.nmembers, 256, 0, L.stream>>>(partial, bpm, out);
+    return cudaGetLastError();
+}

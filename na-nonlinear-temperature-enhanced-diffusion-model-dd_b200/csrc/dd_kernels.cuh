@@ -1,0 +1,75 @@
+// dd_kernels.cuh -- launch interface of the sm_100a kernels (dd_kernels.cu,
+// dd_solver.cu), used by the C ABI layer (dd_capi.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "dd_nodeprog.cuh"
+
+// all launchers return cudaGetLastError() of the launch
+struct DDLaunch {
+    cudaStream_t stream;
+    int nmembers;
+    int own0, own1;  // local rows computed by this launch: [own0, own1)
+    int vr0, vr1;    // local rows whose Newton rows are valid (readable by the tile solver)
+};
+
+cudaError_t dd_launch_time_coefs(const DDLaunch& L, int mode, DDMember* mem, const double* t0_dev,
+                                 const double* dt_dev, int n_t, int advance);
+
+cudaError_t dd_launch_feuler(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem, const DDForcing& F,
+                             const DDStateC& in, const DDState& out);
+
+cudaError_t dd_launch_fields(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem, const DDForcing& F,
+                             const DDStateC& in, const DDState& out, int slot);
+
+cudaError_t dd_launch_predict(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,
+                              const DDForcing& F, const DDStateC& in, const DDPredictOut& out);
+
+// var = DD_T / DD_CL / DD_CD.  Resets then accumulates stats[member].rho.
+cudaError_t dd_launch_assemble(const DDLaunch& L, int mode, int var, const DDGeom& g, const DDMember* mem,
+                               const DDForcing& F, const DDStateC& ustar, const double* T1, const double* cl1,
+                               const double* Y, int cd_swap, const DDRows& R, DDSolveStats* stats);
+
+struct DDSolvePlan {
+    int sweeps;      // red-black SOR sweeps in this pass
+    int tile_i, tile_j;
+    int halo;        // = 2*sweeps (+1 on the last pass), 0 when one tile covers the member
+    int threads;
+    int last_pass;   // compute residual stats and write v_new
+    size_t smem_bytes;
+};
+
+cudaError_t dd_solver_configure();  // opt-in to large dynamic shared memory (once per process)
+
+cudaError_t dd_launch_solve_pass(const DDLaunch& L, const DDGeom& g, const DDRows& R, const double* xin,
+                                 double* xout, const double* vstar, double* vnew, int zero_boundary,
+                                 DDSolveStats* stats, const DDSolvePlan& P);
+
+// correctors.  cs Newton: `cap` iterations; when rtol > 0 the per-iteration global
+// statistics go to it_max / it_min ([member][cap]) and dd_launch_cs_finish applies
+// the reference's exit test (src/prob1base.py:3661).
+cudaError_t dd_launch_correct(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,
+                              const DDForcing& F, const DDStateC& s0, const double* T1, const double* cl1,
+                              const double* cd1, double* cp_out, double* cs_out, int cap, double rtol,
+                              double* it_max, double* it_min);
+
+cudaError_t dd_launch_cs_finish(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,
+                                const DDForcing& F, const DDStateC& s0, const double* cl1, const double* cd1,
+                                double* cs_out, int cap, double rtol, double* it_max, double* it_min,
+                                int* used_out);
+
+// error norms of (state - exact): out[member][8] = H2[cp,T,cl,cd,cs], P2[T,cl,cd]
+// exact == nullptr -> exact solution evaluated from the MMS tables (slot 0 time).
+cudaError_t dd_launch_error_norms(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,
+                                  const DDForcing& F, const DDStateC& s, const DDStateC* exact, double* partial,
+                                  int nblocks_per_member, double* out);
+
+cudaError_t dd_launch_fill_exact(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,
+                                 const DDForcing& F, const DDState& out);
+
+// residual of a Newton step: res = 2 v - dt F_v(state, t1) - Y   (reference last_residual)
+cudaError_t dd_launch_residual(const DDLaunch& L, int mode, int var, const DDGeom& g, const DDMember* mem,
+                               const DDForcing& F, const DDStateC& s, const double* Y, double* res);
+
+int dd_norm_blocks_per_member(const DDGeom& g);

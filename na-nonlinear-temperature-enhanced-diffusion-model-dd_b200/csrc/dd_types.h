@@ -1,0 +1,105 @@
+// dd_types.h -- plain-old-data shared by host code, CUDA kernels and the C ABI.
+//
+// Layout of one field in HBM: [member][row][col], float64, row pitch `ld`
+// (= M+1, columns j contiguous), `nrows` local rows per member.  Local row r
+// is global grid row i = row0 + r (row0 > 0 only for slab-decomposed meshes),
+// which mirrors the reference's C-order (N+1, M+1) arrays
+// (reference src/prob1base.py:242-248).
+#pragma once
+
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define DD_HD __host__ __device__ __forceinline__
+#else
+#define DD_HD inline
+#endif
+
+enum DDForcingMode {
+    DD_FORCING_NONE = 0,       // NoForcingTerms (reference src/prob1base.py:852-869)
+    DD_FORCING_ARRAYS = 1,     // host-evaluated source fields uploaded per step
+    DD_FORCING_SEPARABLE = 2,  // u_v = phi_v(t) X_v(x) Y_v(y): 1-D tables + time profile
+    DD_FORCING_EXPSIN = 3      // MMSCaseExpSin closed form (reference src/prob1_mms_cases.py:296-337)
+};
+
+enum DDPhiKind {
+    DD_PHI_INV1PT = 0,  // p0 / (1 + t)
+    DD_PHI_EXP = 1,     // p0 * exp(-p1 t)
+    DD_PHI_LINEAR = 2,  // p0 - p1 t
+    DD_PHI_OSC = 3,     // p0 * (1 + p1 sin(p2 t))
+    DD_PHI_CONST = 4,   // p0
+    DD_PHI_HOST = 5     // host supplies phi(t0), phi'(t0), phi(t1), phi'(t1) before each step
+};
+
+enum { DD_CP = 0, DD_T = 1, DD_CL = 2, DD_CD = 3, DD_CS = 4, DD_NVAR = 5 };
+
+// Per-member physical parameters (reference ModelConsts, src/prob1base.py:28-45,
+// plus the regularisation factor eta of the RegHCsTriple family, 3452-3466).
+struct DDModel {
+    double K1, K2, K3, K4, DT, Dl_max, phi_l, gamma_T, Kd, Sd, Dd_max, phi_d, phi_T, r_sp;
+    double T_shift;  // T_ref for DefaultModel02 (src/prob1base.py:205-217), 0 for DefaultModel01
+    double eta;
+};
+
+// Per-member, per-time-slot scalars of the manufactured solution
+// (slot 0 = t0, slot 1 = t1 = t0 + dt).
+struct DDTimeCoef {
+    double c[16];
+    // SEPARABLE: c[v] = phi_v(t), c[5+v] = phi_v'(t)
+    // EXPSIN   : see dd_physics.cuh (expsin_time_coefs)
+};
+
+struct DDMember {
+    DDModel m;
+    double t0, dt;
+    int phi_kind[DD_NVAR];
+    int active;  // 0 -> member is skipped (already finished its trajectory)
+    double phi_p[DD_NVAR][4];
+    DDTimeCoef tc[2];
+};
+
+// Grid geometry, global 1-D arrays on the device (length N+1 / M+1).
+// rh[i] = 1/h_i (rh[0] = 0), rhp[i] = 1/hhat_i (0 at i = 0, N); same in y.
+struct DDGeom {
+    int N, M;        // global grid: nodes 0..N x 0..M
+    int row0, nrows; // this batch holds global rows [row0, row0 + nrows)
+    int ld;          // row pitch in doubles
+    long long mstride;  // member stride in doubles (= nrows * ld)
+    const double *x, *y, *h, *k, *hp, *kp, *rh, *rk, *rhp, *rkp;
+};
+
+// 1-D tables for the fused MMS forcing (device pointers).
+struct DDTables {
+    // SEPARABLE: u_v = phi_v(t) sum_{r < nterms} X_{v,r}(x) Y_{v,r}(y).
+    //            X[v][d][r*(N+1) + i], d = 0,1,2 -> X_{v,r}, X', X'' at node i; Y likewise (stride M+1).
+    //            XQ[q][r*3*(N+1) + i*3 + a] for q in {cp, T, cl} = X_{q,r} at the a-th Gauss abscissa of cell i.
+    // EXPSIN   : X[0][0] = sin(pi x), X[0][1] = cos(pi x); XQ[0] = sin(pi x) at the abscissae.
+    int nterms, nx, ny;  // nx = N+1, ny = M+1
+    const double* X[DD_NVAR][3];
+    const double* Y[DD_NVAR][3];
+    const double* XQ[3];
+    const double* YQ[3];
+};
+
+// Host-evaluated forcing arrays: f[v][slot], same layout as the fields
+// (fcp is the cell-averaged source, zero on the boundary).
+struct DDForcingArrays {
+    const double* f[DD_NVAR][2];
+};
+
+// Five state fields (device pointers, member 0 / local row 0).
+struct DDState {
+    double* v[DD_NVAR];
+};
+struct DDStateC {
+    const double* v[DD_NVAR];
+};
+
+// Per-member statistics of one linear solve, reduced on the device.
+struct DDSolveStats {
+    double rho;        // max_i sum_j |a_ij| / |a_ii|  (Gershgorin / Jacobi norm)
+    double resid;      // max |bb - (I - G) x| of the Jacobi-scaled system
+    double xmax;       // max |x|
+    double vmax;       // max |v_new|
+    double bmax;       // max |bb|
+};
