@@ -38,5 +38,7 @@ from .ddoracle import (  # noqa: F401
     grad_norm_p_sq,
     run_trial,
     combined_error_norm,
+    exact_state,
+    error_norms,
 )
 from .mms import make_case, OForcing, CASE_NAMES  # noqa: F401
