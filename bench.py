@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- fp64 cell-steps/s of the RegHCsTriple predictor-corrector step on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one PC step (num_pc_steps = num_newton_steps = 1, 5 cs-Newton iterations: the reference
+defaults) of the whole workload.  Default workload `mesh`: MMSCasePol on 1024 rows per GPU of the
+N = M = 8192 unit-square mesh (h = k = 1/8192, dt = h^1.5 -- BASELINE.json configs[4]; at 8 GPUs it is
+exactly that config), slab-decomposed along i with halo exchange over NCCL.  Other workloads:
+`sweep` (configs[1], the 19-trajectory Pol refinement sweep) and `ensemble` (configs[2]).
+
+One JSON line on rank 0.  `value` = cell-steps/s with state resident in HBM, timed with CUDA events on
+the launching stream (max over ranks); `e2e` = the same step through Batch.upload / step_pc / download
+with pinned HOST buffers; `roofline` = dominant kernel vs the measured HBM peak; `cpu_baseline` = the
+oracle port (NumPy + SuperLU) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "na-nonlinear-temperature-enhanced-diffusion-model-dd_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "fp64 cell-steps/sec (Newton+tridiag)"
+UNIT = "cell-steps/s"
+BYTES_PER_CELL_STEP = 280.0  # PC-RegH step, p = q = 1
+POL = dict(K1=1e-3, K2=1e-3, K3=1e-3, K4=1e-3, DT=1e-3, Dl_max=8.01e-4, phi_l=1e-5, gamma_T=1e-9, Kd=1e-2, Sd=1.0,
+           Dd_max=2.46e-6, phi_d=1e-5, r_sp=5e-2, T_ref=300.0)
+ETA = 50.0
+# algorithmic bytes per node and launch of each kernel class ("kernels")
+KERNEL_BYTES = {"k_predict": 80, "k_assemble<T>": 64, "k_assemble<cl>": 80, "k_assemble<cd>": 104,
+                "k_rbsor_tile<T>": 56, "k_rbsor_tile<cl>": 56, "k_rbsor_tile<cd>": 56, "k_correct": 80,
+                "k_feuler": 80}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def product_model():
+    import prob1base as p1
+    return p1.DefaultModel02(p1.ModelConsts(R0=p1.R0, Ea=p1.Ea, phi_T=p1.Ea / p1.R0, **POL))
+
+
+# ----------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(self.device), "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------
+# workloads on the device
+# ----------------------------------------------------------------------------
+MESH_COLS = 8192
+MESH_ROWS_PER_GPU = 1024
+
+
+def mesh_setup(world, rank, ctx):
+    """rows i of the N = M = 8192 unit-square mesh: 1024 per GPU (+ halo), dt = h^1.5."""
+    import ddmesh
+    import prob1_mms_cases as p1mc
+    import prob1base as p1
+    h = 1.0 / MESH_COLS
+    N = MESH_ROWS_PER_GPU * world
+    x = np.arange(N + 1) * h
+    y = np.linspace(0.0, 1.0, MESH_COLS + 1)
+    model = product_model()
+    mesh = ddmesh.SlabMesh(x, y, world=world, rank=rank, ctx=ctx)
+    mesh.batch.set_model(model, ETA)
+    case = p1mc.MMSCasePol(grid=p1.Grid(np.array([0.0, 0.5, 1.0]), np.array([0.0, 0.5, 1.0])), model=model)
+    mesh.batch.forcing_spec(case.device_spec())
+    mesh.fill_exact(0, 0.0)
+    return mesh, h ** 1.5, N * MESH_COLS
+
+
+def run_b200(args):
+    import torch
+    import ddcore
+    from _ddlib import Context, load_library, profile_read
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream(device=local)
+    lib = load_library()
+    with torch.cuda.stream(stream):
+        ctx = Context(local, stream.cuda_stream)
+        if args.workload == "mesh":
+            mesh, dt, cells = mesh_setup(world, rank, ctx)
+            opt = ddcore.pc_options()
+
+            def step(k):
+                mesh.step_pc(k % 2, (k + 1) % 2, k * dt, dt, opt)
+            workload = (f"pol_mesh: MMSCasePol, {MESH_ROWS_PER_GPU} rows/GPU x {MESH_COLS} cols of the N=M=8192 "
+                        f"unit-square mesh (h=k=1/8192, dt=h^1.5), slab decomposition along i")
+            extra_cfg = {"rows_per_gpu": MESH_ROWS_PER_GPU, "cols": MESH_COLS, "halo_rows": mesh.G,
+                         "l2": "state + work arrays (>2 GB/GPU) exceed the 126 MB L2"}
+        else:
+            raise SystemExit(f"unknown workload {args.workload}")
+
+        def barrier():
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        for k in range(args.warmup):
+            step(k)
+        barrier()
+        launches0 = lib.dd_launch_count()
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for k in range(args.steps):
+            step(args.warmup + k)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clk = clocks.stop() if rank == 0 else None
+        launches = lib.dd_launch_count() - launches0
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        stats = mesh.last_stats
+
+        # per-kernel device time with CUDA events on the same stream (second timed loop, same steps)
+        lib.dd_profile_enable(1)
+        barrier()
+        for k in range(args.steps):
+            step(args.warmup + args.steps + k)
+        barrier()
+        prof = profile_read(True)
+        lib.dd_profile_enable(0)
+
+        # end to end through the host-buffer API (rank-local slab): H2D 5 fields, step, D2H 5 fields
+        e2e = None
+        if args.e2e:
+            shape = mesh.batch.shape
+            pinned_in = {v: torch.empty(shape, dtype=torch.float64).pin_memory().numpy() for v in ddcore.VARS}
+            got = mesh.batch.download(args.steps % 2)
+            for v in ddcore.VARS:
+                pinned_in[v][...] = got[v]
+            pinned_out = {v: torch.empty(shape, dtype=torch.float64).pin_memory().numpy() for v in ddcore.VARS}
+            nb = 5 * shape[0] * shape[1] * 8
+
+            def e2e_step(k):
+                mesh.batch.upload(0, pinned_in)
+                mesh.step_pc(0, 1, k * dt, dt, opt)
+                mesh.batch.download_into(1, pinned_out)
+            e2e_step(0)
+            barrier()
+            e0.record(stream)
+            ne = max(2, min(args.steps, 5))
+            for k in range(ne):
+                e2e_step(k)
+            e1.record(stream)
+            barrier()
+            ems = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ems], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ems = float(t.item())
+            e2e = {"value": cells * ne / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": nb * world,
+                   "d2h_bytes_per_step": nb * world, "steps": ne}
+    if rank != 0:
+        return
+    peak, peak_kind = measured_peak()
+    value = cells * args.steps / (ms * 1e-3)
+    # dominant kernel
+    nodes_rank = (MESH_ROWS_PER_GPU + 1) * (MESH_COLS + 1)
+    top = max(((k, v) for k, v in prof.items() if k in KERNEL_BYTES), key=lambda kv: kv[1][0])
+    tname, (tms, tcount) = top
+    achieved = KERNEL_BYTES[tname] * nodes_rank / (tms / tcount * 1e-3) / 1e9
+    total_prof = sum(v[0] for v in prof.values())
+    roof = {"bound": "hbm", "kernel": tname, "achieved": achieved, "peak": peak, "peak_kind": peak_kind,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "launch_ms": tms / tcount, "share_of_step": tms / total_prof,
+            "step": {"bytes_per_cell_step": BYTES_PER_CELL_STEP,
+                     "achieved": value / world * BYTES_PER_CELL_STEP / 1e9,
+                     "frac": value / world * BYTES_PER_CELL_STEP / 1e9 / peak},
+            "kernels": {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
+                        for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": dict({"workload": workload, "integrator": "PC RegHCsTriple p=q=1, 5 cs-Newton iterations",
+                        "eta": ETA, "forcing": "fused MMS (separable tables)", "solver": stats}, **extra_cfg),
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
+    }
+    if world == 1 and args.cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(threads=1, steps=2, warmup=1)
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------
+# CPU side: the oracle port (NumPy + SciPy SuperLU), test infrastructure used here only as the
+# timed baseline
+# ----------------------------------------------------------------------------
+CPU_SAMPLE_N = 256
+
+
+def _cpu_worker(job):
+    steps, warmup = job
+    from oracle import NOTEBOOK_CONSTS, OForcing, OGrid, PCStepper, exact_state, make_case
+    N = CPU_SAMPLE_N
+    om = NOTEBOOK_CONSTS["pol"]
+    g = OGrid(np.linspace(0, 1, N + 1), np.linspace(0, 1, N + 1))
+    case = make_case("pol", om)
+    forcing = OForcing(case, om, ETA, g)
+    s = exact_state(case, 0.0, g)
+    stepper = PCStepper(g, om, ETA, forcing, keep_residuals=False)
+    dt = (1.0 / N) ** 1.5
+    t = 0.0
+    for _ in range(warmup):
+        s = stepper.step(s, t, dt)
+        t += dt
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        s = stepper.step(s, t, dt)
+        t += dt
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(threads: int, steps: int, warmup: int):
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    if threads <= 1:
+        el = [_cpu_worker((steps, warmup))]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(threads) as pool:
+            el = pool.map(_cpu_worker, [(steps, warmup)] * threads)
+    cells = CPU_SAMPLE_N * CPU_SAMPLE_N * steps
+    value = sum(cells / e for e in el) if threads > 1 else cells / el[0]
+    return {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": (f"oracle port (NumPy + SciPy SuperLU), MMSCasePol N=M={CPU_SAMPLE_N}, dt=h^1.5, "
+                       f"{steps} PC steps per worker after {warmup} warm-up, {threads} independent "
+                       f"trajectories (one per core)"),
+            "host_cpus": os.cpu_count(), "s_per_step": max(el) / steps}
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps = max(1, min(args.steps, 4))
+    base = cpu_baseline(threads=threads, steps=steps, warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": base["s_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "pol_mesh (bounded sample: N=M=256 per core, same case, constants, eta, "
+                                   "dt rule and integrator settings as the CUDA arm)"},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="mesh", choices=["mesh"])
+    ap.add_argument("--no-e2e", dest="e2e", action="store_false")
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

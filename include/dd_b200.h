@@ -172,6 +172,24 @@ int dd_pc_residual(dd_batch* b, int var, int slot_state, const double* t0, const
  * or from slot_exact when >= 0 */
 int dd_error_norms(dd_batch* b, int slot, int slot_exact, const double* t, int n_t, double* out);
 
+/* ---- slab-decomposed meshes: the PC step in phases, halo exchange by the caller in between -----
+ * phase 0: times + predict (needs halo rows of the five input fields); 1/2/3: Newton solve of T/cl/cd into
+ * slot_out on the owned rows (exchange that field's halo afterwards); 4: correctors on all local rows;
+ * 5: cs exit decision (after reducing the work buffers "cs_it_max" (max) / "cs_it_min" (min) over ranks) and
+ * summary[3][4] = rho, ratio (<= 1 means the residual bound is met), resid, bound of the T, cl, cd solves.
+ * All ranks must use the same sweep plan (dd_batch_set_plan) for results independent of the decomposition. */
+int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_out, const double* t0, const double* dt, int n_t,
+                     const dd_pc_options* opt, double* summary, int* cs_iters);
+int dd_batch_set_plan(dd_batch* b, const int sweeps[3]);
+int dd_batch_get_plan(dd_batch* b, int sweeps[3]);
+int dd_sweeps_for_rho(double rho, int max_sweeps); /* SOR sweeps the planner uses for a Gershgorin ratio rho */
+int dd_next_plan(int cur, double rho, double ratio, int max_sweeps); /* next step's sweeps from this step's verified ratio */
+
+/* ---- instrumentation (bench.py) ------------------------------------------ */
+long long dd_launch_count(void);                /* kernels launched by the library since it was loaded */
+int dd_profile_enable(int on);                  /* bracket every launch group with CUDA events */
+int dd_profile_read(const char** names, double* ms, long long* count, int reset); /* returns #classes (<= 16) */
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,7 +95,26 @@ SIGNATURES = {
     "dd_pc_correct": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.c_int, _P(dd_pc_options), _P(C.c_int)]),
     "dd_pc_residual": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp]),
     "dd_error_norms": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int, _dp]),
+    "dd_step_pc_phase": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int, _P(dd_pc_options), _dp,
+                                   _P(C.c_int)]),
+    "dd_batch_set_plan": (C.c_int, [_vp, _P(C.c_int * 3)]),
+    "dd_batch_get_plan": (C.c_int, [_vp, _P(C.c_int * 3)]),
+    "dd_sweeps_for_rho": (C.c_int, [C.c_double, C.c_int]),
+    "dd_next_plan": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int]),
+    "dd_launch_count": (C.c_longlong, []),
+    "dd_profile_enable": (C.c_int, [C.c_int]),
+    "dd_profile_read": (C.c_int, [_P(C.c_char_p), _dp, _P(C.c_longlong), C.c_int]),
 }
+
+
+def profile_read(reset: bool = True):
+    """{kernel class: (device ms, launches)} accumulated since the last reset (profiling must be enabled)."""
+    lib = load_library()
+    names = (C.c_char_p * 16)()
+    ms = (C.c_double * 16)()
+    cnt = (C.c_longlong * 16)()
+    n = lib.dd_profile_read(names, ms, cnt, 1 if reset else 0)
+    return {names[k].decode(): (ms[k], cnt[k]) for k in range(n) if cnt[k] > 0}
 
 _lib = None
 

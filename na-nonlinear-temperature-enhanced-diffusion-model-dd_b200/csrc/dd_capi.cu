@@ -54,6 +54,88 @@ struct dd_batch {
 };
 
 // ---------------------------------------------------------------------------
+// launch accounting: every kernel launched by the library is counted; with profiling on,
+// each launch group is bracketed by CUDA events on the context's stream and its device time is
+// accumulated per kernel class (bench.py reads this for the roofline of the dominant kernel).
+enum ProfClass {
+    PC_TIME = 0, PC_PREDICT, PC_ASM_T, PC_ASM_CL, PC_ASM_CD, PC_SOLVE_T, PC_SOLVE_CL, PC_SOLVE_CD, PC_CORRECT,
+    PC_CS_FINISH, PC_SUMMARISE, PC_FEULER, PC_NORMS, PC_OTHER, PC_NCLASS
+};
+static const char* kProfNames[PC_NCLASS] = {"k_time_coefs", "k_predict", "k_assemble<T>", "k_assemble<cl>",
+                                            "k_assemble<cd>", "k_rbsor_tile<T>", "k_rbsor_tile<cl>",
+                                            "k_rbsor_tile<cd>", "k_correct", "k_cs_decide+k_cs_redo",
+                                            "k_summarise", "k_feuler", "k_error_norms", "other"};
+struct Prof {
+    bool on = false;
+    long long launches = 0;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    struct Rec { int cls; cudaEvent_t a, b; int n; };
+    std::vector<Rec> recs;
+    double ms[PC_NCLASS] = {0};
+    long long count[PC_NCLASS] = {0};
+    cudaEvent_t get() {
+        if (used == pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            pool.push_back(e);
+        }
+        return pool[used++];
+    }
+};
+static Prof g_prof;
+
+struct ProfScope {
+    cudaStream_t st;
+    int cls, n;
+    cudaEvent_t a;
+    bool on;
+    ProfScope(cudaStream_t s, int c, int nl) : st(s), cls(c), n(nl), on(g_prof.on) {
+        g_prof.launches += nl;
+        if (on) {
+            a = g_prof.get();
+            cudaEventRecord(a, st);
+        }
+    }
+    ~ProfScope() {
+        if (on) {
+            cudaEvent_t b = g_prof.get();
+            cudaEventRecord(b, st);
+            g_prof.recs.push_back({cls, a, b, n});
+        }
+    }
+};
+#define CKP(cls, nl, call) do { ProfScope ps_(ctx->stream, cls, nl); CK(call); } while (0)
+
+extern "C" long long dd_launch_count(void) { return g_prof.launches; }
+
+extern "C" int dd_profile_enable(int on) {
+    g_prof.on = on != 0;
+    return DD_OK;
+}
+
+// drains the recorded event pairs (synchronises the events) and returns the accumulated device time
+// per kernel class; names/ms/count arrays of length >= 16; resets the accumulators when `reset`
+extern "C" int dd_profile_read(const char** names, double* ms, long long* count, int reset) {
+    for (auto& r : g_prof.recs) {
+        cudaEventSynchronize(r.b);
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        g_prof.ms[r.cls] += t;
+        g_prof.count[r.cls] += r.n;
+    }
+    g_prof.recs.clear();
+    g_prof.used = 0;
+    for (int c = 0; c < PC_NCLASS; ++c) {
+        if (names) names[c] = kProfNames[c];
+        if (ms) ms[c] = g_prof.ms[c];
+        if (count) count[c] = g_prof.count[c];
+        if (reset) { g_prof.ms[c] = 0; g_prof.count[c] = 0; }
+    }
+    return PC_NCLASS;
+}
+
+// ---------------------------------------------------------------------------
 static int fail(dd_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg;
     return code;
@@ -416,8 +498,16 @@ extern "C" int dd_state_dev_ptr(dd_batch* b, int slot, int var, void** ptr, long
     return DD_OK;
 }
 
+static int ensure_cs_buffers(dd_batch* b, int cap);
+
 extern "C" int dd_work_dev_ptr(dd_batch* b, const char* name, void** ptr) {
     if (!b || !name || !ptr) return DD_ERR_INVALID;
+    if (!strcmp(name, "cs_it_max") || !strcmp(name, "cs_it_min")) {
+        // [member][cap] accumulators of the cs-Newton exit test (allreduced by the slab driver)
+        if (b->cs_cap_alloc <= 0) return fail(b->ctx, DD_ERR_INVALID, "cs statistics not allocated yet");
+        *ptr = !strcmp(name, "cs_it_max") ? b->d_itmax : b->d_itmin;
+        return DD_OK;
+    }
     double* p;
     int rc = get_work(b, name, &p);
     if (rc != DD_OK) return rc;
@@ -483,7 +573,7 @@ static int set_times(dd_batch* b, const double* t0, const double* dt, int n_t) {
         if (!(dt[k] > 0.0)) return fail(ctx, DD_ERR_INVALID, "dt must be > 0");
     CK(cudaMemcpyAsync(b->d_t0, t0, sizeof(double) * n_t, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(b->d_dt, dt, sizeof(double) * n_t, cudaMemcpyHostToDevice, ctx->stream));
-    CK(dd_launch_time_coefs(launch_of(b), b->mode, b->d_mem, b->d_t0, b->d_dt, n_t, 0));
+    CKP(PC_TIME, 1, dd_launch_time_coefs(launch_of(b), b->mode, b->d_mem, b->d_t0, b->d_dt, n_t, 0));
     return DD_OK;
 }
 
@@ -494,7 +584,7 @@ extern "C" int dd_state_fill_exact(dd_batch* b, int slot, const double* t, int n
     std::vector<double> one(n_t, 1.0);
     int rc = set_times(b, t, one.data(), n_t);
     if (rc != DD_OK) return rc;
-    CK(dd_launch_fill_exact(launch_of(b, ROWS_ALL), b->mode, b->g, b->d_mem, b->F, mstate(b, slot)));
+    CKP(PC_OTHER, 1, dd_launch_fill_exact(launch_of(b, ROWS_ALL), b->mode, b->g, b->d_mem, b->F, mstate(b, slot)));
     CK(cudaStreamSynchronize(ctx->stream));
     return DD_OK;
 }
@@ -508,7 +598,7 @@ extern "C" int dd_step_feuler(dd_batch* b, int slot_in, int slot_out, const doub
     CK(cudaSetDevice(ctx->device));
     int rc = set_times(b, t0, dt, n_t);
     if (rc != DD_OK) return rc;
-    CK(dd_launch_feuler(launch_of(b), b->mode, b->g, b->d_mem, b->F, cstate(b, slot_in), mstate(b, slot_out)));
+    CKP(PC_FEULER, 1, dd_launch_feuler(launch_of(b), b->mode, b->g, b->d_mem, b->F, cstate(b, slot_in), mstate(b, slot_out)));
     CK(cudaStreamSynchronize(ctx->stream));
     return DD_OK;
 }
@@ -520,7 +610,7 @@ extern "C" int dd_eval_fields(dd_batch* b, int slot_in, int slot_out, const doub
     std::vector<double> one(n_t, 1.0);
     int rc = set_times(b, t, one.data(), n_t);
     if (rc != DD_OK) return rc;
-    CK(dd_launch_fields(launch_of(b), b->mode, b->g, b->d_mem, b->F, cstate(b, slot_in), mstate(b, slot_out), 0));
+    CKP(PC_OTHER, 1, dd_launch_fields(launch_of(b), b->mode, b->g, b->d_mem, b->F, cstate(b, slot_in), mstate(b, slot_out), 0));
     CK(cudaStreamSynchronize(ctx->stream));
     return DD_OK;
 }
@@ -529,8 +619,9 @@ static int norms_async(dd_batch* b, int slot, int slot_exact, double* out_host) 
     dd_ctx* ctx = b->ctx;
     DDStateC ex;
     if (slot_exact >= 0) ex = cstate(b, slot_exact);
-    CK(dd_launch_error_norms(launch_of(b), b->mode, b->g, b->d_mem, b->F, cstate(b, slot),
-                             slot_exact >= 0 ? &ex : nullptr, b->d_norm_partial, b->norm_bpm, b->d_norm_out));
+    CKP(PC_NORMS, 2, dd_launch_error_norms(launch_of(b, ROWS_OWNED), b->mode, b->g, b->d_mem, b->F, cstate(b, slot),
+                                           slot_exact >= 0 ? &ex : nullptr, b->d_norm_partial, b->norm_bpm,
+                                           b->d_norm_out));
     CK(cudaMemcpyAsync(out_host, b->d_norm_out, sizeof(double) * 8 * b->B, cudaMemcpyDeviceToHost, ctx->stream));
     return DD_OK;
 }
@@ -583,6 +674,27 @@ static int sweeps_for_rho(double rho, int max_sweeps) {
     int k = 2;
     while (k < max_sweeps && (1.0 + k) * pow(lam, k) > 1e-17) ++k;
     return k;
+}
+
+// Sweep plan for the next step from this step's verified residual.  ratio = resid / allowed (<= 1 passed).
+// One SOR sweep multiplies the error by about lam = omega - 1; drop a sweep while the predicted ratio keeps
+// a 10x margin, add one when the margin is gone.  The bound itself is always re-verified after the solve.
+static int next_plan(int cur, double rho, double ratio, int max_sweeps) {
+    double lam = 0.999;
+    if (rho >= 0.0 && rho < 1.0) lam = 2.0 / (1.0 + sqrt(1.0 - rho * rho)) - 1.0;
+    if (lam < 1e-12) lam = 1e-12;
+    int want = cur;
+    if (!(ratio <= 0.1)) {
+        want = cur + 1;
+    } else if (cur > 1 && ratio * 10.0 < lam) {
+        const double r = ratio > 1e-300 ? ratio : 1e-300;
+        int drop = (int)floor(log(r * 10.0) / log(lam));
+        if (drop < 1) drop = 1;
+        want = cur - drop;
+    }
+    if (want > max_sweeps) want = max_sweeps;
+    if (want < 1) want = 1;
+    return want;
 }
 
 // choose tile shape and sweeps per pass
@@ -718,7 +830,8 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
     // so that the tile solver sees valid rows in its halo); tiles cover the owned rows only
     const DDLaunch L = launch_of(b, ROWS_OWNED);
     const DDLaunch La = launch_of(b, ROWS_STENCIL);
-    CK(dd_launch_assemble(La, b->mode, var, b->g, b->d_mem, b->F, ustar, T1, cl1, Y, opt.cd_band_swap, R, st));
+    CKP(PC_ASM_T + (var - DD_T), 2,
+        dd_launch_assemble(La, b->mode, var, b->g, b->d_mem, b->F, ustar, T1, cl1, Y, opt.cd_band_swap, R, st));
     const int vi = var - DD_T;
     int sweeps = opt.fixed_sweeps > 0 ? opt.fixed_sweeps : b->plan_sweeps[vi];
     if (sweeps <= 0) {
@@ -735,26 +848,50 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
     int left = sweeps, passes = 0;
     double *xa = nullptr, *xb = nullptr;
     const double* xin = nullptr;
+    // rows on which the rows R and the iterate x are valid.  On a slab every pass consumes 2 rows per sweep
+    // from each interior side (the halo rows are recomputed redundantly, never exchanged mid-solve); sides
+    // on the physical boundary do not shrink.
+    int v0 = b->cmp0, v1 = b->cmp1;
+    const bool lo_edge = (b->row0 == 0), hi_edge = (b->row0 + b->nrows == b->N + 1);
     while (left > 0) {
         DDSolvePlan P;
         memset(&P, 0, sizeof(P));
         plan_pass(b, left, true, &P);
         if (P.sweeps <= 0) return fail(ctx, DD_ERR_INVALID, "no feasible solver tile");
         double* xout = nullptr;
+        DDLaunch Lp = L;
+        Lp.vr0 = v0;
+        Lp.vr1 = v1;
         if (!P.last_pass) {
             if (!xa) {
                 if ((rc = get_work(b, "xa", &xa)) != DD_OK) return rc;
                 if ((rc = get_work(b, "xb", &xb)) != DD_OK) return rc;
             }
             xout = (xin == xa) ? xb : xa;
+            Lp.own0 = lo_edge ? v0 : v0 + 2 * P.sweeps;
+            Lp.own1 = hi_edge ? v1 : v1 - 2 * P.sweeps;
+            if (Lp.own0 > b->own0 || Lp.own1 < b->own1)
+                return fail(ctx, DD_ERR_INVALID, "halo too shallow for the planned SOR sweeps");
+        } else {
+            const int need = 2 * P.sweeps + 1;
+            if ((!lo_edge && v0 + need > b->own0) || (!hi_edge && v1 - need < b->own1))
+                return fail(ctx, DD_ERR_INVALID, "halo too shallow for the planned SOR sweeps");
         }
         if (P.last_pass && P.sweeps < left) return fail(ctx, DD_ERR_INVALID, "solver plan inconsistency");
-        CK(dd_launch_solve_pass(L, b->g, R, xin, xout, vstar, vnew, var == DD_T ? 1 : 0, st, P));
+        CKP(PC_SOLVE_T + (var - DD_T), 1,
+            dd_launch_solve_pass(Lp, b->g, R, xin, xout, vstar, vnew, var == DD_T ? 1 : 0, st, P));
         left -= P.sweeps;
         xin = xout;
+        if (!P.last_pass) {
+            v0 = Lp.own0;
+            v1 = Lp.own1;
+        }
         ++passes;
     }
-    k_summarise<<<1, 256, 0, ctx->stream>>>(st, b->B, b->d_mem, opt.solve_tol, b->d_summary + k);
+    {
+        ProfScope ps_(ctx->stream, PC_SUMMARISE, 1);
+        k_summarise<<<1, 256, 0, ctx->stream>>>(st, b->B, b->d_mem, opt.solve_tol, b->d_summary + k);
+    }
     CK(cudaGetLastError());
     *sweeps_used = sweeps;
     *passes_used = passes;
@@ -782,7 +919,7 @@ static int pc_step_once(dd_batch* b, int slot_in, int slot_out, const dd_pc_opti
     const DDLaunch Lall = launch_of(b, ROWS_ALL);
     const DDStateC s0 = cstate(b, slot_in);
     const DDState sout = mstate(b, slot_out);
-    CK(dd_launch_predict(L, b->mode, b->g, b->d_mem, b->F, s0, po));
+    CKP(PC_PREDICT, 1, dd_launch_predict(L, b->mode, b->g, b->d_mem, b->F, s0, po));
     DDStateC u;
     u.v[DD_CP] = po.cp1p; u.v[DD_T] = s0.v[DD_T]; u.v[DD_CL] = s0.v[DD_CL]; u.v[DD_CD] = s0.v[DD_CD];
     u.v[DD_CS] = po.cs1p;
@@ -819,11 +956,13 @@ static int pc_step_once(dd_batch* b, int slot_in, int slot_out, const dd_pc_opti
                 k_cs_arm<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(b->d_itmax, b->d_itmin, n);
             }
         }
-        CK(dd_launch_correct(Lall, b->mode, b->g, b->d_mem, b->F, s0, u.v[DD_T], u.v[DD_CL], u.v[DD_CD], cpd, csd, cap,
-                             track ? opt.consec_xs_rtol : 0.0, b->d_itmax, b->d_itmin));
+        CKP(PC_CORRECT, 1,
+            dd_launch_correct(Lall, b->mode, b->g, b->d_mem, b->F, s0, u.v[DD_T], u.v[DD_CL], u.v[DD_CD], cpd, csd,
+                              cap, track ? opt.consec_xs_rtol : 0.0, b->d_itmax, b->d_itmin));
         if (track)
-            CK(dd_launch_cs_finish(Lall, b->mode, b->g, b->d_mem, b->F, s0, u.v[DD_CL], u.v[DD_CD], csd, cap,
-                                   opt.consec_xs_rtol, b->d_itmax, b->d_itmin, b->d_used));
+            CKP(PC_CS_FINISH, 2,
+                dd_launch_cs_finish(Lall, b->mode, b->g, b->d_mem, b->F, s0, u.v[DD_CL], u.v[DD_CD], csd, cap,
+                                    opt.consec_xs_rtol, b->d_itmax, b->d_itmin, b->d_used));
         u.v[DD_CP] = cpd; u.v[DD_CS] = csd;
     }
     // verification of every solve of this step (one small readback)
@@ -844,10 +983,7 @@ static int pc_step_once(dd_batch* b, int slot_in, int slot_out, const dd_pc_opti
                 if (next > b->plan_sweeps[vi]) b->plan_sweeps[vi] = next;
             }
         } else if (opt.fixed_sweeps <= 0 && q >= k - 3) {
-            // follow rho from step to step (the matrices change slowly)
-            int want = sweeps_for_rho(sums[q].rho * 1.02 + 1e-12, opt.max_sweeps) + b->plan_extra[vi];
-            if (want > opt.max_sweeps) want = opt.max_sweeps;
-            b->plan_sweeps[vi] = want;
+            b->plan_sweeps[vi] = next_plan(b->plan_sweeps[vi], sums[q].rho, sums[q].ratio, opt.max_sweeps);
         }
     }
     if (stats) {
@@ -931,7 +1067,7 @@ extern "C" int dd_run_pc(dd_batch* b, int slot_a, int slot_b, const double* t0, 
     if (norms_out && (rc = norms_async(b, cur, -1, norms_out)) != DD_OK) return rc;
     for (int s = 0; s < nsteps; ++s) {
         if ((rc = pc_step_retry(b, cur, nxt, opt, stats)) != DD_OK) return rc;
-        CK(dd_launch_time_coefs(launch_of(b), b->mode, b->d_mem, b->d_t0, b->d_dt, n_t, 1));
+        CKP(PC_TIME, 1, dd_launch_time_coefs(launch_of(b), b->mode, b->d_mem, b->d_t0, b->d_dt, n_t, 1));
         if (norms_out && (rc = norms_async(b, nxt, -1, norms_out + (s + 1) * nstride)) != DD_OK) return rc;
         const int tmp = cur; cur = nxt; nxt = tmp;
     }
@@ -950,8 +1086,8 @@ extern "C" int dd_run_feuler(dd_batch* b, int slot_a, int slot_b, const double* 
     const size_t nstride = (size_t)8 * b->B;
     if (norms_out && (rc = norms_async(b, cur, -1, norms_out)) != DD_OK) return rc;
     for (int s = 0; s < nsteps; ++s) {
-        CK(dd_launch_feuler(launch_of(b), b->mode, b->g, b->d_mem, b->F, cstate(b, cur), mstate(b, nxt)));
-        CK(dd_launch_time_coefs(launch_of(b), b->mode, b->d_mem, b->d_t0, b->d_dt, n_t, 1));
+        CKP(PC_FEULER, 1, dd_launch_feuler(launch_of(b), b->mode, b->g, b->d_mem, b->F, cstate(b, cur), mstate(b, nxt)));
+        CKP(PC_TIME, 1, dd_launch_time_coefs(launch_of(b), b->mode, b->d_mem, b->d_t0, b->d_dt, n_t, 1));
         if (norms_out && (rc = norms_async(b, nxt, -1, norms_out + (s + 1) * nstride)) != DD_OK) return rc;
         const int tmp = cur; cur = nxt; nxt = tmp;
     }
@@ -1071,4 +1207,109 @@ extern "C" int dd_pc_residual(dd_batch* b, int var, int slot_state, const double
     CK(cudaMemcpyAsync(out_host, res, b->field_elems * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return DD_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// phased PC step for slab-decomposed meshes: the caller exchanges halo rows between phases
+//   0: times + predict            (needs halos of the five input fields)
+//   1/2/3: assemble + solve T/cl/cd -> slot_out (owned rows); exchange that field's halo afterwards
+//   4: correctors on all local rows (needs halos of T1, cl1, cd1); accumulates the cs exit statistics
+//   5: cs exit decision (after the caller reduced "cs_it_max"/"cs_it_min" over ranks) and the solve
+//      summaries: summary[3][4] = rho, ratio (<= 1: bound met), resid, bound for T, cl, cd
+// Only num_pc_steps = num_newton_steps = 1.
+// ---------------------------------------------------------------------------
+extern "C" int dd_batch_set_plan(dd_batch* b, const int sweeps[3]) {
+    if (!b || !sweeps) return DD_ERR_INVALID;
+    for (int q = 0; q < 3; ++q) b->plan_sweeps[q] = sweeps[q];
+    return DD_OK;
+}
+
+extern "C" int dd_batch_get_plan(dd_batch* b, int sweeps[3]) {
+    if (!b || !sweeps) return DD_ERR_INVALID;
+    for (int q = 0; q < 3; ++q) sweeps[q] = b->plan_sweeps[q];
+    return DD_OK;
+}
+
+extern "C" int dd_sweeps_for_rho(double rho, int max_sweeps) { return sweeps_for_rho(rho, max_sweeps); }
+
+extern "C" int dd_next_plan(int cur, double rho, double ratio, int max_sweeps) {
+    return next_plan(cur, rho, ratio, max_sweeps);
+}
+
+extern "C" int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_out, const double* t0, const double* dt,
+                                int n_t, const dd_pc_options* opt_in, double* summary, int* cs_iters) {
+    if (!b || !slot_ok(b, slot_in) || !slot_ok(b, slot_out) || slot_in == slot_out) return DD_ERR_INVALID;
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    dd_pc_options opt;
+    if (opt_in) opt = *opt_in; else dd_pc_options_default(&opt);
+    int rc = check_opts(ctx, opt);
+    if (rc != DD_OK) return rc;
+    if (opt.num_pc_steps != 1 || opt.num_newton_steps != 1)
+        return fail(ctx, DD_ERR_INVALID, "phased step supports num_pc_steps = num_newton_steps = 1");
+    if ((rc = ensure_solve_slots(b, 3)) != DD_OK) return rc;
+    DDPredictOut po;
+    if ((rc = get_work(b, "cp1p", &po.cp1p)) != DD_OK) return rc;
+    if ((rc = get_work(b, "cs1p", &po.cs1p)) != DD_OK) return rc;
+    if ((rc = get_work(b, "YT", &po.YT)) != DD_OK) return rc;
+    if ((rc = get_work(b, "Ycl", &po.Ycl)) != DD_OK) return rc;
+    if ((rc = get_work(b, "Ycd", &po.Ycd)) != DD_OK) return rc;
+    const DDStateC s0 = cstate(b, slot_in);
+    const DDState sout = mstate(b, slot_out);
+    DDStateC u;
+    u.v[DD_CP] = po.cp1p; u.v[DD_T] = s0.v[DD_T]; u.v[DD_CL] = s0.v[DD_CL]; u.v[DD_CD] = s0.v[DD_CD];
+    u.v[DD_CS] = po.cs1p;
+    const int cap = opt.num_newton_iterations;
+    const bool track = opt.consec_xs_rtol > 0.0 && cap > 0;
+    int sw = 0, pa = 0;
+    switch (phase) {
+        case 0:
+            if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
+            CKP(PC_PREDICT, 1, dd_launch_predict(launch_of(b, ROWS_STENCIL), b->mode, b->g, b->d_mem, b->F, s0, po));
+            if (track) {
+                const int had = b->cs_cap_alloc;
+                if ((rc = ensure_cs_buffers(b, cap)) != DD_OK) return rc;
+                if (b->cs_cap_alloc != had) {
+                    const long long n = (long long)b->cs_cap_alloc * b->B;
+                    k_cs_arm<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(b->d_itmax, b->d_itmin, n);
+                }
+            }
+            return DD_OK;
+        case 1:
+            return newton_solve(b, DD_T, u, nullptr, nullptr, po.YT, sout.v[DD_T], opt, 0, &sw, &pa);
+        case 2:
+            return newton_solve(b, DD_CL, u, sout.v[DD_T], nullptr, po.Ycl, sout.v[DD_CL], opt, 1, &sw, &pa);
+        case 3:
+            return newton_solve(b, DD_CD, u, sout.v[DD_T], sout.v[DD_CL], po.Ycd, sout.v[DD_CD], opt, 2, &sw, &pa);
+        case 4:
+            CKP(PC_CORRECT, 1,
+                dd_launch_correct(launch_of(b, ROWS_ALL), b->mode, b->g, b->d_mem, b->F, s0, sout.v[DD_T],
+                                  sout.v[DD_CL], sout.v[DD_CD], sout.v[DD_CP], sout.v[DD_CS], cap,
+                                  track ? opt.consec_xs_rtol : 0.0, b->d_itmax, b->d_itmin));
+            return DD_OK;
+        case 5: {
+            if (track)
+                CKP(PC_CS_FINISH, 2,
+                    dd_launch_cs_finish(launch_of(b, ROWS_ALL), b->mode, b->g, b->d_mem, b->F, s0, sout.v[DD_CL],
+                                        sout.v[DD_CD], sout.v[DD_CS], cap, opt.consec_xs_rtol, b->d_itmax,
+                                        b->d_itmin, b->d_used));
+            SolveSummary sums[3];
+            CK(cudaMemcpyAsync(sums, b->d_summary, sizeof(sums), cudaMemcpyDeviceToHost, ctx->stream));
+            int used0 = cap;
+            if (track && cs_iters) CK(cudaMemcpyAsync(&used0, b->d_used, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (summary)
+                for (int q = 0; q < 3; ++q) {
+                    summary[q * 4 + 0] = sums[q].rho;
+                    summary[q * 4 + 1] = sums[q].ratio;
+                    summary[q * 4 + 2] = sums[q].resid;
+                    summary[q * 4 + 3] = sums[q].bound;
+                }
+            if (cs_iters) *cs_iters = used0;
+            return DD_OK;
+        }
+        default:
+            return fail(ctx, DD_ERR_INVALID, "phase must be 0..5");
+    }
 }

@@ -294,6 +294,8 @@ cudaError_t dd_launch_assemble(const DDLaunch& L, int mode, int var, const DDGeo
 // ---------------------------------------------------------------------------
 // correctors
 // ---------------------------------------------------------------------------
+#define DD_CS_SMEM_CAP 1024  // per-iteration statistics staged in shared memory up to this many iterations
+
 template <int MODE>
 __global__ void __launch_bounds__(DD_BLOCK) k_correct(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
                                                       DDStateC s0, const double* __restrict__ T1,
@@ -302,11 +304,21 @@ __global__ void __launch_bounds__(DD_BLOCK) k_correct(DDGeom g, const DDMember* 
                                                       double* __restrict__ cs_out, int cap, double rtol,
                                                       double* it_max, double* it_min, int own0, int own1,
                                                       int bpm) {
-    __shared__ double sh[32];
+    // per-iteration block statistics of the reference's global exit test (max |dx|, min |x|):
+    // warp shuffles + shared-memory atomics, flushed to global memory once per block
+    __shared__ unsigned long long sh_max[DD_CS_SMEM_CAP], sh_min[DD_CS_SMEM_CAP];
     const NodeIdx n = node_index(g, own0, own1, bpm);
     const DDMember& mb = mem[n.member];
     if (!mb.active) return;
     const bool track = rtol > 0.0;
+    const int scap = cap < DD_CS_SMEM_CAP ? cap : DD_CS_SMEM_CAP;
+    if (track) {
+        for (int k = threadIdx.x; k < scap; k += blockDim.x) {
+            sh_max[k] = 0ull;
+            sh_min[k] = 0x7ff0000000000000ull;
+        }
+        __syncthreads();
+    }
     double x = 0.0, y = 0.0, a = 0.0, cp1 = 0.0;
     long long o = 0;
     bool inter = false;
@@ -319,6 +331,7 @@ __global__ void __launch_bounds__(DD_BLOCK) k_correct(DDGeom g, const DDMember* 
         cp_out[o] = cp1;
     }
     const double eta = mb.m.eta;
+    const int lane = threadIdx.x & 31;
     for (int it = 0; it < cap; ++it) {
         double dx = 0.0;
         if (n.valid) {
@@ -327,15 +340,29 @@ __global__ void __launch_bounds__(DD_BLOCK) k_correct(DDGeom g, const DDMember* 
         }
         if (track) {
             // global exit test of the reference: max_all |dx| < rtol |x| at every node
-            double vmax = block_max_nonneg(n.valid ? dx : 0.0, sh);
-            if (threadIdx.x == 0) atomic_max_nonneg(&it_max[(long long)n.member * cap + it], vmax);
+            const double vmax = warp_max_bits(n.valid ? dx : 0.0);
             double ax = n.valid ? fabs(x) : __longlong_as_double(0x7ff0000000000000LL);
             if (ax != ax) ax = 0.0;  // NaN |x| fails the test exactly like 0 does
-            double vmin = block_min_nonneg(ax, sh);
-            if (threadIdx.x == 0) atomic_min_nonneg(&it_min[(long long)n.member * cap + it], vmin);
+            const double vmin = warp_min_bits(ax);
+            if (lane == 0) {
+                if (it < scap) {
+                    atomicMax(&sh_max[it], (unsigned long long)__double_as_longlong(vmax));
+                    atomicMin(&sh_min[it], (unsigned long long)__double_as_longlong(vmin));
+                } else {
+                    atomic_max_nonneg(&it_max[(long long)n.member * cap + it], vmax);
+                    atomic_min_nonneg(&it_min[(long long)n.member * cap + it], vmin);
+                }
+            }
         }
     }
     if (n.valid) cs_out[o] = x * (inter ? 1.0 : 0.0);
+    if (track) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < scap; k += blockDim.x) {
+            atomicMax(reinterpret_cast<unsigned long long*>(&it_max[(long long)n.member * cap + k]), sh_max[k]);
+            atomicMin(reinterpret_cast<unsigned long long*>(&it_min[(long long)n.member * cap + k]), sh_min[k]);
+        }
+    }
 }
 
 cudaError_t dd_launch_correct(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,

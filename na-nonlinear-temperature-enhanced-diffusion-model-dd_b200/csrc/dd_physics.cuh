@@ -23,7 +23,8 @@ DD_HD double dd_Dl(const DDModel& m, double cp) { return m.Dl_max * exp(-m.phi_l
 DD_HD double dd_Dd(const DDModel& m, double cp, double T) {
     const double Te = T + m.T_shift;
     if (Te == 0.0) return 0.0;
-    return m.Dd_max * exp(-m.phi_d * cp) * exp(-m.phi_T / Te);
+    // one exponential: e^{-phi_d cp} e^{-phi_T/Te} = e^{-(phi_d cp + phi_T/Te)} (differs from the product by rounding only)
+    return m.Dd_max * exp(-(m.phi_d * cp + m.phi_T / Te));
 }
 
 // returns Dd and writes dDd/dT = Dd * phi_T / Te^2
@@ -33,8 +34,9 @@ DD_HD double dd_Dd_dT(const DDModel& m, double cp, double T, double* dT) {
         *dT = 0.0;
         return 0.0;
     }
-    const double d = m.Dd_max * exp(-m.phi_d * cp) * exp(-m.phi_T / Te);
-    *dT = d * (m.phi_T / (Te * Te));
+    const double iT = 1.0 / Te;
+    const double d = m.Dd_max * exp(-(m.phi_d * cp + m.phi_T * iT));
+    *dT = d * (m.phi_T * iT * iT);
     return d;
 }
 

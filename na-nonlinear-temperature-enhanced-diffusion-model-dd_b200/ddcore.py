@@ -15,6 +15,7 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
+from _ddlib import DDNotConverged  # noqa: F401
 from _ddlib import (DD_OK, MODE_ARRAYS, MODE_EXPSIN, MODE_NONE, MODE_SEPARABLE, PHI_CONST, PHI_EXP, PHI_HOST,
                     PHI_INV1PT, PHI_LINEAR, PHI_OSC, VARS, Context, as_f64, dd_model, dd_pc_options,
                     dd_step_stats, dptr, _dp, _vp)
@@ -292,6 +293,15 @@ class Batch:
                 arr[v] = dptr(out[name])
         self.ctx.check(self.lib.dd_state_download(self.handle, slot, member, C.byref(arr)), "state_download")
         return out
+
+    def download_into(self, slot: int, out: Dict[str, np.ndarray], member: int = 0):
+        """device -> caller-provided host arrays (e.g. pinned memory)"""
+        arr = (_dp * 5)()
+        for v, name in enumerate(VARS):
+            if name in out:
+                assert out[name].shape == self.shape and out[name].flags["C_CONTIGUOUS"]
+                arr[v] = dptr(out[name])
+        self.ctx.check(self.lib.dd_state_download(self.handle, slot, member, C.byref(arr)), "state_download")
 
     def work_upload(self, name: str, a: np.ndarray, member: int = 0):
         a = as_f64(a)

@@ -1,0 +1,262 @@
+"""Multi-GPU partitioning of the stepping path (one process per GPU, torch.distributed for plumbing).
+
+Two ways the path shards:
+
+* `shard_members`  -- ensembles of independent trajectories: contiguous blocks of members per rank,
+  no communication while stepping; error norms are gathered / all-reduced at the end.
+* `SlabMesh`       -- one fine mesh split into row slabs along i.  Every rank keeps G halo rows on
+  each interior side, recomputes the cheap stencil work on them and exchanges G rows of a field
+  after each kernel that produces it (state at step start; T1, cl1, cd1 after their solves).
+  With a common sweep plan the tiled red-black SOR gives the same iterate as a single-GPU run.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+import ddcore
+from _ddlib import VARS, as_f64, dd_pc_options, dptr
+
+
+def shard_members(nmembers: int, world: int, rank: int) -> Tuple[int, int]:
+    """[first, last) of the members owned by `rank` (contiguous blocks, sizes differ by at most one)."""
+    base, rem = divmod(nmembers, world)
+    first = rank * base + min(rank, rem)
+    return first, first + base + (1 if rank < rem else 0)
+
+
+def slab_rows(nrows_global: int, world: int, rank: int, halo: int) -> Dict[str, int]:
+    """Row partition of a grid with `nrows_global` node rows: owned global rows [a, b), local storage
+    [a - lo, b + hi) with lo/hi = halo (0 at the physical boundary)."""
+    a, b = shard_members(nrows_global, world, rank)
+    lo = 0 if rank == 0 else min(halo, a)
+    hi = 0 if rank == world - 1 else min(halo, nrows_global - b)
+    return dict(a=a, b=b, lo=lo, hi=hi, row0=a - lo, nrows=(b - a) + lo + hi, own0=lo, own1=lo + (b - a))
+
+
+class _DevArray:
+    """__cuda_array_interface__ view of library-owned device memory (for torch.as_tensor)."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def halo_ops(t, part: Dict[str, int], rank: int, world: int, G: int, dist, tag_base: int = 0):
+    """isend/irecv descriptors exchanging G rows of the 2-D tensor `t` (local rows x cols) with both
+    neighbours.  Works for CPU (gloo) and CUDA (nccl) tensors alike."""
+    ops = []
+    o0, o1 = part["own0"], part["own1"]
+    if rank > 0:
+        g = min(G, part["lo"])
+        ops.append(dist.P2POp(dist.isend, t[o0:o0 + g], rank - 1))
+        ops.append(dist.P2POp(dist.irecv, t[o0 - g:o0], rank - 1))
+    if rank < world - 1:
+        g = min(G, part["hi"])
+        ops.append(dist.P2POp(dist.isend, t[o1 - g:o1], rank + 1))
+        ops.append(dist.P2POp(dist.irecv, t[o1:o1 + g], rank + 1))
+    return ops
+
+
+def exchange_halos(tensors: Sequence, part: Dict[str, int], rank: int, world: int, G: int, dist):
+    if world == 1:
+        return
+    ops = []
+    for t in tensors:
+        ops += halo_ops(t, part, rank, world, G, dist)
+    for r in dist.batch_isend_irecv(ops):
+        r.wait()
+
+
+class _DistComm:
+    """Collectives of one rank per process (torch.distributed, NCCL on GPUs)."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+
+    def exchange(self, meshes, slot, which):
+        m = meshes[0]
+        exchange_halos([m.field(slot, v) for v in which], m.part, m.rank, m.world, m.G, self.dist)
+
+    def allreduce(self, tensors, op):
+        d = self.dist
+        d.all_reduce(tensors[0], op={"max": d.ReduceOp.MAX, "min": d.ReduceOp.MIN, "sum": d.ReduceOp.SUM}[op])
+
+
+class _LocalComm:
+    """All slabs live in one process on one GPU (tests, single-GPU emulation of the multi-rank path):
+    halo exchange = device-to-device copies between the slabs' tensors."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+
+    def exchange(self, meshes, slot, which):
+        for m in meshes:
+            p = m.part
+            for v in which:
+                t = m.field(slot, v)
+                if m.rank > 0:
+                    up = meshes[m.rank - 1]
+                    g = min(m.G, p["lo"])
+                    t[p["own0"] - g:p["own0"]].copy_(up.field(slot, v)[up.part["own1"] - g:up.part["own1"]])
+                if m.rank < m.world - 1:
+                    dn = meshes[m.rank + 1]
+                    g = min(m.G, p["hi"])
+                    t[p["own1"]:p["own1"] + g].copy_(dn.field(slot, v)[dn.part["own0"]:dn.part["own0"] + g])
+
+    def allreduce(self, tensors, op):
+        torch = self.torch
+        stacked = torch.stack([t for t in tensors])
+        red = {"max": stacked.max(dim=0).values, "min": stacked.min(dim=0).values, "sum": stacked.sum(dim=0)}[op]
+        for t in tensors:
+            t.copy_(red)
+
+
+class SlabMesh:
+    """One trajectory on a mesh split into row slabs over `world` ranks.  `group` (optional) is the list
+    of all slabs when they live in one process (single-GPU emulation); otherwise one rank per process."""
+
+    def __init__(self, x, y, *, world: int = 1, rank: int = 0, ctx=None, halo: int = 24):
+        self.x, self.y = as_f64(x), as_f64(y)
+        self.world, self.rank = world, rank
+        self.G = halo if world > 1 else 0
+        self.part = slab_rows(len(self.x), world, rank, self.G)
+        p = self.part
+        self.batch = ddcore.Batch(self.x, self.y, 1, ctx=ctx, nslots=2, row0=p["row0"], nrows=p["nrows"],
+                                  own=(p["own0"], p["own1"]))
+        self.last_stats: dict = {}
+        self._tensors: Dict = {}
+        self.group: List["SlabMesh"] = [self]
+        self.comm = None
+        self._rho = None
+        self._extra = [0, 0, 0]
+        if world > 1:
+            import torch
+            self.torch = torch
+
+    @classmethod
+    def local_group(cls, x, y, world: int, ctx=None, halo: int = 24) -> List["SlabMesh"]:
+        """`world` slabs in this process (one GPU) exchanging halos by device copies."""
+        meshes = [cls(x, y, world=world, rank=r, ctx=ctx, halo=halo) for r in range(world)]
+        comm = _LocalComm()
+        for m in meshes:
+            m.group, m.comm = meshes, comm
+        return meshes
+
+    def _comm(self):
+        if self.comm is None:
+            self.comm = _DistComm()
+        return self.comm
+
+    # -- torch views of device fields ---------------------------------------------
+    def _tensor(self, key, ptr, shape=None):
+        t = self._tensors.get(key)
+        if t is None:
+            t = self.torch.as_tensor(_DevArray(ptr, shape or self.batch.shape), device="cuda")
+            self._tensors[key] = t
+        return t
+
+    def field(self, slot: int, var: str):
+        return self._tensor(("s", slot, var), self.batch.dev_ptr(slot, var)[0])
+
+    def exchange(self, slot: int, which: Sequence[str] = VARS):
+        self._comm().exchange(self.group, slot, which)
+
+    # -- state ------------------------------------------------------------------------
+    def fill_exact(self, slot: int, t: float):
+        self.batch.fill_exact(slot, t)
+
+    def owned(self, slot: int) -> Dict[str, np.ndarray]:
+        d = self.batch.download(slot)
+        return {v: a[self.part["own0"]:self.part["own1"]] for v, a in d.items()}
+
+    # -- stepping ---------------------------------------------------------------------
+    def step_pc(self, slot_in: int, slot_out: int, t0: float, dt: float, opt: Optional[dd_pc_options] = None):
+        """One PC step of the whole mesh.  With a local group, call it on any member: all slabs advance."""
+        opt = opt or ddcore.pc_options()
+        if self.world == 1:
+            self.last_stats = self.batch.step_pc(slot_in, slot_out, t0, dt, opt)
+            return self.last_stats
+        torch, comm, group = self.torch, self._comm(), self.group
+        t0a, dta = as_f64([t0]), as_f64([dt])
+        summ = [np.zeros(12) for _ in group]
+        iters = [C.c_int(0) for _ in group]
+
+        def phase(k):
+            for m, sm, it in zip(group, summ, iters):
+                b = m.batch
+                b.ctx.check(b.lib.dd_step_pc_phase(b.handle, k, slot_in, slot_out, dptr(t0a), dptr(dta), 1,
+                                                   C.byref(opt), dptr(sm), C.byref(it)), f"step_pc_phase {k}")
+        track = opt.consec_xs_rtol > 0.0 and opt.num_newton_iterations > 0
+        for attempt in range(40):
+            plan = self._common_plan(opt)
+            phase(0)
+            for k, var in ((1, "T"), (2, "cl"), (3, "cd")):
+                phase(k)
+                comm.exchange(group, slot_out, (var,))
+            phase(4)
+            if track:
+                n = opt.num_newton_iterations
+                comm.allreduce([m._tensor("itmax", m.batch.work_dev_ptr("cs_it_max"), (n,)) for m in group], "max")
+                comm.allreduce([m._tensor("itmin", m.batch.work_dev_ptr("cs_it_min"), (n,)) for m in group], "min")
+            phase(5)
+            ts = [torch.nan_to_num(torch.tensor(sm.reshape(3, 4), device="cuda"), nan=1e300) for sm in summ]
+            comm.allreduce(ts, "max")
+            s = ts[0].cpu().numpy()
+            stats = dict(sweeps=list(plan), rho=list(s[:, 0]), resid=list(s[:, 2]), bound=list(s[:, 3]),
+                         retries=attempt, cs_newton_iters=int(iters[0].value))
+            for m in group:
+                m._rho, m.last_stats = s[:, 0], stats
+            if np.all(s[:, 1] <= 1.0):
+                nxt = [self.batch.lib.dd_next_plan(int(p), float(r), float(q), opt.max_sweeps)
+                       for p, r, q in zip(plan, s[:, 0], s[:, 1])]
+                for m in group:
+                    m._plan = nxt
+                return stats
+            for m in group:
+                m._plan = None
+            extra = [e + (p + 1) // 2 + 1 if r > 1.0 else e for e, p, r in zip(self._extra, plan, s[:, 1])]
+            for m in group:
+                m._extra = extra
+        raise ddcore.DDNotConverged("slab step: linear solve did not reach the residual bound")
+
+    def _common_plan(self, opt) -> List[int]:
+        """Same number of SOR sweeps on every rank, planned from the all-reduced Gershgorin ratios of the
+        previous step (first step: as many sweeps as the halo supports)."""
+        lib = self.batch.lib
+        limit = (self.G - 2) // 2
+        if opt.fixed_sweeps > 0:
+            plan = [opt.fixed_sweeps] * 3
+        elif self._rho is None:
+            plan = [limit] * 3
+        elif getattr(self, "_plan", None) is not None:
+            plan = [min(p, limit) for p in self._plan]
+        else:
+            plan = [lib.dd_sweeps_for_rho(float(r) * 1.02 + 1e-12, opt.max_sweeps) + e
+                    for r, e in zip(self._rho, self._extra)]
+        if max(plan) > limit:
+            raise ddcore.DDNotConverged(f"slab step needs {max(plan)} SOR sweeps but the halo of {self.G} rows "
+                                        f"supports {limit}; create the SlabMesh with a deeper halo")
+        arr = (C.c_int * 3)(*plan)
+        for m in self.group:
+            m.batch.ctx.check(lib.dd_batch_set_plan(m.batch.handle, C.byref(arr)), "set_plan")
+        return plan
+
+    def step_feuler(self, slot_in: int, slot_out: int, t0: float, dt: float):
+        for m in self.group:
+            m.batch.step_feuler(slot_in, slot_out, t0, dt)
+        if self.world > 1:
+            self._comm().exchange(self.group, slot_out, VARS)
+
+    def error_norms(self, slot: int, t: float) -> np.ndarray:
+        if self.world == 1:
+            return self.batch.error_norms(slot, t)[0]
+        ts = [self.torch.tensor(m.batch.error_norms(slot, t)[0], device="cuda") for m in self.group]
+        self._comm().allreduce(ts, "sum")
+        return ts[0].cpu().numpy()

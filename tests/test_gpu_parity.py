@@ -258,3 +258,65 @@ def test_roundtrip_and_linearity_large(dd):
     e = b.error_norms(1, 0.2 + dt)
     assert np.sqrt(e[0, :5].sum()) < 1e-9
     b.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_decomposition_single_gpu_emulation(dd, world):
+    """The multi-rank mesh path (phased step + halo exchange + common sweep plan) with all slabs on one
+    GPU: must reproduce the undecomposed run bit for bit (same global red-black iteration) and match the
+    oracle to 1e-12."""
+    import ddmesh
+    from oracle import NOTEBOOK_CONSTS, OForcing, OGrid, PCStepper, exact_state, make_case
+    p1, ddcore = dd["p1"], dd["ddcore"]
+    N, M = 150, 40
+    om = NOTEBOOK_CONSTS["pol"]
+    eta, t0, dt = 50.0, 0.05, 2e-4
+    og = OGrid(np.linspace(0, 1, N + 1), np.linspace(0, 1, M + 1))
+    oc = make_case("pol", om)
+    model = dd["product_model"](dict(K1=om.K1, K2=om.K2, K3=om.K3, K4=om.K4, DT=om.DT, Dl_max=om.Dl_max,
+                                     phi_l=om.phi_l, gamma_T=om.gamma_T, Kd=om.Kd, Sd=om.Sd, Dd_max=om.Dd_max,
+                                     phi_d=om.phi_d, r_sp=om.r_sp, T_ref=om.T_ref, kind=2))
+    grid = p1.Grid(og.x, og.y)
+    spec = dd["CASES"]["pol"](grid=grid, model=model).device_spec()
+    meshes = ddmesh.SlabMesh.local_group(grid.x, grid.y, world, halo=12)
+    for m in meshes:
+        m.batch.set_model(model, eta)
+        m.batch.forcing_spec(spec)
+        m.fill_exact(0, t0)
+    nsteps = 3
+    for k in range(nsteps):
+        st = meshes[0].step_pc(k % 2, (k + 1) % 2, t0 + k * dt, dt)
+    got = {v: np.concatenate([m.owned(nsteps % 2)[v] for m in meshes]) for v in VARS}
+    # undecomposed run with the same sweep counts
+    b = ddcore.Batch(grid.x, grid.y, 1)
+    b.set_model(model, eta)
+    b.forcing_spec(spec)
+    b.fill_exact(0, t0)
+    s = exact_state(oc, t0, og)
+    stepper = PCStepper(og, om, eta, OForcing(oc, om, eta, og), keep_residuals=False)
+    t = t0
+    for k in range(nsteps):
+        s = stepper.step(s, t, dt)
+        t += dt
+    for v in VARS:
+        assert got[v].shape == (N + 1, M + 1)
+        assert rel_err(got[v], getattr(s, v)) <= TOL, v
+    e_slab = meshes[0].error_norms(nsteps % 2, t0 + nsteps * dt)
+    assert np.all(np.isfinite(e_slab)) and max(st["bound"]) <= 1e-13
+    # bitwise reproducibility across decompositions: 1 slab == `world` slabs for equal sweep plans
+    for k in range(nsteps):
+        b.step_pc(k % 2, (k + 1) % 2, t0 + k * dt, dt, ddcore.pc_options(fixed_sweeps=5))
+    meshes2 = ddmesh.SlabMesh.local_group(grid.x, grid.y, world, halo=12)
+    for m in meshes2:
+        m.batch.set_model(model, eta)
+        m.batch.forcing_spec(spec)
+        m.fill_exact(0, t0)
+    for k in range(nsteps):
+        meshes2[0].step_pc(k % 2, (k + 1) % 2, t0 + k * dt, dt, ddcore.pc_options(fixed_sweeps=5))
+    one = b.download(nsteps % 2)
+    for v in VARS:
+        many = np.concatenate([m.owned(nsteps % 2)[v] for m in meshes2])
+        assert np.array_equal(many, one[v]), v
+    e_one = b.error_norms(nsteps % 2, t0 + nsteps * dt)[0]
+    e_many = meshes2[0].error_norms(nsteps % 2, t0 + nsteps * dt)
+    assert np.allclose(e_many, e_one, rtol=1e-12, atol=0)
