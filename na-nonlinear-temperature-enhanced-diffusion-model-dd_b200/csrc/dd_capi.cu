@@ -11,6 +11,7 @@
 
 #include "../../include/dd_b200.h"
 #include "dd_kernels.cuh"
+#include "dd_tables_host.h"
 
 #define DD_VERSION_STR "dd_b200 0.1 (sm_100a)"
 
@@ -48,9 +49,11 @@ struct dd_batch {
     int cs_cap_alloc;
     double *d_norm_partial, *d_norm_out;
     int norm_bpm;
-    int plan_sweeps[3], plan_extra[3];
+    int plan_sweeps[3], plan_extra[3], plan_floor[3];  // floor: one more than the last count that failed
     bool is_slab;
     int cmp0, cmp1;  // local rows with a complete stencil (slabs: everything but the outermost halo row)
+    int asm0, asm1;  // rows whose Newton rows are exact: their stencil reads predictor output, itself only
+                     // defined on [cmp0, cmp1) -> one more row is lost on every interior side
 };
 
 // ---------------------------------------------------------------------------
@@ -247,7 +250,10 @@ extern "C" int dd_batch_create(dd_ctx* ctx, int N, int M, const double* x, const
     b->is_slab = !(row0 == 0 && nrows == N + 1);
     b->cmp0 = (row0 == 0) ? 0 : 1;
     b->cmp1 = (row0 + nrows == N + 1) ? nrows : nrows - 1;
+    b->asm0 = (row0 == 0) ? 0 : 2;
+    b->asm1 = (row0 + nrows == N + 1) ? nrows : nrows - 2;
     b->plan_extra[0] = b->plan_extra[1] = b->plan_extra[2] = 0;
+    b->plan_floor[0] = b->plan_floor[1] = b->plan_floor[2] = 1;
     const int ld = M + 1;
     b->field_elems = (size_t)nmembers * nrows * ld;
     // geometry (reference Grid.__init__, src/prob1base.py:287-304)
@@ -329,6 +335,7 @@ extern "C" int dd_batch_set_models(dd_batch* b, int first, int count, const dd_m
     for (int k = 0; k < count; ++k) model_to_dev(models[k], &b->h_mem[first + k].m);
     b->plan_sweeps[0] = b->plan_sweeps[1] = b->plan_sweeps[2] = 0;
     b->plan_extra[0] = b->plan_extra[1] = b->plan_extra[2] = 0;
+    b->plan_floor[0] = b->plan_floor[1] = b->plan_floor[2] = 1;
     return push_members(b, first, count);
 }
 
@@ -376,19 +383,30 @@ extern "C" int dd_forcing_separable(dd_batch* b, int nterms, const double* const
     free_tables(b);
     int rc;
     for (int v = 0; v < 5; ++v)
-        for (int d = 0; d < 3; ++d) {
+        for (int d = 0; d < 3; ++d)
             if (!X[v][d] || !Y[v][d]) return fail(ctx, DD_ERR_INVALID, "null separable table");
-            if ((rc = up_table(b, X[v][d], (size_t)nterms * (b->N + 1), &b->F.tab.X[v][d])) != DD_OK) return rc;
-            if ((rc = up_table(b, Y[v][d], (size_t)nterms * (b->M + 1), &b->F.tab.Y[v][d])) != DD_OK) return rc;
-        }
-    for (int q = 0; q < 3; ++q) {
+    for (int q = 0; q < 3; ++q)
         if (!XQ[q] || !YQ[q]) return fail(ctx, DD_ERR_INVALID, "null quadrature table");
-        if ((rc = up_table(b, XQ[q], 3 * (size_t)nterms * (b->N + 1), &b->F.tab.XQ[q])) != DD_OK) return rc;
-        if ((rc = up_table(b, YQ[q], 3 * (size_t)nterms * (b->M + 1), &b->F.tab.YQ[q])) != DD_OK) return rc;
-    }
-    b->F.tab.nterms = nterms;
-    b->F.tab.nx = b->N + 1;
-    b->F.tab.ny = b->M + 1;
+    DDHostTables ht;
+    dd_prepare_tables(nterms, b->N, b->M, X, Y, XQ, YQ, &ht);
+    DDTables& tb = b->F.tab;
+    for (int p = 0; p < ht.nprof; ++p)
+        for (int d = 0; d < 3; ++d) {
+            if ((rc = up_table(b, ht.X[p][d].data(), ht.X[p][d].size(), &tb.X[p][d])) != DD_OK) return rc;
+            if ((rc = up_table(b, ht.Y[p][d].data(), ht.Y[p][d].size(), &tb.Y[p][d])) != DD_OK) return rc;
+        }
+    if ((rc = up_table(b, ht.QX1.data(), ht.QX1.size(), &tb.QX1)) != DD_OK) return rc;
+    if ((rc = up_table(b, ht.QY1.data(), ht.QY1.size(), &tb.QY1)) != DD_OK) return rc;
+    if ((rc = up_table(b, ht.QX2.data(), ht.QX2.size(), &tb.QX2)) != DD_OK) return rc;
+    if ((rc = up_table(b, ht.QY2.data(), ht.QY2.size(), &tb.QY2)) != DD_OK) return rc;
+    if ((rc = up_table(b, ht.QX3.data(), ht.QX3.size(), &tb.QX3)) != DD_OK) return rc;
+    if ((rc = up_table(b, ht.QY3.data(), ht.QY3.size(), &tb.QY3)) != DD_OK) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));  // ht goes out of scope: the copies must have left the host
+    tb.nterms = nterms;
+    tb.nx = b->N + 1;
+    tb.ny = b->M + 1;
+    tb.nprof = ht.nprof;
+    for (int v = 0; v < 5; ++v) tb.var_prof[v] = ht.var_prof[v];
     for (auto& mb : b->h_mem)
         for (int v = 0; v < 5; ++v) {
             mb.phi_kind[v] = phi_kind[v];
@@ -420,8 +438,8 @@ extern "C" int dd_forcing_expsin(dd_batch* b, const double* sx, const double* cx
     if ((rc = up_table(b, cx, b->N + 1, &b->F.tab.X[0][1])) != DD_OK) return rc;
     if ((rc = up_table(b, sy, b->M + 1, &b->F.tab.Y[0][0])) != DD_OK) return rc;
     if ((rc = up_table(b, cy, b->M + 1, &b->F.tab.Y[0][1])) != DD_OK) return rc;
-    if ((rc = up_table(b, sxq, 3 * (size_t)(b->N + 1), &b->F.tab.XQ[0])) != DD_OK) return rc;
-    if ((rc = up_table(b, syq, 3 * (size_t)(b->M + 1), &b->F.tab.YQ[0])) != DD_OK) return rc;
+    if ((rc = up_table(b, sxq, 3 * (size_t)(b->N + 1), &b->F.tab.XQ0)) != DD_OK) return rc;
+    if ((rc = up_table(b, syq, 3 * (size_t)(b->M + 1), &b->F.tab.YQ0)) != DD_OK) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     b->F.tab.nterms = 1;
     b->F.tab.nx = b->N + 1;
@@ -553,16 +571,17 @@ static DDState mstate(const dd_batch* b, int slot) {
 }
 // row ranges: OWNED rows (tile solver), STENCIL rows (every row with a complete stencil: on a slab
 // the halo rows are recomputed redundantly), ALL rows (pointwise work)
-enum RowRange { ROWS_OWNED = 0, ROWS_ALL = 1, ROWS_STENCIL = 2 };
+enum RowRange { ROWS_OWNED = 0, ROWS_ALL = 1, ROWS_STENCIL = 2, ROWS_ASM = 3 };
 static DDLaunch launch_of(const dd_batch* b, int range = ROWS_STENCIL) {
     DDLaunch L;
     L.stream = b->ctx->stream;
     L.nmembers = b->B;
     if (range == ROWS_ALL) { L.own0 = 0; L.own1 = b->nrows; }
     else if (range == ROWS_STENCIL) { L.own0 = b->cmp0; L.own1 = b->cmp1; }
+    else if (range == ROWS_ASM) { L.own0 = b->asm0; L.own1 = b->asm1; }
     else { L.own0 = b->own0; L.own1 = b->own1; }
-    L.vr0 = b->cmp0;
-    L.vr1 = b->cmp1;
+    L.vr0 = b->asm0;
+    L.vr1 = b->asm1;
     return L;
 }
 
@@ -688,7 +707,9 @@ static int next_plan(int cur, double rho, double ratio, int max_sweeps) {
         want = cur + 1;
     } else if (cur > 1 && ratio * 10.0 < lam) {
         const double r = ratio > 1e-300 ? ratio : 1e-300;
-        int drop = (int)floor(log(r * 10.0) / log(lam));
+        // never assume more than a 20x error reduction per sweep when shortening the plan
+        const double lam_eff = lam > 0.05 ? lam : 0.05;
+        int drop = (int)floor(log(r * 10.0) / log(lam_eff));
         if (drop < 1) drop = 1;
         want = cur - drop;
     }
@@ -698,25 +719,28 @@ static int next_plan(int cur, double rho, double ratio, int max_sweeps) {
 }
 
 // choose tile shape and sweeps per pass
-static void plan_pass(const dd_batch* b, int sweeps_left, bool allow_last, DDSolvePlan* P) {
+static void plan_pass(const dd_batch* b, int sweeps_left, bool allow_last, bool const_band, DDSolvePlan* P) {
     const int rows = b->own1 - b->own0, cols = b->M + 1;
-    const size_t cell_bytes = kSmemArrays * sizeof(double);
-    const size_t cells_max = kSmemMax / cell_bytes;
+    // const-band (T) systems stage x, bb, dinv (+ four short 1-D arrays); general systems x, bb and 4 bands
+    const size_t cell_bytes = (const_band ? 3 : kSmemArrays) * sizeof(double);
+    const size_t extra_bytes = const_band ? 4096 : 0;
+    const size_t cells_max = (kSmemMax - extra_bytes) / cell_bytes;
+    P->const_band = const_band ? 1 : 0;
     // whole member in one tile (no halo needed because every edge is a physical boundary)
-    if (!b->is_slab && (size_t)(rows + 2) * (cols + 2) <= cells_max) {
+    if (!b->is_slab && (size_t)(rows + 2) * ((cols + 3) & ~1) <= cells_max) {
         P->sweeps = sweeps_left;
         P->tile_i = rows;
         P->tile_j = cols;
         P->halo = 0;
         P->last_pass = 1;
-        const size_t cells = (size_t)(rows + 2) * (cols + 2);
-        P->smem_bytes = cells * cell_bytes;
+        const size_t cells = (size_t)(rows + 2) * ((cols + 3) & ~1);
+        P->smem_bytes = cells * cell_bytes + (const_band ? 2 * sizeof(double) * (rows + 2 + ((cols + 3) & ~1)) : 0);
         P->threads = cells >= 2048 ? 512 : (cells >= 512 ? 256 : 128);
         return;
     }
     const int sm = b->ctx->sm_count > 0 ? b->ctx->sm_count : 148;
-    static const int cand_i[] = {8, 12, 16, 24, 32, 48, 64};
-    static const int cand_j[] = {16, 32, 48, 64, 96, 128};
+    static const int cand_i[] = {8, 12, 16, 24, 32, 40, 48, 56, 64, 80, 96};
+    static const int cand_j[] = {16, 32, 48, 64, 80, 96, 128, 160, 192};
     double best = 1e300;
     DDSolvePlan bp = *P;
     // sweeps per pass: try everything that fits, cost = (waves * staged cells * sweeps-ish) per sweep done
@@ -725,10 +749,10 @@ static void plan_pass(const dd_batch* b, int sweeps_left, bool allow_last, DDSol
         const int H = 2 * S + (last ? 1 : 0);
         for (int ti : cand_i)
             for (int tj : cand_j) {
-                const size_t cells = (size_t)(ti + 2 * H + 2) * (tj + 2 * H + 2);
+                const size_t cells = (size_t)(ti + 2 * H + 2) * ((tj + 2 * H + 3) & ~1);
                 if (cells > cells_max) continue;
                 const long long tiles = (long long)((rows + ti - 1) / ti) * ((cols + tj - 1) / tj) * b->B;
-                int per_sm = (int)(kSmemMax / (cells * cell_bytes));
+                int per_sm = (int)(kSmemMax / (cells * cell_bytes + extra_bytes));
                 if (per_sm > 4) per_sm = 4;
                 const double waves = ceil((double)tiles / ((double)sm * per_sm));
                 // time ~ waves * per-CTA work / concurrency; work = staging + S sweeps over the staged area
@@ -742,7 +766,8 @@ static void plan_pass(const dd_batch* b, int sweeps_left, bool allow_last, DDSol
                     bp.tile_j = tj;
                     bp.halo = H;
                     bp.last_pass = last;
-                    bp.smem_bytes = cells * cell_bytes;
+                    bp.smem_bytes = cells * cell_bytes +
+                                    (const_band ? 2 * sizeof(double) * ((ti + 2 * H + 2) + ((tj + 2 * H + 3) & ~1)) : 0);
                     bp.threads = cells >= 2048 ? 512 : 256;
                 }
             }
@@ -829,7 +854,7 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
     // rows are assembled on every local row that has a full stencil (slabs: halo rows included,
     // so that the tile solver sees valid rows in its halo); tiles cover the owned rows only
     const DDLaunch L = launch_of(b, ROWS_OWNED);
-    const DDLaunch La = launch_of(b, ROWS_STENCIL);
+    const DDLaunch La = launch_of(b, ROWS_ASM);
     CKP(PC_ASM_T + (var - DD_T), 2,
         dd_launch_assemble(La, b->mode, var, b->g, b->d_mem, b->F, ustar, T1, cl1, Y, opt.cd_band_swap, R, st));
     const int vi = var - DD_T;
@@ -851,12 +876,12 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
     // rows on which the rows R and the iterate x are valid.  On a slab every pass consumes 2 rows per sweep
     // from each interior side (the halo rows are recomputed redundantly, never exchanged mid-solve); sides
     // on the physical boundary do not shrink.
-    int v0 = b->cmp0, v1 = b->cmp1;
+    int v0 = b->asm0, v1 = b->asm1;
     const bool lo_edge = (b->row0 == 0), hi_edge = (b->row0 + b->nrows == b->N + 1);
     while (left > 0) {
         DDSolvePlan P;
         memset(&P, 0, sizeof(P));
-        plan_pass(b, left, true, &P);
+        plan_pass(b, left, true, var == DD_T, &P);
         if (P.sweeps <= 0) return fail(ctx, DD_ERR_INVALID, "no feasible solver tile");
         double* xout = nullptr;
         DDLaunch Lp = L;
@@ -879,7 +904,7 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
         }
         if (P.last_pass && P.sweeps < left) return fail(ctx, DD_ERR_INVALID, "solver plan inconsistency");
         CKP(PC_SOLVE_T + (var - DD_T), 1,
-            dd_launch_solve_pass(Lp, b->g, R, xin, xout, vstar, vnew, var == DD_T ? 1 : 0, st, P));
+            dd_launch_solve_pass(Lp, b->g, b->d_mem, R, xin, xout, vstar, vnew, var == DD_T ? 1 : 0, st, P));
         left -= P.sweeps;
         xin = xout;
         if (!P.last_pass) {
@@ -970,20 +995,25 @@ static int pc_step_once(dd_batch* b, int slot_in, int slot_out, const dd_pc_opti
     CK(cudaMemcpyAsync(sums.data(), b->d_summary, sizeof(SolveSummary) * k, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     *converged = true;
-    for (int q = 0; q < k; ++q) {
-        const int vi = q % 3;
-        if (!(sums[q].ratio <= 1.0)) {
-            *converged = false;
-            if (opt.fixed_sweeps <= 0) {
-                // theory said `want`; it was not enough -> keep a growing margin on top of it
+    for (int q = 0; q < k; ++q)
+        if (!(sums[q].ratio <= 1.0)) *converged = false;
+    if (opt.fixed_sweeps <= 0) {
+        for (int q = 0; q < k; ++q) {
+            const int vi = q % 3;
+            if (!(sums[q].ratio <= 1.0)) {
+                // not enough sweeps: remember the failing count and go (at least) to the theoretical one
+                if (b->plan_floor[vi] < b->plan_sweeps[vi] + 1) b->plan_floor[vi] = b->plan_sweeps[vi] + 1;
                 const int want = sweeps_for_rho(sums[q].rho * 1.02 + 1e-12, opt.max_sweeps);
                 if (b->plan_sweeps[vi] >= want) b->plan_extra[vi] += (b->plan_sweeps[vi] + 1) / 2 + 1;
                 int next = want + b->plan_extra[vi];
+                if (next < b->plan_floor[vi]) next = b->plan_floor[vi];
                 if (next > opt.max_sweeps) next = opt.max_sweeps;
                 if (next > b->plan_sweeps[vi]) b->plan_sweeps[vi] = next;
+            } else if (*converged && q >= k - 3) {
+                int next = next_plan(b->plan_sweeps[vi], sums[q].rho, sums[q].ratio, opt.max_sweeps);
+                if (next < b->plan_floor[vi]) next = b->plan_floor[vi];
+                b->plan_sweeps[vi] = next;
             }
-        } else if (opt.fixed_sweeps <= 0 && q >= k - 3) {
-            b->plan_sweeps[vi] = next_plan(b->plan_sweeps[vi], sums[q].rho, sums[q].ratio, opt.max_sweeps);
         }
     }
     if (stats) {

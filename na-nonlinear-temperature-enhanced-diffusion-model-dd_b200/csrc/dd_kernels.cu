@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(DD_BLOCK) k_assemble(DDGeom g, const DDMember*
     if (n.valid) {
         const long long mo = n.member * g.mstride;
         if (VAR == DD_T)
-            rho = dd_node_asm_T<MODE>(g, mb, F, u, Y, R, mo, n.r, n.j);
+            rho = dd_node_asm_T_const<MODE>(g, mb, F, u, Y, R.bb, R.aW, mo, n.r, n.j);  // aW holds dinv
         else if (VAR == DD_CL)
             rho = dd_node_asm_cl<MODE>(g, mb, F, u, T1, Y, R, mo, n.r, n.j);
         else

@@ -37,12 +37,14 @@ struct DDSolvePlan {
     int halo;        // = 2*sweeps (+1 on the last pass), 0 when one tile covers the member
     int threads;
     int last_pass;   // compute residual stats and write v_new
+    int const_band;  // T system: rows are (bb, dinv) + grid geometry instead of five stored bands
     size_t smem_bytes;
 };
 
 cudaError_t dd_solver_configure();  // opt-in to large dynamic shared memory (once per process)
 
-cudaError_t dd_launch_solve_pass(const DDLaunch& L, const DDGeom& g, const DDRows& R, const double* xin,
+cudaError_t dd_launch_solve_pass(const DDLaunch& L, const DDGeom& g, const DDMember* mem, const DDRows& R,
+                                 const double* xin,
                                  double* xout, const double* vstar, double* vnew, int zero_boundary,
                                  DDSolveStats* stats, const DDSolvePlan& P);
 

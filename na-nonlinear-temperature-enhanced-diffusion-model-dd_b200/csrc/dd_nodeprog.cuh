@@ -24,7 +24,9 @@ DD_HD void dd_node_F(const DDGeom& g, const DDMember& mb, const DDForcing& F, co
     const int i = g.row0 + r;
     const long long o = mo + (long long)r * g.ld + j;
     const bool inter = dd_is_interior(g, i, j);
-    const DDSrc src = dd_sources<MODE>(F, mb, slot, i, j, o, inter, true);
+    DDSpatial sp;
+    dd_src_prepare<MODE>(F, i, j, inter, &sp);
+    const DDSrc src = dd_sources<MODE>(F, mb, sp, slot, i, j, o, inter, true);
     if (!inter) {
         Fout[DD_CP] = src.fcp;  // cell average is zero-padded on the boundary
         Fout[DD_T] = src.fT;
@@ -74,7 +76,9 @@ DD_HD void dd_node_predict(const DDGeom& g, const DDMember& mb, const DDForcing&
     const long long o = mo + (long long)r * g.ld + j;
     const bool inter = dd_is_interior(g, i, j);
     const double dt = mb.dt;
-    const DDSrc s0 = dd_sources<MODE>(F, mb, 0, i, j, o, inter, true);
+    DDSpatial sp;
+    dd_src_prepare<MODE>(F, i, j, inter, &sp);
+    const DDSrc s0 = dd_sources<MODE>(F, mb, sp, 0, i, j, o, inter, true);
     if (!inter) {
         out.YT[o] = dt * s0.fT + 2.0 * s.v[DD_T][o];
         out.Ycl[o] = dt * s0.fcl + 2.0 * s.v[DD_CL][o];
@@ -83,14 +87,14 @@ DD_HD void dd_node_predict(const DDGeom& g, const DDMember& mb, const DDForcing&
         // caller's boundary values are); cs: (...) * mask = 0
         double cpb = s.v[DD_CP][o];
         if (MODE == DD_FORCING_ARRAYS) {
-            const DDSrc s1b = dd_sources<MODE>(F, mb, 1, i, j, o, inter, true);
+            const DDSrc s1b = dd_sources<MODE>(F, mb, sp, 1, i, j, o, inter, true);
             cpb = cpb + 0.5 * dt * (s0.fcp + s1b.fcp);
         }
         out.cp1p[o] = cpb;
         out.cs1p[o] = s.v[DD_CS][o] * 0.0;
         return;
     }
-    const DDSrc s1 = dd_sources<MODE>(F, mb, 1, i, j, o, inter, true);
+    const DDSrc s1 = dd_sources<MODE>(F, mb, sp, 1, i, j, o, inter, true);
     const DDModel& m = mb.m;
     const DDNodeGeo q = dd_node_geo(g, i, j);
     const DDSten cp = dd_load_sten(s.v[DD_CP], o, g.ld);
@@ -127,13 +131,45 @@ DD_HD double dd_node_asm_T(const DDGeom& g, const DDMember& mb, const DDForcing&
     const long long o = mo + (long long)r * g.ld + j;
     DDRow row = {0.0, 0.0, 0.0, 0.0, 0.0};
     if (dd_is_interior(g, i, j)) {
-        const DDSrc s1 = dd_sources<MODE>(F, mb, 1, i, j, o, true, false);
+        DDSpatial sp;
+        dd_src_prepare<MODE>(F, i, j, false, &sp);
+        const DDSrc s1 = dd_sources<MODE>(F, mb, sp, 1, i, j, o, true, false);
         const DDNodeGeo q = dd_node_geo(g, i, j);
         const DDSten T = dd_load_sten(u.v[DD_T], o, g.ld);
         row = dd_row_T(mb.m, q, mb.dt, T, u.v[DD_CP][o], YT[o], s1.fT, i, j, g.N, g.M);
     }
     dd_store_row(R, o, row);
     return dd_row_rho(row);
+}
+
+// T system in "constant band" form: the off-diagonals of A_T are dt DT / (hhat_i h_i) etc. -- pure grid
+// geometry -- so only bb = rhs / d and dinv = 1 / d are stored (16 B instead of 40 B per node); the tile
+// solver rebuilds a_W = dinv * dt DT cW_i from 1-D arrays.  Couplings to boundary nodes need no masking:
+// x is identically 0 on boundary nodes (bb = dinv = 0 there).
+template <int MODE>
+DD_HD double dd_node_asm_T_const(const DDGeom& g, const DDMember& mb, const DDForcing& F, const DDStateC& u,
+                                 const double* YT, double* bb, double* dinv, long long mo, int r, int j) {
+    const int i = g.row0 + r;
+    const long long o = mo + (long long)r * g.ld + j;
+    double vb = 0.0, vd = 0.0, rho = 0.0;
+    if (dd_is_interior(g, i, j)) {
+        DDSpatial sp;
+        dd_src_prepare<MODE>(F, i, j, false, &sp);
+        const DDSrc s1 = dd_sources<MODE>(F, mb, sp, 1, i, j, o, true, false);
+        const DDNodeGeo q = dd_node_geo(g, i, j);
+        const DDSten T = dd_load_sten(u.v[DD_T], o, g.ld);
+        const DDModel& m = mb.m;
+        const double cps = u.v[DD_CP][o], dt = mb.dt;
+        const double sumc = m.DT * (q.cW + q.cE + q.cS + q.cN);
+        const double d = 2.0 + dt * (sumc + m.K3 * cps);
+        const double G0 = 2.0 * T.c - dt * (s1.fT + dd_FT_int(m, q, T, cps));
+        vd = 1.0 / d;
+        vb = (YT[o] - G0) * vd;
+        rho = dt * sumc * vd;
+    }
+    bb[o] = vb;
+    dinv[o] = vd;
+    return rho;
 }
 
 template <int MODE>
@@ -143,7 +179,9 @@ DD_HD double dd_node_asm_cl(const DDGeom& g, const DDMember& mb, const DDForcing
     const long long o = mo + (long long)r * g.ld + j;
     DDRow row = {0.0, 0.0, 0.0, 0.0, 0.0};
     if (dd_is_interior(g, i, j)) {
-        const DDSrc s1 = dd_sources<MODE>(F, mb, 1, i, j, o, true, false);
+        DDSpatial sp;
+        dd_src_prepare<MODE>(F, i, j, false, &sp);
+        const DDSrc s1 = dd_sources<MODE>(F, mb, sp, 1, i, j, o, true, false);
         const DDNodeGeo q = dd_node_geo(g, i, j);
         const DDSten cp = dd_load_sten(u.v[DD_CP], o, g.ld);
         const DDSten T = dd_load_sten(u.v[DD_T], o, g.ld);
@@ -163,7 +201,9 @@ DD_HD double dd_node_asm_cd(const DDGeom& g, const DDMember& mb, const DDForcing
     const long long o = mo + (long long)r * g.ld + j;
     DDRow row = {0.0, 0.0, 0.0, 0.0, 0.0};
     if (dd_is_interior(g, i, j)) {
-        const DDSrc s1 = dd_sources<MODE>(F, mb, 1, i, j, o, true, false);
+        DDSpatial sp;
+        dd_src_prepare<MODE>(F, i, j, false, &sp);
+        const DDSrc s1 = dd_sources<MODE>(F, mb, sp, 1, i, j, o, true, false);
         const DDNodeGeo q = dd_node_geo(g, i, j);
         const DDSten cp = dd_load_sten(u.v[DD_CP], o, g.ld);
         const DDSten T = dd_load_sten(u.v[DD_T], o, g.ld);
@@ -198,8 +238,10 @@ DD_HD void dd_node_correct_prepare(const DDGeom& g, const DDMember& mb, const DD
     const int i = g.row0 + r;
     const long long o = mo + (long long)r * g.ld + j;
     const bool inter = dd_is_interior(g, i, j);
-    const DDSrc q0 = dd_sources<MODE>(F, mb, 0, i, j, o, inter, true);
-    const DDSrc q1 = dd_sources<MODE>(F, mb, 1, i, j, o, inter, true);
+    DDSpatial sp;
+    dd_src_prepare<MODE>(F, i, j, inter, &sp);
+    const DDSrc q0 = dd_sources<MODE>(F, mb, sp, 0, i, j, o, inter, true);
+    const DDSrc q1 = dd_sources<MODE>(F, mb, sp, 1, i, j, o, inter, true);
     const DDModel& m = mb.m;
     *cp1 = inter ? dd_correct_cp(m, mb.dt, s0.v[DD_CP][o], s0.v[DD_T][o], s0.v[DD_CL][o], T1[o], cl1[o], q0.fcp,
                                  q1.fcp)

@@ -221,25 +221,61 @@ DD_HD void dd_time_coefs(int mode, const DDMember& mb, double t, int slot, DDTim
     }
 }
 
-DD_HD void dd_exact_separable(const DDTables& tb, const DDTimeCoef& tc, int i, int j, DDExact* e) {
+// time-independent part of a separable manufactured solution at node (i, j)
+struct DDSpatial {
+    double S[DD_NVAR], Sx[DD_NVAR], Sy[DD_NVAR], Sl[DD_NVAR];  // sum_r X Y, X' Y, X Y', X'' Y + X Y''
+    double Q1, Q2, Q3;                                          // cell-average sums of fcp (see DDTables)
+};
+
+DD_HD void dd_spatial_separable(const DDTables& tb, int i, int j, bool want_q, DDSpatial* sp) {
+    double pS[DD_NVAR], pSx[DD_NVAR], pSy[DD_NVAR], pSl[DD_NVAR];
+#pragma unroll
+    for (int p = 0; p < DD_NVAR; ++p) {
+        double sXY = 0.0, sX1Y = 0.0, sXY1 = 0.0, sLap = 0.0;
+        if (p < tb.nprof) {
+            for (int r = 0; r < tb.nterms; ++r) {
+                const int oi = r * tb.nx + i, oj = r * tb.ny + j;
+                const double X0 = tb.X[p][0][oi], X1 = tb.X[p][1][oi], X2 = tb.X[p][2][oi];
+                const double Y0 = tb.Y[p][0][oj], Y1 = tb.Y[p][1][oj], Y2 = tb.Y[p][2][oj];
+                sXY += X0 * Y0;
+                sX1Y += X1 * Y0;
+                sXY1 += X0 * Y1;
+                sLap += X2 * Y0 + X0 * Y2;
+            }
+        }
+        pS[p] = sXY; pSx[p] = sX1Y; pSy[p] = sXY1; pSl[p] = sLap;
+    }
 #pragma unroll
     for (int v = 0; v < DD_NVAR; ++v) {
-        double sXY = 0.0, sX1Y = 0.0, sXY1 = 0.0, sLap = 0.0;
-        for (int r = 0; r < tb.nterms; ++r) {
-            const int oi = r * tb.nx + i, oj = r * tb.ny + j;
-            const double X0 = tb.X[v][0][oi], X1 = tb.X[v][1][oi], X2 = tb.X[v][2][oi];
-            const double Y0 = tb.Y[v][0][oj], Y1 = tb.Y[v][1][oj], Y2 = tb.Y[v][2][oj];
-            sXY += X0 * Y0;
-            sX1Y += X1 * Y0;
-            sXY1 += X0 * Y1;
-            sLap += X2 * Y0 + X0 * Y2;
+        const int q = tb.var_prof[v];
+        double a = pS[0], bx = pSx[0], by = pSy[0], l = pSl[0];
+#pragma unroll
+        for (int p = 1; p < DD_NVAR; ++p)
+            if (q == p) { a = pS[p]; bx = pSx[p]; by = pSy[p]; l = pSl[p]; }
+        sp->S[v] = a; sp->Sx[v] = bx; sp->Sy[v] = by; sp->Sl[v] = l;
+    }
+    sp->Q1 = sp->Q2 = sp->Q3 = 0.0;
+    if (want_q) {
+        const int R = tb.nterms;
+        double q1 = 0.0, q2 = 0.0, q3 = 0.0;
+        for (int r = 0; r < R; ++r) q1 += tb.QX1[r * tb.nx + i] * tb.QY1[r * tb.ny + j];
+        for (int rs = 0; rs < R * R; ++rs) {
+            q2 += tb.QX2[rs * tb.nx + i] * tb.QY2[rs * tb.ny + j];
+            q3 += tb.QX3[rs * tb.nx + i] * tb.QY3[rs * tb.ny + j];
         }
+        sp->Q1 = q1; sp->Q2 = q2; sp->Q3 = q3;
+    }
+}
+
+DD_HD void dd_exact_separable(const DDSpatial& sp, const DDTimeCoef& tc, DDExact* e) {
+#pragma unroll
+    for (int v = 0; v < DD_NVAR; ++v) {
         const double phi = tc.c[v], dphi = tc.c[5 + v];
-        e->u[v] = phi * sXY;
-        e->ut[v] = dphi * sXY;
-        e->ux[v] = phi * sX1Y;
-        e->uy[v] = phi * sXY1;
-        e->lap[v] = phi * sLap;
+        e->u[v] = phi * sp.S[v];
+        e->ut[v] = dphi * sp.S[v];
+        e->ux[v] = phi * sp.Sx[v];
+        e->uy[v] = phi * sp.Sy[v];
+        e->lap[v] = phi * sp.Sl[v];
     }
 }
 
@@ -301,29 +337,10 @@ DD_HD double dd_src_fcs(const DDModel& m, const DDExact& e) {
 
 // 3x3 Gauss-Legendre cell average of fcp_ptwise = dt cp + cp (K1 (1+cl) + K2 T)
 // over [x_{i-1/2}, x_{i+1/2}] x [y_{j-1/2}, y_{j+1/2}], interior nodes only
-// (reference src/prob1base.py:493-598, 2313-2328).
-DD_HD double dd_fcp_avg_separable(const DDModel& m, const DDTables& tb, const DDTimeCoef& tc, int i, int j) {
-    const double wq[3] = {5.0 / 9.0, 8.0 / 9.0, 5.0 / 9.0};
-    double acc = 0.0;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-#pragma unroll
-        for (int b = 0; b < 3; ++b) {
-            double scp = 0.0, sT = 0.0, scl = 0.0;
-            for (int r = 0; r < tb.nterms; ++r) {
-                const int oi = (r * tb.nx + i) * 3 + a, oj = (r * tb.ny + j) * 3 + b;
-                scp += tb.XQ[0][oi] * tb.YQ[0][oj];
-                sT += tb.XQ[1][oi] * tb.YQ[1][oj];
-                scl += tb.XQ[2][oi] * tb.YQ[2][oj];
-            }
-            const double cp = tc.c[DD_CP] * scp;
-            const double T = tc.c[DD_T] * sT;
-            const double cl = tc.c[DD_CL] * scl;
-            const double f = tc.c[5 + DD_CP] * scp + cp * (m.K1 * (1.0 + cl) + m.K2 * T);
-            acc += wq[a] * wq[b] * f;
-        }
-    }
-    return 0.25 * acc;
+// (reference src/prob1base.py:493-598, 2313-2328); separable form, see DDTables.
+DD_HD double dd_fcp_avg_separable(const DDModel& m, const DDSpatial& sp, const DDTimeCoef& tc) {
+    return 0.25 * (tc.c[5 + DD_CP] * sp.Q1 +
+                   tc.c[DD_CP] * (m.K1 * sp.Q1 + m.K1 * tc.c[DD_CL] * sp.Q2 + m.K2 * tc.c[DD_T] * sp.Q3));
 }
 
 DD_HD double dd_fcp_avg_expsin(const DDModel& m, const DDTables& tb, const DDTimeCoef& tc, int i, int j) {
@@ -332,10 +349,10 @@ DD_HD double dd_fcp_avg_expsin(const DDModel& m, const DDTables& tb, const DDTim
     double acc = 0.0;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        const double sx = tb.XQ[0][i * 3 + a];
+        const double sx = tb.XQ0[i * 3 + a];
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
-            const double W = sx * tb.YQ[0][j * 3 + b];
+            const double W = sx * tb.YQ0[j * 3 + b];
             const double cp = W * exp(A + B * W);
             const double f = cp * (dA + dB * W) + cp * (m.K1 * (1.0 - em * W) + m.K2 * (tau * W));
             acc += wq[a] * wq[b] * f;
@@ -357,13 +374,18 @@ struct DDSrc {
     double fcp, fT, fcl, fcd, fcs;
 };
 
-// All five sources at node (i, j) (global indices) for time slot `slot`.
-// `interior` selects whether the cell-averaged fcp is evaluated (it is zero
-// on the boundary).  `o` is the element offset of the node inside the member,
-// `moff` the member offset (ARRAYS mode).
+// Time-independent preparation of the sources at node (i, j) (global indices): for SEPARABLE
+// solutions the spatial sums are evaluated once and reused for both time slots.
 template <int MODE>
-DD_HD DDSrc dd_sources(const DDForcing& F, const DDMember& mb, int slot, int i, int j, long long off,
-                       bool interior, bool want_cp) {
+DD_HD void dd_src_prepare(const DDForcing& F, int i, int j, bool want_q, DDSpatial* sp) {
+    if (MODE == DD_FORCING_SEPARABLE) dd_spatial_separable(F.tab, i, j, want_q, sp);
+}
+
+// All five sources at the node for time slot `slot`.  `interior` selects whether the cell-averaged
+// fcp is evaluated (it is zero on the boundary); `off` is the node's element offset (ARRAYS mode).
+template <int MODE>
+DD_HD DDSrc dd_sources(const DDForcing& F, const DDMember& mb, const DDSpatial& sp, int slot, int i, int j,
+                       long long off, bool interior, bool want_cp) {
     DDSrc s;
     s.fcp = s.fT = s.fcl = s.fcd = s.fcs = 0.0;
     if (MODE == DD_FORCING_ARRAYS) {
@@ -376,7 +398,7 @@ DD_HD DDSrc dd_sources(const DDForcing& F, const DDMember& mb, int slot, int i, 
         DDExact e;
         const DDTimeCoef& tc = mb.tc[slot];
         if (MODE == DD_FORCING_SEPARABLE)
-            dd_exact_separable(F.tab, tc, i, j, &e);
+            dd_exact_separable(sp, tc, &e);
         else
             dd_exact_expsin(mb.m, F.tab, tc, i, j, &e);
         s.fT = dd_src_fT(mb.m, e);
@@ -384,7 +406,7 @@ DD_HD DDSrc dd_sources(const DDForcing& F, const DDMember& mb, int slot, int i, 
         s.fcd = dd_src_fcd(mb.m, e);
         s.fcs = dd_src_fcs(mb.m, e);
         if (interior && want_cp) {
-            s.fcp = (MODE == DD_FORCING_SEPARABLE) ? dd_fcp_avg_separable(mb.m, F.tab, tc, i, j)
+            s.fcp = (MODE == DD_FORCING_SEPARABLE) ? dd_fcp_avg_separable(mb.m, sp, tc)
                                                    : dd_fcp_avg_expsin(mb.m, F.tab, tc, i, j);
         }
     }
@@ -395,10 +417,13 @@ DD_HD DDSrc dd_sources(const DDForcing& F, const DDMember& mb, int slot, int i, 
 template <int MODE>
 DD_HD void dd_exact_values(const DDForcing& F, const DDMember& mb, int slot, int i, int j, double* u) {
     DDExact e;
-    if (MODE == DD_FORCING_SEPARABLE)
-        dd_exact_separable(F.tab, mb.tc[slot], i, j, &e);
-    else
+    if (MODE == DD_FORCING_SEPARABLE) {
+        DDSpatial sp;
+        dd_spatial_separable(F.tab, i, j, false, &sp);
+        dd_exact_separable(sp, mb.tc[slot], &e);
+    } else {
         dd_exact_expsin(mb.m, F.tab, mb.tc[slot], i, j, &e);
+    }
     for (int v = 0; v < DD_NVAR; ++v) u[v] = e.u[v];
 }
 

@@ -40,6 +40,7 @@ __device__ __forceinline__ double warp_max_nn(double v) {
 
 struct SolveArgs {
     DDGeom g;
+    const DDMember* mem;
     const double *bb, *aW, *aE, *aS, *aN;
     const double* xin;
     double* xout;
@@ -54,6 +55,16 @@ struct SolveArgs {
 
 extern __shared__ double dd_smem[];
 
+// Shared-memory layout: every staged array is split by colour and packed along j, so that a half-sweep
+// touches unit-stride words only (no bank conflicts): cell (si, sj) of colour c = (par0 + si + sj) & 1
+// lives at [c][si][sj >> 1].  PW = SJ / 2 packed columns per row.
+struct Packed {
+    double* base;
+    int plane;  // SI * PW
+    __device__ __forceinline__ double* c(int colour) const { return base + colour * plane; }
+};
+
+template <int CONST_BAND>
 __global__ void __launch_bounds__(512) k_rbsor_tile(SolveArgs A) {
     const DDGeom& g = A.g;
     const int tiles = A.tiles_i * A.tiles_j;
@@ -64,25 +75,28 @@ __global__ void __launch_bounds__(512) k_rbsor_tile(SolveArgs A) {
     // tile in LOCAL rows / columns; the node grid is nrows x (M+1)
     const int r0 = A.own0 + ti * A.tile_i, c0 = tj * A.tile_j;
     const int tr = min(A.tile_i, A.own1 - r0), tc = min(A.tile_j, g.M + 1 - c0);
-    // staged region: tile +- H plus one ring of zeros; local row of smem row 0:
-    const int SI = A.tile_i + 2 * H + 2, SJ = A.tile_j + 2 * H + 2;
+    // staged region: tile +- H plus one ring of zeros; SJ rounded up to even
+    const int SI = A.tile_i + 2 * H + 2, SJ = (A.tile_j + 2 * H + 3) & ~1, PW = SJ >> 1;
     const int rbase = r0 - H - 1, cbase = c0 - H - 1;
-    double* sx = dd_smem;
-    double* sb = sx + (size_t)SI * SJ;
-    double* sW = sb + (size_t)SI * SJ;
-    double* sE = sW + (size_t)SI * SJ;
-    double* sS = sE + (size_t)SI * SJ;
-    double* sN = sS + (size_t)SI * SJ;
+    const int par0 = (g.row0 + rbase + cbase) & 1;  // colour of smem cell (0, 0)
+    const int plane = SI * PW;
+    // CONST_BAND: AW holds dinv; AE/AS/AN are not staged, the geometry factors live in four 1-D arrays
+    Packed X = {dd_smem, plane}, Bb = {dd_smem + 2 * plane, plane}, AW = {dd_smem + 4 * plane, plane},
+           AE = {dd_smem + 6 * plane, plane}, AS = {dd_smem + 8 * plane, plane}, AN = {dd_smem + 10 * plane, plane};
+    double* rowW = dd_smem + 6 * plane;  // [SI], [SI], [SJ], [SJ]  (CONST_BAND only)
+    double* rowE = rowW + SI;
+    double* colS = rowE + SI;
+    double* colN = colS + SJ;
     const long long mo = member * g.mstride;
     const int nthreads = blockDim.x;
 
     // extent of real data inside the staged region (smem coordinates, half-open)
     const int vi0 = max(1, A.vr0 - rbase), vi1 = min(SI - 1, A.vr1 - rbase);
     const int vj0 = max(1, -cbase), vj1 = min(SJ - 1, g.M + 1 - cbase);
-    // only stage what the sweeps can reach
-    const int li0 = max(vi0, 1), li1 = min(vi1, tr + 2 * H + 1);
-    const int lj0 = max(vj0, 1), lj1 = min(vj1, tc + 2 * H + 1);
+    const int li0 = vi0, li1 = min(vi1, tr + 2 * H + 1);
+    const int lj0 = vj0, lj1 = min(vj1, tc + 2 * H + 1);
 
+    // stage: consecutive threads read consecutive columns of a row (coalesced), scatter by colour
     for (int idx = threadIdx.x; idx < SI * SJ; idx += nthreads) {
         const int si = idx / SJ, sj = idx - si * SJ;
         double x = 0.0, b = 0.0, w = 0.0, e = 0.0, s = 0.0, n = 0.0;
@@ -90,17 +104,38 @@ __global__ void __launch_bounds__(512) k_rbsor_tile(SolveArgs A) {
             const long long o = mo + (long long)(rbase + si) * g.ld + (cbase + sj);
             b = A.bb[o];
             w = A.aW[o];
-            e = A.aE[o];
-            s = A.aS[o];
-            n = A.aN[o];
+            if (!CONST_BAND) {
+                e = A.aE[o];
+                s = A.aS[o];
+                n = A.aN[o];
+            }
             if (A.xin) x = A.xin[o];
         }
-        sx[idx] = x;
-        sb[idx] = b;
-        sW[idx] = w;
-        sE[idx] = e;
-        sS[idx] = s;
-        sN[idx] = n;
+        const int col = (par0 + si + sj) & 1, q = col * plane + si * PW + (sj >> 1);
+        X.base[q] = x;
+        Bb.base[q] = b;
+        AW.base[q] = w;
+        if (!CONST_BAND) {
+            AE.base[q] = e;
+            AS.base[q] = s;
+            AN.base[q] = n;
+        }
+    }
+    if (CONST_BAND) {
+        const DDMember& mb = A.mem[member];
+        const double f = mb.dt * mb.m.DT;
+        for (int si = threadIdx.x; si < SI; si += nthreads) {
+            const int i = g.row0 + rbase + si;
+            const bool in = i >= 1 && i <= g.N - 1;
+            rowW[si] = in ? f * g.rhp[i] * g.rh[i] : 0.0;
+            rowE[si] = in ? f * g.rhp[i] * g.rh[i + 1] : 0.0;
+        }
+        for (int sj = threadIdx.x; sj < SJ; sj += nthreads) {
+            const int j = cbase + sj;
+            const bool in = j >= 1 && j <= g.M - 1;
+            colS[sj] = in ? f * g.rkp[j] * g.rk[j] : 0.0;
+            colN[sj] = in ? f * g.rkp[j] * g.rk[j + 1] : 0.0;
+        }
     }
     const double rho = A.stats[member].rho;
     // omega_opt of SOR for a consistently ordered matrix whose Jacobi spectral radius is <= rho
@@ -108,32 +143,36 @@ __global__ void __launch_bounds__(512) k_rbsor_tile(SolveArgs A) {
     if (rho < 1.0) omega = 2.0 / (1.0 + sqrt(1.0 - rho * rho));
     __syncthreads();
 
-    // half-sweeps.  After half-sweep h (1-based) the updated colour is exact on the
-    // region shrunk by h rings (sides on the physical grid edge do not shrink).
-    const bool edge_lo_i = (rbase + li0 == 0);
-    const bool edge_hi_i = (rbase + li1 == g.nrows) && (g.row0 + g.nrows == g.N + 1);
-    const bool edge_lo_j = (cbase + lj0 == 0), edge_hi_j = (cbase + lj1 == g.M + 1);
-    const bool top_is_grid_edge = edge_lo_i && (g.row0 == 0);
+    // half-sweeps over rows 1 .. SI-2 (the zero ring is never updated).  Cells whose inputs are not yet
+    // (or no longer) exact are updated too -- they only ever influence cells outside the final tile,
+    // because invalidity travels one cell per half-sweep from the staged edge; rows that can no longer
+    // matter are skipped.  After 2S half-sweeps the tile (+1 ring on the last pass) equals the global
+    // red-black iteration exactly.
+    const bool shrink_lo = !(g.row0 + rbase + li0 == 0), shrink_hi = !(g.row0 + rbase + li1 == g.N + 1);
     for (int hs = 1; hs <= 2 * A.sweeps; ++hs) {
         const int colour = (hs - 1) & 1;
-        const int ui0 = top_is_grid_edge ? li0 : li0 + hs, ui1 = edge_hi_i ? li1 : li1 - hs;
-        const int uj0 = edge_lo_j ? lj0 : lj0 + hs, uj1 = edge_hi_j ? lj1 : lj1 - hs;
-        const int ni = ui1 - ui0, nj = uj1 - uj0;
-        if (ni > 0 && nj > 0) {
-            const int halfw = (nj + 1) >> 1;
-            for (int idx = threadIdx.x; idx < ni * halfw; idx += nthreads) {
-                const int a = idx / halfw, bcol = idx - a * halfw;
-                const int si = ui0 + a;
-                // first column of this row with the right colour: global parity of (i + j)
-                const int gi = g.row0 + rbase + si;
-                int sj = uj0 + 2 * bcol;
-                if (((gi + cbase + sj) & 1) != colour) sj += 1;
-                if (sj < uj1) {
-                    const int p = si * SJ + sj;
-                    const double gs = sb[p] + sW[p] * sx[p - SJ] + sE[p] * sx[p + SJ] + sS[p] * sx[p - 1] +
-                                      sN[p] * sx[p + 1];
-                    sx[p] = sx[p] + omega * (gs - sx[p]);
-                }
+        const double* xo = X.c(1 - colour);
+        double* xc = X.c(colour);
+        const double *bc = Bb.c(colour), *wc = AW.c(colour), *ec = AE.c(colour), *sc = AS.c(colour),
+                     *nc = AN.c(colour);
+        const int ui0 = shrink_lo ? min(li0 + hs, H + 1) : li0;
+        const int ui1 = shrink_hi ? max(li1 - hs, H + 1 + tr) : li1;
+        // packed slots 0 and PW-1 hold the zero ring columns (sj = 0 and SJ-1) for one colour each; they are
+        // skipped by the column guard below
+        for (int idx = ui0 * PW + threadIdx.x; idx < ui1 * PW; idx += nthreads) {
+            const int si = idx / PW, pk = idx - si * PW;
+            const int o = (colour + par0 + si) & 1;  // sj = 2 pk + o
+            const int sj = 2 * pk + o;
+            if (sj >= 1 && sj <= SJ - 2) {
+                const int p = si * PW + pk;
+                double gs;
+                if (CONST_BAND)
+                    gs = bc[p] + wc[p] * (rowW[si] * xo[p - PW] + rowE[si] * xo[p + PW] + colS[sj] * xo[p - 1 + o] +
+                                          colN[sj] * xo[p + o]);
+                else
+                    gs = bc[p] + wc[p] * xo[p - PW] + ec[p] * xo[p + PW] + sc[p] * xo[p - 1 + o] + nc[p] * xo[p + o];
+                const double xv = xc[p];
+                xc[p] = xv + omega * (gs - xv);
             }
         }
         __syncthreads();
@@ -144,22 +183,30 @@ __global__ void __launch_bounds__(512) k_rbsor_tile(SolveArgs A) {
     for (int idx = threadIdx.x; idx < tr * tc; idx += nthreads) {
         const int a = idx / tc, bcol = idx - a * tc;
         const int si = H + 1 + a, sj = H + 1 + bcol;
-        const int p = si * SJ + sj;
+        const int col = (par0 + si + sj) & 1, o = (sj & 1);
+        const int pk = sj >> 1, p = si * PW + pk;
         const int r = r0 + a, j = c0 + bcol;
-        const long long o = mo + (long long)r * g.ld + j;
-        const double x = sx[p];
+        const long long og = mo + (long long)r * g.ld + j;
+        const double x = X.c(col)[p];
         if (A.last_pass) {
-            const double res = sb[p] + sW[p] * sx[p - SJ] + sE[p] * sx[p + SJ] + sS[p] * sx[p - 1] +
-                               sN[p] * sx[p + 1] - x;
+            const double* xo = X.c(1 - col);
+            const double bbv = Bb.c(col)[p];
+            double res;
+            if (CONST_BAND)
+                res = bbv + AW.c(col)[p] * (rowW[si] * xo[p - PW] + rowE[si] * xo[p + PW] +
+                                            colS[sj] * xo[p - 1 + o] + colN[sj] * xo[p + o]) - x;
+            else
+                res = bbv + AW.c(col)[p] * xo[p - PW] + AE.c(col)[p] * xo[p + PW] + AS.c(col)[p] * xo[p - 1 + o] +
+                      AN.c(col)[p] * xo[p + o] - x;
             const bool inter = dd_is_interior(g, g.row0 + r, j);
-            const double vn = dd_newton_update(inter, A.vstar[o], x, A.zero_boundary);
-            A.vnew[o] = vn;
+            const double vn = dd_newton_update(inter, A.vstar[og], x, A.zero_boundary);
+            A.vnew[og] = vn;
             rmax = nn_max(rmax, res);
             xmax = nn_max(xmax, x);
             vmax = nn_max(vmax, vn);
-            bmax = nn_max(bmax, sb[p]);
+            bmax = nn_max(bmax, bbv);
         } else {
-            A.xout[o] = x;
+            A.xout[og] = x;
         }
     }
     if (A.last_pass) {
@@ -177,14 +224,18 @@ __global__ void __launch_bounds__(512) k_rbsor_tile(SolveArgs A) {
 }
 
 cudaError_t dd_solver_configure() {
-    return cudaFuncSetAttribute(k_rbsor_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_rbsor_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_rbsor_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
-cudaError_t dd_launch_solve_pass(const DDLaunch& L, const DDGeom& g, const DDRows& R, const double* xin,
+cudaError_t dd_launch_solve_pass(const DDLaunch& L, const DDGeom& g, const DDMember* mem, const DDRows& R,
+                                 const double* xin,
                                  double* xout, const double* vstar, double* vnew, int zero_boundary,
                                  DDSolveStats* stats, const DDSolvePlan& P) {
     SolveArgs A;
     A.g = g;
+    A.mem = mem;
     A.bb = R.bb;
     A.aW = R.aW;
     A.aE = R.aE;
@@ -209,6 +260,9 @@ cudaError_t dd_launch_solve_pass(const DDLaunch& L, const DDGeom& g, const DDRow
     A.last_pass = P.last_pass;
     const long long nblocks = (long long)A.tiles_i * A.tiles_j * L.nmembers;
     if (nblocks <= 0 || nblocks > 2147483647LL) return cudaErrorInvalidConfiguration;
-    k_rbsor_tile<<<(unsigned)nblocks, P.threads, P.smem_bytes, L.stream>>>(A);
+    if (P.const_band)
+        k_rbsor_tile<1><<<(unsigned)nblocks, P.threads, P.smem_bytes, L.stream>>>(A);
+    else
+        k_rbsor_tile<0><<<(unsigned)nblocks, P.threads, P.smem_bytes, L.stream>>>(A);
     return cudaGetLastError();
 }

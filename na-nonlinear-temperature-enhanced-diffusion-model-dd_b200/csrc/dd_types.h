@@ -69,16 +69,21 @@ struct DDGeom {
 };
 
 // 1-D tables for the fused MMS forcing (device pointers).
+// SEPARABLE: u_v = phi_v(t) sum_{r < nterms} X_{p,r}(x) Y_{p,r}(y), p = var_prof[v] (variables with
+//   identical spatial tables share one "profile": MMSCasePol has one, NonFullySmoothPol two).
+//   X[p][d][r*nx + i], d = 0,1,2 -> X_{p,r}, X', X'' at node i; Y likewise (stride ny).
+//   The 3x3 Gauss cell average of fcp_ptwise = dt cp + cp (K1 (1 + cl) + K2 T) separates as well:
+//     avg = 1/4 [ phi_cp' Q1 + phi_cp (K1 Q1 + K1 phi_cl Q2 + K2 phi_T Q3) ],
+//     Q1 = sum_r QX1[r][i] QY1[r][j],  Q2 = sum_{r,s} QX2[r*R+s][i] QY2[..][j] (cp x cl),  Q3 (cp x T),
+//   with QX1[r][i] = sum_a w_a X_cp,r(p_a(i)) etc. built on the host from the quadrature samples.
+// EXPSIN: X[0][0] = sin(pi x), X[0][1] = cos(pi x); XQ0 = sin(pi x) at the 3 abscissae of each cell.
 struct DDTables {
-    // SEPARABLE: u_v = phi_v(t) sum_{r < nterms} X_{v,r}(x) Y_{v,r}(y).
-    //            X[v][d][r*(N+1) + i], d = 0,1,2 -> X_{v,r}, X', X'' at node i; Y likewise (stride M+1).
-    //            XQ[q][r*3*(N+1) + i*3 + a] for q in {cp, T, cl} = X_{q,r} at the a-th Gauss abscissa of cell i.
-    // EXPSIN   : X[0][0] = sin(pi x), X[0][1] = cos(pi x); XQ[0] = sin(pi x) at the abscissae.
-    int nterms, nx, ny;  // nx = N+1, ny = M+1
+    int nterms, nx, ny, nprof;  // nx = N+1, ny = M+1
+    int var_prof[DD_NVAR];
     const double* X[DD_NVAR][3];
     const double* Y[DD_NVAR][3];
-    const double* XQ[3];
-    const double* YQ[3];
+    const double *QX1, *QY1, *QX2, *QY2, *QX3, *QY3;
+    const double *XQ0, *YQ0;
 };
 
 // Host-evaluated forcing arrays: f[v][slot], same layout as the fields

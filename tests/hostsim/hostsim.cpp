@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "dd_nodeprog.cuh"
+#include "dd_tables_host.h"
 
 struct HSProblem {
     int N, M;
@@ -34,6 +35,7 @@ struct HSCtx {
     DDMember mb;
     DDForcing F;
     std::vector<double> h, k, hp, kp, rh, rk, rhp, rkp;
+    DDHostTables ht;
 };
 
 static void setup(const HSProblem& P, HSCtx& c, double t0, double dt) {
@@ -64,9 +66,20 @@ static void setup(const HSProblem& P, HSCtx& c, double t0, double dt) {
     c.mb.t0 = t0; c.mb.dt = dt;
     for (int v = 0; v < 5; ++v) { c.mb.phi_kind[v] = P.phi_kind[v]; for (int s = 0; s < 4; ++s) c.mb.phi_p[v][s] = P.phi_p[v][s]; }
     memset(&c.F, 0, sizeof(c.F));
-    for (int v = 0; v < 5; ++v) for (int d = 0; d < 3; ++d) { c.F.tab.X[v][d] = P.X[v][d]; c.F.tab.Y[v][d] = P.Y[v][d]; }
-    for (int s = 0; s < 3; ++s) { c.F.tab.XQ[s] = P.XQ[s]; c.F.tab.YQ[s] = P.YQ[s]; }
-    c.F.tab.nterms = P.nterms; c.F.tab.nx = N + 1; c.F.tab.ny = M + 1;
+    DDTables& tb = c.F.tab;
+    tb.nterms = P.nterms; tb.nx = N + 1; tb.ny = M + 1; tb.nprof = 1;
+    if (P.mode == DD_FORCING_SEPARABLE) {
+        dd_prepare_tables(P.nterms, N, M, P.X, P.Y, P.XQ, P.YQ, &c.ht);
+        tb.nprof = c.ht.nprof;
+        for (int v = 0; v < 5; ++v) tb.var_prof[v] = c.ht.var_prof[v];
+        for (int p = 0; p < c.ht.nprof; ++p)
+            for (int d = 0; d < 3; ++d) { tb.X[p][d] = c.ht.X[p][d].data(); tb.Y[p][d] = c.ht.Y[p][d].data(); }
+        tb.QX1 = c.ht.QX1.data(); tb.QY1 = c.ht.QY1.data(); tb.QX2 = c.ht.QX2.data(); tb.QY2 = c.ht.QY2.data();
+        tb.QX3 = c.ht.QX3.data(); tb.QY3 = c.ht.QY3.data();
+    } else if (P.mode == DD_FORCING_EXPSIN) {
+        tb.X[0][0] = P.X[0][0]; tb.X[0][1] = P.X[0][1]; tb.Y[0][0] = P.Y[0][0]; tb.Y[0][1] = P.Y[0][1];
+        tb.XQ0 = P.XQ[0]; tb.YQ0 = P.YQ[0];
+    }
     for (int v = 0; v < 5; ++v) for (int s = 0; s < 2; ++s) c.F.arr.f[v][s] = P.farr[v][s];
     dd_time_coefs(P.mode, c.mb, t0, 0, &c.mb.tc[0]);
     dd_time_coefs(P.mode, c.mb, t0 + dt, 1, &c.mb.tc[1]);

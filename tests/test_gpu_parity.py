@@ -302,17 +302,17 @@ def test_slab_decomposition_single_gpu_emulation(dd, world):
         assert got[v].shape == (N + 1, M + 1)
         assert rel_err(got[v], getattr(s, v)) <= TOL, v
     e_slab = meshes[0].error_norms(nsteps % 2, t0 + nsteps * dt)
-    assert np.all(np.isfinite(e_slab)) and max(st["bound"]) <= 1e-13
+    assert np.all(np.isfinite(e_slab)) and max(st["bound"]) <= 1e-13, st
     # bitwise reproducibility across decompositions: 1 slab == `world` slabs for equal sweep plans
     for k in range(nsteps):
-        b.step_pc(k % 2, (k + 1) % 2, t0 + k * dt, dt, ddcore.pc_options(fixed_sweeps=5))
+        b.step_pc(k % 2, (k + 1) % 2, t0 + k * dt, dt, ddcore.pc_options(fixed_sweeps=4))
     meshes2 = ddmesh.SlabMesh.local_group(grid.x, grid.y, world, halo=12)
     for m in meshes2:
         m.batch.set_model(model, eta)
         m.batch.forcing_spec(spec)
         m.fill_exact(0, t0)
     for k in range(nsteps):
-        meshes2[0].step_pc(k % 2, (k + 1) % 2, t0 + k * dt, dt, ddcore.pc_options(fixed_sweeps=5))
+        meshes2[0].step_pc(k % 2, (k + 1) % 2, t0 + k * dt, dt, ddcore.pc_options(fixed_sweeps=4))
     one = b.download(nsteps % 2)
     for v in VARS:
         many = np.concatenate([m.owned(nsteps % 2)[v] for m in meshes2])
