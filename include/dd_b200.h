@@ -177,6 +177,9 @@ int dd_error_norms(dd_batch* b, int slot, int slot_exact, const double* t, int n
  * slot_out on the owned rows (exchange that field's halo afterwards); 4: correctors on all local rows;
  * 5: cs exit decision (after reducing the work buffers "cs_it_max" (max) / "cs_it_min" (min) over ranks) and
  * summary[3][4] = rho, ratio (<= 1 means the residual bound is met), resid, bound of the T, cl, cd solves.
+ * Phases 21/22/23 only assemble the T/cl/cd system and 31/32/33 only solve it, so that the caller can
+ * max-reduce the Gershgorin ratio ("solve_stats" work buffer, first double of each 5-double record) over
+ * ranks in between: the SOR relaxation factor is then the same on every rank.
  * All ranks must use the same sweep plan (dd_batch_set_plan) for results independent of the decomposition. */
 int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_out, const double* t0, const double* dt, int n_t,
                      const dd_pc_options* opt, double* summary, int* cs_iters);

@@ -3,6 +3,7 @@
 // orchestration of the predictor-corrector step.  No Python.h, no torch types.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -517,9 +518,17 @@ extern "C" int dd_state_dev_ptr(dd_batch* b, int slot, int var, void** ptr, long
 }
 
 static int ensure_cs_buffers(dd_batch* b, int cap);
+static int ensure_solve_slots(dd_batch* b, int n);
 
 extern "C" int dd_work_dev_ptr(dd_batch* b, const char* name, void** ptr) {
     if (!b || !name || !ptr) return DD_ERR_INVALID;
+    if (!strcmp(name, "solve_stats")) {
+        // DDSolveStats[3][nmembers] of the phased step: 5 doubles each, rho first (all-reduced by the slab driver)
+        int rc0 = ensure_solve_slots(b, 3);
+        if (rc0 != DD_OK) return rc0;
+        *ptr = b->d_stats;
+        return DD_OK;
+    }
     if (!strcmp(name, "cs_it_max") || !strcmp(name, "cs_it_min")) {
         // [member][cap] accumulators of the cs-Newton exit test (allreduced by the slab driver)
         if (b->cs_cap_alloc <= 0) return fail(b->ctx, DD_ERR_INVALID, "cs statistics not allocated yet");
@@ -740,25 +749,38 @@ static void plan_pass(const dd_batch* b, int sweeps_left, bool allow_last, bool 
     }
     const int sm = b->ctx->sm_count > 0 ? b->ctx->sm_count : 148;
     static const int cand_i[] = {8, 12, 16, 24, 32, 40, 48, 56, 64, 80, 96};
-    static const int cand_j[] = {16, 32, 48, 64, 80, 96, 128, 160, 192};
+    static const int cand_sj[] = {64, 96, 128, 160, 192, 256};  // staged width: packed width multiple of 16
+    // development overrides
+    const char* e_ti = getenv("DD_TILE_I");
+    const char* e_sj = getenv("DD_STAGE_J");
+    const char* e_sp = getenv("DD_SWEEPS_PER_PASS");
+    const char* e_th = getenv("DD_THREADS");
     double best = 1e300;
     DDSolvePlan bp = *P;
-    // sweeps per pass: try everything that fits, cost = (waves * staged cells * sweeps-ish) per sweep done
+    bp.sweeps = 0;
+    // sweeps per pass: try everything that fits; cost ~ (waves of CTAs) x (staged cells) x (staging + sweeps)
     for (int S = sweeps_left; S >= 1; --S) {
+        if (e_sp && S != atoi(e_sp) && S != sweeps_left && atoi(e_sp) < sweeps_left) continue;
         const int last = (S == sweeps_left) && allow_last;
         const int H = 2 * S + (last ? 1 : 0);
         for (int ti : cand_i)
-            for (int tj : cand_j) {
-                const size_t cells = (size_t)(ti + 2 * H + 2) * ((tj + 2 * H + 3) & ~1);
+            for (int sj : cand_sj) {
+                if (e_ti && ti != atoi(e_ti)) continue;
+                if (e_sj && sj != atoi(e_sj)) continue;
+                const int tj = sj - 2 * H - 2;
+                if (tj < 8) continue;
+                const size_t cells = (size_t)(ti + 2 * H + 2) * sj;
                 if (cells > cells_max) continue;
                 const long long tiles = (long long)((rows + ti - 1) / ti) * ((cols + tj - 1) / tj) * b->B;
                 int per_sm = (int)(kSmemMax / (cells * cell_bytes + extra_bytes));
                 if (per_sm > 4) per_sm = 4;
+                // measured on B200 (profiles/r01_tile_sweep.log): a pass costs about (4 + S) "sweep units" per
+                // staged cell (staging + epilogue ~ 4 sweeps), CTAs fill the machine in waves, and a single
+                // resident CTA per SM cannot overlap its staging with another CTA's sweeps
                 const double waves = ceil((double)tiles / ((double)sm * per_sm));
-                // time ~ waves * per-CTA work / concurrency; work = staging + S sweeps over the staged area
-                const double work = (double)cells * (6.0 + 2.0 * S) * (per_sm > 1 ? per_sm * 0.6 : 1.0);
+                const double per_cta = (double)cells * (4.0 + S) * (per_sm > 1 ? 1.0 : 1.3);
                 const int npass = (sweeps_left + S - 1) / S;
-                const double cost = waves * work * npass;
+                const double cost = waves * per_sm * per_cta * npass;
                 if (cost < best) {
                     best = cost;
                     bp.sweeps = S;
@@ -766,9 +788,8 @@ static void plan_pass(const dd_batch* b, int sweeps_left, bool allow_last, bool 
                     bp.tile_j = tj;
                     bp.halo = H;
                     bp.last_pass = last;
-                    bp.smem_bytes = cells * cell_bytes +
-                                    (const_band ? 2 * sizeof(double) * ((ti + 2 * H + 2) + ((tj + 2 * H + 3) & ~1)) : 0);
-                    bp.threads = cells >= 2048 ? 512 : 256;
+                    bp.smem_bytes = cells * cell_bytes + (const_band ? 2 * sizeof(double) * ((ti + 2 * H + 2) + sj) : 0);
+                    bp.threads = e_th ? atoi(e_th) : (cells >= 2048 ? 512 : 256);
                 }
             }
     }
@@ -841,7 +862,7 @@ static int ensure_cs_buffers(dd_batch* b, int cap) {
 // assemble + solve one Newton system.  `k` indexes the stats slot.
 static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const double* T1, const double* cl1,
                         const double* Y, double* vnew, const dd_pc_options& opt, int k, int* sweeps_used,
-                        int* passes_used) {
+                        int* passes_used, int what = 3) {
     dd_ctx* ctx = b->ctx;
     DDRows R;
     int rc;
@@ -855,8 +876,10 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
     // so that the tile solver sees valid rows in its halo); tiles cover the owned rows only
     const DDLaunch L = launch_of(b, ROWS_OWNED);
     const DDLaunch La = launch_of(b, ROWS_ASM);
-    CKP(PC_ASM_T + (var - DD_T), 2,
-        dd_launch_assemble(La, b->mode, var, b->g, b->d_mem, b->F, ustar, T1, cl1, Y, opt.cd_band_swap, R, st));
+    if (what & 1)
+        CKP(PC_ASM_T + (var - DD_T), 2,
+            dd_launch_assemble(La, b->mode, var, b->g, b->d_mem, b->F, ustar, T1, cl1, Y, opt.cd_band_swap, R, st));
+    if (!(what & 2)) return DD_OK;
     const int vi = var - DD_T;
     int sweeps = opt.fixed_sweeps > 0 ? opt.fixed_sweeps : b->plan_sweeps[vi];
     if (sweeps <= 0) {
@@ -1306,12 +1329,15 @@ extern "C" int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_ou
                 }
             }
             return DD_OK;
-        case 1:
-            return newton_solve(b, DD_T, u, nullptr, nullptr, po.YT, sout.v[DD_T], opt, 0, &sw, &pa);
-        case 2:
-            return newton_solve(b, DD_CL, u, sout.v[DD_T], nullptr, po.Ycl, sout.v[DD_CL], opt, 1, &sw, &pa);
-        case 3:
-            return newton_solve(b, DD_CD, u, sout.v[DD_T], sout.v[DD_CL], po.Ycd, sout.v[DD_CD], opt, 2, &sw, &pa);
+        case 1: case 21: case 31:
+            return newton_solve(b, DD_T, u, nullptr, nullptr, po.YT, sout.v[DD_T], opt, 0, &sw, &pa,
+                                phase == 1 ? 3 : (phase == 21 ? 1 : 2));
+        case 2: case 22: case 32:
+            return newton_solve(b, DD_CL, u, sout.v[DD_T], nullptr, po.Ycl, sout.v[DD_CL], opt, 1, &sw, &pa,
+                                phase == 2 ? 3 : (phase == 22 ? 1 : 2));
+        case 3: case 23: case 33:
+            return newton_solve(b, DD_CD, u, sout.v[DD_T], sout.v[DD_CL], po.Ycd, sout.v[DD_CD], opt, 2, &sw, &pa,
+                                phase == 3 ? 3 : (phase == 23 ? 1 : 2));
         case 4:
             CKP(PC_CORRECT, 1,
                 dd_launch_correct(launch_of(b, ROWS_ALL), b->mode, b->g, b->d_mem, b->F, s0, sout.v[DD_T],
@@ -1340,6 +1366,6 @@ extern "C" int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_ou
             return DD_OK;
         }
         default:
-            return fail(ctx, DD_ERR_INVALID, "phase must be 0..5");
+            return fail(ctx, DD_ERR_INVALID, "phase must be 0..5, 21..23 or 31..33");
     }
 }

@@ -15,6 +15,8 @@
 //
 // Boundary nodes carry a zero row (bb = a* = 0), so x stays 0 there and no
 // special casing is needed; outside the grid the staging pads with zeros.
+#include <cuda_pipeline.h>
+
 #include "dd_kernels.cuh"
 
 __device__ __forceinline__ void atomic_max_nn(double* addr, double v) {
@@ -96,31 +98,32 @@ __global__ void __launch_bounds__(512) k_rbsor_tile(SolveArgs A) {
     const int li0 = vi0, li1 = min(vi1, tr + 2 * H + 1);
     const int lj0 = vj0, lj1 = min(vj1, tc + 2 * H + 1);
 
-    // stage: consecutive threads read consecutive columns of a row (coalesced), scatter by colour
-    for (int idx = threadIdx.x; idx < SI * SJ; idx += nthreads) {
-        const int si = idx / SJ, sj = idx - si * SJ;
-        double x = 0.0, b = 0.0, w = 0.0, e = 0.0, s = 0.0, n = 0.0;
-        if (si >= li0 && si < li1 && sj >= lj0 && sj < lj1) {
-            const long long o = mo + (long long)(rbase + si) * g.ld + (cbase + sj);
-            b = A.bb[o];
-            w = A.aW[o];
+    // stage with 8-byte asynchronous copies (LDGSTS): every thread queues all its elements at once and waits
+    // a single time, instead of paying one memory round trip per loop iteration.  One warp per staged row,
+    // lanes along j (coalesced), destination scattered by colour; out-of-range elements are zero-filled.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = nthreads >> 5;
+    for (int si = warp; si < SI; si += nwarps) {
+        const bool rowin = si >= li0 && si < li1;
+        const long long orow = mo + (long long)(rbase + si) * g.ld + cbase;
+        for (int sj = lane; sj < SJ; sj += 32) {
+            const bool in = rowin && sj >= lj0 && sj < lj1;
+            const long long o = in ? orow + sj : mo;  // any valid address when nothing is read
+            const size_t zf = in ? 0 : 8;
+            const int col = (par0 + si + sj) & 1, q = col * plane + si * PW + (sj >> 1);
+            __pipeline_memcpy_async(&Bb.base[q], &A.bb[o], 8, zf);
+            __pipeline_memcpy_async(&AW.base[q], &A.aW[o], 8, zf);
             if (!CONST_BAND) {
-                e = A.aE[o];
-                s = A.aS[o];
-                n = A.aN[o];
+                __pipeline_memcpy_async(&AE.base[q], &A.aE[o], 8, zf);
+                __pipeline_memcpy_async(&AS.base[q], &A.aS[o], 8, zf);
+                __pipeline_memcpy_async(&AN.base[q], &A.aN[o], 8, zf);
             }
-            if (A.xin) x = A.xin[o];
-        }
-        const int col = (par0 + si + sj) & 1, q = col * plane + si * PW + (sj >> 1);
-        X.base[q] = x;
-        Bb.base[q] = b;
-        AW.base[q] = w;
-        if (!CONST_BAND) {
-            AE.base[q] = e;
-            AS.base[q] = s;
-            AN.base[q] = n;
+            if (A.xin)
+                __pipeline_memcpy_async(&X.base[q], &A.xin[o], 8, zf);
+            else
+                X.base[q] = 0.0;
         }
     }
+    __pipeline_commit();
     if (CONST_BAND) {
         const DDMember& mb = A.mem[member];
         const double f = mb.dt * mb.m.DT;
@@ -138,6 +141,7 @@ __global__ void __launch_bounds__(512) k_rbsor_tile(SolveArgs A) {
         }
     }
     const double rho = A.stats[member].rho;
+    __pipeline_wait_prior(0);
     // omega_opt of SOR for a consistently ordered matrix whose Jacobi spectral radius is <= rho
     double omega = 1.0;
     if (rho < 1.0) omega = 2.0 / (1.0 + sqrt(1.0 - rho * rho));
@@ -157,56 +161,83 @@ __global__ void __launch_bounds__(512) k_rbsor_tile(SolveArgs A) {
                      *nc = AN.c(colour);
         const int ui0 = shrink_lo ? min(li0 + hs, H + 1) : li0;
         const int ui1 = shrink_hi ? max(li1 - hs, H + 1 + tr) : li1;
-        // packed slots 0 and PW-1 hold the zero ring columns (sj = 0 and SJ-1) for one colour each; they are
-        // skipped by the column guard below
-        for (int idx = ui0 * PW + threadIdx.x; idx < ui1 * PW; idx += nthreads) {
-            const int si = idx / PW, pk = idx - si * PW;
+        // one warp per row, lanes along the packed columns: unit-stride shared-memory accesses, no divisions.
+        // Packed slots holding the zero ring columns (sj = 0, SJ-1) are skipped by the column guard.
+        for (int si = ui0 + warp; si < ui1; si += nwarps) {
             const int o = (colour + par0 + si) & 1;  // sj = 2 pk + o
-            const int sj = 2 * pk + o;
-            if (sj >= 1 && sj <= SJ - 2) {
-                const int p = si * PW + pk;
-                double gs;
-                if (CONST_BAND)
-                    gs = bc[p] + wc[p] * (rowW[si] * xo[p - PW] + rowE[si] * xo[p + PW] + colS[sj] * xo[p - 1 + o] +
-                                          colN[sj] * xo[p + o]);
-                else
-                    gs = bc[p] + wc[p] * xo[p - PW] + ec[p] * xo[p + PW] + sc[p] * xo[p - 1 + o] + nc[p] * xo[p + o];
-                const double xv = xc[p];
-                xc[p] = xv + omega * (gs - xv);
+            const int rowp = si * PW;
+            double rw = 0.0, re = 0.0;
+            if (CONST_BAND) {
+                rw = rowW[si];
+                re = rowE[si];
+            }
+            for (int pk = lane; pk < PW; pk += 32) {
+                const int sj = 2 * pk + o;
+                if (sj >= 1 && sj <= SJ - 2) {
+                    const int p = rowp + pk;
+                    double gs;
+                    if (CONST_BAND)
+                        gs = bc[p] + wc[p] * (rw * xo[p - PW] + re * xo[p + PW] + colS[sj] * xo[p - 1 + o] +
+                                              colN[sj] * xo[p + o]);
+                    else
+                        gs = bc[p] + wc[p] * xo[p - PW] + ec[p] * xo[p + PW] + sc[p] * xo[p - 1 + o] +
+                             nc[p] * xo[p + o];
+                    const double xv = xc[p];
+                    xc[p] = xv + omega * (gs - xv);
+                }
             }
         }
         __syncthreads();
     }
 
-    // epilogue on the tile itself (smem coordinates H+1 .. H+1+tr)
+    // epilogue on the tile itself (smem coordinates H+1 .. H+1+tr); v* is fetched four cells ahead so that
+    // the loads of a batch are in flight together
     double rmax = 0.0, xmax = 0.0, vmax = 0.0, bmax = 0.0;
-    for (int idx = threadIdx.x; idx < tr * tc; idx += nthreads) {
-        const int a = idx / tc, bcol = idx - a * tc;
-        const int si = H + 1 + a, sj = H + 1 + bcol;
-        const int col = (par0 + si + sj) & 1, o = (sj & 1);
-        const int pk = sj >> 1, p = si * PW + pk;
-        const int r = r0 + a, j = c0 + bcol;
-        const long long og = mo + (long long)r * g.ld + j;
-        const double x = X.c(col)[p];
-        if (A.last_pass) {
-            const double* xo = X.c(1 - col);
-            const double bbv = Bb.c(col)[p];
-            double res;
-            if (CONST_BAND)
-                res = bbv + AW.c(col)[p] * (rowW[si] * xo[p - PW] + rowE[si] * xo[p + PW] +
-                                            colS[sj] * xo[p - 1 + o] + colN[sj] * xo[p + o]) - x;
-            else
-                res = bbv + AW.c(col)[p] * xo[p - PW] + AE.c(col)[p] * xo[p + PW] + AS.c(col)[p] * xo[p - 1 + o] +
-                      AN.c(col)[p] * xo[p + o] - x;
-            const bool inter = dd_is_interior(g, g.row0 + r, j);
-            const double vn = dd_newton_update(inter, A.vstar[og], x, A.zero_boundary);
-            A.vnew[og] = vn;
-            rmax = nn_max(rmax, res);
-            xmax = nn_max(xmax, x);
-            vmax = nn_max(vmax, vn);
-            bmax = nn_max(bmax, bbv);
-        } else {
-            A.xout[og] = x;
+    const int ncell = tr * tc;
+    for (int base = threadIdx.x; base < ncell; base += 4 * nthreads) {
+        double vs[4];
+        long long ogs[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = base + u * nthreads;
+            vs[u] = 0.0;
+            ogs[u] = 0;
+            if (idx < ncell) {
+                const int a = idx / tc, bcol = idx - a * tc;
+                ogs[u] = mo + (long long)(r0 + a) * g.ld + (c0 + bcol);
+                if (A.last_pass) vs[u] = A.vstar[ogs[u]];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = base + u * nthreads;
+            if (idx >= ncell) continue;
+            const int a = idx / tc, bcol = idx - a * tc;
+            const int si = H + 1 + a, sj = H + 1 + bcol;
+            const int col = (par0 + si + sj) & 1, o = (sj & 1);
+            const int pk = sj >> 1, p = si * PW + pk;
+            const int r = r0 + a, j = c0 + bcol;
+            const double x = X.c(col)[p];
+            if (A.last_pass) {
+                const double* xo = X.c(1 - col);
+                const double bbv = Bb.c(col)[p];
+                double res;
+                if (CONST_BAND)
+                    res = bbv + AW.c(col)[p] * (rowW[si] * xo[p - PW] + rowE[si] * xo[p + PW] +
+                                                colS[sj] * xo[p - 1 + o] + colN[sj] * xo[p + o]) - x;
+                else
+                    res = bbv + AW.c(col)[p] * xo[p - PW] + AE.c(col)[p] * xo[p + PW] +
+                          AS.c(col)[p] * xo[p - 1 + o] + AN.c(col)[p] * xo[p + o] - x;
+                const bool inter = dd_is_interior(g, g.row0 + r, j);
+                const double vn = dd_newton_update(inter, vs[u], x, A.zero_boundary);
+                A.vnew[ogs[u]] = vn;
+                rmax = nn_max(rmax, res);
+                xmax = nn_max(xmax, x);
+                vmax = nn_max(vmax, vn);
+                bmax = nn_max(bmax, bbv);
+            } else {
+                A.xout[ogs[u]] = x;
+            }
         }
     }
     if (A.last_pass) {

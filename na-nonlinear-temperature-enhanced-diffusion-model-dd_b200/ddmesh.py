@@ -198,7 +198,11 @@ class SlabMesh:
             plan = self._common_plan(opt)
             phase(0)
             for k, var in ((1, "T"), (2, "cl"), (3, "cd")):
-                phase(k)
+                # assemble, make the Gershgorin ratio (hence the SOR relaxation factor) global, solve
+                phase(20 + k)
+                comm.allreduce([m._tensor("stats", m.batch.work_dev_ptr("solve_stats"), (3, 5))[k - 1, 0:1]
+                                for m in group], "max")
+                phase(30 + k)
                 comm.exchange(group, slot_out, (var,))
             phase(4)
             if track:
