@@ -147,6 +147,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its banner on stdout; this program prints one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.Stream(device=local)
     lib = load_library()

@@ -136,6 +136,8 @@ class SlabMesh:
         self.comm = None
         self._rho = None
         self._extra = [0, 0, 0]
+        self._floor = [1, 1, 1]
+        self._plan = None
         if world > 1:
             import torch
             self.torch = torch
@@ -218,8 +220,8 @@ class SlabMesh:
             for m in group:
                 m._rho, m.last_stats = s[:, 0], stats
             if np.all(s[:, 1] <= 1.0):
-                nxt = [self.batch.lib.dd_next_plan(int(p), float(r), float(q), opt.max_sweeps)
-                       for p, r, q in zip(plan, s[:, 0], s[:, 1])]
+                nxt = [max(self.batch.lib.dd_next_plan(int(p), float(r), float(q), opt.max_sweeps), f)
+                       for p, r, q, f in zip(plan, s[:, 0], s[:, 1], self._floor)]
                 for m in group:
                     m._plan = nxt
                 return stats
@@ -229,9 +231,14 @@ class SlabMesh:
             if any(r > 1.0 and p >= limit for p, r in zip(plan, s[:, 1])):
                 raise ddcore.DDNotConverged(f"slab step: {limit} SOR sweeps (all a halo of {self.G} rows supports) "
                                             f"do not reach the residual bound; use a deeper halo. stats={stats}")
-            extra = [e + (p + 1) // 2 + 1 if r > 1.0 else e for e, p, r in zip(self._extra, plan, s[:, 1])]
+            # remember the failing counts (never plan below them again) and fall back to the theoretical plan
+            floor = [max(f, p + 1) if r > 1.0 else f for f, p, r in zip(self._floor, plan, s[:, 1])]
+            extra = [e + (p + 1) // 2 + 1 if (r > 1.0 and p >= lib_plan) else e
+                     for e, p, r, lib_plan in zip(self._extra, plan, s[:, 1],
+                                                  [self.batch.lib.dd_sweeps_for_rho(float(x) * 1.02 + 1e-12,
+                                                                                    opt.max_sweeps) for x in s[:, 0]])]
             for m in group:
-                m._extra = extra
+                m._extra, m._floor = extra, floor
         raise ddcore.DDNotConverged("slab step: linear solve did not reach the residual bound")
 
     def _common_plan(self, opt) -> List[int]:
@@ -246,8 +253,8 @@ class SlabMesh:
         elif getattr(self, "_plan", None) is not None:
             plan = [min(p, limit) for p in self._plan]
         else:
-            plan = [lib.dd_sweeps_for_rho(float(r) * 1.02 + 1e-12, opt.max_sweeps) + e
-                    for r, e in zip(self._rho, self._extra)]
+            plan = [max(lib.dd_sweeps_for_rho(float(r) * 1.02 + 1e-12, opt.max_sweeps) + e, f)
+                    for r, e, f in zip(self._rho, self._extra, self._floor)]
         # never more than the halo supports; the residual bound is verified after every solve, so a clamped
         # plan either passes or the step raises below
         plan = [max(1, min(p, limit)) for p in plan]
