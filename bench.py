@@ -41,8 +41,8 @@ POL = dict(K1=1e-3, K2=1e-3, K3=1e-3, K4=1e-3, DT=1e-3, Dl_max=8.01e-4, phi_l=1e
            Dd_max=2.46e-6, phi_d=1e-5, r_sp=5e-2, T_ref=300.0)
 ETA = 50.0
 # algorithmic bytes per node and launch of each kernel class ("kernels")
-KERNEL_BYTES = {"k_predict": 80, "k_assemble<T>": 64, "k_assemble<cl>": 80, "k_assemble<cd>": 104,
-                "k_rbsor_tile<T>": 56, "k_rbsor_tile<cl>": 56, "k_rbsor_tile<cd>": 56, "k_correct": 80,
+KERNEL_BYTES = {"k_predict": 80, "k_assemble<T>": 40, "k_assemble<cl>": 80, "k_assemble<cd>": 104,
+                "k_rbsor_tile<T>": 32, "k_rbsor_tile<cl>": 56, "k_rbsor_tile<cd>": 56, "k_correct": 80,
                 "k_feuler": 80}
 
 
