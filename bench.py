@@ -43,7 +43,7 @@ ETA = 50.0
 # algorithmic bytes per node and launch of each kernel class ("kernels")
 KERNEL_BYTES = {"k_predict": 80, "k_assemble<T>": 40, "k_assemble<cl>": 80, "k_assemble<cd>": 104,
                 "k_rbsor_tile<T>": 32, "k_rbsor_tile<cl>": 56, "k_rbsor_tile<cd>": 56, "k_correct": 80,
-                "k_feuler": 80}
+                "k_feuler": 80, "k_eval_sources": 40}
 
 
 def measured_peak():
@@ -131,6 +131,8 @@ def mesh_setup(world, rank, ctx):
     case = p1mc.MMSCasePol(grid=p1.Grid(np.array([0.0, 0.5, 1.0]), np.array([0.0, 0.5, 1.0])), model=model)
     mesh.batch.forcing_spec(case.device_spec())
     mesh.fill_exact(0, 0.0)
+    if os.environ.get("DD_BENCH_NOFORCING"):  # development probe: cost of the fused sources
+        mesh.batch.forcing_none()
     return mesh, h ** 1.5, N * MESH_COLS
 
 
@@ -158,8 +160,13 @@ def run_b200(args):
             mesh, dt, cells = mesh_setup(world, rank, ctx)
             opt = ddcore.pc_options()
 
+            clock = {"t": 0.0}
+
             def step(k):
-                mesh.step_pc(k % 2, (k + 1) % 2, k * dt, dt, opt)
+                # times accumulate as in the reference's loop (current_t += dt, src/mms_trial_utils.py:128):
+                # the t1 sources of a step are then bitwise the t0 sources of the next one
+                mesh.step_pc(k % 2, (k + 1) % 2, clock["t"], dt, opt)
+                clock["t"] += dt
             workload = (f"pol_mesh: MMSCasePol, {MESH_ROWS_PER_GPU} rows/GPU x {MESH_COLS} cols of the N=M=8192 "
                         f"unit-square mesh (h=k=1/8192, dt=h^1.5), slab decomposition along i")
             extra_cfg = {"rows_per_gpu": MESH_ROWS_PER_GPU, "cols": MESH_COLS, "halo_rows": mesh.G,

@@ -193,6 +193,8 @@ long long dd_launch_count(void);                /* kernels launched by the libra
 int dd_profile_enable(int on);                  /* bracket every launch group with CUDA events */
 int dd_profile_read(const char** names, double* ms, long long* count, int reset); /* returns #classes (<= 16) */
 
+int dd_probe_math(dd_ctx* ctx, int n, const double* in, double* out_exp, double* out_rcp); /* accuracy probe of the inline device exp / 1/x */
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdd_b200.so")
+LIB_PATH = os.environ.get("DD_LIB", os.path.join(_HERE, "libdd_b200.so"))  # DD_LIB: development override
 
 DD_OK, DD_ERR_INVALID, DD_ERR_CUDA, DD_ERR_NOT_CONVERGED, DD_ERR_NO_DEVICE = 0, -1, -2, -3, -4
 VAR_INDEX = {"cp": 0, "T": 1, "cl": 2, "cd": 3, "cs": 4}
@@ -101,6 +101,7 @@ SIGNATURES = {
     "dd_batch_get_plan": (C.c_int, [_vp, _P(C.c_int * 3)]),
     "dd_sweeps_for_rho": (C.c_int, [C.c_double, C.c_int]),
     "dd_next_plan": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int]),
+    "dd_probe_math": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp]),
     "dd_launch_count": (C.c_longlong, []),
     "dd_profile_enable": (C.c_int, [C.c_int]),
     "dd_profile_read": (C.c_int, [_P(C.c_char_p), _dp, _P(C.c_longlong), C.c_int]),
@@ -161,6 +162,7 @@ class Context:
             raise DDLibraryError(f"dd_ctx_create failed with status {rc}")
         self.handle = h
         self.device = device
+        self.stream = int(stream) if stream else None  # None: the library's own non-blocking stream
 
     @classmethod
     def default(cls) -> "Context":

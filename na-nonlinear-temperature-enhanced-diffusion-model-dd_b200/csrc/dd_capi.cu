@@ -50,6 +50,15 @@ struct dd_batch {
     int cs_cap_alloc;
     double *d_norm_partial, *d_norm_out;
     int norm_bpm;
+    // staged sources: the MMS sources of a time level are evaluated once (k_eval_sources) into one of two
+    // sets of five arrays and the step kernels read them in ARRAYS mode; the t1 set of a step is the t0
+    // set of the next one.  smode / sF is what the step kernels are launched with.
+    int smode;
+    DDForcing sF;
+    bool fused_sources;        // DD_FUSED_SOURCES=1: evaluate the sources inside every kernel instead
+    double* src_set[2][DD_NVAR];
+    bool src_has[2];
+    double src_time[2];
     int plan_sweeps[3], plan_extra[3], plan_floor[3];  // floor: one more than the last count that failed
     bool is_slab;
     int cmp0, cmp1;  // local rows with a complete stencil (slabs: everything but the outermost halo row)
@@ -63,12 +72,12 @@ struct dd_batch {
 // accumulated per kernel class (bench.py reads this for the roofline of the dominant kernel).
 enum ProfClass {
     PC_TIME = 0, PC_PREDICT, PC_ASM_T, PC_ASM_CL, PC_ASM_CD, PC_SOLVE_T, PC_SOLVE_CL, PC_SOLVE_CD, PC_CORRECT,
-    PC_CS_FINISH, PC_SUMMARISE, PC_FEULER, PC_NORMS, PC_OTHER, PC_NCLASS
+    PC_CS_FINISH, PC_SUMMARISE, PC_FEULER, PC_NORMS, PC_OTHER, PC_SOURCES, PC_NCLASS
 };
 static const char* kProfNames[PC_NCLASS] = {"k_time_coefs", "k_predict", "k_assemble<T>", "k_assemble<cl>",
                                             "k_assemble<cd>", "k_rbsor_tile<T>", "k_rbsor_tile<cl>",
                                             "k_rbsor_tile<cd>", "k_correct", "k_cs_decide+k_cs_redo",
-                                            "k_summarise", "k_feuler", "k_error_norms", "other"};
+                                            "k_summarise", "k_feuler", "k_error_norms", "other", "k_eval_sources"};
 struct Prof {
     bool on = false;
     long long launches = 0;
@@ -221,8 +230,10 @@ static int get_work(dd_batch* b, const char* name, double** out) {
         return DD_OK;
     }
     double* p = nullptr;
-    CK(cudaMalloc((void**)&p, b->field_elems * sizeof(double)));
-    CK(cudaMemsetAsync(p, 0, b->field_elems * sizeof(double), ctx->stream));
+    // work fields have room for the even row pitch of the Newton rows / solver iterates (ld + 1 when ld is odd)
+    const size_t padded = (size_t)b->B * b->nrows * (size_t)(b->g.ld + (b->g.ld & 1));
+    CK(cudaMalloc((void**)&p, padded * sizeof(double)));
+    CK(cudaMemsetAsync(p, 0, padded * sizeof(double), ctx->stream));
     b->work[name] = p;
     *out = p;
     return DD_OK;
@@ -284,6 +295,14 @@ extern "C" int dd_batch_create(dd_ctx* ctx, int N, int M, const double* x, const
     CK(cudaMemcpyAsync(b->d_mem, b->h_mem.data(), sizeof(DDMember) * nmembers, cudaMemcpyHostToDevice, ctx->stream));
     b->mode = DD_FORCING_NONE;
     memset(&b->F, 0, sizeof(b->F));
+    b->smode = DD_FORCING_NONE;
+    memset(&b->sF, 0, sizeof(b->sF));
+    {
+        const char* e = getenv("DD_FUSED_SOURCES");
+        b->fused_sources = e && atoi(e) != 0;
+    }
+    memset(b->src_set, 0, sizeof(b->src_set));
+    b->src_has[0] = b->src_has[1] = false;
     b->slots.resize(nslots);
     for (int s = 0; s < nslots; ++s) {
         b->slots[s].resize(DD_NVAR);
@@ -322,6 +341,7 @@ extern "C" int dd_batch_destroy(dd_batch* b) {
 
 static int push_members(dd_batch* b, int first, int count) {
     dd_ctx* ctx = b->ctx;
+    b->src_has[0] = b->src_has[1] = false;  // models / time profiles changed: staged sources are stale
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(b->d_mem + first, b->h_mem.data() + first, sizeof(DDMember) * count, cudaMemcpyHostToDevice,
                        ctx->stream));
@@ -350,6 +370,7 @@ extern "C" int dd_batch_set_active(dd_batch* b, int first, int count, const int*
 // forcing
 // ---------------------------------------------------------------------------
 static void free_tables(dd_batch* b) {
+    b->src_has[0] = b->src_has[1] = false;
     for (double* p : b->table_dev) cudaFree(p);
     b->table_dev.clear();
     memset(&b->F.tab, 0, sizeof(b->F.tab));
@@ -605,6 +626,53 @@ static int set_times(dd_batch* b, const double* t0, const double* dt, int n_t) {
     return DD_OK;
 }
 
+// Select what the step kernels are launched with.  Fused modes (SEPARABLE / EXPSIN) are staged: the sources
+// at t0 and t1 are evaluated into two array sets unless a set already holds that time level (uniform times
+// only).  Must be called after the member times are on the device (set_times / advance).
+static int stage_sources(dd_batch* b, double t0, double dt, bool times_uniform, bool need_slot1) {
+    dd_ctx* ctx = b->ctx;
+    if ((b->mode != DD_FORCING_SEPARABLE && b->mode != DD_FORCING_EXPSIN) || b->fused_sources) {
+        b->smode = b->mode;
+        b->sF = b->F;
+        return DD_OK;
+    }
+    static const char* names[2][DD_NVAR] = {{"src0_cp", "src0_T", "src0_cl", "src0_cd", "src0_cs"},
+                                            {"src1_cp", "src1_T", "src1_cl", "src1_cd", "src1_cs"}};
+    int rc;
+    for (int s = 0; s < 2; ++s)
+        for (int v = 0; v < DD_NVAR; ++v)
+            if (!b->src_set[s][v] && (rc = get_work(b, names[s][v], &b->src_set[s][v])) != DD_OK) return rc;
+    if (!times_uniform) b->src_has[0] = b->src_has[1] = false;
+    const double t1 = t0 + dt;
+    int s0 = -1;
+    for (int s = 0; s < 2; ++s)
+        if (b->src_has[s] && b->src_time[s] == t0) s0 = s;
+    if (s0 < 0) {
+        s0 = 0;
+        if (need_slot1 && b->src_has[0] && b->src_time[0] == t1) s0 = 1;  // keep a set that already holds t1
+        DDState out;
+        for (int v = 0; v < DD_NVAR; ++v) out.v[v] = b->src_set[s0][v];
+        CKP(PC_SOURCES, 1, dd_launch_eval_sources(launch_of(b, ROWS_ALL), b->mode, b->g, b->d_mem, b->F, out, 0));
+        b->src_has[s0] = times_uniform;
+        b->src_time[s0] = t0;
+    }
+    const int s1 = 1 - s0;
+    if (need_slot1 && !(b->src_has[s1] && b->src_time[s1] == t1)) {
+        DDState out;
+        for (int v = 0; v < DD_NVAR; ++v) out.v[v] = b->src_set[s1][v];
+        CKP(PC_SOURCES, 1, dd_launch_eval_sources(launch_of(b, ROWS_ALL), b->mode, b->g, b->d_mem, b->F, out, 1));
+        b->src_has[s1] = times_uniform;
+        b->src_time[s1] = t1;
+    }
+    b->smode = DD_FORCING_ARRAYS;
+    memset(&b->sF, 0, sizeof(b->sF));
+    for (int v = 0; v < DD_NVAR; ++v) {
+        b->sF.arr.f[v][0] = b->src_set[s0][v];
+        b->sF.arr.f[v][1] = b->src_set[s1][v];
+    }
+    return DD_OK;
+}
+
 extern "C" int dd_state_fill_exact(dd_batch* b, int slot, const double* t, int n_t) {
     if (!b || !slot_ok(b, slot) || !t) return DD_ERR_INVALID;
     dd_ctx* ctx = b->ctx;
@@ -626,7 +694,8 @@ extern "C" int dd_step_feuler(dd_batch* b, int slot_in, int slot_out, const doub
     CK(cudaSetDevice(ctx->device));
     int rc = set_times(b, t0, dt, n_t);
     if (rc != DD_OK) return rc;
-    CKP(PC_FEULER, 1, dd_launch_feuler(launch_of(b), b->mode, b->g, b->d_mem, b->F, cstate(b, slot_in), mstate(b, slot_out)));
+    if ((rc = stage_sources(b, t0[0], dt[0], n_t == 1, false)) != DD_OK) return rc;
+    CKP(PC_FEULER, 1, dd_launch_feuler(launch_of(b), b->smode, b->g, b->d_mem, b->sF, cstate(b, slot_in), mstate(b, slot_out)));
     CK(cudaStreamSynchronize(ctx->stream));
     return DD_OK;
 }
@@ -735,6 +804,70 @@ static void plan_pass(const dd_batch* b, int sweeps_left, bool allow_last, bool 
     const size_t extra_bytes = const_band ? 4096 : 0;
     const size_t cells_max = (kSmemMax - extra_bytes) / cell_bytes;
     P->const_band = const_band ? 1 : 0;
+    P->rpw = 0;
+    // ---- register-resident kernel (default): staged region 16*rpw rows x 64 columns, 512 threads ----
+    {
+        const char* e_solver = getenv("DD_SOLVER");
+        const bool want_reg = !(e_solver && !strcmp(e_solver, "smem"));
+        static const int rpw_gen[] = {2, 3, 4}, rpw_cb[] = {2, 3, 4, 6, 8};
+        const int* rp = const_band ? rpw_cb : rpw_gen;
+        const int nrp = const_band ? 5 : 3;
+        const char* e_rpw = getenv("DD_RPW");
+        const char* e_spp = getenv("DD_SWEEPS_PER_PASS");
+        if (want_reg) {
+            // whole member inside one staged region: no halo at all
+            // (halo 1 instead of 0 keeps the staged origin on an even column for the 16-byte loads)
+            if (!b->is_slab && cols <= 60) {
+                for (int q = 0; q < nrp; ++q)
+                    if (rows <= 16 * rp[q] - 4) {
+                        P->rpw = rp[q];
+                        P->sweeps = sweeps_left;
+                        P->tile_i = rows;
+                        P->tile_j = cols + (cols & 1);
+                        P->halo = 1;
+                        P->last_pass = 1;
+                        P->threads = 512;
+                        P->smem_bytes = 0;
+                        return;
+                    }
+            }
+            // tiled: cost per pass ~ staged cells x (load + sweeps + epilogue) in sweep units; loads dominate
+            const double c_load = const_band ? 3.0 : 6.0, c_epi = 1.5;
+            double best = 1e300;
+            DDSolvePlan bp = *P;
+            bp.sweeps = 0;
+            for (int S = sweeps_left; S >= 1; --S) {
+                if (e_spp && atoi(e_spp) < sweeps_left && S != atoi(e_spp)) continue;
+                const int last = (S == sweeps_left) && allow_last;
+                const int H = 2 * S + 1;  // odd on every pass: staged origin on an even column
+                const int tj = 62 - 2 * H;
+                if (tj < 8) continue;
+                for (int q = 0; q < nrp; ++q) {
+                    if (e_rpw && rp[q] != atoi(e_rpw)) continue;
+                    const int SI = 16 * rp[q], ti = SI - 2 * H - 2;
+                    if (ti < 4) continue;
+                    const double tiles = (double)((rows + ti - 1) / ti) * (double)((cols + tj - 1) / tj) * b->B;
+                    const int npass = (sweeps_left + S - 1) / S;
+                    const double cost = tiles * (double)SI * 64.0 * (c_load + S + c_epi) * npass;
+                    if (cost < best) {
+                        best = cost;
+                        bp.rpw = rp[q];
+                        bp.sweeps = S;
+                        bp.tile_i = ti;
+                        bp.tile_j = tj;
+                        bp.halo = H;
+                        bp.last_pass = last;
+                        bp.threads = 512;
+                        bp.smem_bytes = 0;
+                    }
+                }
+            }
+            if (bp.sweeps > 0) {
+                *P = bp;
+                return;
+            }
+        }
+    }
     // whole member in one tile (no halo needed because every edge is a physical boundary)
     if (!b->is_slab && (size_t)(rows + 2) * ((cols + 3) & ~1) <= cells_max) {
         P->sweeps = sweeps_left;
@@ -871,6 +1004,8 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
     if ((rc = get_work(b, "aE", &R.aE)) != DD_OK) return rc;
     if ((rc = get_work(b, "aS", &R.aS)) != DD_OK) return rc;
     if ((rc = get_work(b, "aN", &R.aN)) != DD_OK) return rc;
+    R.ld = b->g.ld + (b->g.ld & 1);
+    R.mstride = (long long)b->nrows * R.ld;
     DDSolveStats* st = b->d_stats + (size_t)k * b->B;
     // rows are assembled on every local row that has a full stencil (slabs: halo rows included,
     // so that the tile solver sees valid rows in its halo); tiles cover the owned rows only
@@ -878,7 +1013,7 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
     const DDLaunch La = launch_of(b, ROWS_ASM);
     if (what & 1)
         CKP(PC_ASM_T + (var - DD_T), 2,
-            dd_launch_assemble(La, b->mode, var, b->g, b->d_mem, b->F, ustar, T1, cl1, Y, opt.cd_band_swap, R, st));
+            dd_launch_assemble(La, b->smode, var, b->g, b->d_mem, b->sF, ustar, T1, cl1, Y, opt.cd_band_swap, R, st));
     if (!(what & 2)) return DD_OK;
     const int vi = var - DD_T;
     int sweeps = opt.fixed_sweeps > 0 ? opt.fixed_sweeps : b->plan_sweeps[vi];
@@ -967,7 +1102,7 @@ static int pc_step_once(dd_batch* b, int slot_in, int slot_out, const dd_pc_opti
     const DDLaunch Lall = launch_of(b, ROWS_ALL);
     const DDStateC s0 = cstate(b, slot_in);
     const DDState sout = mstate(b, slot_out);
-    CKP(PC_PREDICT, 1, dd_launch_predict(L, b->mode, b->g, b->d_mem, b->F, s0, po));
+    CKP(PC_PREDICT, 1, dd_launch_predict(L, b->smode, b->g, b->d_mem, b->sF, s0, po));
     DDStateC u;
     u.v[DD_CP] = po.cp1p; u.v[DD_T] = s0.v[DD_T]; u.v[DD_CL] = s0.v[DD_CL]; u.v[DD_CD] = s0.v[DD_CD];
     u.v[DD_CS] = po.cs1p;
@@ -1005,11 +1140,11 @@ static int pc_step_once(dd_batch* b, int slot_in, int slot_out, const dd_pc_opti
             }
         }
         CKP(PC_CORRECT, 1,
-            dd_launch_correct(Lall, b->mode, b->g, b->d_mem, b->F, s0, u.v[DD_T], u.v[DD_CL], u.v[DD_CD], cpd, csd,
+            dd_launch_correct(Lall, b->smode, b->g, b->d_mem, b->sF, s0, u.v[DD_T], u.v[DD_CL], u.v[DD_CD], cpd, csd,
                               cap, track ? opt.consec_xs_rtol : 0.0, b->d_itmax, b->d_itmin));
         if (track)
             CKP(PC_CS_FINISH, 2,
-                dd_launch_cs_finish(Lall, b->mode, b->g, b->d_mem, b->F, s0, u.v[DD_CL], u.v[DD_CD], csd, cap,
+                dd_launch_cs_finish(Lall, b->smode, b->g, b->d_mem, b->sF, s0, u.v[DD_CL], u.v[DD_CD], csd, cap,
                                     opt.consec_xs_rtol, b->d_itmax, b->d_itmin, b->d_used));
         u.v[DD_CP] = cpd; u.v[DD_CS] = csd;
     }
@@ -1102,6 +1237,7 @@ extern "C" int dd_step_pc(dd_batch* b, int slot_in, int slot_out, const double* 
     int rc = check_opts(ctx, opt);
     if (rc != DD_OK) return rc;
     if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
+    if ((rc = stage_sources(b, t0[0], dt[0], n_t == 1, true)) != DD_OK) return rc;
     return pc_step_retry(b, slot_in, slot_out, opt, stats);
 }
 
@@ -1118,7 +1254,10 @@ extern "C" int dd_run_pc(dd_batch* b, int slot_a, int slot_b, const double* t0, 
     int cur = slot_a, nxt = slot_b;
     const size_t nstride = (size_t)8 * b->B;
     if (norms_out && (rc = norms_async(b, cur, -1, norms_out)) != DD_OK) return rc;
+    double th = t0[0];  // host mirror of the device-side time advance (same IEEE additions)
     for (int s = 0; s < nsteps; ++s) {
+        if ((rc = stage_sources(b, th, dt[0], n_t == 1, true)) != DD_OK) return rc;
+        th = th + dt[0];
         if ((rc = pc_step_retry(b, cur, nxt, opt, stats)) != DD_OK) return rc;
         CKP(PC_TIME, 1, dd_launch_time_coefs(launch_of(b), b->mode, b->d_mem, b->d_t0, b->d_dt, n_t, 1));
         if (norms_out && (rc = norms_async(b, nxt, -1, norms_out + (s + 1) * nstride)) != DD_OK) return rc;
@@ -1138,8 +1277,11 @@ extern "C" int dd_run_feuler(dd_batch* b, int slot_a, int slot_b, const double* 
     int cur = slot_a, nxt = slot_b;
     const size_t nstride = (size_t)8 * b->B;
     if (norms_out && (rc = norms_async(b, cur, -1, norms_out)) != DD_OK) return rc;
+    double th = t0[0];
     for (int s = 0; s < nsteps; ++s) {
-        CKP(PC_FEULER, 1, dd_launch_feuler(launch_of(b), b->mode, b->g, b->d_mem, b->F, cstate(b, cur), mstate(b, nxt)));
+        if ((rc = stage_sources(b, th, dt[0], n_t == 1, false)) != DD_OK) return rc;
+        th = th + dt[0];
+        CKP(PC_FEULER, 1, dd_launch_feuler(launch_of(b), b->smode, b->g, b->d_mem, b->sF, cstate(b, cur), mstate(b, nxt)));
         CKP(PC_TIME, 1, dd_launch_time_coefs(launch_of(b), b->mode, b->d_mem, b->d_t0, b->d_dt, n_t, 1));
         if (norms_out && (rc = norms_async(b, nxt, -1, norms_out + (s + 1) * nstride)) != DD_OK) return rc;
         const int tmp = cur; cur = nxt; nxt = tmp;
@@ -1157,13 +1299,14 @@ extern "C" int dd_pc_predict(dd_batch* b, int slot_in, const double* t0, const d
     CK(cudaSetDevice(ctx->device));
     int rc;
     if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
+    if ((rc = stage_sources(b, t0[0], dt[0], n_t == 1, true)) != DD_OK) return rc;
     DDPredictOut po;
     if ((rc = get_work(b, "cp1p", &po.cp1p)) != DD_OK) return rc;
     if ((rc = get_work(b, "cs1p", &po.cs1p)) != DD_OK) return rc;
     if ((rc = get_work(b, "YT", &po.YT)) != DD_OK) return rc;
     if ((rc = get_work(b, "Ycl", &po.Ycl)) != DD_OK) return rc;
     if ((rc = get_work(b, "Ycd", &po.Ycd)) != DD_OK) return rc;
-    CK(dd_launch_predict(launch_of(b), b->mode, b->g, b->d_mem, b->F, cstate(b, slot_in), po));
+    CK(dd_launch_predict(launch_of(b), b->smode, b->g, b->d_mem, b->sF, cstate(b, slot_in), po));
     CK(cudaStreamSynchronize(ctx->stream));
     return DD_OK;
 }
@@ -1179,6 +1322,7 @@ extern "C" int dd_pc_newton(dd_batch* b, int var, int slot_star, int slot_new, c
     int rc = check_opts(ctx, opt);
     if (rc != DD_OK) return rc;
     if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
+    if ((rc = stage_sources(b, t0[0], dt[0], n_t == 1, true)) != DD_OK) return rc;
     if ((rc = ensure_solve_slots(b, 3)) != DD_OK) return rc;
     static const char* yname[3] = {"YT", "Ycl", "Ycd"};
     double* Y;
@@ -1216,6 +1360,7 @@ extern "C" int dd_pc_correct(dd_batch* b, int slot0, int slot_new, const double*
     int rc = check_opts(ctx, opt);
     if (rc != DD_OK) return rc;
     if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
+    if ((rc = stage_sources(b, t0[0], dt[0], n_t == 1, true)) != DD_OK) return rc;
     const DDLaunch L = launch_of(b, ROWS_ALL);
     const DDStateC s0 = cstate(b, slot0);
     const DDState nw = mstate(b, slot_new);
@@ -1229,10 +1374,10 @@ extern "C" int dd_pc_correct(dd_batch* b, int slot0, int slot_new, const double*
             k_cs_arm<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(b->d_itmax, b->d_itmin, n);
         }
     }
-    CK(dd_launch_correct(L, b->mode, b->g, b->d_mem, b->F, s0, nw.v[DD_T], nw.v[DD_CL], nw.v[DD_CD], nw.v[DD_CP],
+    CK(dd_launch_correct(L, b->smode, b->g, b->d_mem, b->sF, s0, nw.v[DD_T], nw.v[DD_CL], nw.v[DD_CD], nw.v[DD_CP],
                          nw.v[DD_CS], cap, track ? opt.consec_xs_rtol : 0.0, b->d_itmax, b->d_itmin));
     if (track)
-        CK(dd_launch_cs_finish(L, b->mode, b->g, b->d_mem, b->F, s0, nw.v[DD_CL], nw.v[DD_CD], nw.v[DD_CS], cap,
+        CK(dd_launch_cs_finish(L, b->smode, b->g, b->d_mem, b->sF, s0, nw.v[DD_CL], nw.v[DD_CD], nw.v[DD_CS], cap,
                                opt.consec_xs_rtol, b->d_itmax, b->d_itmin, b->d_used));
     if (cs_iters_out) {
         if (track) {
@@ -1252,11 +1397,12 @@ extern "C" int dd_pc_residual(dd_batch* b, int var, int slot_state, const double
     CK(cudaSetDevice(ctx->device));
     int rc;
     if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
+    if ((rc = stage_sources(b, t0[0], dt[0], n_t == 1, true)) != DD_OK) return rc;
     static const char* yname[3] = {"YT", "Ycl", "Ycd"};
     double *Y, *res;
     if ((rc = get_work(b, yname[var - DD_T], &Y)) != DD_OK) return rc;
     if ((rc = get_work(b, "resid", &res)) != DD_OK) return rc;
-    CK(dd_launch_residual(launch_of(b), b->mode, var, b->g, b->d_mem, b->F, cstate(b, slot_state), Y, res));
+    CK(dd_launch_residual(launch_of(b), b->smode, var, b->g, b->d_mem, b->sF, cstate(b, slot_state), Y, res));
     CK(cudaMemcpyAsync(out_host, res, b->field_elems * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return DD_OK;
@@ -1319,7 +1465,8 @@ extern "C" int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_ou
     switch (phase) {
         case 0:
             if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
-            CKP(PC_PREDICT, 1, dd_launch_predict(launch_of(b, ROWS_STENCIL), b->mode, b->g, b->d_mem, b->F, s0, po));
+            if ((rc = stage_sources(b, t0[0], dt[0], n_t == 1, true)) != DD_OK) return rc;
+            CKP(PC_PREDICT, 1, dd_launch_predict(launch_of(b, ROWS_STENCIL), b->smode, b->g, b->d_mem, b->sF, s0, po));
             if (track) {
                 const int had = b->cs_cap_alloc;
                 if ((rc = ensure_cs_buffers(b, cap)) != DD_OK) return rc;
@@ -1340,14 +1487,14 @@ extern "C" int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_ou
                                 phase == 3 ? 3 : (phase == 23 ? 1 : 2));
         case 4:
             CKP(PC_CORRECT, 1,
-                dd_launch_correct(launch_of(b, ROWS_ALL), b->mode, b->g, b->d_mem, b->F, s0, sout.v[DD_T],
+                dd_launch_correct(launch_of(b, ROWS_ALL), b->smode, b->g, b->d_mem, b->sF, s0, sout.v[DD_T],
                                   sout.v[DD_CL], sout.v[DD_CD], sout.v[DD_CP], sout.v[DD_CS], cap,
                                   track ? opt.consec_xs_rtol : 0.0, b->d_itmax, b->d_itmin));
             return DD_OK;
         case 5: {
             if (track)
                 CKP(PC_CS_FINISH, 2,
-                    dd_launch_cs_finish(launch_of(b, ROWS_ALL), b->mode, b->g, b->d_mem, b->F, s0, sout.v[DD_CL],
+                    dd_launch_cs_finish(launch_of(b, ROWS_ALL), b->smode, b->g, b->d_mem, b->sF, s0, sout.v[DD_CL],
                                         sout.v[DD_CD], sout.v[DD_CS], cap, opt.consec_xs_rtol, b->d_itmax,
                                         b->d_itmin, b->d_used));
             SolveSummary sums[3];
@@ -1368,4 +1515,20 @@ extern "C" int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_ou
         default:
             return fail(ctx, DD_ERR_INVALID, "phase must be 0..5, 21..23 or 31..33");
     }
+}
+
+
+// accuracy probe of the inline device exp / reciprocal (host arrays in, host arrays out)
+extern "C" int dd_probe_math(dd_ctx* ctx, int n, const double* in, double* out_exp, double* out_rcp) {
+    if (!ctx || n < 1 || !in || !out_exp || !out_rcp) return DD_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    double* d = nullptr;
+    CK(cudaMalloc((void**)&d, 3 * sizeof(double) * (size_t)n));
+    CK(cudaMemcpyAsync(d, in, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(dd_launch_probe_math(ctx->stream, d, d + n, d + 2 * (size_t)n, n));
+    CK(cudaMemcpyAsync(out_exp, d + n, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_rcp, d + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    return DD_OK;
 }

@@ -5,6 +5,10 @@
 #include "dd_kernels.cuh"
 
 #define DD_BLOCK 256
+// resident CTAs per SM each stencil kernel is compiled for (register cap 65536 / (256 * n)); measured on B200
+#define DD_MINB_PREDICT 4
+#define DD_MINB_ASM 3
+#define DD_MINB 2
 
 struct NodeIdx {
     int member, r, j;
@@ -38,23 +42,19 @@ __device__ __forceinline__ void atomic_min_nonneg(double* addr, double v) {
     atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(fabs(v)));
 }
 
+// warp max / min of non-negative doubles compared as 64-bit patterns, with the integer warp-reduce
+// instruction (REDUX): high words first, then the low words of the lanes that hold the winning high word
 __device__ __forceinline__ double warp_max_bits(double v) {
-    unsigned long long b = (unsigned long long)__double_as_longlong(fabs(v));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        unsigned long long other = __shfl_xor_sync(0xffffffffu, b, o);
-        b = other > b ? other : b;
-    }
-    return __longlong_as_double((long long)b);
+    const unsigned hi = (unsigned)__double2hiint(fabs(v)), lo = (unsigned)__double2loint(v);
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    return __hiloint2double((int)mhi, (int)mlo);
 }
 __device__ __forceinline__ double warp_min_bits(double v) {
-    unsigned long long b = (unsigned long long)__double_as_longlong(fabs(v));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        unsigned long long other = __shfl_xor_sync(0xffffffffu, b, o);
-        b = other < b ? other : b;
-    }
-    return __longlong_as_double((long long)b);
+    const unsigned hi = (unsigned)__double2hiint(fabs(v)), lo = (unsigned)__double2loint(v);
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+    return __hiloint2double((int)mhi, (int)mlo);
 }
 
 // block-wide max of a non-negative value; result valid in thread 0
@@ -116,7 +116,7 @@ cudaError_t dd_launch_time_coefs(const DDLaunch& L, int mode, DDMember* mem, con
 // forward Euler / field evaluation / exact fill / residual
 // ---------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(DD_BLOCK) k_feuler(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
+__global__ void __launch_bounds__(DD_BLOCK, DD_MINB) k_feuler(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
                                                      DDStateC in, DDState out, int own0, int own1, int bpm) {
     const NodeIdx n = node_index(g, own0, own1, bpm);
     if (!n.valid) return;
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(DD_BLOCK) k_feuler(DDGeom g, const DDMember* _
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(DD_BLOCK) k_fields(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
+__global__ void __launch_bounds__(DD_BLOCK, DD_MINB) k_fields(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
                                                      DDStateC in, DDState out, int slot, int own0, int own1,
                                                      int bpm) {
     const NodeIdx n = node_index(g, own0, own1, bpm);
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(DD_BLOCK) k_fields(DDGeom g, const DDMember* _
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(DD_BLOCK) k_fill_exact(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
+__global__ void __launch_bounds__(DD_BLOCK, DD_MINB) k_fill_exact(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
                                                          DDState out, int own0, int own1, int bpm) {
     const NodeIdx n = node_index(g, own0, own1, bpm);
     if (!n.valid) return;
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(DD_BLOCK) k_fill_exact(DDGeom g, const DDMembe
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(DD_BLOCK) k_residual(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
+__global__ void __launch_bounds__(DD_BLOCK, DD_MINB) k_residual(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
                                                        DDStateC s, const double* __restrict__ Y,
                                                        double* __restrict__ res, int var, int own0, int own1,
                                                        int bpm) {
@@ -164,6 +164,28 @@ __global__ void __launch_bounds__(DD_BLOCK) k_residual(DDGeom g, const DDMember*
     dd_node_F<MODE>(g, mb, F, s, mo, n.r, n.j, 1, Fv);
     const long long o = mo + (long long)n.r * g.ld + n.j;
     res[o] = 2.0 * s.v[var][o] - mb.dt * Fv[var] - Y[o];
+}
+
+// sources of one time slot for every node (staged-sources path: evaluated once per step and time
+// level, consumed by the step kernels in ARRAYS mode)
+template <int MODE>
+__global__ void __launch_bounds__(DD_BLOCK) k_eval_sources(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
+                                                           DDState out, int slot, int own0, int own1, int bpm) {
+    const NodeIdx n = node_index(g, own0, own1, bpm);
+    if (!n.valid) return;
+    const DDMember& mb = mem[n.member];
+    if (!mb.active) return;
+    const int i = g.row0 + n.r;
+    const long long o = n.member * g.mstride + (long long)n.r * g.ld + n.j;
+    const bool inter = dd_is_interior(g, i, n.j);
+    DDSpatial sp;
+    dd_src_prepare<MODE>(F, i, n.j, inter, &sp);
+    const DDSrc s = dd_sources<MODE>(F, mb, sp, slot, i, n.j, o, inter, true);
+    out.v[DD_CP][o] = s.fcp;
+    out.v[DD_T][o] = s.fT;
+    out.v[DD_CL][o] = s.fcl;
+    out.v[DD_CD][o] = s.fcd;
+    out.v[DD_CS][o] = s.fcs;
 }
 
 #define DD_DISPATCH_MODE(mode, CALL)                               \
@@ -204,6 +226,20 @@ cudaError_t dd_launch_fill_exact(const DDLaunch& L, int mode, const DDGeom& g, c
     return cudaGetLastError();
 }
 
+cudaError_t dd_launch_eval_sources(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,
+                                   const DDForcing& F, const DDState& out, int slot) {
+    const int bpm = blocks_per_member(g, L);
+    if (mode == DD_FORCING_SEPARABLE)
+        k_eval_sources<DD_FORCING_SEPARABLE><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(g, mem, F, out, slot, L.own0,
+                                                                                          L.own1, bpm);
+    else if (mode == DD_FORCING_EXPSIN)
+        k_eval_sources<DD_FORCING_EXPSIN><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(g, mem, F, out, slot, L.own0,
+                                                                                       L.own1, bpm);
+    else
+        return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
 cudaError_t dd_launch_residual(const DDLaunch& L, int mode, int var, const DDGeom& g, const DDMember* mem,
                                const DDForcing& F, const DDStateC& s, const double* Y, double* res) {
     const int bpm = blocks_per_member(g, L);
@@ -216,7 +252,7 @@ cudaError_t dd_launch_residual(const DDLaunch& L, int mode, int var, const DDGeo
 // PC phase 1
 // ---------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(DD_BLOCK) k_predict(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
+__global__ void __launch_bounds__(DD_BLOCK, DD_MINB_PREDICT) k_predict(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
                                                       DDStateC in, DDPredictOut out, int own0, int own1, int bpm) {
     const NodeIdx n = node_index(g, own0, own1, bpm);
     if (!n.valid) return;
@@ -247,7 +283,7 @@ __global__ void k_reset_stats(DDSolveStats* stats, int nmem) {
 }
 
 template <int MODE, int VAR>
-__global__ void __launch_bounds__(DD_BLOCK) k_assemble(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
+__global__ void __launch_bounds__(DD_BLOCK, DD_MINB_ASM) k_assemble(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
                                                        DDStateC u, const double* __restrict__ T1,
                                                        const double* __restrict__ cl1, const double* __restrict__ Y,
                                                        int cd_swap, DDRows R, DDSolveStats* stats, int own0,
@@ -258,13 +294,13 @@ __global__ void __launch_bounds__(DD_BLOCK) k_assemble(DDGeom g, const DDMember*
     if (!mb.active) return;  // whole block belongs to one member
     double rho = 0.0;
     if (n.valid) {
-        const long long mo = n.member * g.mstride;
+        const long long mo = n.member * g.mstride, moR = n.member * R.mstride;
         if (VAR == DD_T)
-            rho = dd_node_asm_T_const<MODE>(g, mb, F, u, Y, R.bb, R.aW, mo, n.r, n.j);  // aW holds dinv
+            rho = dd_node_asm_T_const<MODE>(g, mb, F, u, Y, R, mo, moR, n.r, n.j);
         else if (VAR == DD_CL)
-            rho = dd_node_asm_cl<MODE>(g, mb, F, u, T1, Y, R, mo, n.r, n.j);
+            rho = dd_node_asm_cl<MODE>(g, mb, F, u, T1, Y, R, mo, moR, n.r, n.j);
         else
-            rho = dd_node_asm_cd<MODE>(g, mb, F, u, T1, cl1, Y, cd_swap, R, mo, n.r, n.j);
+            rho = dd_node_asm_cd<MODE>(g, mb, F, u, T1, cl1, Y, cd_swap, R, mo, moR, n.r, n.j);
     }
     rho = block_max_nonneg(rho, sh);
     if (threadIdx.x == 0) atomic_max_nonneg(&stats[n.member].rho, rho);
@@ -401,7 +437,7 @@ __global__ void k_cs_decide(const DDMember* __restrict__ mem, int nmem, int cap,
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(DD_BLOCK) k_cs_redo(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
+__global__ void __launch_bounds__(DD_BLOCK, DD_MINB) k_cs_redo(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
                                                       DDStateC s0, const double* __restrict__ cl1,
                                                       const double* __restrict__ cd1, double* __restrict__ cs_out,
                                                       int cap, const int* __restrict__ used, int own0, int own1,
@@ -439,7 +475,7 @@ cudaError_t dd_launch_cs_finish(const DDLaunch& L, int mode, const DDGeom& g, co
 // two-stage deterministic reduction: per-block partials, then one block per member
 // ---------------------------------------------------------------------------
 template <int MODE, bool FROM_ARRAY>
-__global__ void __launch_bounds__(DD_BLOCK) k_error_partial(DDGeom g, const DDMember* __restrict__ mem,
+__global__ void __launch_bounds__(DD_BLOCK, DD_MINB) k_error_partial(DDGeom g, const DDMember* __restrict__ mem,
                                                             DDForcing F, DDStateC s, DDStateC ex,
                                                             double* __restrict__ partial, int own0, int own1,
                                                             int bpm) {
@@ -541,5 +577,20 @@ cudaError_t dd_launch_error_norms(const DDLaunch& L, int mode, const DDGeom& g, 
         return cudaErrorInvalidValue;
     }
     k_error_final<<<L.nmembers, 256, 0, L.stream>>>(partial, bpm, out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// accuracy probe for the inline device math (tests only evaluate it; no product path uses it)
+// ---------------------------------------------------------------------------
+__global__ void k_probe_math(const double* in, double* out_exp, double* out_rcp, int n) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    out_exp[k] = dd_exp(in[k]);
+    out_rcp[k] = dd_rcp(in[k]);
+}
+
+cudaError_t dd_launch_probe_math(cudaStream_t st, const double* in, double* out_exp, double* out_rcp, int n) {
+    k_probe_math<<<(n + 255) / 256, 256, 0, st>>>(in, out_exp, out_rcp, n);
     return cudaGetLastError();
 }

@@ -38,6 +38,7 @@ struct DDSolvePlan {
     int threads;
     int last_pass;   // compute residual stats and write v_new
     int const_band;  // T system: rows are (bb, dinv) + grid geometry instead of five stored bands
+    int rpw;         // > 0: register-resident kernel with this many rows per warp (staged 16*rpw x 64)
     size_t smem_bytes;
 };
 
@@ -75,3 +76,9 @@ cudaError_t dd_launch_residual(const DDLaunch& L, int mode, int var, const DDGeo
                                const DDForcing& F, const DDStateC& s, const double* Y, double* res);
 
 int dd_norm_blocks_per_member(const DDGeom& g);
+
+// all five MMS sources of time slot `slot` on the launch's rows -> out (fcp, fT, fcl, fcd, fcs)
+cudaError_t dd_launch_eval_sources(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,
+                                   const DDForcing& F, const DDState& out, int slot);
+
+cudaError_t dd_launch_probe_math(cudaStream_t st, const double* in, double* out_exp, double* out_rcp, int n);

@@ -10,6 +10,8 @@
 
 struct DDRows {
     double *bb, *aW, *aE, *aS, *aN;  // Jacobi-scaled five-point rows (see dd_physics.cuh)
+    int ld;                          // row pitch of these arrays: even, so that the solver can fetch the two
+    long long mstride;               // colours of a packed column with one aligned 16-byte load
 };
 
 DD_HD bool dd_is_interior(const DDGeom& g, int i, int j) { return i > 0 && i < g.N && j > 0 && j < g.M; }
@@ -126,9 +128,10 @@ DD_HD double dd_row_rho(const DDRow& r) { return fabs(r.aW) + fabs(r.aE) + fabs(
 
 template <int MODE>
 DD_HD double dd_node_asm_T(const DDGeom& g, const DDMember& mb, const DDForcing& F, const DDStateC& u,
-                           const double* YT, const DDRows& R, long long mo, int r, int j) {
+                           const double* YT, const DDRows& R, long long mo, long long moR, int r, int j) {
     const int i = g.row0 + r;
     const long long o = mo + (long long)r * g.ld + j;
+    const long long oR = moR + (long long)r * R.ld + j;
     DDRow row = {0.0, 0.0, 0.0, 0.0, 0.0};
     if (dd_is_interior(g, i, j)) {
         DDSpatial sp;
@@ -138,7 +141,7 @@ DD_HD double dd_node_asm_T(const DDGeom& g, const DDMember& mb, const DDForcing&
         const DDSten T = dd_load_sten(u.v[DD_T], o, g.ld);
         row = dd_row_T(mb.m, q, mb.dt, T, u.v[DD_CP][o], YT[o], s1.fT, i, j, g.N, g.M);
     }
-    dd_store_row(R, o, row);
+    dd_store_row(R, oR, row);
     return dd_row_rho(row);
 }
 
@@ -148,9 +151,10 @@ DD_HD double dd_node_asm_T(const DDGeom& g, const DDMember& mb, const DDForcing&
 // x is identically 0 on boundary nodes (bb = dinv = 0 there).
 template <int MODE>
 DD_HD double dd_node_asm_T_const(const DDGeom& g, const DDMember& mb, const DDForcing& F, const DDStateC& u,
-                                 const double* YT, double* bb, double* dinv, long long mo, int r, int j) {
+                                 const double* YT, const DDRows& R, long long mo, long long moR, int r, int j) {
     const int i = g.row0 + r;
     const long long o = mo + (long long)r * g.ld + j;
+    const long long oR = moR + (long long)r * R.ld + j;
     double vb = 0.0, vd = 0.0, rho = 0.0;
     if (dd_is_interior(g, i, j)) {
         DDSpatial sp;
@@ -163,20 +167,22 @@ DD_HD double dd_node_asm_T_const(const DDGeom& g, const DDMember& mb, const DDFo
         const double sumc = m.DT * (q.cW + q.cE + q.cS + q.cN);
         const double d = 2.0 + dt * (sumc + m.K3 * cps);
         const double G0 = 2.0 * T.c - dt * (s1.fT + dd_FT_int(m, q, T, cps));
-        vd = 1.0 / d;
+        vd = dd_rcp(d);
         vb = (YT[o] - G0) * vd;
         rho = dt * sumc * vd;
     }
-    bb[o] = vb;
-    dinv[o] = vd;
+    R.bb[oR] = vb;
+    R.aW[oR] = vd;  // aW holds dinv in the constant-band form
     return rho;
 }
 
 template <int MODE>
 DD_HD double dd_node_asm_cl(const DDGeom& g, const DDMember& mb, const DDForcing& F, const DDStateC& u,
-                            const double* T1, const double* Ycl, const DDRows& R, long long mo, int r, int j) {
+                            const double* T1, const double* Ycl, const DDRows& R, long long mo, long long moR, int r,
+                            int j) {
     const int i = g.row0 + r;
     const long long o = mo + (long long)r * g.ld + j;
+    const long long oR = moR + (long long)r * R.ld + j;
     DDRow row = {0.0, 0.0, 0.0, 0.0, 0.0};
     if (dd_is_interior(g, i, j)) {
         DDSpatial sp;
@@ -189,16 +195,17 @@ DD_HD double dd_node_asm_cl(const DDGeom& g, const DDMember& mb, const DDForcing
         const double wW = T1[o - g.ld] - T.w, wE = T1[o + g.ld] - T.e;
         row = dd_row_cl(mb.m, q, mb.dt, cp, T, cl, wW, wE, Ycl[o], s1.fcl, i, j, g.N, g.M);
     }
-    dd_store_row(R, o, row);
+    dd_store_row(R, oR, row);
     return dd_row_rho(row);
 }
 
 template <int MODE>
 DD_HD double dd_node_asm_cd(const DDGeom& g, const DDMember& mb, const DDForcing& F, const DDStateC& u,
                             const double* T1, const double* cl1, const double* Ycd, int swap, const DDRows& R,
-                            long long mo, int r, int j) {
+                            long long mo, long long moR, int r, int j) {
     const int i = g.row0 + r;
     const long long o = mo + (long long)r * g.ld + j;
+    const long long oR = moR + (long long)r * R.ld + j;
     DDRow row = {0.0, 0.0, 0.0, 0.0, 0.0};
     if (dd_is_interior(g, i, j)) {
         DDSpatial sp;
@@ -215,7 +222,7 @@ DD_HD double dd_node_asm_cd(const DDGeom& g, const DDMember& mb, const DDForcing
         row = dd_row_cd(mb.m, q, mb.dt, cp, T, clc, cd, u.v[DD_CS][o], w, cl1[o] - clc, Ycd[o], s1.fcd, swap, i, j,
                         g.N, g.M);
     }
-    dd_store_row(R, o, row);
+    dd_store_row(R, oR, row);
     return dd_row_rho(row);
 }
 

@@ -14,17 +14,61 @@
 #define DD_PI 3.14159265358979323846
 
 // ---------------------------------------------------------------------------
+// exp / reciprocal with a short instruction sequence on the device.  The stencil kernels are
+// instruction-issue bound (profiles/): the library exp() carries full-range special-case code, so the
+// common range |x| < 700 is handled inline (Cody-Waite reduction with the fdlibm ln2 split, degree-13
+// Taylor polynomial on |r| <= ln2/2: truncation 4e-18, total error < 2 ulp) and everything else
+// (overflow, underflow, NaN) still goes to exp().  1/x uses the IEEE-rounded reciprocal instruction
+// sequence.  Host builds (tests/hostsim) use libm.
+// ---------------------------------------------------------------------------
+DD_HD double dd_exp(double x) {
+#ifdef __CUDA_ARCH__
+    if (!(fabs(x) < 700.0)) return exp(x);
+    const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);  // round(x / ln2) in the low word
+    const int k = __double2loint(t);
+    const double kf = t - 6755399441055744.0;
+    double r = fma(-kf, 6.93147180369123816490e-01, x);
+    r = fma(-kf, 1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;           // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);         // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);        // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);        // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);       // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);         // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);        // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);        // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);        // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);       // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);       // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));  // p * 2^k, result is normal
+#else
+    return exp(x);
+#endif
+}
+
+DD_HD double dd_rcp(double x) {
+#ifdef __CUDA_ARCH__
+    return __drcp_rn(x);
+#else
+    return 1.0 / x;
+#endif
+}
+
+// ---------------------------------------------------------------------------
 // model coefficient functions (reference src/prob1base.py:96-217, 3452-3466)
 // ---------------------------------------------------------------------------
 
-DD_HD double dd_Dl(const DDModel& m, double cp) { return m.Dl_max * exp(-m.phi_l * cp); }
+DD_HD double dd_Dl(const DDModel& m, double cp) { return m.Dl_max * dd_exp(-m.phi_l * cp); }
 
 // Dd(cp, T) = Dd_max e^{-phi_d cp} e^{-phi_T/(T+T_shift)}, 0 where T+T_shift == 0
 DD_HD double dd_Dd(const DDModel& m, double cp, double T) {
     const double Te = T + m.T_shift;
     if (Te == 0.0) return 0.0;
     // one exponential: e^{-phi_d cp} e^{-phi_T/Te} = e^{-(phi_d cp + phi_T/Te)} (differs from the product by rounding only)
-    return m.Dd_max * exp(-(m.phi_d * cp + m.phi_T / Te));
+    return m.Dd_max * dd_exp(-(m.phi_d * cp + m.phi_T * dd_rcp(Te)));
 }
 
 // returns Dd and writes dDd/dT = Dd * phi_T / Te^2
@@ -34,13 +78,13 @@ DD_HD double dd_Dd_dT(const DDModel& m, double cp, double T, double* dT) {
         *dT = 0.0;
         return 0.0;
     }
-    const double iT = 1.0 / Te;
-    const double d = m.Dd_max * exp(-(m.phi_d * cp + m.phi_T * iT));
+    const double iT = dd_rcp(Te);
+    const double d = m.Dd_max * dd_exp(-(m.phi_d * cp + m.phi_T * iT));
     *dT = d * (m.phi_T * iT * iT);
     return d;
 }
 
-DD_HD double dd_H(double x, double eta) { return 1.0 / (1.0 + exp(-eta * x)); }
+DD_HD double dd_H(double x, double eta) { return dd_rcp(1.0 + dd_exp(-eta * x)); }
 
 // ---------------------------------------------------------------------------
 // stencil helpers
@@ -442,7 +486,7 @@ DD_HD DDRow dd_make_row(double d, double oW, double oE, double oS, double oN, do
                         int M) {
     // d: diagonal of A;  oX: -A(i,j; neighbour) (so that x_c = (rhs + sum oX x_X)/d)
     DDRow r;
-    const double inv = 1.0 / d;
+    const double inv = dd_rcp(d);
     r.bb = rhs * inv;
     r.aW = (i > 1) ? oW * inv : 0.0;
     r.aE = (i < N - 1) ? oE * inv : 0.0;
@@ -527,7 +571,7 @@ DD_HD double dd_correct_cp(const DDModel& m, double dt, double cp0, double T0, d
     const double a0 = -m.K2 * T0 - m.K1 * (cl0 + 1.0);
     const double a1 = -m.K2 * T1 - m.K1 * (cl1 + 1.0);
     const double num = (1.0 + (dt / 2.0) * a0) * cp0 + (dt / 2.0) * (fcp0 + fcp1);
-    return num / (1.0 - (dt / 2.0) * a1);
+    return num * dd_rcp(1.0 - (dt / 2.0) * a1);
 }
 
 // implicit cs corrector (reference corrector_cs_step 3665-3702): y, a of
@@ -540,8 +584,8 @@ DD_HD void dd_cs_ya(const DDModel& m, double dt, double cs0, double cl0, double 
 
 // one Newton update (reference _newton_iterations 3654-3663); returns dx
 DD_HD double dd_cs_newton_dx(double x, double y, double a, double eta) {
-    const double ex = exp(-eta * x);
+    const double ex = dd_exp(-eta * x);
     const double f = 2.0 * x + (2.0 * x - y) * ex - y + a;
     const double J = 2.0 + 2.0 * ex - eta * (2.0 * x - y) * ex;
-    return -f / J;
+    return -f * dd_rcp(J);
 }

@@ -40,6 +40,17 @@ __device__ __forceinline__ double warp_max_nn(double v) {
     return __longlong_as_double((long long)b);
 }
 
+// shared-memory access by 32-bit shared-window address: the sweep loop is integer-issue bound when the
+// compiler rebuilds generic 64-bit addresses per array and per row (profiles/README.md, r01 solver capture)
+__device__ __forceinline__ double lds64(unsigned a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts64(unsigned a, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+
 struct SolveArgs {
     DDGeom g;
     const DDMember* mem;
@@ -50,12 +61,30 @@ struct SolveArgs {
     double* vnew;
     DDSolveStats* stats;
     int zero_boundary;
+    int ldR;            // row pitch of bb / a* / xin / xout (even)
+    long long mstrideR; // their member stride
     int own0, own1;  // local rows that are tiled (owned rows of a slab; all rows otherwise)
     int vr0, vr1;    // local rows holding valid assembled rows
     int sweeps, halo, tile_i, tile_j, tiles_i, tiles_j, last_pass;
 };
 
 extern __shared__ double dd_smem[];
+
+#ifdef DD_SOLVER_TIMING
+// development instrumentation: cycles per phase summed over CTAs (staging, sweeps, epilogue, count)
+__device__ unsigned long long dd_solver_cycles[4];
+#define DD_TICK(k)                                                                   \
+    do {                                                                             \
+        __syncthreads();                                                             \
+        if (threadIdx.x == 0) {                                                      \
+            const long long now_ = clock64();                                        \
+            atomicAdd(&dd_solver_cycles[k], (unsigned long long)(now_ - tick_));     \
+            tick_ = now_;                                                            \
+        }                                                                            \
+    } while (0)
+#else
+#define DD_TICK(k)
+#endif
 
 // Shared-memory layout: every staged array is split by colour and packed along j, so that a half-sweep
 // touches unit-stride words only (no bank conflicts): cell (si, sj) of colour c = (par0 + si + sj) & 1
@@ -91,6 +120,9 @@ __global__ void __launch_bounds__(512) k_rbsor_tile(SolveArgs A) {
     double* colN = colS + SJ;
     const long long mo = member * g.mstride;
     const int nthreads = blockDim.x;
+#ifdef DD_SOLVER_TIMING
+    long long tick_ = clock64();
+#endif
 
     // extent of real data inside the staged region (smem coordinates, half-open)
     const int vi0 = max(1, A.vr0 - rbase), vi1 = min(SI - 1, A.vr1 - rbase);
@@ -104,10 +136,11 @@ __global__ void __launch_bounds__(512) k_rbsor_tile(SolveArgs A) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = nthreads >> 5;
     for (int si = warp; si < SI; si += nwarps) {
         const bool rowin = si >= li0 && si < li1;
-        const long long orow = mo + (long long)(rbase + si) * g.ld + cbase;
+        const long long moR = member * A.mstrideR;
+        const long long orow = moR + (long long)(rbase + si) * A.ldR + cbase;
         for (int sj = lane; sj < SJ; sj += 32) {
             const bool in = rowin && sj >= lj0 && sj < lj1;
-            const long long o = in ? orow + sj : mo;  // any valid address when nothing is read
+            const long long o = in ? orow + sj : moR;  // any valid address when nothing is read
             const size_t zf = in ? 0 : 8;
             const int col = (par0 + si + sj) & 1, q = col * plane + si * PW + (sj >> 1);
             __pipeline_memcpy_async(&Bb.base[q], &A.bb[o], 8, zf);
@@ -142,6 +175,7 @@ __global__ void __launch_bounds__(512) k_rbsor_tile(SolveArgs A) {
     }
     const double rho = A.stats[member].rho;
     __pipeline_wait_prior(0);
+    DD_TICK(0);
     // omega_opt of SOR for a consistently ordered matrix whose Jacobi spectral radius is <= rho
     double omega = 1.0;
     if (rho < 1.0) omega = 2.0 / (1.0 + sqrt(1.0 - rho * rho));
@@ -155,41 +189,60 @@ __global__ void __launch_bounds__(512) k_rbsor_tile(SolveArgs A) {
     const bool shrink_lo = !(g.row0 + rbase + li0 == 0), shrink_hi = !(g.row0 + rbase + li1 == g.N + 1);
     for (int hs = 1; hs <= 2 * A.sweeps; ++hs) {
         const int colour = (hs - 1) & 1;
-        const double* xo = X.c(1 - colour);
-        double* xc = X.c(colour);
-        const double *bc = Bb.c(colour), *wc = AW.c(colour), *ec = AE.c(colour), *sc = AS.c(colour),
-                     *nc = AN.c(colour);
+        // element offsets inside dd_smem: arrays are 2 * plane doubles apart, colours plane doubles apart
+        const int o_xc = colour * plane, o_xo = (1 - colour) * plane;
+        const int o_bb = o_xc + 2 * plane, o_w = o_xc + 4 * plane, o_e = o_xc + 6 * plane, o_s = o_xc + 8 * plane,
+                  o_n = o_xc + 10 * plane;
         const int ui0 = shrink_lo ? min(li0 + hs, H + 1) : li0;
         const int ui1 = shrink_hi ? max(li1 - hs, H + 1 + tr) : li1;
-        // one warp per row, lanes along the packed columns: unit-stride shared-memory accesses, no divisions.
-        // Packed slots holding the zero ring columns (sj = 0, SJ-1) are skipped by the column guard.
-        for (int si = ui0 + warp; si < ui1; si += nwarps) {
-            const int o = (colour + par0 + si) & 1;  // sj = 2 pk + o
-            const int rowp = si * PW;
-            double rw = 0.0, re = 0.0;
-            if (CONST_BAND) {
-                rw = rowW[si];
-                re = rowE[si];
-            }
+        // One warp per row, lanes along the packed columns (unit-stride shared-memory accesses).  The sweep is
+        // latency bound (one dependent load -> 4 FMA -> store chain per cell), so every warp works on RU rows at
+        // once: all loads first, then the arithmetic, then the stores.  Reads touch only the other colour, writes
+        // only this one, so the batched order is exact.  Zero-ring columns (sj = 0, SJ-1) are skipped.
+        constexpr int RU = 4;
+        for (int sib = ui0 + warp; sib < ui1; sib += RU * nwarps) {
             for (int pk = lane; pk < PW; pk += 32) {
-                const int sj = 2 * pk + o;
-                if (sj >= 1 && sj <= SJ - 2) {
-                    const int p = rowp + pk;
+                double xw[RU], xe[RU], xs[RU], xn[RU], bv[RU], wv[RU], ev[RU], sv[RU], nv[RU], xv[RU];
+                bool on[RU];
+#pragma unroll
+                for (int u = 0; u < RU; ++u) {
+                    const int si = sib + u * nwarps;
+                    const int o = (colour + par0 + si) & 1, sj = 2 * pk + o;
+                    on[u] = si < ui1 && sj >= 1 && sj <= SJ - 2;
+                    const int c = on[u] ? si * PW + pk : PW + 1;  // any in-range cell when masked off
+                    xw[u] = dd_smem[o_xo + c - PW];
+                    xe[u] = dd_smem[o_xo + c + PW];
+                    xs[u] = dd_smem[o_xo + c + o - 1];
+                    xn[u] = dd_smem[o_xo + c + o];
+                    bv[u] = dd_smem[o_bb + c];
+                    wv[u] = dd_smem[o_w + c];
+                    xv[u] = dd_smem[o_xc + c];
+                    if (!CONST_BAND) {
+                        ev[u] = dd_smem[o_e + c];
+                        sv[u] = dd_smem[o_s + c];
+                        nv[u] = dd_smem[o_n + c];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < RU; ++u) {
+                    const int si = sib + u * nwarps;
                     double gs;
-                    if (CONST_BAND)
-                        gs = bc[p] + wc[p] * (rw * xo[p - PW] + re * xo[p + PW] + colS[sj] * xo[p - 1 + o] +
-                                              colN[sj] * xo[p + o]);
-                    else
-                        gs = bc[p] + wc[p] * xo[p - PW] + ec[p] * xo[p + PW] + sc[p] * xo[p - 1 + o] +
-                             nc[p] * xo[p + o];
-                    const double xv = xc[p];
-                    xc[p] = xv + omega * (gs - xv);
+                    if (CONST_BAND) {
+                        const int sj = 2 * pk + ((colour + par0 + si) & 1);
+                        const int sic = on[u] ? si : 0, sjc = on[u] ? sj : 0;
+                        gs = bv[u] + wv[u] * (rowW[sic] * xw[u] + rowE[sic] * xe[u] + colS[sjc] * xs[u] +
+                                              colN[sjc] * xn[u]);
+                    } else {
+                        gs = bv[u] + wv[u] * xw[u] + ev[u] * xe[u] + sv[u] * xs[u] + nv[u] * xn[u];
+                    }
+                    if (on[u]) dd_smem[o_xc + si * PW + pk] = xv[u] + omega * (gs - xv[u]);
                 }
             }
         }
         __syncthreads();
     }
 
+    DD_TICK(1);
     // epilogue on the tile itself (smem coordinates H+1 .. H+1+tr); v* is fetched four cells ahead so that
     // the loads of a batch are in flight together
     double rmax = 0.0, xmax = 0.0, vmax = 0.0, bmax = 0.0;
@@ -236,7 +289,7 @@ __global__ void __launch_bounds__(512) k_rbsor_tile(SolveArgs A) {
                 vmax = nn_max(vmax, vn);
                 bmax = nn_max(bmax, bbv);
             } else {
-                A.xout[ogs[u]] = x;
+                A.xout[member * A.mstrideR + (long long)r * A.ldR + j] = x;
             }
         }
     }
@@ -252,12 +305,272 @@ __global__ void __launch_bounds__(512) k_rbsor_tile(SolveArgs A) {
             atomic_max_nn(&A.stats[member].bmax, bmax);
         }
     }
+    DD_TICK(2);
+#ifdef DD_SOLVER_TIMING
+    if (threadIdx.x == 0) atomicAdd(&dd_solver_cycles[3], 1ull);
+#endif
 }
+
+
+// ---------------------------------------------------------------------------
+// Register-resident variant.  The shared-memory kernel above is bound by shared-memory bandwidth (11 words
+// per cell update).  Here every thread owns fixed cells for the whole pass -- rows {warp + 16 k}, packed
+// column = lane, both colours -- and keeps their coefficients in registers, loaded straight from global
+// memory; only x lives in shared memory (5 words per update).  Staged region: 16 * RPW rows x 64 columns.
+// Same exactness argument as above (invalid data moves one cell per half-sweep).
+// ---------------------------------------------------------------------------
+#define DD_REG_WARPS 16
+#define DD_REG_SJ 64
+#define DD_REG_PW 32
+
+template <int CONST_BAND, int RPW>
+__global__ void __launch_bounds__(DD_REG_WARPS * 32, 1) k_rbsor_reg(SolveArgs A) {
+    const DDGeom& g = A.g;
+    const int tiles = A.tiles_i * A.tiles_j;
+    const int member = blockIdx.x / tiles;
+    const int t = blockIdx.x - member * tiles;
+    const int ti = t / A.tiles_j, tj = t - ti * A.tiles_j;
+    const int H = A.halo;
+    const int r0 = A.own0 + ti * A.tile_i, c0 = tj * A.tile_j;
+    const int tr = min(A.tile_i, A.own1 - r0), tc = min(A.tile_j, g.M + 1 - c0);
+    constexpr int SI = DD_REG_WARPS * RPW, SJ = DD_REG_SJ, PW = DD_REG_PW, plane = SI * PW;
+    const int rbase = r0 - H - 1, cbase = c0 - H - 1;
+    const int par0 = (g.row0 + rbase + cbase) & 1;
+    const long long mo = member * g.mstride;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* sx = dd_smem;  // [colour][si][pk]
+#ifdef DD_SOLVER_TIMING
+    long long tick_ = clock64();
+#endif
+    // real data inside the staged region (smem coordinates, half-open)
+    const int li0 = max(1, A.vr0 - rbase), li1 = min(min(SI - 1, A.vr1 - rbase), tr + 2 * H + 1);
+    const int lj0 = max(1, -cbase), lj1 = min(min(SJ - 1, g.M + 1 - cbase), tc + 2 * H + 1);
+
+    // ---- load: coefficients of the thread's own cells into registers, x into shared memory -----------
+    // The two cells of a packed column are adjacent in memory and the row arrays have an even pitch, so one
+    // aligned 16-byte load fetches both colours (cbase is even: tile_j even, H odd).
+    double cb[RPW][2], cw[RPW][2], ce[RPW][2], cs[RPW][2], cn[RPW][2];
+    const long long moR = member * A.mstrideR;
+    const int flip = (par0 + warp) & 1;  // colour of the even column of the pair (rows of a thread share parity)
+    const int colj = cbase + 2 * lane;   // global column of the even cell
+    const bool pair_ok = colj >= 0 && colj + 1 < A.ldR;
+#pragma unroll
+    for (int k = 0; k < RPW; ++k) {
+        const int si = warp + DD_REG_WARPS * k;
+        const int row = rbase + si;
+        const bool rowok = pair_ok && si >= li0 && si < li1;
+        const long long o = moR + (long long)row * A.ldR + colj;
+        const int sj0 = 2 * lane;
+        const bool ok0 = rowok && sj0 >= lj0 && sj0 < lj1, ok1 = rowok && sj0 + 1 >= lj0 && sj0 + 1 < lj1;
+        double2 vb = make_double2(0.0, 0.0), vw = vb, ve = vb, vs2 = vb, vn = vb, vx = vb;
+        if (rowok) {
+            vb = *reinterpret_cast<const double2*>(A.bb + o);
+            vw = *reinterpret_cast<const double2*>(A.aW + o);
+            if (!CONST_BAND) {
+                ve = *reinterpret_cast<const double2*>(A.aE + o);
+                vs2 = *reinterpret_cast<const double2*>(A.aS + o);
+                vn = *reinterpret_cast<const double2*>(A.aN + o);
+            }
+            if (A.xin) vx = *reinterpret_cast<const double2*>(A.xin + o);
+        }
+        // element .x is column sj0 (colour `flip`), .y is column sj0 + 1 (colour 1 - flip)
+        const double b0 = ok0 ? vb.x : 0.0, b1 = ok1 ? vb.y : 0.0, w0 = ok0 ? vw.x : 0.0, w1 = ok1 ? vw.y : 0.0;
+        cb[k][0] = flip ? b1 : b0;  cb[k][1] = flip ? b0 : b1;
+        cw[k][0] = flip ? w1 : w0;  cw[k][1] = flip ? w0 : w1;
+        if (!CONST_BAND) {
+            const double e0 = ok0 ? ve.x : 0.0, e1 = ok1 ? ve.y : 0.0, s0 = ok0 ? vs2.x : 0.0, s1 = ok1 ? vs2.y : 0.0;
+            const double n0 = ok0 ? vn.x : 0.0, n1 = ok1 ? vn.y : 0.0;
+            ce[k][0] = flip ? e1 : e0;  ce[k][1] = flip ? e0 : e1;
+            cs[k][0] = flip ? s1 : s0;  cs[k][1] = flip ? s0 : s1;
+            cn[k][0] = flip ? n1 : n0;  cn[k][1] = flip ? n0 : n1;
+        }
+        const double x0 = ok0 ? vx.x : 0.0, x1 = ok1 ? vx.y : 0.0;
+        sx[(flip ? 1 : 0) * plane + si * PW + lane] = x0;
+        sx[(flip ? 0 : 1) * plane + si * PW + lane] = x1;
+    }
+    // constant-band geometry factors of the thread's rows and of its two columns
+    double rW[RPW], rE[RPW], cS2[2], cN2[2];
+    if (CONST_BAND) {
+        const DDMember& mb = A.mem[member];
+        const double f = mb.dt * mb.m.DT;
+#pragma unroll
+        for (int k = 0; k < RPW; ++k) {
+            const int i = g.row0 + rbase + warp + DD_REG_WARPS * k;
+            const bool ok = i >= 1 && i <= g.N - 1;
+            rW[k] = ok ? f * g.rhp[i] * g.rh[i] : 0.0;
+            rE[k] = ok ? f * g.rhp[i] * g.rh[i + 1] : 0.0;
+        }
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+            const int j = cbase + 2 * lane + o;
+            const bool ok = j >= 1 && j <= g.M - 1;
+            cS2[o] = ok ? f * g.rkp[j] * g.rk[j] : 0.0;
+            cN2[o] = ok ? f * g.rkp[j] * g.rk[j + 1] : 0.0;
+        }
+    }
+    const double rho = A.stats[member].rho;
+    double omega = 1.0;
+    if (rho < 1.0) omega = 2.0 / (1.0 + sqrt(1.0 - rho * rho));
+    DD_TICK(0);
+    __syncthreads();
+
+    // ---- sweeps ---------------------------------------------------------------------------------------
+    for (int sw = 0; sw < A.sweeps; ++sw) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {  // colour is a compile-time index into the register arrays
+        const double* xo = sx + (1 - c) * plane;
+        double* xc = sx + c * plane;
+        double xnew[RPW];
+#pragma unroll
+        for (int k = 0; k < RPW; ++k) {
+            const int si = warp + DD_REG_WARPS * k;
+            const int o = (c + par0 + si) & 1;
+            const int p = si * PW + lane;
+            // rows 0 / SI-1 and columns 0 / SJ-1 form the zero ring: their cells carry zero coefficients and
+            // stay 0; neighbours outside the array are never dereferenced
+            const bool edge = si == 0 || si == SI - 1 || (lane == 0 && o == 0) || (lane == PW - 1 && o == 1);
+            double xw = 0.0, xe = 0.0, xs = 0.0, xn = 0.0;
+            if (!edge) {
+                xw = xo[p - PW];
+                xe = xo[p + PW];
+                xs = xo[p + o - 1];
+                xn = xo[p + o];
+            }
+            const double xv = xc[p];
+            double gs;
+            if (CONST_BAND)
+                gs = cb[k][c] + cw[k][c] * (rW[k] * xw + rE[k] * xe + (o ? cS2[1] : cS2[0]) * xs +
+                                            (o ? cN2[1] : cN2[0]) * xn);
+            else
+                gs = cb[k][c] + cw[k][c] * xw + ce[k][c] * xe + cs[k][c] * xs + cn[k][c] * xn;
+            xnew[k] = xv + omega * (gs - xv);
+        }
+#pragma unroll
+        for (int k = 0; k < RPW; ++k) xc[(warp + DD_REG_WARPS * k) * PW + lane] = xnew[k];
+        __syncthreads();
+      }
+    }
+    DD_TICK(1);
+
+    // ---- epilogue ------------------------------------------------------------------------------------------
+    // (1) owner threads: residual statistics of their cells inside the tile (coefficients are in registers);
+    //     non-final passes store x with one aligned 16-byte store per pair
+    double rmax = 0.0, xmax = 0.0, vmax = 0.0, bmax = 0.0;
+#pragma unroll
+    for (int k = 0; k < RPW; ++k) {
+        const int si = warp + DD_REG_WARPS * k;
+        const bool rowin = si >= H + 1 && si < H + 1 + tr;
+        if (A.last_pass) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int o = (c + par0 + si) & 1, sj = 2 * lane + o;
+                if (!(rowin && sj >= H + 1 && sj < H + 1 + tc)) continue;
+                const int p = si * PW + lane;
+                const double* xo = sx + (1 - c) * plane;
+                const double x = sx[c * plane + p];
+                const double xw = xo[p - PW], xe = xo[p + PW], xs = xo[p + o - 1], xn = xo[p + o];
+                double res;
+                if (CONST_BAND)
+                    res = cb[k][c] + cw[k][c] * (rW[k] * xw + rE[k] * xe + (o ? cS2[1] : cS2[0]) * xs +
+                                                 (o ? cN2[1] : cN2[0]) * xn) - x;
+                else
+                    res = cb[k][c] + cw[k][c] * xw + ce[k][c] * xe + cs[k][c] * xs + cn[k][c] * xn - x;
+                rmax = nn_max(rmax, res);
+                xmax = nn_max(xmax, x);
+                bmax = nn_max(bmax, cb[k][c]);
+            }
+        } else if (rowin && pair_ok) {
+            const int sj0 = 2 * lane;
+            const bool m0 = sj0 >= H + 1 && sj0 < H + 1 + tc, m1 = sj0 + 1 >= H + 1 && sj0 + 1 < H + 1 + tc;
+            const long long o = moR + (long long)(rbase + si) * A.ldR + colj;
+            const double x0 = sx[(flip ? 1 : 0) * plane + si * PW + lane];
+            const double x1 = sx[(flip ? 0 : 1) * plane + si * PW + lane];
+            if (m0 && m1)
+                *reinterpret_cast<double2*>(A.xout + o) = make_double2(x0, x1);
+            else if (m0)
+                A.xout[o] = x0;
+            else if (m1)
+                A.xout[o + 1] = x1;
+        }
+    }
+    // (2) all threads, lanes along consecutive columns: v_new = v* + x with coalesced loads and stores
+    if (A.last_pass) {
+        const int ncell = tr * tc;
+        for (int base = threadIdx.x; base < ncell; base += 4 * DD_REG_WARPS * 32) {
+            double vsv[4];
+            long long ogv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * DD_REG_WARPS * 32;
+                vsv[u] = 0.0;
+                ogv[u] = 0;
+                if (idx < ncell) {
+                    const int a = idx / tc, bcol = idx - a * tc;
+                    ogv[u] = mo + (long long)(r0 + a) * g.ld + (c0 + bcol);
+                    vsv[u] = A.vstar[ogv[u]];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * DD_REG_WARPS * 32;
+                if (idx >= ncell) continue;
+                const int a = idx / tc, bcol = idx - a * tc;
+                const int si = H + 1 + a, sj = H + 1 + bcol;
+                const double x = sx[((par0 + si + sj) & 1) * plane + si * PW + (sj >> 1)];
+                const bool inter = dd_is_interior(g, g.row0 + r0 + a, c0 + bcol);
+                const double vn = dd_newton_update(inter, vsv[u], x, A.zero_boundary);
+                A.vnew[ogv[u]] = vn;
+                vmax = nn_max(vmax, vn);
+            }
+        }
+    }
+    if (A.last_pass) {
+        // one atomic per quantity and CTA (the four addresses are shared by every CTA of the member)
+        rmax = warp_max_nn(rmax);
+        xmax = warp_max_nn(xmax);
+        vmax = warp_max_nn(vmax);
+        bmax = warp_max_nn(bmax);
+        __syncthreads();  // x planes are dead from here on: reuse the first words as scratch
+        if (lane == 0) {
+            sx[warp * 4 + 0] = rmax;
+            sx[warp * 4 + 1] = xmax;
+            sx[warp * 4 + 2] = vmax;
+            sx[warp * 4 + 3] = bmax;
+        }
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            double m = 0.0;
+            for (int w = 0; w < DD_REG_WARPS; ++w) m = nn_max(m, sx[w * 4 + threadIdx.x]);
+            double* dst = threadIdx.x == 0 ? &A.stats[member].resid
+                        : threadIdx.x == 1 ? &A.stats[member].xmax
+                        : threadIdx.x == 2 ? &A.stats[member].vmax : &A.stats[member].bmax;
+            atomic_max_nn(dst, m);
+        }
+    }
+    DD_TICK(2);
+#ifdef DD_SOLVER_TIMING
+    if (threadIdx.x == 0) atomicAdd(&dd_solver_cycles[3], 1ull);
+#endif
+}
+
+#ifdef DD_SOLVER_TIMING
+extern "C" void dd_solver_timing_read(unsigned long long out[4], int reset) {
+    cudaMemcpyFromSymbol(out, dd_solver_cycles, sizeof(unsigned long long) * 4);
+    if (reset) {
+        unsigned long long z[4] = {0, 0, 0, 0};
+        cudaMemcpyToSymbol(dd_solver_cycles, z, sizeof(z));
+    }
+}
+#endif
 
 cudaError_t dd_solver_configure() {
     cudaError_t e = cudaFuncSetAttribute(k_rbsor_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_rbsor_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    e = cudaFuncSetAttribute(k_rbsor_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_rbsor_reg<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_rbsor_reg<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
 }
 
 cudaError_t dd_launch_solve_pass(const DDLaunch& L, const DDGeom& g, const DDMember* mem, const DDRows& R,
@@ -267,6 +580,8 @@ cudaError_t dd_launch_solve_pass(const DDLaunch& L, const DDGeom& g, const DDMem
     SolveArgs A;
     A.g = g;
     A.mem = mem;
+    A.ldR = R.ld;
+    A.mstrideR = R.mstride;
     A.bb = R.bb;
     A.aW = R.aW;
     A.aE = R.aE;
@@ -291,9 +606,32 @@ cudaError_t dd_launch_solve_pass(const DDLaunch& L, const DDGeom& g, const DDMem
     A.last_pass = P.last_pass;
     const long long nblocks = (long long)A.tiles_i * A.tiles_j * L.nmembers;
     if (nblocks <= 0 || nblocks > 2147483647LL) return cudaErrorInvalidConfiguration;
-    if (P.const_band)
+    if (P.rpw > 0) {
+        // register-resident kernel: 512 threads, x only in shared memory (2 colours x 16 rpw rows x 32 packed cols)
+        const size_t smem = (size_t)2 * DD_REG_WARPS * P.rpw * DD_REG_PW * sizeof(double);
+#define DD_LAUNCH_REG(CB, RPW) k_rbsor_reg<CB, RPW><<<(unsigned)nblocks, DD_REG_WARPS * 32, smem, L.stream>>>(A)
+        if (P.const_band) {
+            switch (P.rpw) {
+                case 2: DD_LAUNCH_REG(1, 2); break;
+                case 3: DD_LAUNCH_REG(1, 3); break;
+                case 4: DD_LAUNCH_REG(1, 4); break;
+                case 6: DD_LAUNCH_REG(1, 6); break;
+                case 8: DD_LAUNCH_REG(1, 8); break;
+                default: return cudaErrorInvalidValue;
+            }
+        } else {
+            switch (P.rpw) {
+                case 2: DD_LAUNCH_REG(0, 2); break;
+                case 3: DD_LAUNCH_REG(0, 3); break;
+                case 4: DD_LAUNCH_REG(0, 4); break;
+                default: return cudaErrorInvalidValue;
+            }
+        }
+#undef DD_LAUNCH_REG
+    } else if (P.const_band) {
         k_rbsor_tile<1><<<(unsigned)nblocks, P.threads, P.smem_bytes, L.stream>>>(A);
-    else
+    } else {
         k_rbsor_tile<0><<<(unsigned)nblocks, P.threads, P.smem_bytes, L.stream>>>(A);
+    }
     return cudaGetLastError();
 }

@@ -71,6 +71,29 @@ def exchange_halos(tensors: Sequence, part: Dict[str, int], rank: int, world: in
         r.wait()
 
 
+def _shares_torch_stream(ctx, torch) -> bool:
+    return ctx.stream is not None and ctx.stream == torch.cuda.current_stream().cuda_stream
+
+
+class _Ordered:
+    """Orders torch-side communication against the library's stream: when the context runs on torch's
+    current stream nothing is needed, otherwise the two streams are joined by synchronising around the
+    communication call."""
+
+    def __init__(self, meshes, torch):
+        self.meshes, self.torch = meshes, torch
+        self.same = all(_shares_torch_stream(m.batch.ctx, torch) for m in meshes)
+
+    def __enter__(self):
+        if not self.same:
+            for m in self.meshes:
+                m.batch.ctx.synchronize()
+
+    def __exit__(self, *a):
+        if not self.same:
+            self.torch.cuda.current_stream().synchronize()
+
+
 class _DistComm:
     """Collectives of one rank per process (torch.distributed, NCCL on GPUs)."""
 
@@ -81,11 +104,13 @@ class _DistComm:
 
     def exchange(self, meshes, slot, which):
         m = meshes[0]
-        exchange_halos([m.field(slot, v) for v in which], m.part, m.rank, m.world, m.G, self.dist)
+        with _Ordered(meshes, self.torch):
+            exchange_halos([m.field(slot, v) for v in which], m.part, m.rank, m.world, m.G, self.dist)
 
-    def allreduce(self, tensors, op):
+    def allreduce(self, tensors, op, meshes=()):
         d = self.dist
-        d.all_reduce(tensors[0], op={"max": d.ReduceOp.MAX, "min": d.ReduceOp.MIN, "sum": d.ReduceOp.SUM}[op])
+        with _Ordered(meshes, self.torch):
+            d.all_reduce(tensors[0], op={"max": d.ReduceOp.MAX, "min": d.ReduceOp.MIN, "sum": d.ReduceOp.SUM}[op])
 
 
 class _LocalComm:
@@ -97,6 +122,10 @@ class _LocalComm:
         self.torch = torch
 
     def exchange(self, meshes, slot, which):
+        with _Ordered(meshes, self.torch):
+            self._exchange(meshes, slot, which)
+
+    def _exchange(self, meshes, slot, which):
         for m in meshes:
             p = m.part
             for v in which:
@@ -110,12 +139,14 @@ class _LocalComm:
                     g = min(m.G, p["hi"])
                     t[p["own1"]:p["own1"] + g].copy_(dn.field(slot, v)[dn.part["own0"]:dn.part["own0"] + g])
 
-    def allreduce(self, tensors, op):
+    def allreduce(self, tensors, op, meshes=()):
         torch = self.torch
-        stacked = torch.stack([t for t in tensors])
-        red = {"max": stacked.max(dim=0).values, "min": stacked.min(dim=0).values, "sum": stacked.sum(dim=0)}[op]
-        for t in tensors:
-            t.copy_(red)
+        with _Ordered(meshes, torch):
+            stacked = torch.stack([t for t in tensors])
+            red = {"max": stacked.max(dim=0).values, "min": stacked.min(dim=0).values,
+                   "sum": stacked.sum(dim=0)}[op]
+            for t in tensors:
+                t.copy_(red)
 
 
 class SlabMesh:
@@ -203,14 +234,16 @@ class SlabMesh:
                 # assemble, make the Gershgorin ratio (hence the SOR relaxation factor) global, solve
                 phase(20 + k)
                 comm.allreduce([m._tensor("stats", m.batch.work_dev_ptr("solve_stats"), (3, 5))[k - 1, 0:1]
-                                for m in group], "max")
+                                for m in group], "max", group)
                 phase(30 + k)
                 comm.exchange(group, slot_out, (var,))
             phase(4)
             if track:
                 n = opt.num_newton_iterations
-                comm.allreduce([m._tensor("itmax", m.batch.work_dev_ptr("cs_it_max"), (n,)) for m in group], "max")
-                comm.allreduce([m._tensor("itmin", m.batch.work_dev_ptr("cs_it_min"), (n,)) for m in group], "min")
+                comm.allreduce([m._tensor("itmax", m.batch.work_dev_ptr("cs_it_max"), (n,)) for m in group], "max",
+                               group)
+                comm.allreduce([m._tensor("itmin", m.batch.work_dev_ptr("cs_it_min"), (n,)) for m in group], "min",
+                               group)
             phase(5)
             ts = [torch.nan_to_num(torch.tensor(sm.reshape(3, 4), device="cuda"), nan=1e300) for sm in summ]
             comm.allreduce(ts, "max")

@@ -179,7 +179,7 @@ extern "C" int hs_pc_step(const HSProblem* P, const double* const in[5], double*
         for (int j = 0; j <= P->M; ++j) HS_MODE(P->mode, (dd_node_predict<MODE>(g, c.mb, c.F, s0, po, 0, r, j)));
     DDStateC u;
     u.v[DD_CP] = cp1p.data(); u.v[DD_T] = in[DD_T]; u.v[DD_CL] = in[DD_CL]; u.v[DD_CD] = in[DD_CD]; u.v[DD_CS] = cs1p.data();
-    DDRows R = {bb.data(), aW.data(), aE.data(), aS.data(), aN.data()};
+    DDRows R = {bb.data(), aW.data(), aE.data(), aS.data(), aN.data(), g.ld, g.mstride};
     int pp = 0;
     std::vector<double> cpc(n), csc(n);
     for (int pc = 0; pc < npc; ++pc) {
@@ -191,9 +191,9 @@ extern "C" int hs_pc_step(const HSProblem* P, const double* const in[5], double*
                 for (int r = 0; r <= P->N; ++r)
                     for (int j = 0; j <= P->M; ++j) {
                         double rr = 0.0;
-                        if (var == DD_T) { HS_MODE(P->mode, (rr = dd_node_asm_T<MODE>(g, c.mb, c.F, u, YT.data(), R, 0, r, j))); }
-                        else if (var == DD_CL) { HS_MODE(P->mode, (rr = dd_node_asm_cl<MODE>(g, c.mb, c.F, u, dst[0], Ycl.data(), R, 0, r, j))); }
-                        else { HS_MODE(P->mode, (rr = dd_node_asm_cd<MODE>(g, c.mb, c.F, u, dst[0], dst[1], Ycd.data(), swap, R, 0, r, j))); }
+                        if (var == DD_T) { HS_MODE(P->mode, (rr = dd_node_asm_T<MODE>(g, c.mb, c.F, u, YT.data(), R, 0, 0, r, j))); }
+                        else if (var == DD_CL) { HS_MODE(P->mode, (rr = dd_node_asm_cl<MODE>(g, c.mb, c.F, u, dst[0], Ycl.data(), R, 0, 0, r, j))); }
+                        else { HS_MODE(P->mode, (rr = dd_node_asm_cd<MODE>(g, c.mb, c.F, u, dst[0], dst[1], Ycd.data(), swap, R, 0, 0, r, j))); }
                         rho = fmax(rho, rr);
                     }
                 const double res = rbsor(g, R, x, rho, sweeps);

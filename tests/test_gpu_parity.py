@@ -320,3 +320,46 @@ def test_slab_decomposition_single_gpu_emulation(dd, world):
     e_one = b.error_norms(nsteps % 2, t0 + nsteps * dt)[0]
     e_many = meshes2[0].error_norms(nsteps % 2, t0 + nsteps * dt)
     assert np.allclose(e_many, e_one, rtol=1e-12, atol=0)
+
+
+def test_inline_device_math_accuracy(dd):
+    """dd_exp / dd_rcp on the device vs NumPy: <= 2 ulp over the ranges the scheme uses, exact special cases."""
+    from _ddlib import Context, dptr
+    ctx = Context.default()
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.uniform(-50, 50, 200000), rng.uniform(-1e-3, 1e-3, 100000), rng.uniform(-699, 699, 100000),
+                        np.array([0.0, -0.0, 1.0, -1.0, 699.999, -699.999, 710.0, -750.0, np.inf, -np.inf, np.nan])])
+    e, r = np.empty_like(x), np.empty_like(x)
+    ctx.check(ctx.lib.dd_probe_math(ctx.handle, len(x), dptr(x), dptr(e), dptr(r)), "probe")
+    with np.errstate(all="ignore"):
+        ref_e, ref_r = np.exp(x), 1.0 / x
+    fin = np.isfinite(ref_e) & (ref_e > 1e-300)
+    ulp = np.abs(e[fin] - ref_e[fin]) / np.spacing(ref_e[fin])
+    assert ulp.max() <= 2.0, ulp.max()
+    assert np.array_equal(np.isnan(e), np.isnan(ref_e)) and np.array_equal(np.isinf(e), np.isinf(ref_e))
+    fr = np.isfinite(ref_r)
+    assert np.all(np.abs(r[fr] - ref_r[fr]) <= np.abs(np.spacing(ref_r[fr])))
+
+
+@pytest.mark.parametrize("name", ["steps_pol_12x9_pc", "steps_expsin_8x8_pc", "steps_scp_fast1e1_12x9_pc",
+                                  "steps_nfsp_h1h2_8x8_fe"])
+def test_fused_sources_path_matches_reference(dd, name, monkeypatch):
+    """DD_FUSED_SOURCES=1 evaluates the MMS sources inside every kernel (no staged source arrays); both
+    paths must reproduce the reference."""
+    monkeypatch.setenv("DD_FUSED_SOURCES", "1")
+    desc, z = load_fixture(name)
+    b, model, grid = make_batch(dd, desc, z)
+    dt, t = desc["dt"], desc["t0"]
+    b.upload(0, {v: z["init_" + v] for v in VARS})
+    cur, nxt = 0, 1
+    for n in range(desc["nsteps"]):
+        if desc["integrator"] == "pc":
+            b.step_pc(cur, nxt, t, dt, pc_opts(dd, desc["pc"]))
+        else:
+            b.step_feuler(cur, nxt, t, dt)
+        t += dt
+        cur, nxt = nxt, cur
+        got = b.download(cur)
+        for v in VARS:
+            assert rel_err(got[v], z[f"step{n + 1}_{v}"]) <= TOL, f"step {n + 1} {v}"
+    b.close()
