@@ -78,6 +78,11 @@ typedef struct dd_pc_options {
     double solve_tol;          /* bound on |x - x_exact|_inf / |v_new|_inf per linear solve, default 1e-14 */
     int max_sweeps;            /* give up (DD_ERR_NOT_CONVERGED) beyond this many SOR sweeps, default 20000 */
     int fixed_sweeps;          /* > 0: use exactly this many sweeps and skip the adaptive plan */
+    int extrapolate_guess;     /* 1: when consecutive steps ping-pong between two slots, start the SOR iteration
+                                  from the previous step's increment instead of zero.  Default 0: measured on the
+                                  bench mesh it saves one sweep per solve and costs as much in the first load
+                                  (the zeroed-T-boundary layer keeps early increments from being smooth in time) */
+    int _pad;
 } dd_pc_options;
 
 /* what one dd_step_pc call did (worst member of the batch) */

@@ -39,7 +39,8 @@ class dd_model(C.Structure):
 class dd_pc_options(C.Structure):
     _fields_ = [("num_pc_steps", C.c_int), ("num_newton_steps", C.c_int), ("num_newton_iterations", C.c_int),
                 ("cd_band_swap", C.c_int), ("consec_xs_rtol", C.c_double), ("solve_tol", C.c_double),
-                ("max_sweeps", C.c_int), ("fixed_sweeps", C.c_int)]
+                ("max_sweeps", C.c_int), ("fixed_sweeps", C.c_int),
+                ("extrapolate_guess", C.c_int), ("_pad", C.c_int)]
 
 
 class dd_step_stats(C.Structure):

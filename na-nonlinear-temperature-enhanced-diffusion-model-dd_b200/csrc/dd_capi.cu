@@ -59,12 +59,33 @@ struct dd_batch {
     double* src_set[2][DD_NVAR];
     bool src_has[2];
     double src_time[2];
-    int plan_sweeps[3], plan_extra[3], plan_floor[3];  // floor: one more than the last count that failed
+    // sweep controller, one set per kind of initial iterate (0: zero, 1: extrapolated; the latter needs
+    // far fewer sweeps); floor: one more than the last count that failed
+    struct Ctl { int sweeps[3], extra[3], floor[3]; } ctl[2];
+    int cm;  // set in use by the solves being issued
+    // extrapolated initial iterate: when a step reads slot a and writes slot b right after a step that read
+    // b and wrote a (ping-pong), slot b still holds the state of two steps ago and v_n - v_{n-1} starts the solves
+    bool prev_valid, use_guess;
+    int prev_in, prev_out;
+    double prev_dt, cur_dt;  // first member's step size (the increment scales with it)
     bool is_slab;
     int cmp0, cmp1;  // local rows with a complete stencil (slabs: everything but the outermost halo row)
     int asm0, asm1;  // rows whose Newton rows are exact: their stencil reads predictor output, itself only
                      // defined on [cmp0, cmp1) -> one more row is lost on every interior side
 };
+
+static void reset_ctl(dd_batch* b, bool all) {
+    for (int m = 0; m < 2; ++m)
+        for (int q = 0; q < 3; ++q) {
+            b->ctl[m].sweeps[q] = 0;
+            if (all) {
+                b->ctl[m].extra[q] = 0;
+                b->ctl[m].floor[q] = 1;
+            }
+        }
+    if (all) b->cm = 0;
+}
+
 
 // ---------------------------------------------------------------------------
 // launch accounting: every kernel launched by the library is counted; with profiling on,
@@ -264,8 +285,10 @@ extern "C" int dd_batch_create(dd_ctx* ctx, int N, int M, const double* x, const
     b->cmp1 = (row0 + nrows == N + 1) ? nrows : nrows - 1;
     b->asm0 = (row0 == 0) ? 0 : 2;
     b->asm1 = (row0 + nrows == N + 1) ? nrows : nrows - 2;
-    b->plan_extra[0] = b->plan_extra[1] = b->plan_extra[2] = 0;
-    b->plan_floor[0] = b->plan_floor[1] = b->plan_floor[2] = 1;
+    reset_ctl(b, true);
+    b->prev_valid = b->use_guess = false;
+    b->prev_in = b->prev_out = -1;
+    b->prev_dt = b->cur_dt = 0.0;
     const int ld = M + 1;
     b->field_elems = (size_t)nmembers * nrows * ld;
     // geometry (reference Grid.__init__, src/prob1base.py:287-304)
@@ -318,7 +341,6 @@ extern "C" int dd_batch_create(dd_ctx* ctx, int N, int M, const double* x, const
     b->norm_bpm = dd_norm_blocks_per_member(g);
     CK(cudaMalloc((void**)&b->d_norm_partial, sizeof(double) * 8 * (size_t)b->norm_bpm * nmembers));
     CK(cudaMalloc((void**)&b->d_norm_out, sizeof(double) * 8 * nmembers));
-    b->plan_sweeps[0] = b->plan_sweeps[1] = b->plan_sweeps[2] = 0;
     CK(cudaStreamSynchronize(ctx->stream));
     *out = b;
     return DD_OK;
@@ -342,6 +364,7 @@ extern "C" int dd_batch_destroy(dd_batch* b) {
 static int push_members(dd_batch* b, int first, int count) {
     dd_ctx* ctx = b->ctx;
     b->src_has[0] = b->src_has[1] = false;  // models / time profiles changed: staged sources are stale
+    b->prev_valid = false;
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(b->d_mem + first, b->h_mem.data() + first, sizeof(DDMember) * count, cudaMemcpyHostToDevice,
                        ctx->stream));
@@ -354,9 +377,7 @@ static int push_members(dd_batch* b, int first, int count) {
 extern "C" int dd_batch_set_models(dd_batch* b, int first, int count, const dd_model* models) {
     if (!b || !models || first < 0 || count < 1 || first + count > b->B) return DD_ERR_INVALID;
     for (int k = 0; k < count; ++k) model_to_dev(models[k], &b->h_mem[first + k].m);
-    b->plan_sweeps[0] = b->plan_sweeps[1] = b->plan_sweeps[2] = 0;
-    b->plan_extra[0] = b->plan_extra[1] = b->plan_extra[2] = 0;
-    b->plan_floor[0] = b->plan_floor[1] = b->plan_floor[2] = 1;
+    reset_ctl(b, true);
     return push_members(b, first, count);
 }
 
@@ -506,6 +527,7 @@ static bool slot_ok(const dd_batch* b, int s) { return s >= 0 && s < b->nslots; 
 
 extern "C" int dd_state_upload(dd_batch* b, int slot, int member, const double* const fields[5]) {
     if (!b || !fields || !slot_ok(b, slot) || member < 0 || member >= b->B) return DD_ERR_INVALID;
+    b->prev_valid = false;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
     const size_t per = (size_t)b->nrows * b->g.ld;
@@ -620,6 +642,7 @@ static int set_times(dd_batch* b, const double* t0, const double* dt, int n_t) {
     if (!t0 || !dt || (n_t != 1 && n_t != b->B)) return fail(ctx, DD_ERR_INVALID, "t0/dt: need 1 or nmembers values");
     for (int k = 0; k < n_t; ++k)
         if (!(dt[k] > 0.0)) return fail(ctx, DD_ERR_INVALID, "dt must be > 0");
+    b->cur_dt = dt[0];
     CK(cudaMemcpyAsync(b->d_t0, t0, sizeof(double) * n_t, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(b->d_dt, dt, sizeof(double) * n_t, cudaMemcpyHostToDevice, ctx->stream));
     CKP(PC_TIME, 1, dd_launch_time_coefs(launch_of(b), b->mode, b->d_mem, b->d_t0, b->d_dt, n_t, 0));
@@ -680,6 +703,7 @@ extern "C" int dd_state_fill_exact(dd_batch* b, int slot, const double* t, int n
     std::vector<double> one(n_t, 1.0);
     int rc = set_times(b, t, one.data(), n_t);
     if (rc != DD_OK) return rc;
+    b->prev_valid = false;
     CKP(PC_OTHER, 1, dd_launch_fill_exact(launch_of(b, ROWS_ALL), b->mode, b->g, b->d_mem, b->F, mstate(b, slot)));
     CK(cudaStreamSynchronize(ctx->stream));
     return DD_OK;
@@ -690,6 +714,7 @@ extern "C" int dd_state_fill_exact(dd_batch* b, int slot, const double* t, int n
 // ---------------------------------------------------------------------------
 extern "C" int dd_step_feuler(dd_batch* b, int slot_in, int slot_out, const double* t0, const double* dt, int n_t) {
     if (!b || !slot_ok(b, slot_in) || !slot_ok(b, slot_out) || slot_in == slot_out) return DD_ERR_INVALID;
+    b->prev_valid = false;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
     int rc = set_times(b, t0, dt, n_t);
@@ -702,6 +727,7 @@ extern "C" int dd_step_feuler(dd_batch* b, int slot_in, int slot_out, const doub
 
 extern "C" int dd_eval_fields(dd_batch* b, int slot_in, int slot_out, const double* t, int n_t) {
     if (!b || !slot_ok(b, slot_in) || !slot_ok(b, slot_out) || slot_in == slot_out || !t) return DD_ERR_INVALID;
+    b->prev_valid = false;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
     std::vector<double> one(n_t, 1.0);
@@ -752,6 +778,7 @@ extern "C" void dd_pc_options_default(dd_pc_options* o) {
     o->solve_tol = 1e-14;
     o->max_sweeps = 20000;
     o->fixed_sweeps = 0;
+    o->extrapolate_guess = 0;
 }
 
 static const size_t kSmemMax = 227 * 1024;
@@ -784,11 +811,13 @@ static int next_plan(int cur, double rho, double ratio, int max_sweeps) {
     if (!(ratio <= 0.1)) {
         want = cur + 1;
     } else if (cur > 1 && ratio * 10.0 < lam) {
-        const double r = ratio > 1e-300 ? ratio : 1e-300;
+        // a residual at rounding level (ratio ~ 0) says nothing about how many sweeps were in excess
+        const double r = ratio > 1e-6 ? ratio : 1e-6;
         // never assume more than a 20x error reduction per sweep when shortening the plan
         const double lam_eff = lam > 0.05 ? lam : 0.05;
         int drop = (int)floor(log(r * 10.0) / log(lam_eff));
         if (drop < 1) drop = 1;
+        if (drop > cur / 2) drop = cur / 2;  // a failed step costs a whole retry: shorten the plan gradually
         want = cur - drop;
     }
     if (want > max_sweeps) want = max_sweeps;
@@ -995,7 +1024,7 @@ static int ensure_cs_buffers(dd_batch* b, int cap) {
 // assemble + solve one Newton system.  `k` indexes the stats slot.
 static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const double* T1, const double* cl1,
                         const double* Y, double* vnew, const dd_pc_options& opt, int k, int* sweeps_used,
-                        int* passes_used, int what = 3) {
+                        int* passes_used, int what = 3, const double* vold = nullptr) {
     dd_ctx* ctx = b->ctx;
     DDRows R;
     int rc;
@@ -1016,7 +1045,7 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
             dd_launch_assemble(La, b->smode, var, b->g, b->d_mem, b->sF, ustar, T1, cl1, Y, opt.cd_band_swap, R, st));
     if (!(what & 2)) return DD_OK;
     const int vi = var - DD_T;
-    int sweeps = opt.fixed_sweeps > 0 ? opt.fixed_sweeps : b->plan_sweeps[vi];
+    int sweeps = opt.fixed_sweeps > 0 ? opt.fixed_sweeps : b->ctl[b->cm].sweeps[vi];
     if (sweeps <= 0) {
         // first use: read the Gershgorin ratio back once to seed the plan
         CK(cudaMemsetAsync(b->d_summary + k, 0, sizeof(SolveSummary), ctx->stream));
@@ -1025,12 +1054,12 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
         CK(cudaMemcpyAsync(&s, b->d_summary + k, sizeof(s), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         sweeps = sweeps_for_rho(s.rho, opt.max_sweeps);
-        b->plan_sweeps[vi] = sweeps;
+        b->ctl[b->cm].sweeps[vi] = sweeps;
     }
     const double* vstar = ustar.v[var];
     int left = sweeps, passes = 0;
     double *xa = nullptr, *xb = nullptr;
-    const double* xin = nullptr;
+    const double* xin = nullptr;  // nullptr = zero initial iterate, or vstar - vold on the first pass
     // rows on which the rows R and the iterate x are valid.  On a slab every pass consumes 2 rows per sweep
     // from each interior side (the halo rows are recomputed redundantly, never exchanged mid-solve); sides
     // on the physical boundary do not shrink.
@@ -1061,8 +1090,17 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
                 return fail(ctx, DD_ERR_INVALID, "halo too shallow for the planned SOR sweeps");
         }
         if (P.last_pass && P.sweeps < left) return fail(ctx, DD_ERR_INVALID, "solver plan inconsistency");
+        const double* vo = passes == 0 ? vold : nullptr;
+        if (vo && P.rpw <= 0) {
+            // shared-memory kernel: it stages x from an array
+            double* x0 = nullptr;
+            if ((rc = get_work(b, "x0", &x0)) != DD_OK) return rc;
+            CKP(PC_SOLVE_T + (var - DD_T), 1, dd_launch_make_guess(Lp, b->g, R, vstar, vo, x0));
+            xin = x0;
+            vo = nullptr;
+        }
         CKP(PC_SOLVE_T + (var - DD_T), 1,
-            dd_launch_solve_pass(Lp, b->g, b->d_mem, R, xin, xout, vstar, vnew, var == DD_T ? 1 : 0, st, P));
+            dd_launch_solve_pass(Lp, b->g, b->d_mem, R, xin, vo, xout, vstar, vnew, var == DD_T ? 1 : 0, st, P));
         left -= P.sweeps;
         xin = xout;
         if (!P.last_pass) {
@@ -1085,6 +1123,23 @@ struct StepIO {
     int slot_in, slot_out;
 };
 
+// Decides whether this step may start its solves from the previous step's increment, and disarms the
+// record so that a retry of the same step (whose output slot then holds a rejected result) starts from zero.
+static bool take_guess(dd_batch* b, int slot_in, int slot_out, const dd_pc_options& opt) {
+    static const bool off = getenv("DD_NO_GUESS") != nullptr;
+    bool ok = !off && opt.extrapolate_guess && b->prev_valid && b->prev_in == slot_out &&
+                    b->prev_out == slot_in && slot_in != slot_out && b->prev_dt == b->cur_dt;
+    b->prev_valid = false;
+    b->cm = ok ? 1 : 0;
+    return ok;
+}
+static void record_step(dd_batch* b, int slot_in, int slot_out) {
+    b->prev_in = slot_in;
+    b->prev_out = slot_out;
+    b->prev_dt = b->cur_dt;
+    b->prev_valid = true;
+}
+
 // one PC step; times must already be on the device (set_times or advance)
 static int pc_step_once(dd_batch* b, int slot_in, int slot_out, const dd_pc_options& opt, dd_step_stats* stats,
                         bool* converged) {
@@ -1106,6 +1161,7 @@ static int pc_step_once(dd_batch* b, int slot_in, int slot_out, const dd_pc_opti
     DDStateC u;
     u.v[DD_CP] = po.cp1p; u.v[DD_T] = s0.v[DD_T]; u.v[DD_CL] = s0.v[DD_CL]; u.v[DD_CD] = s0.v[DD_CD];
     u.v[DD_CS] = po.cs1p;
+    const bool guess = take_guess(b, slot_in, slot_out, opt);
     static const char* tmpn[3][2] = {{"T1a", "T1b"}, {"cl1a", "cl1b"}, {"cd1a", "cd1b"}};
     int pp = 0, k = 0;
     int sweeps[3] = {0, 0, 0}, passes[3] = {0, 0, 0};
@@ -1120,9 +1176,15 @@ static int pc_step_once(dd_batch* b, int slot_in, int slot_out, const dd_pc_opti
                     return rc;
                 }
             }
-            if ((rc = newton_solve(b, DD_T, u, nullptr, nullptr, po.YT, dst[0], opt, k++, &sweeps[0], &passes[0])) != DD_OK) return rc;
-            if ((rc = newton_solve(b, DD_CL, u, dst[0], nullptr, po.Ycl, dst[1], opt, k++, &sweeps[1], &passes[1])) != DD_OK) return rc;
-            if ((rc = newton_solve(b, DD_CD, u, dst[0], dst[1], po.Ycd, dst[2], opt, k++, &sweeps[2], &passes[2])) != DD_OK) return rc;
+            // the first Newton solve of the step starts from the previous step's increment when it is available
+            const bool gs = guess && pc == 0 && nw == 0;
+            b->cm = gs ? 1 : 0;
+            if ((rc = newton_solve(b, DD_T, u, nullptr, nullptr, po.YT, dst[0], opt, k++, &sweeps[0], &passes[0], 3,
+                                   gs ? sout.v[DD_T] : nullptr)) != DD_OK) return rc;
+            if ((rc = newton_solve(b, DD_CL, u, dst[0], nullptr, po.Ycl, dst[1], opt, k++, &sweeps[1], &passes[1], 3,
+                                   gs ? sout.v[DD_CL] : nullptr)) != DD_OK) return rc;
+            if ((rc = newton_solve(b, DD_CD, u, dst[0], dst[1], po.Ycd, dst[2], opt, k++, &sweeps[2], &passes[2], 3,
+                                   gs ? sout.v[DD_CD] : nullptr)) != DD_OK) return rc;
             u.v[DD_T] = dst[0]; u.v[DD_CL] = dst[1]; u.v[DD_CD] = dst[2];
             pp ^= 1;
         }
@@ -1158,19 +1220,20 @@ static int pc_step_once(dd_batch* b, int slot_in, int slot_out, const dd_pc_opti
     if (opt.fixed_sweeps <= 0) {
         for (int q = 0; q < k; ++q) {
             const int vi = q % 3;
+            b->cm = (guess && q < 3) ? 1 : 0;
             if (!(sums[q].ratio <= 1.0)) {
                 // not enough sweeps: remember the failing count and go (at least) to the theoretical one
-                if (b->plan_floor[vi] < b->plan_sweeps[vi] + 1) b->plan_floor[vi] = b->plan_sweeps[vi] + 1;
+                if (b->ctl[b->cm].floor[vi] < b->ctl[b->cm].sweeps[vi] + 1) b->ctl[b->cm].floor[vi] = b->ctl[b->cm].sweeps[vi] + 1;
                 const int want = sweeps_for_rho(sums[q].rho * 1.02 + 1e-12, opt.max_sweeps);
-                if (b->plan_sweeps[vi] >= want) b->plan_extra[vi] += (b->plan_sweeps[vi] + 1) / 2 + 1;
-                int next = want + b->plan_extra[vi];
-                if (next < b->plan_floor[vi]) next = b->plan_floor[vi];
+                if (b->ctl[b->cm].sweeps[vi] >= want) b->ctl[b->cm].extra[vi] += (b->ctl[b->cm].sweeps[vi] + 1) / 2 + 1;
+                int next = want + b->ctl[b->cm].extra[vi];
+                if (next < b->ctl[b->cm].floor[vi]) next = b->ctl[b->cm].floor[vi];
                 if (next > opt.max_sweeps) next = opt.max_sweeps;
-                if (next > b->plan_sweeps[vi]) b->plan_sweeps[vi] = next;
-            } else if (*converged && q >= k - 3) {
-                int next = next_plan(b->plan_sweeps[vi], sums[q].rho, sums[q].ratio, opt.max_sweeps);
-                if (next < b->plan_floor[vi]) next = b->plan_floor[vi];
-                b->plan_sweeps[vi] = next;
+                if (next > b->ctl[b->cm].sweeps[vi]) b->ctl[b->cm].sweeps[vi] = next;
+            } else if (*converged && (q >= k - 3 || q < 3)) {
+                int next = next_plan(b->ctl[b->cm].sweeps[vi], sums[q].rho, sums[q].ratio, opt.max_sweeps);
+                if (next < b->ctl[b->cm].floor[vi]) next = b->ctl[b->cm].floor[vi];
+                b->ctl[b->cm].sweeps[vi] = next;
             }
         }
     }
@@ -1210,17 +1273,20 @@ static int pc_step_retry(dd_batch* b, int slot_in, int slot_out, const dd_pc_opt
         int rc = pc_step_once(b, slot_in, slot_out, opt, stats, &ok);
         if (rc != DD_OK) return rc;
         if (stats) stats->retries = retries;
-        if (ok) return DD_OK;
+        if (ok) {
+            record_step(b, slot_in, slot_out);
+            return DD_OK;
+        }
         bool can_grow = opt.fixed_sweeps <= 0;
         if (can_grow) {
             can_grow = false;
             for (int q = 0; q < 3; ++q)
-                if (b->plan_sweeps[q] < opt.max_sweeps) can_grow = true;
+                if (b->ctl[0].sweeps[q] < opt.max_sweeps) can_grow = true;  // retries start from zero
         }
         if (!can_grow || retries >= 40) {
             char msg[256];
             snprintf(msg, sizeof(msg), "linear solve did not reach the residual bound (sweeps T/cl/cd = %d/%d/%d)",
-                     b->plan_sweeps[0], b->plan_sweeps[1], b->plan_sweeps[2]);
+                     b->ctl[0].sweeps[0], b->ctl[0].sweeps[1], b->ctl[0].sweeps[2]);
             return fail(ctx, DD_ERR_NOT_CONVERGED, msg);
         }
         ++retries;
@@ -1270,6 +1336,7 @@ extern "C" int dd_run_pc(dd_batch* b, int slot_a, int slot_b, const double* t0, 
 extern "C" int dd_run_feuler(dd_batch* b, int slot_a, int slot_b, const double* t0, const double* dt, int n_t,
                              int nsteps, double* norms_out) {
     if (!b || !slot_ok(b, slot_a) || !slot_ok(b, slot_b) || slot_a == slot_b || nsteps < 0) return DD_ERR_INVALID;
+    b->prev_valid = false;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
     int rc;
@@ -1315,6 +1382,7 @@ extern "C" int dd_pc_newton(dd_batch* b, int var, int slot_star, int slot_new, c
                             int n_t, const dd_pc_options* opt_in, dd_step_stats* stats) {
     if (!b || !slot_ok(b, slot_star) || !slot_ok(b, slot_new) || slot_star == slot_new || var < DD_T || var > DD_CD)
         return DD_ERR_INVALID;
+    b->prev_valid = false;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
     dd_pc_options opt;
@@ -1329,6 +1397,7 @@ extern "C" int dd_pc_newton(dd_batch* b, int var, int slot_star, int slot_new, c
     if ((rc = get_work(b, yname[var - DD_T], &Y)) != DD_OK) return rc;
     const DDStateC u = cstate(b, slot_star);
     const DDState nw = mstate(b, slot_new);
+    b->cm = 0;
     for (int attempt = 0;; ++attempt) {
         int sw = 0, pa = 0;
         if ((rc = newton_solve(b, var, u, nw.v[DD_T], nw.v[DD_CL], Y, nw.v[var], opt, 0, &sw, &pa)) != DD_OK) return rc;
@@ -1341,18 +1410,19 @@ extern "C" int dd_pc_newton(dd_batch* b, int var, int slot_star, int slot_new, c
             stats->bound[vi] = s.bound; stats->retries = attempt;
         }
         if (s.ratio <= 1.0) return DD_OK;
-        if (opt.fixed_sweeps > 0 || b->plan_sweeps[vi] >= opt.max_sweeps || attempt >= 40)
+        if (opt.fixed_sweeps > 0 || b->ctl[b->cm].sweeps[vi] >= opt.max_sweeps || attempt >= 40)
             return fail(ctx, DD_ERR_NOT_CONVERGED, "linear solve did not reach the residual bound");
         const int want = sweeps_for_rho(s.rho * 1.02 + 1e-12, opt.max_sweeps);
-        if (b->plan_sweeps[vi] >= want) b->plan_extra[vi] += (b->plan_sweeps[vi] + 1) / 2 + 1;
-        const int next = want + b->plan_extra[vi];
-        b->plan_sweeps[vi] = next > opt.max_sweeps ? opt.max_sweeps : next;
+        if (b->ctl[b->cm].sweeps[vi] >= want) b->ctl[b->cm].extra[vi] += (b->ctl[b->cm].sweeps[vi] + 1) / 2 + 1;
+        const int next = want + b->ctl[b->cm].extra[vi];
+        b->ctl[b->cm].sweeps[vi] = next > opt.max_sweeps ? opt.max_sweeps : next;
     }
 }
 
 extern "C" int dd_pc_correct(dd_batch* b, int slot0, int slot_new, const double* t0, const double* dt, int n_t,
                              const dd_pc_options* opt_in, int* cs_iters_out) {
     if (!b || !slot_ok(b, slot0) || !slot_ok(b, slot_new) || slot0 == slot_new) return DD_ERR_INVALID;
+    b->prev_valid = false;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
     dd_pc_options opt;
@@ -1420,13 +1490,13 @@ extern "C" int dd_pc_residual(dd_batch* b, int var, int slot_state, const double
 // ---------------------------------------------------------------------------
 extern "C" int dd_batch_set_plan(dd_batch* b, const int sweeps[3]) {
     if (!b || !sweeps) return DD_ERR_INVALID;
-    for (int q = 0; q < 3; ++q) b->plan_sweeps[q] = sweeps[q];
+    for (int q = 0; q < 3; ++q) b->ctl[0].sweeps[q] = b->ctl[1].sweeps[q] = sweeps[q];
     return DD_OK;
 }
 
 extern "C" int dd_batch_get_plan(dd_batch* b, int sweeps[3]) {
     if (!b || !sweeps) return DD_ERR_INVALID;
-    for (int q = 0; q < 3; ++q) sweeps[q] = b->plan_sweeps[q];
+    for (int q = 0; q < 3; ++q) sweeps[q] = b->ctl[b->cm].sweeps[q];
     return DD_OK;
 }
 
@@ -1467,6 +1537,7 @@ extern "C" int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_ou
             if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
             if ((rc = stage_sources(b, t0[0], dt[0], n_t == 1, true)) != DD_OK) return rc;
             CKP(PC_PREDICT, 1, dd_launch_predict(launch_of(b, ROWS_STENCIL), b->smode, b->g, b->d_mem, b->sF, s0, po));
+            b->use_guess = take_guess(b, slot_in, slot_out, opt);
             if (track) {
                 const int had = b->cs_cap_alloc;
                 if ((rc = ensure_cs_buffers(b, cap)) != DD_OK) return rc;
@@ -1478,13 +1549,13 @@ extern "C" int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_ou
             return DD_OK;
         case 1: case 21: case 31:
             return newton_solve(b, DD_T, u, nullptr, nullptr, po.YT, sout.v[DD_T], opt, 0, &sw, &pa,
-                                phase == 1 ? 3 : (phase == 21 ? 1 : 2));
+                                phase == 1 ? 3 : (phase == 21 ? 1 : 2), b->use_guess ? sout.v[DD_T] : nullptr);
         case 2: case 22: case 32:
             return newton_solve(b, DD_CL, u, sout.v[DD_T], nullptr, po.Ycl, sout.v[DD_CL], opt, 1, &sw, &pa,
-                                phase == 2 ? 3 : (phase == 22 ? 1 : 2));
+                                phase == 2 ? 3 : (phase == 22 ? 1 : 2), b->use_guess ? sout.v[DD_CL] : nullptr);
         case 3: case 23: case 33:
             return newton_solve(b, DD_CD, u, sout.v[DD_T], sout.v[DD_CL], po.Ycd, sout.v[DD_CD], opt, 2, &sw, &pa,
-                                phase == 3 ? 3 : (phase == 23 ? 1 : 2));
+                                phase == 3 ? 3 : (phase == 23 ? 1 : 2), b->use_guess ? sout.v[DD_CD] : nullptr);
         case 4:
             CKP(PC_CORRECT, 1,
                 dd_launch_correct(launch_of(b, ROWS_ALL), b->smode, b->g, b->d_mem, b->sF, s0, sout.v[DD_T],
@@ -1510,6 +1581,7 @@ extern "C" int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_ou
                     summary[q * 4 + 3] = sums[q].bound;
                 }
             if (cs_iters) *cs_iters = used0;
+            record_step(b, slot_in, slot_out);
             return DD_OK;
         }
         default:

@@ -45,9 +45,13 @@ struct DDSolvePlan {
 cudaError_t dd_solver_configure();  // opt-in to large dynamic shared memory (once per process)
 
 cudaError_t dd_launch_solve_pass(const DDLaunch& L, const DDGeom& g, const DDMember* mem, const DDRows& R,
-                                 const double* xin,
+                                 const double* xin /* nullable: zero initial iterate */,
+                                 const double* vold /* nullable, register kernel, xin null: start from vstar - vold */,
                                  double* xout, const double* vstar, double* vnew, int zero_boundary,
                                  DDSolveStats* stats, const DDSolvePlan& P);
+// x0 = vstar - vold (0 off the interior) on local rows [L.vr0, L.vr1), row pitch of R
+cudaError_t dd_launch_make_guess(const DDLaunch& L, const DDGeom& g, const DDRows& R, const double* vstar,
+                                 const double* vold, double* x0);
 
 // correctors.  cs Newton: `cap` iterations; when rtol > 0 the per-iteration global
 // statistics go to it_max / it_min ([member][cap]) and dd_launch_cs_finish applies

@@ -56,6 +56,7 @@ struct SolveArgs {
     const DDMember* mem;
     const double *bb, *aW, *aE, *aS, *aN;
     const double* xin;
+    const double* vold;  // first pass only, register kernel: initial iterate vstar - vold (xin is null then)
     double* xout;
     const double* vstar;
     double* vnew;
@@ -371,7 +372,17 @@ __global__ void __launch_bounds__(DD_REG_WARPS * 32, 1) k_rbsor_reg(SolveArgs A)
                 vs2 = *reinterpret_cast<const double2*>(A.aS + o);
                 vn = *reinterpret_cast<const double2*>(A.aN + o);
             }
-            if (A.xin) vx = *reinterpret_cast<const double2*>(A.xin + o);
+            if (A.xin) {
+                vx = *reinterpret_cast<const double2*>(A.xin + o);
+            } else if (A.vold) {
+                // the previous step's increment as initial iterate (states have the grid's own row pitch)
+                const int gi = g.row0 + row;
+                if (gi >= 1 && gi <= g.N - 1) {
+                    const long long og = mo + (long long)row * g.ld + colj;
+                    if (ok0 && colj >= 1 && colj <= g.M - 1) vx.x = A.vstar[og] - A.vold[og];
+                    if (ok1 && colj + 1 <= g.M - 1) vx.y = A.vstar[og + 1] - A.vold[og + 1];
+                }
+            }
         }
         // element .x is column sj0 (colour `flip`), .y is column sj0 + 1 (colour 1 - flip)
         const double b0 = ok0 ? vb.x : 0.0, b1 = ok1 ? vb.y : 0.0, w0 = ok0 ? vw.x : 0.0, w1 = ok1 ? vw.y : 0.0;
@@ -563,6 +574,24 @@ extern "C" void dd_solver_timing_read(unsigned long long out[4], int reset) {
 }
 #endif
 
+// initial iterate as an array (row pitch of the Newton rows) for the shared-memory kernel
+__global__ void k_make_guess(DDGeom g, const double* __restrict__ vstar, const double* __restrict__ vold,
+                             double* __restrict__ x0, int ldR, long long mstrideR, int r0, int r1) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, r = r0 + blockIdx.y;
+    const long long member = blockIdx.z;
+    if (j > g.M || r >= r1) return;
+    const long long o = member * g.mstride + (long long)r * g.ld + j;
+    x0[member * mstrideR + (long long)r * ldR + j] = dd_is_interior(g, g.row0 + r, j) ? vstar[o] - vold[o] : 0.0;
+}
+
+cudaError_t dd_launch_make_guess(const DDLaunch& L, const DDGeom& g, const DDRows& R, const double* vstar,
+                                 const double* vold, double* x0) {
+    const dim3 grid((unsigned)((g.M + 1 + 255) / 256), (unsigned)(L.vr1 - L.vr0), (unsigned)L.nmembers);
+    if (grid.y == 0 || grid.y > 65535u || grid.z > 65535u) return cudaErrorInvalidConfiguration;
+    k_make_guess<<<grid, 256, 0, L.stream>>>(g, vstar, vold, x0, R.ld, R.mstride, L.vr0, L.vr1);
+    return cudaGetLastError();
+}
+
 cudaError_t dd_solver_configure() {
     cudaError_t e = cudaFuncSetAttribute(k_rbsor_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
@@ -574,9 +603,10 @@ cudaError_t dd_solver_configure() {
 }
 
 cudaError_t dd_launch_solve_pass(const DDLaunch& L, const DDGeom& g, const DDMember* mem, const DDRows& R,
-                                 const double* xin,
+                                 const double* xin, const double* vold,
                                  double* xout, const double* vstar, double* vnew, int zero_boundary,
                                  DDSolveStats* stats, const DDSolvePlan& P) {
+    if (vold && (xin || P.rpw <= 0)) return cudaErrorInvalidValue;  // see dd_launch_make_guess for the other kernel
     SolveArgs A;
     A.g = g;
     A.mem = mem;
@@ -588,6 +618,7 @@ cudaError_t dd_launch_solve_pass(const DDLaunch& L, const DDGeom& g, const DDMem
     A.aS = R.aS;
     A.aN = R.aN;
     A.xin = xin;
+    A.vold = vold;
     A.xout = xout;
     A.vstar = vstar;
     A.vnew = vnew;

@@ -108,7 +108,8 @@ def _eval1d(f, c):
 # ----------------------------------------------------------------------------
 
 def pc_options(num_pc_steps=1, num_newton_steps=1, num_newton_iterations=5, consec_xs_rtol=1e-6,
-               cd_band_swap=True, solve_tol=1e-14, max_sweeps=20000, fixed_sweeps=0) -> dd_pc_options:
+               cd_band_swap=True, solve_tol=1e-14, max_sweeps=20000, fixed_sweeps=0,
+               extrapolate_guess=False) -> dd_pc_options:
     o = dd_pc_options()
     o.num_pc_steps = int(num_pc_steps)
     o.num_newton_steps = int(num_newton_steps)
@@ -118,6 +119,7 @@ def pc_options(num_pc_steps=1, num_newton_steps=1, num_newton_iterations=5, cons
     o.solve_tol = float(solve_tol)
     o.max_sweeps = int(max_sweeps)
     o.fixed_sweeps = int(fixed_sweeps)
+    o.extrapolate_guess = 1 if extrapolate_guess else 0
     return o
 
 

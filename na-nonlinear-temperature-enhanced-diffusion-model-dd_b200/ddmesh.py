@@ -166,9 +166,10 @@ class SlabMesh:
         self.group: List["SlabMesh"] = [self]
         self.comm = None
         self._rho = None
-        self._extra = [0, 0, 0]
-        self._floor = [1, 1, 1]
-        self._plan = None
+        # sweep controller state, one set per kind of initial iterate (0: zero, 1: previous increment);
+        # mirrors the library's own controller (dd_capi.cu), which the phased step bypasses
+        self._ctl = [dict(extra=[0, 0, 0], floor=[1, 1, 1], plan=None) for _ in range(2)]
+        self._prev = None  # (slot_in, slot_out, dt) of the last accepted step
         if world > 1:
             import torch
             self.torch = torch
@@ -203,6 +204,7 @@ class SlabMesh:
 
     # -- state ------------------------------------------------------------------------
     def fill_exact(self, slot: int, t: float):
+        self._prev = None
         self.batch.fill_exact(slot, t)
 
     def owned(self, slot: int) -> Dict[str, np.ndarray]:
@@ -228,7 +230,10 @@ class SlabMesh:
                                                    C.byref(opt), dptr(sm), C.byref(it)), f"step_pc_phase {k}")
         track = opt.consec_xs_rtol > 0.0 and opt.num_newton_iterations > 0
         for attempt in range(40):
-            plan = self._common_plan(opt)
+            # same rule as the library (take_guess in dd_capi.cu): ping-pong steps start from the last increment
+            mode = int(bool(opt.extrapolate_guess) and attempt == 0 and self._prev == (slot_out, slot_in, dt))
+            ctl = self._ctl[mode]
+            plan = self._common_plan(opt, ctl)
             phase(0)
             for k, var in ((1, "T"), (2, "cl"), (3, "cd")):
                 # assemble, make the Gershgorin ratio (hence the SOR relaxation factor) global, solve
@@ -248,33 +253,35 @@ class SlabMesh:
             ts = [torch.nan_to_num(torch.tensor(sm.reshape(3, 4), device="cuda"), nan=1e300) for sm in summ]
             comm.allreduce(ts, "max")
             s = ts[0].cpu().numpy()
-            stats = dict(sweeps=list(plan), rho=list(s[:, 0]), resid=list(s[:, 2]), bound=list(s[:, 3]),
+            stats = dict(sweeps=list(plan), guess=mode, rho=list(s[:, 0]), resid=list(s[:, 2]), bound=list(s[:, 3]),
                          retries=attempt, cs_newton_iters=int(iters[0].value))
             for m in group:
                 m._rho, m.last_stats = s[:, 0], stats
             if np.all(s[:, 1] <= 1.0):
                 nxt = [max(self.batch.lib.dd_next_plan(int(p), float(r), float(q), opt.max_sweeps), f)
-                       for p, r, q, f in zip(plan, s[:, 0], s[:, 1], self._floor)]
+                       for p, r, q, f in zip(plan, s[:, 0], s[:, 1], ctl["floor"])]
                 for m in group:
-                    m._plan = nxt
+                    m._ctl[mode]["plan"] = nxt
+                    m._prev = (slot_in, slot_out, dt)
                 return stats
             for m in group:
-                m._plan = None
+                m._ctl[mode]["plan"] = None
+                m._prev = None
             limit = (self.G - 3) // 2
             if any(r > 1.0 and p >= limit for p, r in zip(plan, s[:, 1])):
                 raise ddcore.DDNotConverged(f"slab step: {limit} SOR sweeps (all a halo of {self.G} rows supports) "
                                             f"do not reach the residual bound; use a deeper halo. stats={stats}")
             # remember the failing counts (never plan below them again) and fall back to the theoretical plan
-            floor = [max(f, p + 1) if r > 1.0 else f for f, p, r in zip(self._floor, plan, s[:, 1])]
+            floor = [max(f, p + 1) if r > 1.0 else f for f, p, r in zip(ctl["floor"], plan, s[:, 1])]
             extra = [e + (p + 1) // 2 + 1 if (r > 1.0 and p >= lib_plan) else e
-                     for e, p, r, lib_plan in zip(self._extra, plan, s[:, 1],
+                     for e, p, r, lib_plan in zip(ctl["extra"], plan, s[:, 1],
                                                   [self.batch.lib.dd_sweeps_for_rho(float(x) * 1.02 + 1e-12,
                                                                                     opt.max_sweeps) for x in s[:, 0]])]
             for m in group:
-                m._extra, m._floor = extra, floor
+                m._ctl[mode]["extra"], m._ctl[mode]["floor"] = extra, floor
         raise ddcore.DDNotConverged("slab step: linear solve did not reach the residual bound")
 
-    def _common_plan(self, opt) -> List[int]:
+    def _common_plan(self, opt, ctl) -> List[int]:
         """Same number of SOR sweeps on every rank, planned from the all-reduced Gershgorin ratios of the
         previous step (first step: as many sweeps as the halo supports)."""
         lib = self.batch.lib
@@ -283,11 +290,11 @@ class SlabMesh:
             plan = [opt.fixed_sweeps] * 3
         elif self._rho is None:
             plan = [limit] * 3
-        elif getattr(self, "_plan", None) is not None:
-            plan = [min(p, limit) for p in self._plan]
+        elif ctl["plan"] is not None:
+            plan = [min(p, limit) for p in ctl["plan"]]
         else:
             plan = [max(lib.dd_sweeps_for_rho(float(r) * 1.02 + 1e-12, opt.max_sweeps) + e, f)
-                    for r, e, f in zip(self._rho, self._extra, self._floor)]
+                    for r, e, f in zip(self._rho, ctl["extra"], ctl["floor"])]
         # never more than the halo supports; the residual bound is verified after every solve, so a clamped
         # plan either passes or the step raises below
         plan = [max(1, min(p, limit)) for p in plan]

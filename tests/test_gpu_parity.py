@@ -363,3 +363,54 @@ def test_fused_sources_path_matches_reference(dd, name, monkeypatch):
         for v in VARS:
             assert rel_err(got[v], z[f"step{n + 1}_{v}"]) <= TOL, f"step {n + 1} {v}"
     b.close()
+
+
+@pytest.mark.parametrize("case,N,M,solver", [("pol", 100, 130, "reg"), ("scp_fast1e1", 129, 129, "reg"),
+                                             ("pol", 100, 130, "smem")])
+def test_extrapolated_initial_iterate(dd, case, N, M, solver, monkeypatch):
+    """Ping-pong stepping starts each SOR solve from the previous step's increment.  The converged result
+    must not depend on that: 6 steps with and without it agree with the oracle's direct solves to TOL, and
+    the extrapolated start gets there with fewer sweeps."""
+    from oracle import NOTEBOOK_CONSTS, OForcing, OGrid, PCStepper, exact_state, make_case
+    p1, ddcore = dd["p1"], dd["ddcore"]
+    if solver == "smem":
+        monkeypatch.setenv("DD_SOLVER", "smem")  # read at every solve: the shared-memory tile kernel
+    om = NOTEBOOK_CONSTS["pol"]
+    eta, t0, nsteps = 50.0, 0.1, 6
+    dt = (1.0 / max(N, M)) ** 1.5
+    og = OGrid(np.linspace(0, 1, N + 1), np.linspace(0, 1, M + 1))
+    oc = make_case(case, om)
+    of = OForcing(oc, om, eta, og)
+    s = exact_state(oc, t0, og)
+    init = s.fields()
+    stepper = PCStepper(og, om, eta, of, keep_residuals=False)
+    t = t0
+    for _ in range(nsteps):
+        s = stepper.step(s, t, dt)
+        t += dt
+    ref = s.fields()
+    model = dd["product_model"](dict(K1=om.K1, K2=om.K2, K3=om.K3, K4=om.K4, DT=om.DT, Dl_max=om.Dl_max,
+                                     phi_l=om.phi_l, gamma_T=om.gamma_T, Kd=om.Kd, Sd=om.Sd, Dd_max=om.Dd_max,
+                                     phi_d=om.phi_d, r_sp=om.r_sp, T_ref=om.T_ref, kind=2))
+    grid = p1.Grid(og.x, og.y)
+    total = {}
+    for guess in (False, True):
+        b = ddcore.Batch(grid.x, grid.y, 1)
+        b.set_model(model, eta)
+        b.forcing_spec(dd["CASES"][case](grid=grid, model=model).device_spec())
+        b.upload(0, init)
+        opt = ddcore.pc_options(extrapolate_guess=guess)
+        cur, nxt, t, sweeps = 0, 1, t0, 0
+        for n in range(nsteps):
+            st = b.step_pc(cur, nxt, t, dt, opt)
+            assert max(st["bound"]) <= 1e-13
+            if n >= 3:
+                sweeps += sum(st["sweeps"])
+            t += dt
+            cur, nxt = nxt, cur
+        got = b.download(cur)
+        for v in VARS:
+            assert rel_err(got[v], ref[v]) <= TOL, (guess, v)
+        total[guess] = sweeps
+        b.close()
+    assert total[True] <= total[False], total
