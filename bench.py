@@ -136,7 +136,117 @@ def mesh_setup(world, rank, ctx):
     return mesh, h ** 1.5, N * MESH_COLS
 
 
+def ensemble_members(n, seed=20250503):
+    """Member parameters of configs[2]: eta ~ logU[10, 1000]; K1..K4, DT, Kd each base * U[0.5, 1.5]."""
+    import prob1base as p1
+    rng = np.random.default_rng(seed)
+    etas = 10.0 ** rng.uniform(1.0, 3.0, n)
+    f = rng.uniform(0.5, 1.5, (n, 6))
+    models = []
+    for k in range(n):
+        c = dict(POL)
+        for q, name in enumerate(("K1", "K2", "K3", "K4", "DT", "Kd")):
+            c[name] = POL[name] * f[k, q]
+        models.append(p1.DefaultModel02(p1.ModelConsts(R0=p1.R0, Ea=p1.Ea, phi_T=p1.Ea / p1.R0, **c)))
+    return models, etas
+
+
+def sweep_trials():
+    """configs[1]: Pol spatial N = 2..256 at dt = h^1.5, temporal N = 256, eta sweep at N = 32."""
+    tr = [dict(N=n, dt=(1.0 / n) ** 1.5, Tf=0.01, eta=ETA) for n in (2, 4, 8, 16, 32, 64, 128, 256)]
+    tr += [dict(N=256, dt=d, Tf=0.01, eta=ETA) for d in (1e-2, 5e-3, 2.5e-3, 1.25e-3)]
+    tr += [dict(N=32, dt=5e-4, Tf=0.01, eta=float(e)) for e in (10, 50, 100, 200, 300, 500, 1000)]
+    return tr
+
+
+def run_studies(args):
+    """`--workload ensemble | sweep`: independent trajectories split over the ranks, no communication while
+    stepping, one gather of the error scalars at the end.  Wall-clock around whole trials
+    (time loop + per-step error norms on the device), device idle on both sides."""
+    import torch
+    import ddensemble
+    import prob1_mms_cases as p1mc
+    import prob1base as p1
+    from _ddlib import Context, load_library
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = load_library()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    if args.workload == "ensemble":
+        n = args.members * world
+        models, etas = ensemble_members(n)
+        grid = p1.make_uniform_grid(32, 32)
+        ens = ddensemble.TrajectoryEnsemble(grid, p1mc.MMSCaseSlowlyChangingPeaks_Fast1e1, models, etas, world=world,
+                                            rank=rank, ctx=Context(local), chunk=args.members)
+        dt = 5e-4
+
+        def job(nsteps):
+            return ens.run_for_errors(nsteps * dt, dt)
+        job(max(1, args.warmup))
+        barrier()
+        launches0 = lib.dd_launch_count()
+        t0 = time.perf_counter()
+        res = job(args.steps)
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        all_err = ens.gather(res["overall"], dist, "cuda")
+        cell_steps = n * 32 * 32 * args.steps
+        workload = (f"scp_fast1e1_ensemble: {args.members} members/GPU of MMSCaseSlowlyChangingPeaks_Fast1e1, N=M=32, "
+                    f"dt=5e-4, per-member eta and K1..K4, DT, Kd (rng 20250503), error norms every step")
+        extra = {"members": n, "finite_errors": int(np.isfinite(all_err).sum()), "solver": ens.last_stats[-1]}
+    else:
+        trials = sweep_trials()
+        sw = ddensemble.RefinementSweep(p1mc.MMSCasePol, product_model(), trials, world=world, rank=rank,
+                                        device=local)
+        sw.run_for_errors()
+        barrier()
+        launches0 = lib.dd_launch_count()
+        t0 = time.perf_counter()
+        res = sw.run_for_errors()
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        merged = sw.merge(res, dist, "cuda")
+        cell_steps = sum(t["N"] * t["M"] * t["nsteps"] for t in sw.trials)
+        workload = ("pol_sweep: MMSCasePol spatial N=2..256 (dt=h^1.5) + temporal N=256 (4 dt) + eta sweep N=32 "
+                    "(7 eta), Tf=0.01: 19 trials, batches by (grid, steps) on concurrent streams")
+        extra = {"trials": len(trials), "overall_errors": [float(x) for x in merged["overall"]]}
+    launches = lib.dd_launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([el], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        el = float(t.item())
+    if rank != 0:
+        return
+    peak, peak_kind = measured_peak()
+    value = cell_steps / el
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": el * 1e3 / max(1, args.steps), "higher_is_better": True,
+            "scaling": "weak" if args.workload == "ensemble" else "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": dict({"workload": workload, "timing": "host wall clock around whole "
+                                                 "trials, device synchronised on both sides"}, **extra),
+            "clocks": None, "e2e": None, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "whole step (SMEM/L2-resident grids: HBM is not the binding "
+                         "roof for these sizes, SURVEY.md 8d)", "achieved": value / world * BYTES_PER_CELL_STEP / 1e9,
+                         "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                         "frac": value / world * BYTES_PER_CELL_STEP / 1e9 / peak, "traffic": None}}
+    print(json.dumps(line), flush=True)
+
+
 def run_b200(args):
+    if args.workload != "mesh":
+        return run_studies(args)
     import torch
     import ddcore
     from _ddlib import Context, load_library, profile_read
@@ -342,7 +452,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="mesh", choices=["mesh"])
+    ap.add_argument("--workload", default="mesh", choices=["mesh", "ensemble", "sweep"])
+    ap.add_argument("--members", type=int, default=12500, help="ensemble workload: members per GPU")
     ap.add_argument("--no-e2e", dest="e2e", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()

@@ -187,10 +187,13 @@ class Context:
     def synchronize(self):
         self.check(self.lib.dd_ctx_synchronize(self.handle), "synchronize")
 
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.dd_ctx_destroy(self.handle)
+            self.handle = None
+
     def __del__(self):
         try:
-            if getattr(self, "handle", None):
-                self.lib.dd_ctx_destroy(self.handle)
-                self.handle = None
+            self.close()
         except Exception:
             pass

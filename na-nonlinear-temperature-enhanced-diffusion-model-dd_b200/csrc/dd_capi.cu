@@ -8,6 +8,8 @@
 
 #include <map>
 #include <string>
+#include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "../../include/dd_b200.h"
@@ -99,9 +101,11 @@ static const char* kProfNames[PC_NCLASS] = {"k_time_coefs", "k_predict", "k_asse
                                             "k_assemble<cd>", "k_rbsor_tile<T>", "k_rbsor_tile<cl>",
                                             "k_rbsor_tile<cd>", "k_correct", "k_cs_decide+k_cs_redo",
                                             "k_summarise", "k_feuler", "k_error_norms", "other", "k_eval_sources"};
+// shared by every context of the process; contexts may be driven from different host threads
 struct Prof {
     bool on = false;
-    long long launches = 0;
+    std::atomic<long long> launches{0};
+    std::mutex mu;  // guards pool / recs while profiling is on
     std::vector<cudaEvent_t> pool;
     size_t used = 0;
     struct Rec { int cls; cudaEvent_t a, b; int n; };
@@ -127,12 +131,14 @@ struct ProfScope {
     ProfScope(cudaStream_t s, int c, int nl) : st(s), cls(c), n(nl), on(g_prof.on) {
         g_prof.launches += nl;
         if (on) {
+            std::lock_guard<std::mutex> lk(g_prof.mu);
             a = g_prof.get();
             cudaEventRecord(a, st);
         }
     }
     ~ProfScope() {
         if (on) {
+            std::lock_guard<std::mutex> lk(g_prof.mu);
             cudaEvent_t b = g_prof.get();
             cudaEventRecord(b, st);
             g_prof.recs.push_back({cls, a, b, n});
@@ -141,7 +147,7 @@ struct ProfScope {
 };
 #define CKP(cls, nl, call) do { ProfScope ps_(ctx->stream, cls, nl); CK(call); } while (0)
 
-extern "C" long long dd_launch_count(void) { return g_prof.launches; }
+extern "C" long long dd_launch_count(void) { return g_prof.launches.load(); }
 
 extern "C" int dd_profile_enable(int on) {
     g_prof.on = on != 0;
@@ -151,6 +157,7 @@ extern "C" int dd_profile_enable(int on) {
 // drains the recorded event pairs (synchronises the events) and returns the accumulated device time
 // per kernel class; names/ms/count arrays of length >= 16; resets the accumulators when `reset`
 extern "C" int dd_profile_read(const char** names, double* ms, long long* count, int reset) {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
     for (auto& r : g_prof.recs) {
         cudaEventSynchronize(r.b);
         float t = 0.f;
@@ -652,7 +659,10 @@ static int set_times(dd_batch* b, const double* t0, const double* dt, int n_t) {
 // Select what the step kernels are launched with.  Fused modes (SEPARABLE / EXPSIN) are staged: the sources
 // at t0 and t1 are evaluated into two array sets unless a set already holds that time level (uniform times
 // only).  Must be called after the member times are on the device (set_times / advance).
-static int stage_sources(dd_batch* b, double t0, double dt, bool times_uniform, bool need_slot1) {
+// `carry` (run loops with per-member times, where the time-keyed cache cannot be used): in: the set that
+// already holds every member's sources at this step's t0 (-1: none), out: the set holding them at t1
+static int stage_sources(dd_batch* b, double t0, double dt, bool times_uniform, bool need_slot1,
+                         int* carry = nullptr) {
     dd_ctx* ctx = b->ctx;
     if ((b->mode != DD_FORCING_SEPARABLE && b->mode != DD_FORCING_EXPSIN) || b->fused_sources) {
         b->smode = b->mode;
@@ -670,7 +680,9 @@ static int stage_sources(dd_batch* b, double t0, double dt, bool times_uniform, 
     int s0 = -1;
     for (int s = 0; s < 2; ++s)
         if (b->src_has[s] && b->src_time[s] == t0) s0 = s;
-    if (s0 < 0) {
+    if (s0 < 0 && carry && *carry >= 0) {
+        s0 = *carry;
+    } else if (s0 < 0) {
         s0 = 0;
         if (need_slot1 && b->src_has[0] && b->src_time[0] == t1) s0 = 1;  // keep a set that already holds t1
         DDState out;
@@ -687,6 +699,7 @@ static int stage_sources(dd_batch* b, double t0, double dt, bool times_uniform, 
         b->src_has[s1] = times_uniform;
         b->src_time[s1] = t1;
     }
+    if (carry) *carry = need_slot1 ? s1 : -1;
     b->smode = DD_FORCING_ARRAYS;
     memset(&b->sF, 0, sizeof(b->sF));
     for (int v = 0; v < DD_NVAR; ++v) {
@@ -1321,8 +1334,9 @@ extern "C" int dd_run_pc(dd_batch* b, int slot_a, int slot_b, const double* t0, 
     const size_t nstride = (size_t)8 * b->B;
     if (norms_out && (rc = norms_async(b, cur, -1, norms_out)) != DD_OK) return rc;
     double th = t0[0];  // host mirror of the device-side time advance (same IEEE additions)
+    int carry = -1;
     for (int s = 0; s < nsteps; ++s) {
-        if ((rc = stage_sources(b, th, dt[0], n_t == 1, true)) != DD_OK) return rc;
+        if ((rc = stage_sources(b, th, dt[0], n_t == 1, true, &carry)) != DD_OK) return rc;
         th = th + dt[0];
         if ((rc = pc_step_retry(b, cur, nxt, opt, stats)) != DD_OK) return rc;
         CKP(PC_TIME, 1, dd_launch_time_coefs(launch_of(b), b->mode, b->d_mem, b->d_t0, b->d_dt, n_t, 1));

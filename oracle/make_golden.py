@@ -109,6 +109,16 @@ def scenarios():
                   levels=[dict(N=32, M=32, dt=1e-2 / 2 ** k) for k in range(4)], integrator="pc", pc={}))
     S.append(dict(name="trial_fe_pol", kind="trial", case="pol", model=dict(NOTEBOOK["pol"], kind=2), eta=50.0,
                   Tf=0.01, levels=[dict(N=8, M=8, dt=1e-3), dict(N=8, M=8, dt=5e-4)], integrator="fe", pc={}))
+    # E. the convergence-study driver (src/cvg_studies_base.py): observed rates with their status strings and one
+    #    small spatial + temporal study (the driver's constructor convention has no regularisation factor, so the
+    #    RegHCsTriple classes are passed as functools.partial objects)
+    S.append(dict(name="cvg_study_pol", kind="cvg", case="pol", model=dict(NOTEBOOK["pol"], kind=2), eta=50.0,
+                  params=dict(Tf=4e-3, N_base_spatial=4, num_spatial_refinements=4, dt_fixed_spatial=1e-3,
+                              N_fixed_temporal=12, dt_base_temporal=2e-3, num_temporal_refinements=3),
+                  rate_cases=[[1.0, 0.25, 0.0625, 0.015625], [4e-5, 1.6e-5, 4.3e-6, 1.1e-6, 2.8e-7],
+                              [1.0, 2.0, 1.5], [1.0, 1.0, 0.5], [0.5, 0.25, 0.3], [3.0, 2.0, 2.0 - 1e-17, 1.0],
+                              [0.0, 0.0, 0.0], [1.0, 0.1, 0.01, 0.001], [1.0, 0.5, 0.25]],
+                  rate_factors=[2.0, 2.0, 2.0, 2.0, 2.0, 2.0, 2.0, 10.0, 3.0]))
     return S
 
 
@@ -241,6 +251,38 @@ def run_trial(d):
     return out
 
 
+def run_cvg(d):
+    import contextlib
+    import functools
+    import io
+    p1, p1mc, _ = _ref()
+    import cvg_studies_base as cvg  # the reference's driver
+    model = ref_model(p1, d["model"])
+    eta = d["eta"]
+    cfg = (functools.partial(p1.SemiDiscreteField_RegHCsTriple, regularization_factor=eta),
+           ref_case_cls(p1mc, d["case"]),
+           functools.partial(p1.ForcingTerms_RegHCsTriple, regularization_factor=eta),
+           functools.partial(p1.P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_RegHCsTriple,
+                             regularization_factor=eta),
+           "study")
+    with contextlib.redirect_stdout(io.StringIO()):
+        rep = cvg.run_convergence_studies([cfg], dict(d["params"], model=model))["study"]
+    out = {}
+    for kind in ("spatial", "temporal"):
+        out[kind + "_errors"] = np.array(rep[kind]["errors"], dtype=np.float64)
+        out[kind + "_rates"] = np.array(rep[kind]["rates"], dtype=np.float64)
+        out[kind + "_statuses"] = np.array(json.dumps(rep[kind]["statuses"]))
+        print("  ", kind, rep[kind]["errors"], rep[kind]["rates"], flush=True)
+    for k, (errs, fac) in enumerate(zip(d["rate_cases"], d["rate_factors"])):
+        try:
+            res = cvg.calculate_observed_rates(errs, fac)
+            out[f"rates{k}"] = np.array([r for r, _ in res], dtype=np.float64)
+            out[f"rates{k}_status"] = np.array(json.dumps([st for _, st in res]))
+        except Exception as e:  # the driver's own failure modes are part of its behaviour
+            out[f"rates{k}_raises"] = np.array(type(e).__name__)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -254,7 +296,7 @@ def main():
         if args.only and args.only not in d["name"]:
             continue
         print("scenario", d["name"], flush=True)
-        arrays = run_steps(d) if d["kind"] == "steps" else run_trial(d)
+        arrays = {"steps": run_steps, "trial": run_trial, "cvg": run_cvg}[d["kind"]](d)
         np.savez_compressed(os.path.join(OUT_DIR, d["name"] + ".npz"),
                             __desc__=np.array(json.dumps(d)), __meta__=np.array(json.dumps(meta)), **arrays)
 

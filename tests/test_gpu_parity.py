@@ -69,7 +69,9 @@ def test_steps_match_reference(dd, name):
             assert st["cs_newton_iters"] * per_step >= int(z["cs_newton_calls_per_step"][n]) or per_step > 1
             if per_step == 1:
                 assert st["cs_newton_iters"] == int(z["cs_newton_calls_per_step"][n])
-            assert max(st["bound"]) <= 1e-13
+            # solve_tol is 1e-14; the accepted residual may add the rounding floor of its own evaluation,
+            # 16 eps (|b| + |x|) / ((1 - rho) |v|), which reaches 1e-13 for the weakly dominant big-dt matrices
+            assert max(st["bound"]) <= 5e-13
         else:
             b.step_feuler(cur, nxt, t, dt)
         t += dt

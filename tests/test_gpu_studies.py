@@ -1,0 +1,119 @@
+"""GPU tests (-m gpu) of the study layer on the device path: the convergence-study driver against the
+reference driver's golden numbers, a refinement sweep against the reference's trial fixtures, and an
+ensemble with per-member constants against the oracle.  Tolerance of the error norms: 1e-9 relative +
+1e-13 absolute (differences of nearly equal fields); rates follow from the errors."""
+import functools
+import json
+
+import numpy as np
+import pytest
+
+from golden_util import VARS, load_fixture
+
+pytestmark = pytest.mark.gpu
+
+
+def close(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.all(np.abs(a - b) <= 1e-9 * np.abs(b) + 1e-13)
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import cvg_studies_base as cvg
+    import ddensemble
+    import prob1base as p1
+    from test_hostsim import CASES, product_model
+    return dict(cvg=cvg, ens=ddensemble, p1=p1, CASES=CASES, product_model=product_model)
+
+
+def test_convergence_study_driver_matches_reference(mods):
+    cvg, p1 = mods["cvg"], mods["p1"]
+    desc, z = load_fixture("cvg_study_pol")
+    model, eta = mods["product_model"](desc["model"]), desc["eta"]
+    cfg = (functools.partial(p1.SemiDiscreteField_RegHCsTriple, regularization_factor=eta),
+           mods["CASES"][desc["case"]],
+           functools.partial(p1.ForcingTerms_RegHCsTriple, regularization_factor=eta),
+           functools.partial(p1.P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_RegHCsTriple,
+                             regularization_factor=eta),
+           "study")
+    cvg.VERBOSE = False
+    rep = cvg.run_convergence_studies([cfg], dict(desc["params"], model=model))["study"]
+    for kind in ("spatial", "temporal"):
+        assert close(rep[kind]["errors"], z[kind + "_errors"]), (kind, rep[kind]["errors"], z[kind + "_errors"])
+        assert rep[kind]["statuses"] == json.loads(str(z[kind + "_statuses"]))
+        got, want = np.array(rep[kind]["rates"]), z[kind + "_rates"]
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        ok = ~np.isnan(want)
+        assert np.all(np.abs(got[ok] - want[ok]) <= 1e-6)
+
+
+@pytest.mark.parametrize("name", ["trial_spatial_pol", "trial_eta_pol", "trial_temporal_expsin"])
+def test_refinement_sweep_matches_trial_fixtures(mods, name):
+    """All levels of a study launched together (shared batches, concurrent streams) give the reference's
+    per-level numbers."""
+    desc, z = load_fixture(name)
+    model = mods["product_model"](desc["model"])
+    trials = [dict(N=lv["N"], M=lv["M"], dt=lv["dt"], Tf=desc["Tf"], eta=lv.get("eta", desc["eta"]))
+              for lv in desc["levels"]]
+    sw = mods["ens"].RefinementSweep(mods["CASES"][desc["case"]], model, trials, pc=desc["pc"])
+    res = sw.run_for_errors()
+    assert res["owned"].all()
+    for li in range(len(trials)):
+        assert sw.trials[li]["dt_used"] == float(z[f"L{li}_dt_used"])
+        assert close(res["overall"][li], z[f"L{li}_overall"]), (li, res["overall"][li], z[f"L{li}_overall"])
+        assert close(res["per_var"][li], z[f"L{li}_per_var"])
+
+
+def test_sweep_split_over_two_ranks_covers_every_trial(mods):
+    desc, z = load_fixture("trial_spatial_pol")
+    model = mods["product_model"](desc["model"])
+    trials = [dict(N=lv["N"], M=lv["M"], dt=lv["dt"], Tf=desc["Tf"], eta=desc["eta"]) for lv in desc["levels"]]
+    parts = [mods["ens"].RefinementSweep(mods["CASES"]["pol"], model, trials, world=2, rank=r).run_for_errors()
+             for r in range(2)]
+    assert np.array_equal(parts[0]["owned"] ^ parts[1]["owned"], np.ones(len(trials), dtype=bool))
+    merged = np.where(parts[0]["owned"], parts[0]["overall"], parts[1]["overall"])
+    assert close(merged, [float(z[f"L{li}_overall"]) for li in range(len(trials))])
+
+
+def test_ensemble_with_member_constants_matches_oracle(mods):
+    """SCP_Fast1e1 members with perturbed K1..K4, DT, Kd and log-uniform eta (the draw of SURVEY 8d config 3):
+    batched device run, sharded 2 ways, against the oracle member by member."""
+    from oracle import NOTEBOOK_CONSTS, OForcing, OGrid, make_case, run_trial
+    import dataclasses
+    p1, ens = mods["p1"], mods["ens"]
+    rng = np.random.default_rng(20250503)
+    n, N = 6, 12
+    base = NOTEBOOK_CONSTS["pol"]
+    etas = 10.0 ** rng.uniform(1.0, 3.0, n)
+    omodels, models = [], []
+    for _ in range(n):
+        f = rng.uniform(0.5, 1.5, 6)
+        om = dataclasses.replace(base, K1=base.K1 * f[0], K2=base.K2 * f[1], K3=base.K3 * f[2], K4=base.K4 * f[3],
+                                 DT=base.DT * f[4], Kd=base.Kd * f[5])
+        omodels.append(om)
+        models.append(mods["product_model"](dict(
+            K1=om.K1, K2=om.K2, K3=om.K3, K4=om.K4, DT=om.DT, Dl_max=om.Dl_max, phi_l=om.phi_l,
+            gamma_T=om.gamma_T, Kd=om.Kd, Sd=om.Sd, Dd_max=om.Dd_max, phi_d=om.phi_d, r_sp=om.r_sp,
+            T_ref=om.T_ref, kind=2)))
+    grid = p1.make_uniform_grid(N, N)
+    og = OGrid(np.array(grid.x), np.array(grid.y))
+    Tf, dt = 0.004, 5e-4
+    want = []
+    for om, eta in zip(omodels, etas):
+        oc = make_case("scp_fast1e1", om)
+        r = run_trial(oc, og, om, float(eta), OForcing(oc, om, float(eta), og), Tf=Tf, dt=dt)
+        want.append([r["overall"]] + [r["per_var"][v] for v in VARS])
+    want = np.array(want)
+    got = np.zeros_like(want)
+    for rank in range(2):
+        e = ens.TrajectoryEnsemble(grid, mods["CASES"]["scp_fast1e1"], models, etas, world=2, rank=rank, chunk=2)
+        res = e.run_for_errors(Tf, dt)
+        assert res["nsteps"] == 8
+        got[e.first:e.last, 0] = res["overall"]
+        got[e.first:e.last, 1:] = res["per_var"]
+    assert close(got, want), (got, want)
+    # one shared model object + scalar eta is the degenerate ensemble
+    e = ens.TrajectoryEnsemble(grid, mods["CASES"]["scp_fast1e1"], models[0], [etas[0]] * 3)
+    res = e.run_for_errors(Tf, dt)
+    assert close(res["overall"], [want[0, 0]] * 3)

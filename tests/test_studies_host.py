@@ -1,0 +1,134 @@
+"""CPU tests of the study / ensemble host layer: observed rates against the reference driver's golden
+values, the vectorised combined error norm against the scalar one, cost balancing, and the world_size-2
+gathers over gloo."""
+import json
+import multiprocessing as mp
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from golden_util import load_fixture
+
+
+def test_observed_rates_match_reference_driver():
+    import cvg_studies_base as cvg
+    desc, z = load_fixture("cvg_study_pol")
+    for k, (errs, fac) in enumerate(zip(desc["rate_cases"], desc["rate_factors"])):
+        if f"rates{k}_raises" in z:
+            with pytest.raises(ZeroDivisionError):
+                cvg.calculate_observed_rates(errs, fac)
+            assert str(z[f"rates{k}_raises"]) == "ZeroDivisionError"
+            continue
+        got = cvg.calculate_observed_rates(errs, fac)
+        assert [s for _, s in got] == json.loads(str(z[f"rates{k}_status"]))
+        np.testing.assert_array_equal(np.array([r for r, _ in got]), z[f"rates{k}"])  # NaN == NaN here
+    with pytest.raises(AssertionError):
+        cvg.calculate_observed_rates([1.0, 0.5])
+    with pytest.raises(AssertionError):
+        cvg.calculate_observed_rates([1.0, 0.5, 0.25], 1.0)
+    with pytest.raises(AssertionError):
+        cvg.calculate_observed_rates([1.0, -0.5, 0.25])
+    assert cvg.RateStatus.OK == "OK" and cvg.TimeStepData._fields == ("t", "h_norm_sq_errors",
+                                                                      "grad_h_norm_p_sq_errors")
+
+
+def test_vectorised_combined_norm_equals_scalar_one():
+    import ddensemble
+    import mms_trial_utils as mtu
+    rng = np.random.default_rng(20250503)
+    K, B = 9, 7
+    norms = rng.random((K, B, 8)) * 1e-6
+    norms[3, 2, 1] = np.nan          # a NaN never replaces the running maximum
+    norms[:, 5, :] = 0.0
+    dt = rng.random(B) * 1e-2 + 1e-3
+    res = ddensemble.combined_error_norms(norms, dt)
+    names, integral = list(mtu.VARS), ["T", "cl", "cd"]
+    for m in range(B):
+        series = mtu._series_from_norms(np.arange(K) * dt[m], norms[:, m, :], names, integral)
+        want = mtu.NumericalErrorSummary(dt[m], series, names, integral)
+        assert res["overall"][m] == want.overall_combined_error or (
+            np.isnan(res["overall"][m]) and np.isnan(want.overall_combined_error))
+        for v, name in enumerate(names):
+            a, b = res["per_var"][m, v], want.per_variable_sup_errors[name]
+            assert a == b or (np.isnan(a) and np.isnan(b)), (m, name, a, b)
+
+
+def test_steps_and_dt_follow_the_trial_rule():
+    import ddensemble
+    assert ddensemble.steps_and_dt(0.01, (1 / 256) ** 1.5) == (41, 0.01 / 41)
+    assert ddensemble.steps_and_dt(0.01, 0.3536) == (1, 0.01)
+    assert ddensemble.steps_and_dt(1.0, 0.25, 0.5) == (2, 0.25)
+
+
+def test_sweep_groups_and_balance():
+    import ddensemble
+    import prob1_mms_cases as p1mc
+    trials = [dict(N=n, dt=(1.0 / n) ** 1.5, Tf=0.01, eta=50.0) for n in (2, 4, 8, 16, 32, 64, 128, 256)]
+    trials += [dict(N=256, dt=1e-2 / 2 ** k, Tf=0.01, eta=50.0) for k in range(4)]
+    trials += [dict(N=32, dt=5e-4, Tf=0.01, eta=e) for e in (10, 50, 100, 200, 300, 500, 1000)]
+    sw = ddensemble.RefinementSweep(p1mc.MMSCasePol, None, trials, world=4, rank=1)
+    assert len(sw.trials) == 19
+    assert sum(len(g["members"]) for g in sw.groups) == 19
+    eta_group = [g for g in sw.groups if g["key"] == (32, 32, 20)]
+    assert len(eta_group) == 1 and len(eta_group[0]["members"]) == 7   # the eta study shares one batch
+    assert [t["nsteps"] for t in sw.trials[:8]] == [1, 1, 1, 1, 2, 6, 15, 41]
+    # every rank computes the same assignment; the heaviest group sits alone on its rank
+    costs = [g["cost"] for g in sw.groups]
+    owner = ddensemble.RefinementSweep.balance(costs, 4)
+    assert owner == sw.assignment
+    heavy = int(np.argmax(costs))
+    assert sum(1 for o in owner if o == owner[heavy]) == 1
+    loads = [sum(c for c, o in zip(costs, owner) if o == r) for r in range(4)]
+    assert max(loads) == costs[heavy]
+    assert ddensemble.RefinementSweep.balance([5, 5, 5, 5], 2) == [0, 1, 0, 1]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gather_worker(rank, world, port, out):
+    import torch.distributed as dist
+    import ddensemble
+    import prob1_mms_cases as p1mc
+    from ddmesh import shard_members
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = 11
+        a, b = shard_members(n, world, rank)
+        local = np.stack([np.arange(a, b, dtype=np.float64), 10.0 * np.arange(a, b)], axis=1)
+        full = ddensemble.gather_members(local, n, world, rank, dist)
+        trials = [dict(N=4 * (k + 1), dt=1e-3, Tf=2e-3, eta=50.0) for k in range(5)]
+        sw = ddensemble.RefinementSweep(p1mc.MMSCasePol, None, trials, world=world, rank=rank)
+        owned = np.array([sw.assignment[[k in g["members"] for g in sw.groups].index(True)] == rank
+                          for k in range(5)])
+        res = dict(overall=np.where(owned, np.arange(5) + 1.0, np.nan),
+                   per_var=np.where(owned[:, None], np.arange(25).reshape(5, 5) + 0.5, np.nan), owned=owned)
+        merged = sw.merge(res, dist)
+        out.put((rank, full, merged["overall"], merged["per_var"]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_member_gather_and_sweep_merge_gloo():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [out.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, full, overall, per_var in got:
+        assert full.shape == (11, 2)
+        np.testing.assert_array_equal(full[:, 0], np.arange(11.0))
+        np.testing.assert_array_equal(full[:, 1], 10.0 * np.arange(11.0))
+        np.testing.assert_array_equal(overall, np.arange(5) + 1.0)
+        np.testing.assert_array_equal(per_var, np.arange(25).reshape(5, 5) + 0.5)
