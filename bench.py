@@ -126,7 +126,7 @@ def mesh_setup(world, rank, ctx):
     x = np.arange(N + 1) * h
     y = np.linspace(0.0, 1.0, MESH_COLS + 1)
     model = product_model()
-    mesh = ddmesh.SlabMesh(x, y, world=world, rank=rank, ctx=ctx)
+    mesh = ddmesh.SlabMesh(x, y, world=world, rank=rank, ctx=ctx, nslots=3)
     mesh.batch.set_model(model, ETA)
     case = p1mc.MMSCasePol(grid=p1.Grid(np.array([0.0, 0.5, 1.0]), np.array([0.0, 0.5, 1.0])), model=model)
     mesh.batch.forcing_spec(case.device_spec())
@@ -241,7 +241,7 @@ def run_studies(args):
                          "roof for these sizes, SURVEY.md 8d)", "achieved": value / world * BYTES_PER_CELL_STEP / 1e9,
                          "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                          "frac": value / world * BYTES_PER_CELL_STEP / 1e9 / peak, "traffic": None}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def run_b200(args):
@@ -275,7 +275,9 @@ def run_b200(args):
             def step(k):
                 # times accumulate as in the reference's loop (current_t += dt, src/mms_trial_utils.py:128):
                 # the t1 sources of a step are then bitwise the t0 sources of the next one
-                mesh.step_pc(k % 2, (k + 1) % 2, clock["t"], dt, opt)
+                # verification is deferred by one step (three rotating slots): the host enqueues step k + 1
+                # before it reads the convergence summaries of step k; flush() settles the last one
+                mesh.step_pc(k % 3, (k + 1) % 3, clock["t"], dt, opt, defer=not args.sync_steps)
                 clock["t"] += dt
             workload = (f"pol_mesh: MMSCasePol, {MESH_ROWS_PER_GPU} rows/GPU x {MESH_COLS} cols of the N=M=8192 "
                         f"unit-square mesh (h=k=1/8192, dt=h^1.5), slab decomposition along i")
@@ -292,6 +294,7 @@ def run_b200(args):
 
         for k in range(args.warmup):
             step(k)
+        mesh.flush()
         barrier()
         launches0 = lib.dd_launch_count()
         clocks = ClockSampler(local)
@@ -302,6 +305,7 @@ def run_b200(args):
         e0.record(stream)
         for k in range(args.steps):
             step(args.warmup + k)
+        mesh.flush()  # the last step is verified inside the timed region
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -318,6 +322,7 @@ def run_b200(args):
         barrier()
         for k in range(args.steps):
             step(args.warmup + args.steps + k)
+        mesh.flush()
         barrier()
         prof = profile_read(True)
         lib.dd_profile_enable(0)
@@ -327,7 +332,7 @@ def run_b200(args):
         if args.e2e:
             shape = mesh.batch.shape
             pinned_in = {v: torch.empty(shape, dtype=torch.float64).pin_memory().numpy() for v in ddcore.VARS}
-            got = mesh.batch.download(args.steps % 2)
+            got = mesh.batch.download((args.warmup + 2 * args.steps) % 3)
             for v in ddcore.VARS:
                 pinned_in[v][...] = got[v]
             pinned_out = {v: torch.empty(shape, dtype=torch.float64).pin_memory().numpy() for v in ddcore.VARS}
@@ -380,7 +385,7 @@ def run_b200(args):
     }
     if world == 1 and args.cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(threads=1, steps=2, warmup=1)
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ----------------------------------------------------------------------------
@@ -443,10 +448,26 @@ def run_reference(args):
                                    "dt rule and integrator settings as the CUDA arm)"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+def _emit(line: dict):
+    """The one JSON line goes to the process's original stdout; everything else any library prints (NCCL's
+    version banner included) was redirected to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    fd = _REAL_STDOUT if _REAL_STDOUT is not None else 1
+    while data:
+        data = data[os.write(fd, data):]
+
+
+_REAL_STDOUT = None
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # C-level stdout of this process -> stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -454,6 +475,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="mesh", choices=["mesh", "ensemble", "sweep"])
     ap.add_argument("--members", type=int, default=12500, help="ensemble workload: members per GPU")
+    ap.add_argument("--sync-steps", action="store_true", help="verify every step before enqueuing the next one")
     ap.add_argument("--no-e2e", dest="e2e", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()

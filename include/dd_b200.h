@@ -143,6 +143,14 @@ int dd_step_feuler(dd_batch* b, int slot_in, int slot_out, const double* t0, con
 /* P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_RegHCsTriple.step, src/prob1base.py:3117-3149 */
 int dd_step_pc(dd_batch* b, int slot_in, int slot_out, const double* t0, const double* dt, int n_t,
                const dd_pc_options* opt, dd_step_stats* stats /* may be NULL */);
+/* The same step with deferred verification: the step is enqueued and the call returns after reading the
+ * convergence summaries of the PREVIOUS deferred step (have_prev = 1 and prev_stats filled then), so the host
+ * never drains the stream between steps.  A rejected step is redone with more sweeps, together with the step
+ * enqueued after it; this needs the input of the rejected step, so rotate three slots (a->b, b->c, c->a).
+ * Every other entry point that reads or writes the batch first settles a pending step (dd_step_pc_flush). */
+int dd_step_pc_deferred(dd_batch* b, int slot_in, int slot_out, const double* t0, const double* dt, int n_t,
+                        const dd_pc_options* opt, dd_step_stats* prev_stats /* nullable */, int* have_prev /* nullable */);
+int dd_step_pc_flush(dd_batch* b, dd_step_stats* stats /* nullable */, int* have_stats /* nullable */);
 /* nsteps PC steps with times advanced on the device (current_t += dt, src/mms_trial_utils.py:128);
  * result ends in slot_a if nsteps is even else slot_b; optional per-step error norms into
  * norms_out[(nsteps+1)][nmembers][8] (index 0 = initial state) */
@@ -181,7 +189,9 @@ int dd_error_norms(dd_batch* b, int slot, int slot_exact, const double* t, int n
  * phase 0: times + predict (needs halo rows of the five input fields); 1/2/3: Newton solve of T/cl/cd into
  * slot_out on the owned rows (exchange that field's halo afterwards); 4: correctors on all local rows;
  * 5: cs exit decision (after reducing the work buffers "cs_it_max" (max) / "cs_it_min" (min) over ranks) and
- * summary[3][4] = rho, ratio (<= 1 means the residual bound is met), resid, bound of the T, cl, cd solves.
+ * summary[3][4] = rho, ratio (<= 1 means the residual bound is met), resid, bound of the T, cl, cd solves;
+ * 6: as 5 without the read-back (nothing is waited for): the caller reduces the device buffers "summary"
+ *    (3 x 4 doubles) and "cs_used" (int per member) itself, e.g. while the next step is already running.
  * Phases 21/22/23 only assemble the T/cl/cd system and 31/32/33 only solve it, so that the caller can
  * max-reduce the Gershgorin ratio ("solve_stats" work buffer, first double of each 5-double record) over
  * ranks in between: the SOR relaxation factor is then the same on every rank.

@@ -85,6 +85,9 @@ SIGNATURES = {
     "dd_work_download": (C.c_int, [_vp, C.c_char_p, C.c_int, _dp]),
     "dd_step_feuler": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.c_int]),
     "dd_step_pc": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.c_int, _P(dd_pc_options), _P(dd_step_stats)]),
+    "dd_step_pc_deferred": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.c_int, _P(dd_pc_options), _P(dd_step_stats),
+                                      _P(C.c_int)]),
+    "dd_step_pc_flush": (C.c_int, [_vp, _P(dd_step_stats), _P(C.c_int)]),
     "dd_run_pc": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, _P(dd_pc_options), _dp,
                             _P(dd_step_stats)]),
     "dd_run_feuler": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, _dp]),

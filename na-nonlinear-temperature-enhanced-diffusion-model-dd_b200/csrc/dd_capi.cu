@@ -67,6 +67,22 @@ struct dd_batch {
     int cm;  // set in use by the solves being issued
     // extrapolated initial iterate: when a step reads slot a and writes slot b right after a step that read
     // b and wrote a (ping-pong), slot b still holds the state of two steps ago and v_n - v_{n-1} starts the solves
+    // step records: summaries come back through pinned host memory; with deferred verification the record
+    // of step n is read while step n + 1 is already running (two records, used alternately)
+    struct StepRec {
+        bool active = false;      // enqueued, summary not read yet
+        int slot_in = 0, slot_out = 0, nsolves = 0, n_t = 0;
+        bool guess = false;
+        dd_pc_options opt;
+        std::vector<double> t0, dt;
+        int sweeps[3] = {0, 0, 0}, passes[3] = {0, 0, 0};
+        std::vector<int> solve_sweeps;   // sweeps used by each solve of the step
+        SolveSummary* h_sums = nullptr;  // pinned [cap_sums]
+        int* h_used = nullptr;           // pinned [B]
+        int cap_sums = 0;
+        cudaEvent_t done = nullptr;
+    } rec[2];
+    int rec_cur;
     bool prev_valid, use_guess;
     int prev_in, prev_out;
     double prev_dt, cur_dt;  // first member's step size (the increment scales with it)
@@ -75,6 +91,8 @@ struct dd_batch {
     int asm0, asm1;  // rows whose Newton rows are exact: their stencil reads predictor output, itself only
                      // defined on [cmp0, cmp1) -> one more row is lost on every interior side
 };
+
+static int flush_pending(dd_batch* b, dd_step_stats* stats, int* have);  // verifies a deferred step
 
 static void reset_ctl(dd_batch* b, bool all) {
     for (int m = 0; m < 2; ++m)
@@ -296,6 +314,7 @@ extern "C" int dd_batch_create(dd_ctx* ctx, int N, int M, const double* x, const
     b->prev_valid = b->use_guess = false;
     b->prev_in = b->prev_out = -1;
     b->prev_dt = b->cur_dt = 0.0;
+    b->rec_cur = 0;
     const int ld = M + 1;
     b->field_elems = (size_t)nmembers * nrows * ld;
     // geometry (reference Grid.__init__, src/prob1base.py:287-304)
@@ -361,6 +380,11 @@ extern "C" int dd_batch_destroy(dd_batch* b) {
     for (double* p : b->table_dev) cudaFree(p);
     for (auto& s : b->slots) for (double* p : s) cudaFree(p);
     for (auto& kv : b->work) cudaFree(kv.second);
+    for (auto& r : b->rec) {
+        if (r.h_sums) cudaFreeHost(r.h_sums);
+        if (r.h_used) cudaFreeHost(r.h_used);
+        if (r.done) cudaEventDestroy(r.done);
+    }
     cudaFree(b->d_mem); cudaFree(b->d_t0); cudaFree(b->d_dt); cudaFree(b->d_stats); cudaFree(b->d_summary);
     cudaFree(b->d_itmax); cudaFree(b->d_itmin); cudaFree(b->d_used); cudaFree(b->d_norm_partial);
     cudaFree(b->d_norm_out);
@@ -383,6 +407,7 @@ static int push_members(dd_batch* b, int first, int count) {
 // static part only (model, phi, active) -- kernels never change those.
 extern "C" int dd_batch_set_models(dd_batch* b, int first, int count, const dd_model* models) {
     if (!b || !models || first < 0 || count < 1 || first + count > b->B) return DD_ERR_INVALID;
+    { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
     for (int k = 0; k < count; ++k) model_to_dev(models[k], &b->h_mem[first + k].m);
     reset_ctl(b, true);
     return push_members(b, first, count);
@@ -416,6 +441,7 @@ static int up_table(dd_batch* b, const double* h, size_t n, const double** dst) 
 
 extern "C" int dd_forcing_none(dd_batch* b) {
     if (!b) return DD_ERR_INVALID;
+    { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
     free_tables(b);
@@ -429,6 +455,7 @@ extern "C" int dd_forcing_separable(dd_batch* b, int nterms, const double* const
     if (!b || !X || !Y || !XQ || !YQ || !phi_kind || !phi_p || nterms < 1 || nterms > 16) return DD_ERR_INVALID;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
+    { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
     CK(cudaStreamSynchronize(ctx->stream));
     free_tables(b);
     int rc;
@@ -468,6 +495,7 @@ extern "C" int dd_forcing_separable(dd_batch* b, int nterms, const double* const
 
 extern "C" int dd_forcing_set_phi(dd_batch* b, int first, int count, const int* phi_kind, const double* phi_p) {
     if (!b || !phi_kind || !phi_p || first < 0 || count < 1 || first + count > b->B) return DD_ERR_INVALID;
+    { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
     for (int k = 0; k < count; ++k)
         for (int v = 0; v < 5; ++v) {
             b->h_mem[first + k].phi_kind[v] = phi_kind[k * 5 + v];
@@ -481,6 +509,7 @@ extern "C" int dd_forcing_expsin(dd_batch* b, const double* sx, const double* cx
     if (!b || !sx || !cx || !sy || !cy || !sxq || !syq) return DD_ERR_INVALID;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
+    { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
     CK(cudaStreamSynchronize(ctx->stream));
     free_tables(b);
     int rc;
@@ -505,6 +534,7 @@ extern "C" int dd_forcing_arrays(dd_batch* b, int member, const double* const f[
     if (!b || !f || member < 0 || member >= b->B) return DD_ERR_INVALID;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
+    { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
     if (b->mode != DD_FORCING_ARRAYS) {
         CK(cudaStreamSynchronize(ctx->stream));
         free_tables(b);
@@ -537,6 +567,7 @@ extern "C" int dd_state_upload(dd_batch* b, int slot, int member, const double* 
     b->prev_valid = false;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
+    { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
     const size_t per = (size_t)b->nrows * b->g.ld;
     for (int v = 0; v < 5; ++v)
         if (fields[v])
@@ -550,6 +581,7 @@ extern "C" int dd_state_download(dd_batch* b, int slot, int member, double* cons
     if (!b || !fields || !slot_ok(b, slot) || member < 0 || member >= b->B) return DD_ERR_INVALID;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
+    { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
     const size_t per = (size_t)b->nrows * b->g.ld;
     for (int v = 0; v < 5; ++v)
         if (fields[v])
@@ -579,6 +611,19 @@ extern "C" int dd_work_dev_ptr(dd_batch* b, const char* name, void** ptr) {
         *ptr = b->d_stats;
         return DD_OK;
     }
+    if (!strcmp(name, "summary")) {
+        // SolveSummary[3] of the phased step: rho, ratio, resid, bound per solve (all-reduced by the slab driver)
+        int rc0 = ensure_solve_slots(b, 3);
+        if (rc0 != DD_OK) return rc0;
+        *ptr = b->d_summary;
+        return DD_OK;
+    }
+    if (!strcmp(name, "cs_used")) {
+        // int[nmembers]: cs-Newton iterations used (phase 5 / 6)
+        if (!b->d_used) return fail(b->ctx, DD_ERR_INVALID, "cs statistics not allocated yet");
+        *ptr = b->d_used;
+        return DD_OK;
+    }
     if (!strcmp(name, "cs_it_max") || !strcmp(name, "cs_it_min")) {
         // [member][cap] accumulators of the cs-Newton exit test (allreduced by the slab driver)
         if (b->cs_cap_alloc <= 0) return fail(b->ctx, DD_ERR_INVALID, "cs statistics not allocated yet");
@@ -596,6 +641,7 @@ extern "C" int dd_work_upload(dd_batch* b, const char* name, int member, const d
     if (!b || !name || !host || member < 0 || member >= b->B) return DD_ERR_INVALID;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
+    { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
     double* p;
     int rc = get_work(b, name, &p);
     if (rc != DD_OK) return rc;
@@ -609,6 +655,7 @@ extern "C" int dd_work_download(dd_batch* b, const char* name, int member, doubl
     if (!b || !name || !host || member < 0 || member >= b->B) return DD_ERR_INVALID;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
+    { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
     double* p;
     int rc = get_work(b, name, &p);
     if (rc != DD_OK) return rc;
@@ -713,6 +760,7 @@ extern "C" int dd_state_fill_exact(dd_batch* b, int slot, const double* t, int n
     if (!b || !slot_ok(b, slot) || !t) return DD_ERR_INVALID;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
+    { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
     std::vector<double> one(n_t, 1.0);
     int rc = set_times(b, t, one.data(), n_t);
     if (rc != DD_OK) return rc;
@@ -730,6 +778,7 @@ extern "C" int dd_step_feuler(dd_batch* b, int slot_in, int slot_out, const doub
     b->prev_valid = false;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
+    { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
     int rc = set_times(b, t0, dt, n_t);
     if (rc != DD_OK) return rc;
     if ((rc = stage_sources(b, t0[0], dt[0], n_t == 1, false)) != DD_OK) return rc;
@@ -743,6 +792,7 @@ extern "C" int dd_eval_fields(dd_batch* b, int slot_in, int slot_out, const doub
     b->prev_valid = false;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
+    { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
     std::vector<double> one(n_t, 1.0);
     int rc = set_times(b, t, one.data(), n_t);
     if (rc != DD_OK) return rc;
@@ -766,6 +816,7 @@ extern "C" int dd_error_norms(dd_batch* b, int slot, int slot_exact, const doubl
     if (!b || !slot_ok(b, slot) || !out || (slot_exact >= 0 && !slot_ok(b, slot_exact))) return DD_ERR_INVALID;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
+    { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
     if (slot_exact < 0) {
         if (!t) return DD_ERR_INVALID;
         std::vector<double> one(n_t, 1.0);
@@ -1153,13 +1204,27 @@ static void record_step(dd_batch* b, int slot_in, int slot_out) {
     b->prev_valid = true;
 }
 
-// one PC step; times must already be on the device (set_times or advance)
-static int pc_step_once(dd_batch* b, int slot_in, int slot_out, const dd_pc_options& opt, dd_step_stats* stats,
-                        bool* converged) {
+static int rec_prepare(dd_batch* b, dd_batch::StepRec& R, int nsolves) {
+    dd_ctx* ctx = b->ctx;
+    if (R.cap_sums < nsolves) {
+        if (R.h_sums) cudaFreeHost(R.h_sums);
+        R.h_sums = nullptr;
+        CK(cudaMallocHost((void**)&R.h_sums, sizeof(SolveSummary) * nsolves));
+        R.cap_sums = nsolves;
+    }
+    if (!R.h_used) CK(cudaMallocHost((void**)&R.h_used, sizeof(int) * b->B));
+    if (!R.done) CK(cudaEventCreateWithFlags(&R.done, cudaEventDisableTiming));
+    return DD_OK;
+}
+
+// Enqueues one PC step and the read-back of its summaries into the record R (nothing is waited for).
+static int pc_step_enqueue(dd_batch* b, int slot_in, int slot_out, const dd_pc_options& opt, dd_batch::StepRec& R) {
     dd_ctx* ctx = b->ctx;
     int rc;
     const int P = opt.num_pc_steps, Q = opt.num_newton_steps;
     if ((rc = ensure_solve_slots(b, 3 * P * Q)) != DD_OK) return rc;
+    if ((rc = rec_prepare(b, R, 3 * P * Q)) != DD_OK) return rc;
+    R.solve_sweeps.clear();
     DDPredictOut po;
     if ((rc = get_work(b, "cp1p", &po.cp1p)) != DD_OK) return rc;
     if ((rc = get_work(b, "cs1p", &po.cs1p)) != DD_OK) return rc;
@@ -1198,6 +1263,7 @@ static int pc_step_once(dd_batch* b, int slot_in, int slot_out, const dd_pc_opti
                                    gs ? sout.v[DD_CL] : nullptr)) != DD_OK) return rc;
             if ((rc = newton_solve(b, DD_CD, u, dst[0], dst[1], po.Ycd, dst[2], opt, k++, &sweeps[2], &passes[2], 3,
                                    gs ? sout.v[DD_CD] : nullptr)) != DD_OK) return rc;
+            for (int q = 0; q < 3; ++q) R.solve_sweeps.push_back(sweeps[q]);
             u.v[DD_T] = dst[0]; u.v[DD_CL] = dst[1]; u.v[DD_CD] = dst[2];
             pp ^= 1;
         }
@@ -1223,10 +1289,36 @@ static int pc_step_once(dd_batch* b, int slot_in, int slot_out, const dd_pc_opti
                                     opt.consec_xs_rtol, b->d_itmax, b->d_itmin, b->d_used));
         u.v[DD_CP] = cpd; u.v[DD_CS] = csd;
     }
-    // verification of every solve of this step (one small readback)
-    std::vector<SolveSummary> sums(k);
-    CK(cudaMemcpyAsync(sums.data(), b->d_summary, sizeof(SolveSummary) * k, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    // verification of every solve of this step: one small read-back, waited for in pc_step_finish
+    CK(cudaMemcpyAsync(R.h_sums, b->d_summary, sizeof(SolveSummary) * k, cudaMemcpyDeviceToHost, ctx->stream));
+    const bool track_used = opt.consec_xs_rtol > 0.0 && opt.num_newton_iterations > 0;
+    if (track_used)
+        CK(cudaMemcpyAsync(R.h_used, b->d_used, sizeof(int) * b->B, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(R.done, ctx->stream));
+    R.active = true;
+    R.slot_in = slot_in;
+    R.slot_out = slot_out;
+    R.nsolves = k;
+    R.guess = guess;
+    R.opt = opt;
+    for (int q = 0; q < 3; ++q) {
+        R.sweeps[q] = sweeps[q];
+        R.passes[q] = passes[q];
+    }
+    return DD_OK;
+}
+
+// Waits for the summaries of the step in R, updates the sweep controller and fills `stats`.
+static int pc_step_finish(dd_batch* b, dd_batch::StepRec& R, dd_step_stats* stats, bool* converged) {
+    dd_ctx* ctx = b->ctx;
+    CK(cudaEventSynchronize(R.done));
+    R.active = false;
+    const dd_pc_options& opt = R.opt;
+    const int k = R.nsolves;
+    const bool guess = R.guess;
+    const SolveSummary* sums = R.h_sums;
+    const int* sweeps = R.sweeps;
+    const int* passes = R.passes;
     *converged = true;
     for (int q = 0; q < k; ++q)
         if (!(sums[q].ratio <= 1.0)) *converged = false;
@@ -1234,19 +1326,21 @@ static int pc_step_once(dd_batch* b, int slot_in, int slot_out, const dd_pc_opti
         for (int q = 0; q < k; ++q) {
             const int vi = q % 3;
             b->cm = (guess && q < 3) ? 1 : 0;
+            dd_batch::Ctl& c = b->ctl[b->cm];
+            const int used = R.solve_sweeps[q];  // with deferred verification the plan may have moved on since
             if (!(sums[q].ratio <= 1.0)) {
                 // not enough sweeps: remember the failing count and go (at least) to the theoretical one
-                if (b->ctl[b->cm].floor[vi] < b->ctl[b->cm].sweeps[vi] + 1) b->ctl[b->cm].floor[vi] = b->ctl[b->cm].sweeps[vi] + 1;
+                if (c.floor[vi] < used + 1) c.floor[vi] = used + 1;
                 const int want = sweeps_for_rho(sums[q].rho * 1.02 + 1e-12, opt.max_sweeps);
-                if (b->ctl[b->cm].sweeps[vi] >= want) b->ctl[b->cm].extra[vi] += (b->ctl[b->cm].sweeps[vi] + 1) / 2 + 1;
-                int next = want + b->ctl[b->cm].extra[vi];
-                if (next < b->ctl[b->cm].floor[vi]) next = b->ctl[b->cm].floor[vi];
+                if (used >= want) c.extra[vi] += (used + 1) / 2 + 1;
+                int next = want + c.extra[vi];
+                if (next < c.floor[vi]) next = c.floor[vi];
                 if (next > opt.max_sweeps) next = opt.max_sweeps;
-                if (next > b->ctl[b->cm].sweeps[vi]) b->ctl[b->cm].sweeps[vi] = next;
+                if (next > c.sweeps[vi]) c.sweeps[vi] = next;
             } else if (*converged && (q >= k - 3 || q < 3)) {
-                int next = next_plan(b->ctl[b->cm].sweeps[vi], sums[q].rho, sums[q].ratio, opt.max_sweeps);
-                if (next < b->ctl[b->cm].floor[vi]) next = b->ctl[b->cm].floor[vi];
-                b->ctl[b->cm].sweeps[vi] = next;
+                int next = next_plan(used, sums[q].rho, sums[q].ratio, opt.max_sweeps);
+                if (next < c.floor[vi]) next = c.floor[vi];
+                c.sweeps[vi] = next;
             }
         }
     }
@@ -1260,16 +1354,23 @@ static int pc_step_once(dd_batch* b, int slot_in, int slot_out, const dd_pc_opti
         }
         stats->cs_newton_iters = opt.num_newton_iterations;
         if (opt.consec_xs_rtol > 0.0 && opt.num_newton_iterations > 0) {
-            std::vector<int> used(b->B);
-            CK(cudaMemcpyAsync(used.data(), b->d_used, sizeof(int) * b->B, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
             int mx = 0;
             for (int m = 0; m < b->B; ++m)
-                if (b->h_mem[m].active && used[m] > mx) mx = used[m];
+                if (b->h_mem[m].active && R.h_used[m] > mx) mx = R.h_used[m];
             stats->cs_newton_iters = mx;
         }
     }
     return DD_OK;
+}
+
+// one PC step, verified before returning; times must already be on the device (set_times or advance)
+static int pc_step_once(dd_batch* b, int slot_in, int slot_out, const dd_pc_options& opt, dd_step_stats* stats,
+                        bool* converged) {
+    dd_batch::StepRec& R = b->rec[b->rec_cur];
+    if (R.active) return fail(b->ctx, DD_ERR_INVALID, "internal: a deferred step is still pending");
+    int rc = pc_step_enqueue(b, slot_in, slot_out, opt, R);
+    if (rc != DD_OK) return rc;
+    return pc_step_finish(b, R, stats, converged);
 }
 
 static int check_opts(dd_ctx* ctx, const dd_pc_options& o) {
@@ -1311,6 +1412,7 @@ extern "C" int dd_step_pc(dd_batch* b, int slot_in, int slot_out, const double* 
     if (!b || !slot_ok(b, slot_in) || !slot_ok(b, slot_out) || slot_in == slot_out) return DD_ERR_INVALID;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
+    { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
     dd_pc_options opt;
     if (opt_in) opt = *opt_in; else dd_pc_options_default(&opt);
     int rc = check_opts(ctx, opt);
@@ -1320,11 +1422,101 @@ extern "C" int dd_step_pc(dd_batch* b, int slot_in, int slot_out, const double* 
     return pc_step_retry(b, slot_in, slot_out, opt, stats);
 }
 
+// ---------------------------------------------------------------------------
+// deferred verification: the summaries of step n are read while step n + 1 is already running, so the
+// host never drains the stream between steps.  A rejected step is redone (with more sweeps) together
+// with the step enqueued after it; that needs the input of the rejected step, i.e. three rotating slots.
+// ---------------------------------------------------------------------------
+static int redo_step(dd_batch* b, dd_batch::StepRec& R, dd_step_stats* stats) {
+    // R is inactive here; its fields stay valid because pc_step_once works on rec[rec_cur], which is R itself
+    // only after the copies below have been taken
+    const std::vector<double> t0 = R.t0, dt = R.dt;
+    const dd_pc_options opt = R.opt;
+    const int in = R.slot_in, out = R.slot_out, n_t = R.n_t;
+    int rc;
+    if ((rc = set_times(b, t0.data(), dt.data(), n_t)) != DD_OK) return rc;
+    if ((rc = stage_sources(b, t0[0], dt[0], n_t == 1, true)) != DD_OK) return rc;
+    if ((rc = pc_step_retry(b, in, out, opt, stats)) != DD_OK) return rc;
+    if (stats) stats->retries += 1;
+    return DD_OK;
+}
+
+static int flush_pending(dd_batch* b, dd_step_stats* stats, int* have) {
+    if (have) *have = 0;
+    dd_batch::StepRec& R = b->rec[b->rec_cur];
+    if (!R.active) return DD_OK;
+    dd_ctx* ctx = b->ctx;
+    bool ok = false;
+    int rc = pc_step_finish(b, R, stats, &ok);
+    if (rc != DD_OK) return rc;
+    if (have) *have = 1;
+    if (stats) stats->retries = 0;
+    if (ok) {
+        record_step(b, R.slot_in, R.slot_out);
+        return DD_OK;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return redo_step(b, R, stats);
+}
+
+extern "C" int dd_step_pc_flush(dd_batch* b, dd_step_stats* stats, int* have_stats) {
+    if (!b) return DD_ERR_INVALID;
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    return flush_pending(b, stats, have_stats);
+}
+
+extern "C" int dd_step_pc_deferred(dd_batch* b, int slot_in, int slot_out, const double* t0, const double* dt,
+                                   int n_t, const dd_pc_options* opt_in, dd_step_stats* prev_stats,
+                                   int* have_prev) {
+    if (!b || !slot_ok(b, slot_in) || !slot_ok(b, slot_out) || slot_in == slot_out) return DD_ERR_INVALID;
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    if (have_prev) *have_prev = 0;
+    dd_pc_options opt;
+    if (opt_in) opt = *opt_in; else dd_pc_options_default(&opt);
+    int rc = check_opts(ctx, opt);
+    if (rc != DD_OK) return rc;
+    dd_batch::StepRec& Old = b->rec[b->rec_cur];
+    dd_batch::StepRec& New = b->rec[b->rec_cur ^ 1];
+    if (Old.active && (slot_in != Old.slot_out))
+        return fail(ctx, DD_ERR_INVALID, "deferred step must continue from the output slot of the pending step");
+    if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
+    if ((rc = stage_sources(b, t0[0], dt[0], n_t == 1, true)) != DD_OK) return rc;
+    New.t0.assign(t0, t0 + n_t);
+    New.dt.assign(dt, dt + n_t);
+    New.n_t = n_t;
+    if ((rc = pc_step_enqueue(b, slot_in, slot_out, opt, New)) != DD_OK) return rc;
+    if (Old.active) {
+        bool ok = false;
+        if ((rc = pc_step_finish(b, Old, prev_stats, &ok)) != DD_OK) return rc;
+        if (have_prev) *have_prev = 1;
+        if (prev_stats) prev_stats->retries = 0;
+        if (ok) {
+            record_step(b, Old.slot_in, Old.slot_out);
+        } else {
+            // the step just enqueued started from a rejected state: drop it, redo both
+            if (New.slot_out == Old.slot_in)
+                return fail(ctx, DD_ERR_NOT_CONVERGED,
+                            "a deferred step was rejected after its input slot had been reused; rotate three slots");
+            CK(cudaStreamSynchronize(ctx->stream));
+            New.active = false;
+            if ((rc = redo_step(b, Old, prev_stats)) != DD_OK) return rc;
+            if ((rc = set_times(b, New.t0.data(), New.dt.data(), n_t)) != DD_OK) return rc;
+            if ((rc = stage_sources(b, New.t0[0], New.dt[0], n_t == 1, true)) != DD_OK) return rc;
+            if ((rc = pc_step_enqueue(b, slot_in, slot_out, opt, New)) != DD_OK) return rc;
+        }
+    }
+    b->rec_cur ^= 1;
+    return DD_OK;
+}
+
 extern "C" int dd_run_pc(dd_batch* b, int slot_a, int slot_b, const double* t0, const double* dt, int n_t, int nsteps,
                          const dd_pc_options* opt_in, double* norms_out, dd_step_stats* stats) {
     if (!b || !slot_ok(b, slot_a) || !slot_ok(b, slot_b) || slot_a == slot_b || nsteps < 0) return DD_ERR_INVALID;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
+    { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
     dd_pc_options opt;
     if (opt_in) opt = *opt_in; else dd_pc_options_default(&opt);
     int rc = check_opts(ctx, opt);
@@ -1353,6 +1545,7 @@ extern "C" int dd_run_feuler(dd_batch* b, int slot_a, int slot_b, const double* 
     b->prev_valid = false;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
+    { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
     int rc;
     if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
     int cur = slot_a, nxt = slot_b;
@@ -1378,6 +1571,7 @@ extern "C" int dd_pc_predict(dd_batch* b, int slot_in, const double* t0, const d
     if (!b || !slot_ok(b, slot_in)) return DD_ERR_INVALID;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
+    { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
     int rc;
     if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
     if ((rc = stage_sources(b, t0[0], dt[0], n_t == 1, true)) != DD_OK) return rc;
@@ -1399,6 +1593,7 @@ extern "C" int dd_pc_newton(dd_batch* b, int var, int slot_star, int slot_new, c
     b->prev_valid = false;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
+    { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
     dd_pc_options opt;
     if (opt_in) opt = *opt_in; else dd_pc_options_default(&opt);
     int rc = check_opts(ctx, opt);
@@ -1439,6 +1634,7 @@ extern "C" int dd_pc_correct(dd_batch* b, int slot0, int slot_new, const double*
     b->prev_valid = false;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
+    { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
     dd_pc_options opt;
     if (opt_in) opt = *opt_in; else dd_pc_options_default(&opt);
     int rc = check_opts(ctx, opt);
@@ -1479,6 +1675,7 @@ extern "C" int dd_pc_residual(dd_batch* b, int var, int slot_state, const double
     if (!b || !slot_ok(b, slot_state) || var < DD_T || var > DD_CD || !out_host) return DD_ERR_INVALID;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
+    { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
     int rc;
     if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
     if ((rc = stage_sources(b, t0[0], dt[0], n_t == 1, true)) != DD_OK) return rc;
@@ -1525,6 +1722,7 @@ extern "C" int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_ou
     if (!b || !slot_ok(b, slot_in) || !slot_ok(b, slot_out) || slot_in == slot_out) return DD_ERR_INVALID;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
+    { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
     dd_pc_options opt;
     if (opt_in) opt = *opt_in; else dd_pc_options_default(&opt);
     int rc = check_opts(ctx, opt);
@@ -1576,6 +1774,15 @@ extern "C" int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_ou
                                   sout.v[DD_CL], sout.v[DD_CD], sout.v[DD_CP], sout.v[DD_CS], cap,
                                   track ? opt.consec_xs_rtol : 0.0, b->d_itmax, b->d_itmin));
             return DD_OK;
+        case 6:
+            // as 5 without the read-back: the driver reduces "summary" / "cs_used" on the device itself
+            if (track)
+                CKP(PC_CS_FINISH, 2,
+                    dd_launch_cs_finish(launch_of(b, ROWS_ALL), b->smode, b->g, b->d_mem, b->sF, s0, sout.v[DD_CL],
+                                        sout.v[DD_CD], sout.v[DD_CS], cap, opt.consec_xs_rtol, b->d_itmax,
+                                        b->d_itmin, b->d_used));
+            record_step(b, slot_in, slot_out);
+            return DD_OK;
         case 5: {
             if (track)
                 CKP(PC_CS_FINISH, 2,
@@ -1599,7 +1806,7 @@ extern "C" int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_ou
             return DD_OK;
         }
         default:
-            return fail(ctx, DD_ERR_INVALID, "phase must be 0..5, 21..23 or 31..33");
+            return fail(ctx, DD_ERR_INVALID, "phase must be 0..6, 21..23 or 31..33");
     }
 }
 

@@ -347,13 +347,27 @@ class Batch:
         t0, dt, n = self._times(t0, dt)
         self.ctx.check(self.lib.dd_step_feuler(self.handle, slot_in, slot_out, dptr(t0), dptr(dt), n), "step_feuler")
 
-    def step_pc(self, slot_in: int, slot_out: int, t0, dt, opt: Optional[dd_pc_options] = None) -> dict:
+    def step_pc(self, slot_in: int, slot_out: int, t0, dt, opt: Optional[dd_pc_options] = None,
+                defer: bool = False) -> Optional[dict]:
+        """One PC step.  defer=True: the step is only enqueued and the statistics of the previous deferred step
+        are returned (None for the first); rotate three slots and call flush() at the end (dd_b200.h)."""
         t0, dt, n = self._times(t0, dt)
         opt = opt or pc_options()
         st = dd_step_stats()
+        if defer:
+            have = C.c_int(0)
+            self.ctx.check(self.lib.dd_step_pc_deferred(self.handle, slot_in, slot_out, dptr(t0), dptr(dt), n,
+                                                        C.byref(opt), C.byref(st), C.byref(have)), "step_pc_deferred")
+            return st.as_dict() if have.value else None
         self.ctx.check(self.lib.dd_step_pc(self.handle, slot_in, slot_out, dptr(t0), dptr(dt), n, C.byref(opt),
                                            C.byref(st)), "step_pc")
         return st.as_dict()
+
+    def flush(self) -> Optional[dict]:
+        """Settles a pending deferred step; returns its statistics (None when nothing was pending)."""
+        st, have = dd_step_stats(), C.c_int(0)
+        self.ctx.check(self.lib.dd_step_pc_flush(self.handle, C.byref(st), C.byref(have)), "step_pc_flush")
+        return st.as_dict() if have.value else None
 
     def run_pc(self, slot_a: int, slot_b: int, t0, dt, nsteps: int, opt: Optional[dd_pc_options] = None,
                norms: bool = False):

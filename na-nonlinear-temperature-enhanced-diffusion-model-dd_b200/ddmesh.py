@@ -40,8 +40,8 @@ def slab_rows(nrows_global: int, world: int, rank: int, halo: int) -> Dict[str, 
 class _DevArray:
     """__cuda_array_interface__ view of library-owned device memory (for torch.as_tensor)."""
 
-    def __init__(self, ptr: int, shape):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False),
+    def __init__(self, ptr: int, shape, typestr: str = "<f8"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
                                          "version": 2}
 
 
@@ -153,13 +153,13 @@ class SlabMesh:
     """One trajectory on a mesh split into row slabs over `world` ranks.  `group` (optional) is the list
     of all slabs when they live in one process (single-GPU emulation); otherwise one rank per process."""
 
-    def __init__(self, x, y, *, world: int = 1, rank: int = 0, ctx=None, halo: int = 24):
+    def __init__(self, x, y, *, world: int = 1, rank: int = 0, ctx=None, halo: int = 24, nslots: int = 2):
         self.x, self.y = as_f64(x), as_f64(y)
         self.world, self.rank = world, rank
         self.G = halo if world > 1 else 0
         self.part = slab_rows(len(self.x), world, rank, self.G)
         p = self.part
-        self.batch = ddcore.Batch(self.x, self.y, 1, ctx=ctx, nslots=2, row0=p["row0"], nrows=p["nrows"],
+        self.batch = ddcore.Batch(self.x, self.y, 1, ctx=ctx, nslots=nslots, row0=p["row0"], nrows=p["nrows"],
                                   own=(p["own0"], p["own1"]))
         self.last_stats: dict = {}
         self._tensors: Dict = {}
@@ -170,14 +170,15 @@ class SlabMesh:
         # mirrors the library's own controller (dd_capi.cu), which the phased step bypasses
         self._ctl = [dict(extra=[0, 0, 0], floor=[1, 1, 1], plan=None) for _ in range(2)]
         self._prev = None  # (slot_in, slot_out, dt) of the last accepted step
+        self._pending = None  # record of a deferred, not yet verified step
         if world > 1:
             import torch
             self.torch = torch
 
     @classmethod
-    def local_group(cls, x, y, world: int, ctx=None, halo: int = 24) -> List["SlabMesh"]:
+    def local_group(cls, x, y, world: int, ctx=None, halo: int = 24, nslots: int = 2) -> List["SlabMesh"]:
         """`world` slabs in this process (one GPU) exchanging halos by device copies."""
-        meshes = [cls(x, y, world=world, rank=r, ctx=ctx, halo=halo) for r in range(world)]
+        meshes = [cls(x, y, world=world, rank=r, ctx=ctx, halo=halo, nslots=nslots) for r in range(world)]
         comm = _LocalComm()
         for m in meshes:
             m.group, m.comm = meshes, comm
@@ -189,10 +190,10 @@ class SlabMesh:
         return self.comm
 
     # -- torch views of device fields ---------------------------------------------
-    def _tensor(self, key, ptr, shape=None):
+    def _tensor(self, key, ptr, shape=None, dtype="<f8"):
         t = self._tensors.get(key)
         if t is None:
-            t = self.torch.as_tensor(_DevArray(ptr, shape or self.batch.shape), device="cuda")
+            t = self.torch.as_tensor(_DevArray(ptr, shape or self.batch.shape, dtype), device="cuda")
             self._tensors[key] = t
         return t
 
@@ -212,74 +213,171 @@ class SlabMesh:
         return {v: a[self.part["own0"]:self.part["own1"]] for v, a in d.items()}
 
     # -- stepping ---------------------------------------------------------------------
-    def step_pc(self, slot_in: int, slot_out: int, t0: float, dt: float, opt: Optional[dd_pc_options] = None):
-        """One PC step of the whole mesh.  With a local group, call it on any member: all slabs advance."""
+    def step_pc(self, slot_in: int, slot_out: int, t0: float, dt: float, opt: Optional[dd_pc_options] = None,
+                defer: bool = False):
+        """One PC step of the whole mesh.  With a local group, call it on any member: all slabs advance.
+
+        defer=True: the step is only enqueued; the convergence summaries of the previous deferred step are read
+        instead (its statistics are returned, None for the first), so the host never drains the stream between
+        steps.  A rejected step is redone together with its successor, which needs its input: rotate three
+        slots and call flush() at the end."""
         opt = opt or ddcore.pc_options()
         if self.world == 1:
-            self.last_stats = self.batch.step_pc(slot_in, slot_out, t0, dt, opt)
-            return self.last_stats
+            st = self.batch.step_pc(slot_in, slot_out, t0, dt, opt, defer=defer)
+            if st is not None:
+                self.last_stats = st
+            return st
+        if not defer:
+            self.flush()
+            return self._step_verified(slot_in, slot_out, t0, dt, opt)
+        old = self._pending
+        if old is not None and slot_in != old["slot_out"]:
+            raise AssertionError("deferred step must continue from the output slot of the pending step")
+        new = self._enqueue(slot_in, slot_out, t0, dt, opt, 0)
+        stats = None
+        if old is not None:
+            ok, stats = self._finish(old)
+            if not ok:
+                if slot_out == old["slot_in"]:
+                    raise ddcore.DDNotConverged("a deferred step was rejected after its input slot had been "
+                                                "reused; rotate three slots")
+                for m in self.group:
+                    m.batch.ctx.synchronize()
+                    m._pending = None
+                self._on_reject(old, stats)
+                stats = self._step_verified(old["slot_in"], old["slot_out"], old["t0"], old["dt"], old["opt"], 1)
+                new = self._enqueue(slot_in, slot_out, t0, dt, opt, 0)
+        for m in self.group:
+            m._pending = new
+        return stats
+
+    def flush(self):
+        """Settles a pending deferred step (redoing it with more sweeps when it was rejected)."""
+        if self.world == 1:
+            st = self.batch.flush()
+            if st is not None:
+                self.last_stats = st
+            return st
+        old = self._pending
+        if old is None:
+            return None
+        for m in self.group:
+            m._pending = None
+        ok, stats = self._finish(old)
+        if not ok:
+            for m in self.group:
+                m.batch.ctx.synchronize()
+            self._on_reject(old, stats)
+            stats = self._step_verified(old["slot_in"], old["slot_out"], old["t0"], old["dt"], old["opt"], 1)
+        return stats
+
+    def _step_verified(self, slot_in, slot_out, t0, dt, opt, first_attempt: int = 0):
+        for attempt in range(first_attempt, 40):
+            rec = self._enqueue(slot_in, slot_out, t0, dt, opt, attempt)
+            ok, stats = self._finish(rec)
+            if ok:
+                return stats
+            self._on_reject(rec, stats)
+        raise ddcore.DDNotConverged("slab step: linear solve did not reach the residual bound")
+
+    def _enqueue(self, slot_in, slot_out, t0, dt, opt, attempt):
+        """All phases of one step, the reductions over ranks and the read-back of the reduced summaries into
+        pinned host memory; nothing is waited for."""
         torch, comm, group = self.torch, self._comm(), self.group
         t0a, dta = as_f64([t0]), as_f64([dt])
-        summ = [np.zeros(12) for _ in group]
-        iters = [C.c_int(0) for _ in group]
+        # same rule as the library (take_guess in dd_capi.cu): ping-pong steps start from the last increment
+        mode = int(bool(opt.extrapolate_guess) and attempt == 0 and self._prev == (slot_out, slot_in, dt))
+        ctl = self._ctl[mode]
+        plan = self._common_plan(opt, ctl)
 
         def phase(k):
-            for m, sm, it in zip(group, summ, iters):
+            for m in group:
                 b = m.batch
                 b.ctx.check(b.lib.dd_step_pc_phase(b.handle, k, slot_in, slot_out, dptr(t0a), dptr(dta), 1,
-                                                   C.byref(opt), dptr(sm), C.byref(it)), f"step_pc_phase {k}")
+                                                   C.byref(opt), None, None), f"step_pc_phase {k}")
         track = opt.consec_xs_rtol > 0.0 and opt.num_newton_iterations > 0
-        for attempt in range(40):
-            # same rule as the library (take_guess in dd_capi.cu): ping-pong steps start from the last increment
-            mode = int(bool(opt.extrapolate_guess) and attempt == 0 and self._prev == (slot_out, slot_in, dt))
-            ctl = self._ctl[mode]
-            plan = self._common_plan(opt, ctl)
-            phase(0)
-            for k, var in ((1, "T"), (2, "cl"), (3, "cd")):
-                # assemble, make the Gershgorin ratio (hence the SOR relaxation factor) global, solve
-                phase(20 + k)
-                comm.allreduce([m._tensor("stats", m.batch.work_dev_ptr("solve_stats"), (3, 5))[k - 1, 0:1]
-                                for m in group], "max", group)
-                phase(30 + k)
-                comm.exchange(group, slot_out, (var,))
-            phase(4)
+        phase(0)
+        for k, var in ((1, "T"), (2, "cl"), (3, "cd")):
+            # assemble, make the Gershgorin ratio (hence the SOR relaxation factor) global, solve
+            phase(20 + k)
+            comm.allreduce([m._tensor("stats", m.batch.work_dev_ptr("solve_stats"), (3, 5))[k - 1, 0:1]
+                            for m in group], "max", group)
+            phase(30 + k)
+            comm.exchange(group, slot_out, (var,))
+        phase(4)
+        if track:
+            n = opt.num_newton_iterations
+            comm.allreduce([m._tensor("itmax", m.batch.work_dev_ptr("cs_it_max"), (n,)) for m in group], "max",
+                           group)
+            comm.allreduce([m._tensor("itmin", m.batch.work_dev_ptr("cs_it_min"), (n,)) for m in group], "min",
+                           group)
+        phase(6)
+        with _Ordered(group, torch):
+            summ = [m._tensor("summary", m.batch.work_dev_ptr("summary"), (3, 4)) for m in group]
+            red = [torch.nan_to_num(t, nan=1e300) for t in summ]
+        comm.allreduce(red, "max", group)
+        with _Ordered(group, torch):
+            host = self._host_buffers(attempt)
+            host["summary"].copy_(red[0], non_blocking=True)
             if track:
-                n = opt.num_newton_iterations
-                comm.allreduce([m._tensor("itmax", m.batch.work_dev_ptr("cs_it_max"), (n,)) for m in group], "max",
-                               group)
-                comm.allreduce([m._tensor("itmin", m.batch.work_dev_ptr("cs_it_min"), (n,)) for m in group], "min",
-                               group)
-            phase(5)
-            ts = [torch.nan_to_num(torch.tensor(sm.reshape(3, 4), device="cuda"), nan=1e300) for sm in summ]
-            comm.allreduce(ts, "max")
-            s = ts[0].cpu().numpy()
-            stats = dict(sweeps=list(plan), guess=mode, rho=list(s[:, 0]), resid=list(s[:, 2]), bound=list(s[:, 3]),
-                         retries=attempt, cs_newton_iters=int(iters[0].value))
-            for m in group:
-                m._rho, m.last_stats = s[:, 0], stats
-            if np.all(s[:, 1] <= 1.0):
-                nxt = [max(self.batch.lib.dd_next_plan(int(p), float(r), float(q), opt.max_sweeps), f)
-                       for p, r, q, f in zip(plan, s[:, 0], s[:, 1], ctl["floor"])]
-                for m in group:
-                    m._ctl[mode]["plan"] = nxt
-                    m._prev = (slot_in, slot_out, dt)
-                return stats
-            for m in group:
-                m._ctl[mode]["plan"] = None
-                m._prev = None
-            limit = (self.G - 3) // 2
-            if any(r > 1.0 and p >= limit for p, r in zip(plan, s[:, 1])):
-                raise ddcore.DDNotConverged(f"slab step: {limit} SOR sweeps (all a halo of {self.G} rows supports) "
-                                            f"do not reach the residual bound; use a deeper halo. stats={stats}")
-            # remember the failing counts (never plan below them again) and fall back to the theoretical plan
-            floor = [max(f, p + 1) if r > 1.0 else f for f, p, r in zip(ctl["floor"], plan, s[:, 1])]
-            extra = [e + (p + 1) // 2 + 1 if (r > 1.0 and p >= lib_plan) else e
-                     for e, p, r, lib_plan in zip(ctl["extra"], plan, s[:, 1],
-                                                  [self.batch.lib.dd_sweeps_for_rho(float(x) * 1.02 + 1e-12,
-                                                                                    opt.max_sweeps) for x in s[:, 0]])]
-            for m in group:
-                m._ctl[mode]["extra"], m._ctl[mode]["floor"] = extra, floor
-        raise ddcore.DDNotConverged("slab step: linear solve did not reach the residual bound")
+                used = self._tensor("cs_used", self.batch.work_dev_ptr("cs_used"), (1,), dtype="<i4")
+                host["used"].copy_(used, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+        return dict(slot_in=slot_in, slot_out=slot_out, t0=t0, dt=dt, opt=opt, plan=plan, mode=mode, attempt=attempt,
+                    host=host, done=done, track=track)
+
+    def _host_buffers(self, attempt):
+        """Two alternating sets of pinned read-back buffers (one step may be pending while the next is enqueued)."""
+        torch = self.torch
+        if not hasattr(self, "_hostbuf"):
+            self._hostbuf = [dict(summary=torch.zeros((3, 4), dtype=torch.float64).pin_memory(),
+                                  used=torch.zeros((1,), dtype=torch.int32).pin_memory()) for _ in range(2)]
+            self._hostsel = 0
+        self._hostsel ^= 1
+        return self._hostbuf[self._hostsel]
+
+    def _finish(self, rec):
+        """Waits for the reduced summaries of the step in `rec`; updates the sweep controller."""
+        rec["done"].synchronize()
+        opt, plan, mode = rec["opt"], rec["plan"], rec["mode"]
+        ctl = self._ctl[mode]
+        s = rec["host"]["summary"].numpy().copy()
+        iters = int(rec["host"]["used"][0]) if rec["track"] else int(opt.num_newton_iterations)
+        stats = dict(sweeps=list(plan), guess=mode, rho=[float(x) for x in s[:, 0]],
+                     resid=[float(x) for x in s[:, 2]], bound=[float(x) for x in s[:, 3]],
+                     ratio=[float(x) for x in s[:, 1]], retries=rec["attempt"], cs_newton_iters=iters)
+        ok = bool(np.all(s[:, 1] <= 1.0))
+        for m in self.group:
+            m._rho, m.last_stats = s[:, 0], stats
+        if ok:
+            nxt = [max(self.batch.lib.dd_next_plan(int(p), float(r), float(q), opt.max_sweeps), f)
+                   for p, r, q, f in zip(plan, s[:, 0], s[:, 1], ctl["floor"])]
+            for m in self.group:
+                m._ctl[mode]["plan"] = nxt
+                m._prev = (rec["slot_in"], rec["slot_out"], rec["dt"])
+        return ok, stats
+
+    def _on_reject(self, rec, stats):
+        """Remembers the failing sweep counts (never plan below them again) and falls back to the theoretical
+        plan; raises when the halo cannot support more sweeps."""
+        opt, plan, mode = rec["opt"], rec["plan"], rec["mode"]
+        ctl = self._ctl[mode]
+        ratio, rho = stats["ratio"], stats["rho"]
+        for m in self.group:
+            m._ctl[mode]["plan"] = None
+            m._prev = None
+        limit = (self.G - 3) // 2
+        if any(r > 1.0 and p >= limit for p, r in zip(plan, ratio)) or opt.fixed_sweeps > 0:
+            raise ddcore.DDNotConverged(f"slab step: {limit} SOR sweeps (all a halo of {self.G} rows supports) "
+                                        f"do not reach the residual bound; use a deeper halo. stats={stats}")
+        lib = self.batch.lib
+        floor = [max(f, p + 1) if r > 1.0 else f for f, p, r in zip(ctl["floor"], plan, ratio)]
+        theory = [lib.dd_sweeps_for_rho(float(x) * 1.02 + 1e-12, opt.max_sweeps) for x in rho]
+        extra = [e + (p + 1) // 2 + 1 if (r > 1.0 and p >= th) else e
+                 for e, p, r, th in zip(ctl["extra"], plan, ratio, theory)]
+        for m in self.group:
+            m._ctl[mode]["extra"], m._ctl[mode]["floor"] = extra, floor
 
     def _common_plan(self, opt, ctl) -> List[int]:
         """Same number of SOR sweeps on every rank, planned from the all-reduced Gershgorin ratios of the

@@ -1,0 +1,7 @@
+set -x
+python bench.py --steps 10 --warmup 5 > gpurun_out/r01c_bench.json 2> gpurun_out/r01c_bench.err || exit 1
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r01c_bench_reference.json 2>> gpurun_out/r01c_bench.err
+python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > /dev/null 2>&1 || exit 1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01c_launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu1.log 2>&1
+tail -2 gpurun_out/ncu1.log
+cut -c1-400 gpurun_out/r01c_bench.json

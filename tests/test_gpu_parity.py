@@ -416,3 +416,87 @@ def test_extrapolated_initial_iterate(dd, case, N, M, solver, monkeypatch):
         total[guess] = sweeps
         b.close()
     assert total[True] <= total[False], total
+
+
+def _pol_problem(dd, N, M):
+    from oracle import NOTEBOOK_CONSTS, OForcing, OGrid, PCStepper, exact_state, make_case
+    p1 = dd["p1"]
+    om = NOTEBOOK_CONSTS["pol"]
+    og = OGrid(np.linspace(0, 1, N + 1), np.linspace(0, 1, M + 1))
+    oc = make_case("pol", om)
+    model = dd["product_model"](dict(K1=om.K1, K2=om.K2, K3=om.K3, K4=om.K4, DT=om.DT, Dl_max=om.Dl_max,
+                                     phi_l=om.phi_l, gamma_T=om.gamma_T, Kd=om.Kd, Sd=om.Sd, Dd_max=om.Dd_max,
+                                     phi_d=om.phi_d, r_sp=om.r_sp, T_ref=om.T_ref, kind=2))
+    grid = p1.Grid(og.x, og.y)
+    spec = dd["CASES"]["pol"](grid=grid, model=model).device_spec()
+    stepper = PCStepper(og, om, 50.0, OForcing(oc, om, 50.0, og), keep_residuals=False)
+    return dict(og=og, oc=oc, model=model, grid=grid, spec=spec, stepper=stepper, exact_state=exact_state)
+
+
+def test_deferred_verification_single_gpu(dd):
+    """Steps enqueued before the previous one is verified (three rotating slots): same fields as the
+    verified-per-step path; a plan that is too short is rejected one step late and both steps are redone."""
+    import ctypes as C
+    ddcore = dd["ddcore"]
+    N, M, t0, dt, nsteps = 90, 70, 0.05, 3e-4, 7
+    P = _pol_problem(dd, N, M)
+    s, t = P["exact_state"](P["oc"], t0, P["og"]), t0
+    for _ in range(nsteps):
+        s = P["stepper"].step(s, t, dt)
+        t += dt
+    for sabotage in (False, True):
+        b = ddcore.Batch(P["grid"].x, P["grid"].y, 1, nslots=3)
+        b.set_model(P["model"], 50.0)
+        b.forcing_spec(P["spec"])
+        b.fill_exact(0, t0)
+        seen, retries = 0, 0
+        for k in range(nsteps):
+            if sabotage and k == 3:
+                # a one-sweep plan cannot meet the bound: step 3 is rejected when step 4 has been enqueued
+                b.ctx.check(b.lib.dd_batch_set_plan(b.handle, C.byref((C.c_int * 3)(1, 1, 1))), "set_plan")
+            st = b.step_pc(k % 3, (k + 1) % 3, t0 + k * dt, dt, defer=True)
+            assert (st is None) == (k == 0)
+            if st is not None:
+                seen += 1
+                retries += st["retries"]
+                assert max(st["bound"]) <= 5e-13
+        st = b.flush()
+        assert st is not None and b.flush() is None
+        retries += st["retries"]
+        assert seen == nsteps - 1 and (retries > 0) == sabotage
+        got = b.download(nsteps % 3)
+        for v in VARS:
+            assert rel_err(got[v], getattr(s, v)) <= TOL, (sabotage, v)
+        b.close()
+
+
+def test_deferred_verification_slab_emulation(dd):
+    """The same through the multi-rank driver (two slabs on one GPU), including a rejected step."""
+    import ddmesh
+    N, M, t0, dt, nsteps = 120, 40, 0.05, 2e-4, 6
+    P = _pol_problem(dd, N, M)
+    s, t = P["exact_state"](P["oc"], t0, P["og"]), t0
+    for _ in range(nsteps):
+        s = P["stepper"].step(s, t, dt)
+        t += dt
+    for sabotage in (False, True):
+        meshes = ddmesh.SlabMesh.local_group(P["grid"].x, P["grid"].y, 2, halo=12, nslots=3)
+        for m in meshes:
+            m.batch.set_model(P["model"], 50.0)
+            m.batch.forcing_spec(P["spec"])
+            m.fill_exact(0, t0)
+        retries = 0
+        for k in range(nsteps):
+            if sabotage and k == 2:
+                for m in meshes:
+                    m._ctl[0]["plan"] = [1, 1, 1]
+            st = meshes[0].step_pc(k % 3, (k + 1) % 3, t0 + k * dt, dt, defer=True)
+            assert (st is None) == (k == 0)
+            retries += st["retries"] if st else 0
+        st = meshes[0].flush()
+        retries += st["retries"]
+        # (with a 12-row halo the first plans are clamped, so an honest rejection may also happen unprovoked)
+        assert (retries > 0 or not sabotage) and meshes[0].flush() is None
+        got = {v: np.concatenate([m.owned(nsteps % 3)[v] for m in meshes]) for v in VARS}
+        for v in VARS:
+            assert rel_err(got[v], getattr(s, v)) <= TOL, (sabotage, v)
