@@ -3,10 +3,10 @@
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 SRC="$HERE/na-nonlinear-temperature-enhanced-diffusion-model-dd_b200/csrc"
-OUT="$HERE/na-nonlinear-temperature-enhanced-diffusion-model-dd_b200/libdd_b200.so"
+OUT="${DD_OUT:-$HERE/na-nonlinear-temperature-enhanced-diffusion-model-dd_b200/libdd_b200.so}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "$NVCC" -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo \
   -Xcompiler -fPIC -Xcompiler -fvisibility=default --shared \
-  ${DD_PTXAS_V:+-Xptxas -v} \
+  ${DD_PTXAS_V:+-Xptxas -v} ${DD_EXTRA_FLAGS:-} \
   -o "$OUT" "$SRC/dd_kernels.cu" "$SRC/dd_solver.cu" "$SRC/dd_capi.cu" -lcudart
 echo "built $OUT"

@@ -83,7 +83,7 @@ struct dd_batch {
         cudaEvent_t done = nullptr;
     } rec[2];
     int rec_cur;
-    bool prev_valid, use_guess;
+    bool prev_valid, use_guess, phase_fused_T;
     int prev_in, prev_out;
     double prev_dt, cur_dt;  // first member's step size (the increment scales with it)
     bool is_slab;
@@ -311,7 +311,7 @@ extern "C" int dd_batch_create(dd_ctx* ctx, int N, int M, const double* x, const
     b->asm0 = (row0 == 0) ? 0 : 2;
     b->asm1 = (row0 + nrows == N + 1) ? nrows : nrows - 2;
     reset_ctl(b, true);
-    b->prev_valid = b->use_guess = false;
+    b->prev_valid = b->use_guess = b->phase_fused_T = false;
     b->prev_in = b->prev_out = -1;
     b->prev_dt = b->cur_dt = 0.0;
     b->rec_cur = 0;
@@ -1086,19 +1086,44 @@ static int ensure_cs_buffers(dd_batch* b, int cap) {
 }
 
 // assemble + solve one Newton system.  `k` indexes the stats slot.
+static int get_rows(dd_batch* b, DDRows* R) {
+    int rc;
+    if ((rc = get_work(b, "bb", &R->bb)) != DD_OK) return rc;
+    if ((rc = get_work(b, "aW", &R->aW)) != DD_OK) return rc;
+    if ((rc = get_work(b, "aE", &R->aE)) != DD_OK) return rc;
+    if ((rc = get_work(b, "aS", &R->aS)) != DD_OK) return rc;
+    if ((rc = get_work(b, "aN", &R->aN)) != DD_OK) return rc;
+    R->ld = b->g.ld + (b->g.ld & 1);
+    R->mstride = (long long)b->nrows * R->ld;
+    return DD_OK;
+}
+
+// Predictor of the step; on wide grids with array (or no) sources the marching kernel, which also assembles
+// the T system of the first Newton step (*fused_T = true: the caller then only solves it, solve slot 0).
+static int launch_predictor(dd_batch* b, const DDStateC& s0, const DDPredictOut& po, bool* fused_T) {
+    dd_ctx* ctx = b->ctx;
+    const DDLaunch L = launch_of(b, ROWS_STENCIL);
+    *fused_T = false;
+    if (dd_predict_march_ok(b->g, L, b->smode)) {
+        DDRows R;
+        int rc = get_rows(b, &R);
+        if (rc != DD_OK) return rc;
+        g_prof.launches += 1;  // the statistics reset
+        CKP(PC_PREDICT, 1, dd_launch_predict_march(L, b->smode, b->g, b->d_mem, b->sF, s0, po, true, R, b->d_stats));
+        *fused_T = true;
+        return DD_OK;
+    }
+    CKP(PC_PREDICT, 1, dd_launch_predict(L, b->smode, b->g, b->d_mem, b->sF, s0, po));
+    return DD_OK;
+}
+
 static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const double* T1, const double* cl1,
                         const double* Y, double* vnew, const dd_pc_options& opt, int k, int* sweeps_used,
                         int* passes_used, int what = 3, const double* vold = nullptr) {
     dd_ctx* ctx = b->ctx;
     DDRows R;
     int rc;
-    if ((rc = get_work(b, "bb", &R.bb)) != DD_OK) return rc;
-    if ((rc = get_work(b, "aW", &R.aW)) != DD_OK) return rc;
-    if ((rc = get_work(b, "aE", &R.aE)) != DD_OK) return rc;
-    if ((rc = get_work(b, "aS", &R.aS)) != DD_OK) return rc;
-    if ((rc = get_work(b, "aN", &R.aN)) != DD_OK) return rc;
-    R.ld = b->g.ld + (b->g.ld & 1);
-    R.mstride = (long long)b->nrows * R.ld;
+    if ((rc = get_rows(b, &R)) != DD_OK) return rc;
     DDSolveStats* st = b->d_stats + (size_t)k * b->B;
     // rows are assembled on every local row that has a full stencil (slabs: halo rows included,
     // so that the tile solver sees valid rows in its halo); tiles cover the owned rows only
@@ -1231,11 +1256,11 @@ static int pc_step_enqueue(dd_batch* b, int slot_in, int slot_out, const dd_pc_o
     if ((rc = get_work(b, "YT", &po.YT)) != DD_OK) return rc;
     if ((rc = get_work(b, "Ycl", &po.Ycl)) != DD_OK) return rc;
     if ((rc = get_work(b, "Ycd", &po.Ycd)) != DD_OK) return rc;
-    const DDLaunch L = launch_of(b, ROWS_STENCIL);
     const DDLaunch Lall = launch_of(b, ROWS_ALL);
     const DDStateC s0 = cstate(b, slot_in);
     const DDState sout = mstate(b, slot_out);
-    CKP(PC_PREDICT, 1, dd_launch_predict(L, b->smode, b->g, b->d_mem, b->sF, s0, po));
+    bool fused_T = false;
+    if ((rc = launch_predictor(b, s0, po, &fused_T)) != DD_OK) return rc;
     DDStateC u;
     u.v[DD_CP] = po.cp1p; u.v[DD_T] = s0.v[DD_T]; u.v[DD_CL] = s0.v[DD_CL]; u.v[DD_CD] = s0.v[DD_CD];
     u.v[DD_CS] = po.cs1p;
@@ -1257,8 +1282,10 @@ static int pc_step_enqueue(dd_batch* b, int slot_in, int slot_out, const dd_pc_o
             // the first Newton solve of the step starts from the previous step's increment when it is available
             const bool gs = guess && pc == 0 && nw == 0;
             b->cm = gs ? 1 : 0;
-            if ((rc = newton_solve(b, DD_T, u, nullptr, nullptr, po.YT, dst[0], opt, k++, &sweeps[0], &passes[0], 3,
-                                   gs ? sout.v[DD_T] : nullptr)) != DD_OK) return rc;
+            // the marching predictor has already assembled the T system of the very first Newton step
+            const int whatT = (fused_T && pc == 0 && nw == 0) ? 2 : 3;
+            if ((rc = newton_solve(b, DD_T, u, nullptr, nullptr, po.YT, dst[0], opt, k++, &sweeps[0], &passes[0],
+                                   whatT, gs ? sout.v[DD_T] : nullptr)) != DD_OK) return rc;
             if ((rc = newton_solve(b, DD_CL, u, dst[0], nullptr, po.Ycl, dst[1], opt, k++, &sweeps[1], &passes[1], 3,
                                    gs ? sout.v[DD_CL] : nullptr)) != DD_OK) return rc;
             if ((rc = newton_solve(b, DD_CD, u, dst[0], dst[1], po.Ycd, dst[2], opt, k++, &sweeps[2], &passes[2], 3,
@@ -1748,7 +1775,7 @@ extern "C" int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_ou
         case 0:
             if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
             if ((rc = stage_sources(b, t0[0], dt[0], n_t == 1, true)) != DD_OK) return rc;
-            CKP(PC_PREDICT, 1, dd_launch_predict(launch_of(b, ROWS_STENCIL), b->smode, b->g, b->d_mem, b->sF, s0, po));
+            if ((rc = launch_predictor(b, s0, po, &b->phase_fused_T)) != DD_OK) return rc;
             b->use_guess = take_guess(b, slot_in, slot_out, opt);
             if (track) {
                 const int had = b->cs_cap_alloc;
@@ -1759,9 +1786,13 @@ extern "C" int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_ou
                 }
             }
             return DD_OK;
-        case 1: case 21: case 31:
-            return newton_solve(b, DD_T, u, nullptr, nullptr, po.YT, sout.v[DD_T], opt, 0, &sw, &pa,
-                                phase == 1 ? 3 : (phase == 21 ? 1 : 2), b->use_guess ? sout.v[DD_T] : nullptr);
+        case 1: case 21: case 31: {
+            int what = phase == 1 ? 3 : (phase == 21 ? 1 : 2);
+            if (b->phase_fused_T) what &= 2;  // phase 0 assembled the T system already
+            if (!what) return DD_OK;
+            return newton_solve(b, DD_T, u, nullptr, nullptr, po.YT, sout.v[DD_T], opt, 0, &sw, &pa, what,
+                                b->use_guess ? sout.v[DD_T] : nullptr);
+        }
         case 2: case 22: case 32:
             return newton_solve(b, DD_CL, u, sout.v[DD_T], nullptr, po.Ycl, sout.v[DD_CL], opt, 1, &sw, &pa,
                                 phase == 2 ? 3 : (phase == 22 ? 1 : 2), b->use_guess ? sout.v[DD_CL] : nullptr);

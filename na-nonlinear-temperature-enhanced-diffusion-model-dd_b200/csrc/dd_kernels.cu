@@ -270,6 +270,238 @@ cudaError_t dd_launch_predict(const DDLaunch& L, int mode, const DDGeom& g, cons
 }
 
 // ---------------------------------------------------------------------------
+// PC phase 1, marching form (sources as arrays / none; grids at least a few warps wide).
+//
+// One warp owns 31 consecutive columns (lane 0 is a halo lane that only produces the face between its
+// column and lane 1's) and walks down DD_MARCH_ROWS rows.  Rows r-1, r, r+1 of the four stencil fields live
+// in registers and row r+2 is requested one iteration ahead, so every state value is loaded once per warp
+// column and the loads of the next row are in flight while the current one is computed.  A face quantity
+// (flux a (u' - u) / h with its exponential coefficient) is evaluated ONCE: the E face of row r is carried
+// to row r+1 as its W face, the N face of column j goes to lane j+1 as its S face by a shuffle.  The
+// expressions are the per-node ones of dd_physics.cuh (same operands in the same order), so both nodes
+// adjacent to a face see bit-identical values whatever warp or block computed them.
+//
+// FUSE_T also assembles the constant-band T system of the first Newton step (dd_node_asm_T_const): it only
+// needs cp1p and Y_T at the node itself, which this kernel has just produced.
+// ---------------------------------------------------------------------------
+#ifndef DD_MARCH_ROWS
+#define DD_MARCH_ROWS 32
+#endif
+#ifndef DD_MARCH_WARPS
+#define DD_MARCH_WARPS 4
+#endif
+#ifndef DD_MARCH_MINB
+#define DD_MARCH_MINB 4
+#endif
+
+struct DDMarchCell {
+    double cp, T, cl, cd;
+};
+
+__device__ __forceinline__ double dd_ldg0(const double* p, long long o) { return p ? __ldg(p + o) : 0.0; }
+
+__device__ __forceinline__ DDMarchCell dd_march_load(const DDStateC& s, long long o, bool ok) {
+    DDMarchCell c;
+    c.cp = ok ? __ldg(s.v[DD_CP] + o) : 0.0;
+    c.T = ok ? __ldg(s.v[DD_T] + o) : 0.0;
+    c.cl = ok ? __ldg(s.v[DD_CL] + o) : 0.0;
+    c.cd = ok ? __ldg(s.v[DD_CD] + o) : 0.0;
+    return c;
+}
+
+struct DDMarchSrc {
+    double fcp0, fcp1, fcs0, fcs1, fT0, fcl0, fcd0, fT1;
+};
+
+template <bool FUSE_T>
+__device__ __forceinline__ DDMarchSrc dd_march_src(const DDForcingArrays& A, long long o, bool ok) {
+    DDMarchSrc q;
+    q.fcp0 = ok ? dd_ldg0(A.f[DD_CP][0], o) : 0.0;
+    q.fcp1 = ok ? dd_ldg0(A.f[DD_CP][1], o) : 0.0;
+    q.fcs0 = ok ? dd_ldg0(A.f[DD_CS][0], o) : 0.0;
+    q.fcs1 = ok ? dd_ldg0(A.f[DD_CS][1], o) : 0.0;
+    q.fT0 = ok ? dd_ldg0(A.f[DD_T][0], o) : 0.0;
+    q.fcl0 = ok ? dd_ldg0(A.f[DD_CL][0], o) : 0.0;
+    q.fcd0 = ok ? dd_ldg0(A.f[DD_CD][0], o) : 0.0;
+    q.fT1 = (FUSE_T && ok) ? dd_ldg0(A.f[DD_T][1], o) : 0.0;
+    return q;
+}
+
+// fluxes through the face between cells a (lower index) and b, metric factor rm = 1 / spacing
+struct DDMarchFace {
+    double T, cl, cd;
+};
+__device__ __forceinline__ DDMarchFace dd_march_face(const DDModel& m, const DDMarchCell& a, const DDMarchCell& b,
+                                                     double rm) {
+    DDMarchFace f;
+    const double cpf = 0.5 * (b.cp + a.cp);
+    f.T = (b.T - a.T) * rm;
+    f.cl = dd_Dl(m, cpf) * ((b.cl - a.cl) * rm);
+    f.cd = dd_Dd(m, cpf, 0.5 * (b.T + a.T)) * ((b.cd - a.cd) * rm);
+    return f;
+}
+
+template <bool FUSE_T>
+__global__ void __launch_bounds__(DD_MARCH_WARPS * 32, DD_MARCH_MINB)
+k_predict_march(DDGeom g, const DDMember* __restrict__ mem, DDForcingArrays A, DDStateC s, DDPredictOut out,
+                DDRows R, DDSolveStats* stats, int r0, int r1, int nwc, int wcb, int nrb) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int bid = blockIdx.x;
+    const int member = bid / (wcb * nrb);
+    bid -= member * (wcb * nrb);
+    const int rbk = bid / wcb, cbk = bid - rbk * wcb;
+    const DDMember& mb = mem[member];
+    if (!mb.active) return;
+    const int wc = cbk * (blockDim.x >> 5) + warp;
+    if (wc >= nwc) return;  // whole warp
+    const DDModel& m = mb.m;
+    const double dt = mb.dt;
+    const int j = wc * 31 + lane - 1;
+    const int ra = r0 + rbk * DD_MARCH_ROWS, rz = min(ra + DD_MARCH_ROWS, r1);
+    const bool col = j >= 0 && j <= g.M;
+    const bool owner = lane >= 1 && col;
+    const bool jint = j >= 1 && j <= g.M - 1;
+    const bool colN = j >= 0 && j + 1 <= g.M;  // column j+1 exists: the N face of this column is defined
+    const long long mo = member * g.mstride, moR = member * R.mstride;
+    // y metrics of this column
+    double rkp = 0.0, rkS = 0.0, rkN = 0.0;
+    if (colN) rkN = g.rk[j + 1];
+    if (jint) {
+        rkp = g.rkp[j];
+        rkS = g.rk[j];
+    }
+    const double cS = rkp * rkS, cN = rkp * rkN;
+
+    // rows ra-1, ra, ra+1 and (ra, j+1)
+    DDMarchCell P = dd_march_load(s, mo + (long long)(ra - 1) * g.ld + j, col && ra - 1 >= 0);
+    DDMarchCell C = dd_march_load(s, mo + (long long)ra * g.ld + j, col);
+    DDMarchCell N = dd_march_load(s, mo + (long long)(ra + 1) * g.ld + j, col && ra + 1 < g.nrows);
+    DDMarchCell Cn = dd_march_load(s, mo + (long long)ra * g.ld + j + 1, colN);
+    double csC = col ? __ldg(s.v[DD_CS] + mo + (long long)ra * g.ld + j) : 0.0;
+    DDMarchSrc src = dd_march_src<FUSE_T>(A, mo + (long long)ra * g.ld + j, owner);
+    // W face of the first row (only an interior node uses it)
+    DDMarchFace W = {0.0, 0.0, 0.0};
+    double wadv = 0.0;
+    {
+        const int i = g.row0 + ra;
+        if (jint && i >= 1 && i <= g.N - 1) {
+            W = dd_march_face(m, P, C, g.rh[i]);
+            wadv = 0.5 * (m.gamma_T * C.T * (C.cl + 1.0) + m.gamma_T * P.T * (P.cl + 1.0));
+        }
+    }
+    double rho = 0.0;
+    for (int r = ra; r < rz; ++r) {
+        const int i = g.row0 + r;
+        const long long o = mo + (long long)r * g.ld + j;
+        // requests for the next iteration
+        const bool nxt = r + 1 < rz;
+        const DDMarchCell NN = dd_march_load(s, o + 2LL * g.ld, col && nxt && r + 2 < g.nrows);
+        const DDMarchCell Nn = dd_march_load(s, o + g.ld + 1, colN && nxt);
+        const double csN = (col && nxt) ? __ldg(s.v[DD_CS] + o + g.ld) : 0.0;
+        const DDMarchSrc srcN = dd_march_src<FUSE_T>(A, o + g.ld, owner && nxt);
+
+        const bool irow = i >= 1 && i <= g.N - 1;
+        const bool inter = irow && jint;
+        // E face (rows r | r+1): used by this node and, as its W face, by the node below
+        DDMarchFace E = {0.0, 0.0, 0.0};
+        double eadv = 0.0;
+        if (jint && i >= 0 && i <= g.N - 1 && r + 1 < g.nrows) {
+            E = dd_march_face(m, C, N, g.rh[i + 1]);
+            eadv = 0.5 * (m.gamma_T * N.T * (N.cl + 1.0) + m.gamma_T * C.T * (C.cl + 1.0));
+        }
+        // N face (columns j | j+1): used by this node and, as its S face, by lane + 1
+        DDMarchFace Nf = {0.0, 0.0, 0.0};
+        if (irow && colN) Nf = dd_march_face(m, C, Cn, rkN);
+        DDMarchFace S;
+        S.T = __shfl_up_sync(0xffffffffu, Nf.T, 1);
+        S.cl = __shfl_up_sync(0xffffffffu, Nf.cl, 1);
+        S.cd = __shfl_up_sync(0xffffffffu, Nf.cd, 1);
+
+        if (owner) {
+            const long long oR = moR + (long long)r * R.ld + j;
+            if (inter) {
+                const double rhp = g.rhp[i];
+                const double lap = rhp * (E.T - W.T) + rkp * (Nf.T - S.T);
+                const double FT0 = m.DT * lap - m.K3 * C.cp * C.T;
+                const double Fcl0 = (rhp * (E.cl - W.cl) + rkp * (Nf.cl - S.cl)) - rhp * (eadv - wadv) -
+                                    m.K4 * C.cp * (C.cl + 1.0);
+                const double Fcd0 = (rhp * (E.cd - W.cd) + rkp * (Nf.cd - S.cd)) + dd_reaction(m, C.cl, C.cd, csC);
+                const double YT = dt * (src.fT0 + FT0) + 2.0 * C.T;
+                const double cp1p = dd_predict_cp(m, dt, C.cp, C.T, C.cl, src.fcp0, src.fcp1);
+                out.Ycl[o] = dt * (src.fcl0 + Fcl0) + 2.0 * C.cl;
+                out.Ycd[o] = dt * (src.fcd0 + Fcd0) + 2.0 * C.cd;
+                out.cp1p[o] = cp1p;
+                out.cs1p[o] = dd_predict_cs(m, dt, csC, C.cl, C.cd, src.fcs0, src.fcs1);
+                out.YT[o] = YT;
+                if (FUSE_T) {
+                    const double sumc = m.DT * (rhp * g.rh[i] + rhp * g.rh[i + 1] + cS + cN);
+                    const double d = 2.0 + dt * (sumc + m.K3 * cp1p);
+                    const double FT1 = m.DT * lap - m.K3 * cp1p * C.T;
+                    const double G0 = 2.0 * C.T - dt * (src.fT1 + FT1);
+                    const double vd = dd_rcp(d);
+                    R.bb[oR] = (YT - G0) * vd;
+                    R.aW[oR] = vd;
+                    rho = fmax(rho, dt * sumc * vd);
+                }
+            } else {
+                out.YT[o] = dt * src.fT0 + 2.0 * C.T;
+                out.Ycl[o] = dt * src.fcl0 + 2.0 * C.cl;
+                out.Ycd[o] = dt * src.fcd0 + 2.0 * C.cd;
+                out.cp1p[o] = C.cp + 0.5 * dt * (src.fcp0 + src.fcp1);
+                out.cs1p[o] = csC * 0.0;
+                if (FUSE_T) {
+                    R.bb[oR] = 0.0;
+                    R.aW[oR] = 0.0;
+                }
+            }
+        }
+        W = E;
+        wadv = eadv;
+        P = C;
+        C = N;
+        N = NN;
+        Cn = Nn;
+        csC = csN;
+        src = srcN;
+    }
+    if (FUSE_T) {
+        rho = warp_max_bits(rho);
+        if (lane == 0) atomic_max_nonneg(&stats[member].rho, rho);
+    }
+}
+
+bool dd_predict_march_ok(const DDGeom& g, const DDLaunch& L, int mode) {
+    static const bool off = getenv("DD_NO_MARCH") != nullptr;
+    return !off && (mode == DD_FORCING_ARRAYS || mode == DD_FORCING_NONE) && g.M + 1 >= 4 * 31 &&
+           L.own1 - L.own0 >= DD_MARCH_ROWS / 2;
+}
+
+__global__ void k_reset_stats(DDSolveStats* stats, int nmem);
+
+cudaError_t dd_launch_predict_march(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,
+                                    const DDForcing& F, const DDStateC& in, const DDPredictOut& out, bool fuse_T,
+                                    const DDRows& R, DDSolveStats* stats) {
+    DDForcingArrays A;
+    memset(&A, 0, sizeof(A));
+    if (mode == DD_FORCING_ARRAYS) A = F.arr;
+    const int nwc = (g.M + 1 + 30) / 31;
+    const int wpb = nwc < DD_MARCH_WARPS ? nwc : DD_MARCH_WARPS;
+    const int wcb = (nwc + wpb - 1) / wpb;
+    const int nrb = (L.own1 - L.own0 + DD_MARCH_ROWS - 1) / DD_MARCH_ROWS;
+    const long long nblocks = (long long)wcb * nrb * L.nmembers;
+    if (nblocks <= 0 || nblocks > 2147483647LL) return cudaErrorInvalidConfiguration;
+    if (fuse_T) {
+        k_reset_stats<<<(L.nmembers + 127) / 128, 128, 0, L.stream>>>(stats, L.nmembers);
+        k_predict_march<true><<<(unsigned)nblocks, wpb * 32, 0, L.stream>>>(g, mem, A, in, out, R, stats, L.own0,
+                                                                             L.own1, nwc, wcb, nrb);
+    } else {
+        k_predict_march<false><<<(unsigned)nblocks, wpb * 32, 0, L.stream>>>(g, mem, A, in, out, R, stats, L.own0,
+                                                                              L.own1, nwc, wcb, nrb);
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // assemble Newton rows (+ Gershgorin ratio per member)
 // ---------------------------------------------------------------------------
 __global__ void k_reset_stats(DDSolveStats* stats, int nmem) {

@@ -44,6 +44,12 @@ struct DDSolvePlan {
 
 cudaError_t dd_solver_configure();  // opt-in to large dynamic shared memory (once per process)
 
+// marching form of the predictor (sources as arrays or none, wide grids); fuse_T also assembles the
+// constant-band T system of the first Newton step into R.bb / R.aW and the Gershgorin ratio into stats
+bool dd_predict_march_ok(const DDGeom& g, const DDLaunch& L, int mode);
+cudaError_t dd_launch_predict_march(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,
+                                    const DDForcing& F, const DDStateC& in, const DDPredictOut& out, bool fuse_T,
+                                    const DDRows& R, DDSolveStats* stats);
 cudaError_t dd_launch_solve_pass(const DDLaunch& L, const DDGeom& g, const DDMember* mem, const DDRows& R,
                                  const double* xin /* nullable: zero initial iterate */,
                                  const double* vold /* nullable, register kernel, xin null: start from vstar - vold */,
