@@ -41,9 +41,19 @@ POL = dict(K1=1e-3, K2=1e-3, K3=1e-3, K4=1e-3, DT=1e-3, Dl_max=8.01e-4, phi_l=1e
            Dd_max=2.46e-6, phi_d=1e-5, r_sp=5e-2, T_ref=300.0)
 ETA = 50.0
 # algorithmic bytes per node and launch of each kernel class ("kernels")
-KERNEL_BYTES = {"k_predict": 80, "k_assemble<T>": 40, "k_assemble<cl>": 80, "k_assemble<cd>": 104,
+KERNEL_BYTES = {"k_predict": 88, "k_assemble<T>": 40, "k_assemble<cl>": 80, "k_assemble<cd>": 104,
                 "k_rbsor_tile<T>": 32, "k_rbsor_tile<cl>": 56, "k_rbsor_tile<cd>": 56, "k_correct": 80,
                 "k_feuler": 80, "k_eval_sources": 40}
+
+
+def captured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01c_traffic.json")) as f:
+            t = json.load(f)
+        return float(t["kernels"][kernel]["dram_bytes_per_launch"]), t["source"]
+    except Exception:
+        return None, None
 
 
 def measured_peak():
@@ -393,10 +403,15 @@ def run_b200(args):
     nodes_rank = (MESH_ROWS_PER_GPU + 1) * (MESH_COLS + 1)
     top = max(((k, v) for k, v in prof.items() if k in KERNEL_BYTES), key=lambda kv: kv[1][0])
     tname, (tms, tcount) = top
-    achieved = KERNEL_BYTES[tname] * nodes_rank / (tms / tcount * 1e-3) / 1e9
+    # a solve that is split into several passes spreads its algorithmic bytes over its launches
+    lps = max(1.0, tcount / args.steps) if tname.startswith("k_rbsor") else 1.0
+    alg_per_launch = KERNEL_BYTES[tname] * nodes_rank / lps
+    achieved = alg_per_launch / (tms / tcount * 1e-3) / 1e9
     total_prof = sum(v[0] for v in prof.values())
+    traffic, traffic_src = captured_traffic(tname)
     roof = {"bound": "hbm", "kernel": tname, "achieved": achieved, "peak": peak, "peak_kind": peak_kind,
-            "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": alg_per_launch, "launches_per_step": lps,
             "launch_ms": tms / tcount, "share_of_step": tms / total_prof,
             "step": {"bytes_per_cell_step": BYTES_PER_CELL_STEP,
                      "achieved": value / world * BYTES_PER_CELL_STEP / 1e9,

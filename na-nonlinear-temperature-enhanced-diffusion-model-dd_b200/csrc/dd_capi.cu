@@ -1100,7 +1100,7 @@ static int get_rows(dd_batch* b, DDRows* R) {
 
 // Predictor of the step; on wide grids with array (or no) sources the marching kernel, which also assembles
 // the T system of the first Newton step (*fused_T = true: the caller then only solves it, solve slot 0).
-static int launch_predictor(dd_batch* b, const DDStateC& s0, const DDPredictOut& po, bool* fused_T) {
+static int launch_predictor(dd_batch* b, const DDStateC& s0, const DDPredictOut& po, bool* fused_T, bool need_YT) {
     dd_ctx* ctx = b->ctx;
     const DDLaunch L = launch_of(b, ROWS_STENCIL);
     *fused_T = false;
@@ -1109,7 +1109,8 @@ static int launch_predictor(dd_batch* b, const DDStateC& s0, const DDPredictOut&
         int rc = get_rows(b, &R);
         if (rc != DD_OK) return rc;
         g_prof.launches += 1;  // the statistics reset
-        CKP(PC_PREDICT, 1, dd_launch_predict_march(L, b->smode, b->g, b->d_mem, b->sF, s0, po, true, R, b->d_stats));
+        CKP(PC_PREDICT, 1, dd_launch_predict_march(L, b->smode, b->g, b->d_mem, b->sF, s0, po, true, R, b->d_stats,
+                                                       need_YT));
         *fused_T = true;
         return DD_OK;
     }
@@ -1260,7 +1261,7 @@ static int pc_step_enqueue(dd_batch* b, int slot_in, int slot_out, const dd_pc_o
     const DDStateC s0 = cstate(b, slot_in);
     const DDState sout = mstate(b, slot_out);
     bool fused_T = false;
-    if ((rc = launch_predictor(b, s0, po, &fused_T)) != DD_OK) return rc;
+    if ((rc = launch_predictor(b, s0, po, &fused_T, P * Q > 1)) != DD_OK) return rc;
     DDStateC u;
     u.v[DD_CP] = po.cp1p; u.v[DD_T] = s0.v[DD_T]; u.v[DD_CL] = s0.v[DD_CL]; u.v[DD_CD] = s0.v[DD_CD];
     u.v[DD_CS] = po.cs1p;
@@ -1775,7 +1776,7 @@ extern "C" int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_ou
         case 0:
             if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
             if ((rc = stage_sources(b, t0[0], dt[0], n_t == 1, true)) != DD_OK) return rc;
-            if ((rc = launch_predictor(b, s0, po, &b->phase_fused_T)) != DD_OK) return rc;
+            if ((rc = launch_predictor(b, s0, po, &b->phase_fused_T, false)) != DD_OK) return rc;
             b->use_guess = take_guess(b, slot_in, slot_out, opt);
             if (track) {
                 const int had = b->cs_cap_alloc;

@@ -344,7 +344,7 @@ __device__ __forceinline__ DDMarchFace dd_march_face(const DDModel& m, const DDM
 template <bool FUSE_T>
 __global__ void __launch_bounds__(DD_MARCH_WARPS * 32, DD_MARCH_MINB)
 k_predict_march(DDGeom g, const DDMember* __restrict__ mem, DDForcingArrays A, DDStateC s, DDPredictOut out,
-                DDRows R, DDSolveStats* stats, int r0, int r1, int nwc, int wcb, int nrb) {
+                DDRows R, DDSolveStats* stats, int r0, int r1, int nwc, int wcb, int nrb, int store_YT) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int bid = blockIdx.x;
     const int member = bid / (wcb * nrb);
@@ -432,7 +432,7 @@ k_predict_march(DDGeom g, const DDMember* __restrict__ mem, DDForcingArrays A, D
                 out.Ycd[o] = dt * (src.fcd0 + Fcd0) + 2.0 * C.cd;
                 out.cp1p[o] = cp1p;
                 out.cs1p[o] = dd_predict_cs(m, dt, csC, C.cl, C.cd, src.fcs0, src.fcs1);
-                out.YT[o] = YT;
+                if (store_YT) out.YT[o] = YT;  // only later Newton steps / the class-level pieces read it
                 if (FUSE_T) {
                     const double sumc = m.DT * (rhp * g.rh[i] + rhp * g.rh[i + 1] + cS + cN);
                     const double d = 2.0 + dt * (sumc + m.K3 * cp1p);
@@ -444,7 +444,7 @@ k_predict_march(DDGeom g, const DDMember* __restrict__ mem, DDForcingArrays A, D
                     rho = fmax(rho, dt * sumc * vd);
                 }
             } else {
-                out.YT[o] = dt * src.fT0 + 2.0 * C.T;
+                if (store_YT) out.YT[o] = dt * src.fT0 + 2.0 * C.T;
                 out.Ycl[o] = dt * src.fcl0 + 2.0 * C.cl;
                 out.Ycd[o] = dt * src.fcd0 + 2.0 * C.cd;
                 out.cp1p[o] = C.cp + 0.5 * dt * (src.fcp0 + src.fcp1);
@@ -480,7 +480,7 @@ __global__ void k_reset_stats(DDSolveStats* stats, int nmem);
 
 cudaError_t dd_launch_predict_march(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,
                                     const DDForcing& F, const DDStateC& in, const DDPredictOut& out, bool fuse_T,
-                                    const DDRows& R, DDSolveStats* stats) {
+                                    const DDRows& R, DDSolveStats* stats, bool store_YT) {
     DDForcingArrays A;
     memset(&A, 0, sizeof(A));
     if (mode == DD_FORCING_ARRAYS) A = F.arr;
@@ -493,10 +493,10 @@ cudaError_t dd_launch_predict_march(const DDLaunch& L, int mode, const DDGeom& g
     if (fuse_T) {
         k_reset_stats<<<(L.nmembers + 127) / 128, 128, 0, L.stream>>>(stats, L.nmembers);
         k_predict_march<true><<<(unsigned)nblocks, wpb * 32, 0, L.stream>>>(g, mem, A, in, out, R, stats, L.own0,
-                                                                             L.own1, nwc, wcb, nrb);
+                                                                             L.own1, nwc, wcb, nrb, store_YT ? 1 : 0);
     } else {
         k_predict_march<false><<<(unsigned)nblocks, wpb * 32, 0, L.stream>>>(g, mem, A, in, out, R, stats, L.own0,
-                                                                              L.own1, nwc, wcb, nrb);
+                                                                              L.own1, nwc, wcb, nrb, 1);
     }
     return cudaGetLastError();
 }

@@ -49,7 +49,7 @@ cudaError_t dd_solver_configure();  // opt-in to large dynamic shared memory (on
 bool dd_predict_march_ok(const DDGeom& g, const DDLaunch& L, int mode);
 cudaError_t dd_launch_predict_march(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,
                                     const DDForcing& F, const DDStateC& in, const DDPredictOut& out, bool fuse_T,
-                                    const DDRows& R, DDSolveStats* stats);
+                                    const DDRows& R, DDSolveStats* stats, bool store_YT);
 cudaError_t dd_launch_solve_pass(const DDLaunch& L, const DDGeom& g, const DDMember* mem, const DDRows& R,
                                  const double* xin /* nullable: zero initial iterate */,
                                  const double* vold /* nullable, register kernel, xin null: start from vstar - vold */,
