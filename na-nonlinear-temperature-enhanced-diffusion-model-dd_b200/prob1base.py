@@ -798,7 +798,12 @@ class _DeviceBinding:
 # semidiscrete field (reference :2133-2293 base, 2429-2839 Field01, 3553-3593 RegH)
 # ----------------------------------------------------------------------------
 
-class SemiDiscreteField_RegHCsTriple:
+class SemiDiscreteFieldBase(ABC):
+    """Name kept for callers that annotate with it (reference :2133; src/mms_trial_utils.py,
+    src/cvg_studies_base.py evaluate `p1.SemiDiscreteFieldBase` at import time)."""
+
+
+class SemiDiscreteField_RegHCsTriple(SemiDiscreteFieldBase):
     """[Cs-Cd-int] = Kd (Sd - cd)(1 + cl) H_eta(cs).  F*(state, t) run on the device."""
 
     def __init__(self, *, grid: Grid, model: DefaultModel01, forcing_terms: ForcingTermsBase,
@@ -921,7 +926,12 @@ class _LazyResiduals(dict):
         return super().__len__()
 
 
-class P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_RegHCsTriple(TimeIntegratorBase):
+class P_ModifiedEuler_C_Trapezoidal_TimeIntegratorBase(ABC):
+    """Name kept for callers that annotate with it (reference :2906)."""
+
+
+class P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_RegHCsTriple(P_ModifiedEuler_C_Trapezoidal_TimeIntegratorBase,
+                                                                TimeIntegratorBase):
     """Predictor-corrector / Newton step of the RegHCsTriple family (reference :2906-3149, 3596-3702)."""
 
     def __init__(self, semi_discrete_field, *, num_pc_steps=1, num_newton_steps=1, regularization_factor: float,

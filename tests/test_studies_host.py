@@ -132,3 +132,41 @@ def test_member_gather_and_sweep_merge_gloo():
         np.testing.assert_array_equal(full[:, 1], 10.0 * np.arange(11.0))
         np.testing.assert_array_equal(overall, np.arange(5) + 1.0)
         np.testing.assert_array_equal(per_var, np.arange(25).reshape(5, 5) + 0.5)
+
+
+REF_SRC = "/root/reference/src"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SRC), reason="the reference tree only exists in the build container")
+def test_reference_study_modules_load_on_this_core():
+    """north_star: the reference's own mms_trial_utils / cvg_studies_base / prob1_mms_cases run unchanged on top of
+    this package's prob1base.  Here (no GPU): they import (their annotations are evaluated against our names),
+    their pure-host parts agree with ours, and the reference's case classes get a device description from our
+    MMSCaseSymbolic."""
+    import importlib.util
+    import prob1base as p1
+    import prob1_mms_cases as ours
+    import cvg_studies_base as our_cvg
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location("ref_" + name, os.path.join(REF_SRC, name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)   # `import prob1base as p1` inside resolves to this package's module
+        return mod
+
+    ref_cvg, ref_mtu, ref_cases = load("cvg_studies_base"), load("mms_trial_utils"), load("prob1_mms_cases")
+    assert ref_cvg.p1 is p1 and ref_mtu.p1 is p1
+    errs = [4e-5, 1.6e-5, 4.3e-6, 1.1e-6, 2.8e-7]
+    assert ref_cvg.calculate_observed_rates(errs) == our_cvg.calculate_observed_rates(errs)
+    grid = p1.make_uniform_grid(6, 5)
+    model = p1.DefaultModel02(p1.default_model_consts)
+    for name in ("MMSCasePol", "MMSCaseExpSin", "MMSCaseSlowlyChangingPeaks_Fast1e1",
+                 "MMSCaseNonFullySmoothPol_cpcsH1_TclcdH2"):
+        theirs, mine = getattr(ref_cases, name)(grid=grid, model=model), getattr(ours, name)(grid=grid, model=model)
+        for v in ("cp", "T", "cl", "cd", "cs"):
+            a, b = getattr(theirs, v)(0.3, grid.xx, grid.yy), getattr(mine, v)(0.3, grid.xx, grid.yy)
+            np.testing.assert_allclose(a, b, rtol=1e-14, atol=1e-300)
+        if name != "MMSCaseExpSin":   # ExpSin's closed form is keyed on our own class; the others factorise
+            assert theirs.device_spec() is not None, name
+    trial = ref_mtu.MMSTrial  # constructing it needs a device (state upload); the class itself resolves
+    assert callable(trial)
