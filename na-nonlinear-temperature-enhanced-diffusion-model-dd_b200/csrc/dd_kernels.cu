@@ -293,6 +293,12 @@ cudaError_t dd_launch_predict(const DDLaunch& L, int mode, const DDGeom& g, cons
 #ifndef DD_MARCH_MINB
 #define DD_MARCH_MINB 4
 #endif
+#ifndef DD_MARCH_UNROLL
+#define DD_MARCH_UNROLL 1
+#endif
+#define DD_PRAGMA_(x) _Pragma(#x)
+#define DD_PRAGMA(x) DD_PRAGMA_(x)
+#define DD_MARCH_LOOP DD_PRAGMA(unroll DD_MARCH_UNROLL)
 
 struct DDMarchCell {
     double cp, T, cl, cd;
@@ -390,6 +396,7 @@ k_predict_march(DDGeom g, const DDMember* __restrict__ mem, DDForcingArrays A, D
         }
     }
     double rho = 0.0;
+    DD_MARCH_LOOP
     for (int r = ra; r < rz; ++r) {
         const int i = g.row0 + r;
         const long long o = mo + (long long)r * g.ld + j;
@@ -538,9 +545,15 @@ __global__ void __launch_bounds__(DD_BLOCK, DD_MINB_ASM) k_assemble(DDGeom g, co
     if (threadIdx.x == 0) atomic_max_nonneg(&stats[n.member].rho, rho);
 }
 
+cudaError_t dd_launch_assemble_march(const DDLaunch& L, int mode, int var, const DDGeom& g, const DDMember* mem,
+                                     const DDForcing& F, const DDStateC& ustar, const double* T1, const double* cl1,
+                                     const double* Y, int cd_swap, const DDRows& R, DDSolveStats* stats);
+
 cudaError_t dd_launch_assemble(const DDLaunch& L, int mode, int var, const DDGeom& g, const DDMember* mem,
                                const DDForcing& F, const DDStateC& ustar, const double* T1, const double* cl1,
                                const double* Y, int cd_swap, const DDRows& R, DDSolveStats* stats) {
+    if (var != DD_T && dd_predict_march_ok(g, L, mode))
+        return dd_launch_assemble_march(L, mode, var, g, mem, F, ustar, T1, cl1, Y, cd_swap, R, stats);
     const int bpm = blocks_per_member(g, L);
     k_reset_stats<<<(L.nmembers + 127) / 128, 128, 0, L.stream>>>(stats, L.nmembers);
 #define DD_ASM(VAR)                                                                                             \
@@ -556,6 +569,270 @@ cudaError_t dd_launch_assemble(const DDLaunch& L, int mode, int var, const DDGeo
         return cudaErrorInvalidValue;
     }
 #undef DD_ASM
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// marching assembly of the cl and cd Newton rows (same scheme as k_predict_march: one warp = 31 columns +
+// a halo lane, rows r-1, r, r+1 in registers, next row requested one iteration ahead, every face coefficient
+// and flux evaluated once and shared by the two adjacent nodes).  Expressions as in dd_row_cl / dd_row_cd.
+// ---------------------------------------------------------------------------
+struct DDMarchA {
+    double cp, T, v, t1;  // linearisation state cp1p, T*, v* (cl* or cd*) and the new T1
+};
+
+__device__ __forceinline__ DDMarchA dd_marchA_load(const double* __restrict__ cp, const double* __restrict__ T,
+                                                   const double* __restrict__ v, const double* __restrict__ t1,
+                                                   long long o, bool ok) {
+    DDMarchA c;
+    c.cp = ok ? __ldg(cp + o) : 0.0;
+    c.T = ok ? __ldg(T + o) : 0.0;
+    c.v = ok ? __ldg(v + o) : 0.0;
+    c.t1 = ok ? __ldg(t1 + o) : 0.0;
+    return c;
+}
+
+struct DDMarchGeom {
+    int member, wc, j, ra, rz, lane;
+    bool col, owner, jint, colN;
+    long long mo, moR;
+    double rkp, rkN, cS, cN;
+};
+
+__device__ __forceinline__ bool dd_march_setup(const DDGeom& g, const DDRows& R, int r0, int r1, int nwc, int wcb,
+                                               int nrb, DDMarchGeom* q) {
+    q->lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    int bid = blockIdx.x;
+    q->member = bid / (wcb * nrb);
+    bid -= q->member * (wcb * nrb);
+    const int rbk = bid / wcb, cbk = bid - rbk * wcb;
+    q->wc = cbk * (blockDim.x >> 5) + warp;
+    if (q->wc >= nwc) return false;
+    q->j = q->wc * 31 + q->lane - 1;
+    q->ra = r0 + rbk * DD_MARCH_ROWS;
+    q->rz = min(q->ra + DD_MARCH_ROWS, r1);
+    const int j = q->j;
+    q->col = j >= 0 && j <= g.M;
+    q->owner = q->lane >= 1 && q->col;
+    q->jint = j >= 1 && j <= g.M - 1;
+    q->colN = j >= 0 && j + 1 <= g.M;
+    q->mo = q->member * g.mstride;
+    q->moR = q->member * R.mstride;
+    double rkS = 0.0;
+    q->rkp = q->rkN = 0.0;
+    if (q->colN) q->rkN = g.rk[j + 1];
+    if (q->jint) {
+        q->rkp = g.rkp[j];
+        rkS = g.rk[j];
+    }
+    q->cS = q->rkp * rkS;
+    q->cN = q->rkp * q->rkN;
+    return true;
+}
+
+__global__ void __launch_bounds__(DD_MARCH_WARPS * 32, DD_MARCH_MINB)
+k_assemble_cl_march(DDGeom g, const DDMember* __restrict__ mem, const double* __restrict__ f1, DDStateC u,
+                    const double* __restrict__ T1, const double* __restrict__ Ycl, DDRows R, DDSolveStats* stats,
+                    int r0, int r1, int nwc, int wcb, int nrb) {
+    DDMarchGeom q;
+    if (!dd_march_setup(g, R, r0, r1, nwc, wcb, nrb, &q)) return;
+    const DDMember& mb = mem[q.member];
+    if (!mb.active) return;
+    const DDModel& m = mb.m;
+    const double dt = mb.dt;
+    const int j = q.j;
+    const double *cpA = u.v[DD_CP], *TA = u.v[DD_T], *clA = u.v[DD_CL];
+    const long long oa = q.mo + (long long)q.ra * g.ld + j;
+    DDMarchA P = dd_marchA_load(cpA, TA, clA, T1, oa - g.ld, q.col && q.ra - 1 >= 0);
+    DDMarchA C = dd_marchA_load(cpA, TA, clA, T1, oa, q.col);
+    DDMarchA N = dd_marchA_load(cpA, TA, clA, T1, oa + g.ld, q.col && q.ra + 1 < g.nrows);
+    // two rows of requests in flight: row r+3 of the rolling fields and row r+2 of everything else are
+    // asked for while row r is computed
+    DDMarchA N2 = dd_marchA_load(cpA, TA, clA, T1, oa + 2LL * g.ld, q.col && q.ra + 1 < q.rz && q.ra + 2 < g.nrows);
+    double cpn = q.colN ? __ldg(cpA + oa + 1) : 0.0, cln = q.colN ? __ldg(clA + oa + 1) : 0.0;
+    double yc = q.owner ? __ldg(Ycl + oa) : 0.0, fc = q.owner ? dd_ldg0(f1, oa) : 0.0;
+    const bool has1 = q.ra + 1 < q.rz;
+    double cpn1 = (q.colN && has1) ? __ldg(cpA + oa + g.ld + 1) : 0.0;
+    double cln1 = (q.colN && has1) ? __ldg(clA + oa + g.ld + 1) : 0.0;
+    double yc1 = (q.owner && has1) ? __ldg(Ycl + oa + g.ld) : 0.0, fc1 = (q.owner && has1) ? dd_ldg0(f1, oa + g.ld) : 0.0;
+    // W face of the first row
+    double DlW = 0.0, flW = 0.0, advW = 0.0;
+    {
+        const int i = g.row0 + q.ra;
+        if (q.jint && i >= 1 && i <= g.N - 1) {
+            DlW = dd_Dl(m, 0.5 * (C.cp + P.cp));
+            flW = DlW * ((C.v - P.v) * g.rh[i]);
+            advW = 0.5 * (m.gamma_T * C.T * (C.v + 1.0) + m.gamma_T * P.T * (P.v + 1.0));
+        }
+    }
+    double rho = 0.0;
+    DD_MARCH_LOOP
+    for (int r = q.ra; r < q.rz; ++r) {
+        const int i = g.row0 + r;
+        const long long o = q.mo + (long long)r * g.ld + j;
+        const bool nx2 = r + 2 < q.rz;
+        const DDMarchA NN = dd_marchA_load(cpA, TA, clA, T1, o + 3LL * g.ld, q.col && nx2 && r + 3 < g.nrows);
+        const double cpnN = (q.colN && nx2) ? __ldg(cpA + o + 2LL * g.ld + 1) : 0.0;
+        const double clnN = (q.colN && nx2) ? __ldg(clA + o + 2LL * g.ld + 1) : 0.0;
+        const double ycN = (q.owner && nx2) ? __ldg(Ycl + o + 2LL * g.ld) : 0.0;
+        const double fcN = (q.owner && nx2) ? dd_ldg0(f1, o + 2LL * g.ld) : 0.0;
+
+        const bool irow = i >= 1 && i <= g.N - 1;
+        const bool inter = irow && q.jint;
+        double DlE = 0.0, flE = 0.0, advE = 0.0;
+        if (q.jint && i >= 0 && i <= g.N - 1 && r + 1 < g.nrows) {
+            DlE = dd_Dl(m, 0.5 * (N.cp + C.cp));
+            flE = DlE * ((N.v - C.v) * g.rh[i + 1]);
+            advE = 0.5 * (m.gamma_T * N.T * (N.v + 1.0) + m.gamma_T * C.T * (C.v + 1.0));
+        }
+        double DlN = 0.0, flN = 0.0;
+        if (irow && q.colN) {
+            DlN = dd_Dl(m, 0.5 * (cpn + C.cp));
+            flN = DlN * ((cln - C.v) * q.rkN);
+        }
+        const double DlS = __shfl_up_sync(0xffffffffu, DlN, 1);
+        const double flS = __shfl_up_sync(0xffffffffu, flN, 1);
+        if (q.owner) {
+            DDRow row = {0.0, 0.0, 0.0, 0.0, 0.0};
+            if (inter) {
+                const double rhp = g.rhp[i];
+                const double dW = DlW * (rhp * g.rh[i]), dE = DlE * (rhp * g.rh[i + 1]);
+                const double S = DlS * q.cS, Nn = DlN * q.cN;
+                const double W = dW + (m.gamma_T * P.T) * (0.5 * rhp);
+                const double E = dE - (m.gamma_T * N.T) * (0.5 * rhp);
+                const double Cc = -(dW + dE + S + Nn) - m.K4 * C.cp;
+                const double Fcl = fc + ((rhp * (flE - flW) + q.rkp * (flN - flS)) - rhp * (advE - advW) -
+                                         m.K4 * C.cp * (C.v + 1.0));
+                const double jw = (i > 1) ? m.gamma_T * (1.0 + P.v) * (P.t1 - P.T) : 0.0;
+                const double je = (i < g.N - 1) ? m.gamma_T * (1.0 + N.v) * (N.t1 - N.T) : 0.0;
+                const double JT = (jw - je) * (0.5 * rhp);
+                const double rhs = yc - 2.0 * C.v + dt * Fcl + dt * JT;
+                row = dd_make_row(2.0 - dt * Cc, dt * W, dt * E, dt * S, dt * Nn, rhs, i, j, g.N, g.M);
+                rho = fmax(rho, dd_row_rho(row));
+            }
+            dd_store_row(R, q.moR + (long long)r * R.ld + j, row);
+        }
+        DlW = DlE; flW = flE; advW = advE;
+        P = C; C = N; N = N2; N2 = NN;
+        cpn = cpn1; cln = cln1; yc = yc1; fc = fc1;
+        cpn1 = cpnN; cln1 = clnN; yc1 = ycN; fc1 = fcN;
+    }
+    rho = warp_max_bits(rho);
+    if (q.lane == 0) atomic_max_nonneg(&stats[q.member].rho, rho);
+}
+
+__global__ void __launch_bounds__(DD_MARCH_WARPS * 32, DD_MARCH_MINB)
+k_assemble_cd_march(DDGeom g, const DDMember* __restrict__ mem, const double* __restrict__ f1, DDStateC u,
+                    const double* __restrict__ T1, const double* __restrict__ cl1, const double* __restrict__ Ycd,
+                    int swap, DDRows R, DDSolveStats* stats, int r0, int r1, int nwc, int wcb, int nrb) {
+    DDMarchGeom q;
+    if (!dd_march_setup(g, R, r0, r1, nwc, wcb, nrb, &q)) return;
+    const DDMember& mb = mem[q.member];
+    if (!mb.active) return;
+    const DDModel& m = mb.m;
+    const double dt = mb.dt;
+    const int j = q.j;
+    const double *cpA = u.v[DD_CP], *TA = u.v[DD_T], *clA = u.v[DD_CL], *cdA = u.v[DD_CD], *csA = u.v[DD_CS];
+    const long long oa = q.mo + (long long)q.ra * g.ld + j;
+    DDMarchA P = dd_marchA_load(cpA, TA, cdA, T1, oa - g.ld, q.col && q.ra - 1 >= 0);
+    DDMarchA C = dd_marchA_load(cpA, TA, cdA, T1, oa, q.col);
+    DDMarchA N = dd_marchA_load(cpA, TA, cdA, T1, oa + g.ld, q.col && q.ra + 1 < g.nrows);
+    DDMarchA Cn = dd_marchA_load(cpA, TA, cdA, T1, oa + 1, q.colN);
+    double yc = q.owner ? __ldg(Ycd + oa) : 0.0, fc = q.owner ? dd_ldg0(f1, oa) : 0.0;
+    double clc = q.owner ? __ldg(clA + oa) : 0.0, cl1c = q.owner ? __ldg(cl1 + oa) : 0.0;
+    double csc = q.owner ? __ldg(csA + oa) : 0.0;
+    // W face of the first row: coefficient, flux, T-Jacobian term
+    double DdW = 0.0, flW = 0.0, jtW = 0.0;
+    {
+        const int i = g.row0 + q.ra;
+        if (q.jint && i >= 1 && i <= g.N - 1) {
+            double dTf;
+            DdW = dd_Dd_dT(m, 0.5 * (C.cp + P.cp), 0.5 * (C.T + P.T), &dTf);
+            const double gx = (C.v - P.v) * g.rh[i];
+            flW = DdW * gx;
+            jtW = (gx * dTf) * (0.5 * ((C.t1 - C.T) + (P.t1 - P.T)));
+        }
+    }
+    double rho = 0.0;
+    DD_MARCH_LOOP
+    for (int r = q.ra; r < q.rz; ++r) {
+        const int i = g.row0 + r;
+        const long long o = q.mo + (long long)r * g.ld + j;
+        const bool nxt = r + 1 < q.rz;
+        const DDMarchA NN = dd_marchA_load(cpA, TA, cdA, T1, o + 2LL * g.ld, q.col && nxt && r + 2 < g.nrows);
+        const DDMarchA CnN = dd_marchA_load(cpA, TA, cdA, T1, o + g.ld + 1, q.colN && nxt);
+        const bool pn = q.owner && nxt;
+        const double ycN = pn ? __ldg(Ycd + o + g.ld) : 0.0, fcN = pn ? dd_ldg0(f1, o + g.ld) : 0.0;
+        const double clcN = pn ? __ldg(clA + o + g.ld) : 0.0, cl1cN = pn ? __ldg(cl1 + o + g.ld) : 0.0;
+        const double cscN = pn ? __ldg(csA + o + g.ld) : 0.0;
+
+        const bool irow = i >= 1 && i <= g.N - 1;
+        const bool inter = irow && q.jint;
+        double DdE = 0.0, flE = 0.0, jtE = 0.0;
+        if (q.jint && i >= 0 && i <= g.N - 1 && r + 1 < g.nrows) {
+            double dTf;
+            DdE = dd_Dd_dT(m, 0.5 * (N.cp + C.cp), 0.5 * (N.T + C.T), &dTf);
+            const double gx = (N.v - C.v) * g.rh[i + 1];
+            flE = DdE * gx;
+            jtE = (gx * dTf) * (0.5 * ((N.t1 - N.T) + (C.t1 - C.T)));
+        }
+        double DdN = 0.0, flN = 0.0, jtN = 0.0;
+        if (irow && q.colN) {
+            double dTf;
+            DdN = dd_Dd_dT(m, 0.5 * (Cn.cp + C.cp), 0.5 * (Cn.T + C.T), &dTf);
+            const double gy = (Cn.v - C.v) * q.rkN;
+            flN = DdN * gy;
+            jtN = (gy * dTf) * (0.5 * ((Cn.t1 - Cn.T) + (C.t1 - C.T)));
+        }
+        const double DdS = __shfl_up_sync(0xffffffffu, DdN, 1);
+        const double flS = __shfl_up_sync(0xffffffffu, flN, 1);
+        const double jtS = __shfl_up_sync(0xffffffffu, jtN, 1);
+        if (q.owner) {
+            DDRow row = {0.0, 0.0, 0.0, 0.0, 0.0};
+            if (inter) {
+                const double rhp = g.rhp[i];
+                const double W = DdW * (rhp * g.rh[i]), E = DdE * (rhp * g.rh[i + 1]);
+                const double S = DdS * q.cS, Nn = DdN * q.cN;
+                const double KH = m.Kd * dd_H(csc, m.eta);
+                const double Cc = -(W + E + S + Nn) - KH * (clc + 1.0);
+                const double Fcd = fc + (rhp * (flE - flW) + q.rkp * (flN - flS)) + (m.Sd - C.v) * (clc + 1.0) * KH;
+                const double JT = rhp * (-jtW + jtE) + q.rkp * (-jtS + jtN);
+                const double Jcl = KH * (m.Sd - C.v) * (cl1c - clc);
+                const double rhs = yc - 2.0 * C.v + dt * Fcd + dt * JT + dt * Jcl;
+                const double oW = swap ? S : W, oS = swap ? W : S;
+                row = dd_make_row(2.0 - dt * Cc, dt * oW, dt * E, dt * oS, dt * Nn, rhs, i, j, g.N, g.M);
+                rho = fmax(rho, dd_row_rho(row));
+            }
+            dd_store_row(R, q.moR + (long long)r * R.ld + j, row);
+        }
+        DdW = DdE; flW = flE; jtW = jtE;
+        P = C; C = N; N = NN; Cn = CnN;
+        yc = ycN; fc = fcN; clc = clcN; cl1c = cl1cN; csc = cscN;
+    }
+    rho = warp_max_bits(rho);
+    if (q.lane == 0) atomic_max_nonneg(&stats[q.member].rho, rho);
+}
+
+cudaError_t dd_launch_assemble_march(const DDLaunch& L, int mode, int var, const DDGeom& g, const DDMember* mem,
+                                     const DDForcing& F, const DDStateC& ustar, const double* T1, const double* cl1,
+                                     const double* Y, int cd_swap, const DDRows& R, DDSolveStats* stats) {
+    const double* f1 = (mode == DD_FORCING_ARRAYS) ? F.arr.f[var][1] : nullptr;
+    const int nwc = (g.M + 1 + 30) / 31;
+    const int wpb = nwc < DD_MARCH_WARPS ? nwc : DD_MARCH_WARPS;
+    const int wcb = (nwc + wpb - 1) / wpb;
+    const int nrb = (L.own1 - L.own0 + DD_MARCH_ROWS - 1) / DD_MARCH_ROWS;
+    const long long nblocks = (long long)wcb * nrb * L.nmembers;
+    if (nblocks <= 0 || nblocks > 2147483647LL) return cudaErrorInvalidConfiguration;
+    k_reset_stats<<<(L.nmembers + 127) / 128, 128, 0, L.stream>>>(stats, L.nmembers);
+    if (var == DD_CL)
+        k_assemble_cl_march<<<(unsigned)nblocks, wpb * 32, 0, L.stream>>>(g, mem, f1, ustar, T1, Y, R, stats, L.own0,
+                                                                          L.own1, nwc, wcb, nrb);
+    else if (var == DD_CD)
+        k_assemble_cd_march<<<(unsigned)nblocks, wpb * 32, 0, L.stream>>>(g, mem, f1, ustar, T1, cl1, Y, cd_swap, R,
+                                                                          stats, L.own0, L.own1, nwc, wcb, nrb);
+    else
+        return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 
