@@ -324,6 +324,67 @@ __global__ void __launch_bounds__(512) k_rbsor_tile(SolveArgs A) {
 #define DD_REG_SJ 64
 #define DD_REG_PW 32
 
+__device__ __forceinline__ void dd_prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// Coefficients of the thread's own cells into registers (index [k][colour]) and the initial iterate into the
+// colour planes.  The two cells of a packed column are adjacent in memory and the row arrays have an even
+// pitch, so one aligned 16-byte load fetches both (cbase is even: tile_j even, H odd).  FLIP = colour of the
+// even column.  Cells outside the valid rows / the grid keep zero coefficients and a zero iterate.
+template <int CONST_BAND, int RPW, int FLIP>
+__device__ __forceinline__ void reg_load_cells(const SolveArgs& A, const DDGeom& g, long long moR, long long mo,
+                                               int rbase, int colj, bool pair_ok, int li0, int li1, int lj0,
+                                               int lj1, int lane, int warp, double (&cb)[RPW][2],
+                                               double (&cw)[RPW][2], double (&ce)[RPW][2], double (&cs)[RPW][2],
+                                               double (&cn)[RPW][2], double* sx) {
+    constexpr int SI = DD_REG_WARPS * RPW, PW = DD_REG_PW, plane = SI * PW;
+    constexpr int c0 = FLIP ? 1 : 0, c1 = 1 - c0;  // colours of the even / odd column
+    const int sj0 = 2 * lane;
+    const bool in0 = sj0 >= lj0 && sj0 < lj1, in1 = sj0 + 1 >= lj0 && sj0 + 1 < lj1;
+#pragma unroll
+    for (int k = 0; k < RPW; ++k) {
+        const int si = warp + DD_REG_WARPS * k;
+        const int row = rbase + si;
+        const bool rowok = pair_ok && si >= li0 && si < li1 && (in0 || in1);
+        double2 vb = make_double2(0.0, 0.0), vw = vb, ve = vb, vs2 = vb, vn = vb, vx = vb;
+        if (rowok) {
+            const long long o = moR + (long long)row * A.ldR + colj;
+            vb = *reinterpret_cast<const double2*>(A.bb + o);
+            vw = *reinterpret_cast<const double2*>(A.aW + o);
+            if (!CONST_BAND) {
+                ve = *reinterpret_cast<const double2*>(A.aE + o);
+                vs2 = *reinterpret_cast<const double2*>(A.aS + o);
+                vn = *reinterpret_cast<const double2*>(A.aN + o);
+            }
+            if (A.xin) {
+                vx = *reinterpret_cast<const double2*>(A.xin + o);
+            } else if (A.vold) {
+                // the previous step's increment as initial iterate (states have the grid's own row pitch)
+                const int gi = g.row0 + row;
+                if (gi >= 1 && gi <= g.N - 1) {
+                    const long long og = mo + (long long)row * g.ld + colj;
+                    if (colj >= 1 && colj <= g.M - 1) vx.x = A.vstar[og] - A.vold[og];
+                    if (colj + 1 >= 1 && colj + 1 <= g.M - 1) vx.y = A.vstar[og + 1] - A.vold[og + 1];
+                }
+            }
+            if (!(in0 && in1)) {  // only the pair that straddles the left / right end of the grid
+                if (!in0) vb.x = vw.x = ve.x = vs2.x = vn.x = vx.x = 0.0;
+                if (!in1) vb.y = vw.y = ve.y = vs2.y = vn.y = vx.y = 0.0;
+            }
+        }
+        cb[k][c0] = vb.x;  cb[k][c1] = vb.y;
+        cw[k][c0] = vw.x;  cw[k][c1] = vw.y;
+        if (!CONST_BAND) {
+            ce[k][c0] = ve.x;   ce[k][c1] = ve.y;
+            cs[k][c0] = vs2.x;  cs[k][c1] = vs2.y;
+            cn[k][c0] = vn.x;   cn[k][c1] = vn.y;
+        }
+        sx[c0 * plane + si * PW + lane] = vx.x;
+        sx[c1 * plane + si * PW + lane] = vx.y;
+    }
+}
+
 template <int CONST_BAND, int RPW>
 __global__ void __launch_bounds__(DD_REG_WARPS * 32, 1) k_rbsor_reg(SolveArgs A) {
     const DDGeom& g = A.g;
@@ -355,50 +416,38 @@ __global__ void __launch_bounds__(DD_REG_WARPS * 32, 1) k_rbsor_reg(SolveArgs A)
     const int flip = (par0 + warp) & 1;  // colour of the even column of the pair (rows of a thread share parity)
     const int colj = cbase + 2 * lane;   // global column of the even cell
     const bool pair_ok = colj >= 0 && colj + 1 < A.ldR;
+    // `flip` is uniform in the warp: one branch selects the variant that files the two cells of a pair under
+    // their colours at compile time (no per-value selects)
+    // Ask L2 for everything this CTA is going to read before the first load is issued: the loads below come in
+    // register-limited groups, and only the first group should pay the DRAM latency.  (Prefetches hold no
+    // registers and no scoreboard slot.)
+    {
 #pragma unroll
-    for (int k = 0; k < RPW; ++k) {
-        const int si = warp + DD_REG_WARPS * k;
-        const int row = rbase + si;
-        const bool rowok = pair_ok && si >= li0 && si < li1;
-        const long long o = moR + (long long)row * A.ldR + colj;
-        const int sj0 = 2 * lane;
-        const bool ok0 = rowok && sj0 >= lj0 && sj0 < lj1, ok1 = rowok && sj0 + 1 >= lj0 && sj0 + 1 < lj1;
-        double2 vb = make_double2(0.0, 0.0), vw = vb, ve = vb, vs2 = vb, vn = vb, vx = vb;
-        if (rowok) {
-            vb = *reinterpret_cast<const double2*>(A.bb + o);
-            vw = *reinterpret_cast<const double2*>(A.aW + o);
-            if (!CONST_BAND) {
-                ve = *reinterpret_cast<const double2*>(A.aE + o);
-                vs2 = *reinterpret_cast<const double2*>(A.aS + o);
-                vn = *reinterpret_cast<const double2*>(A.aN + o);
-            }
-            if (A.xin) {
-                vx = *reinterpret_cast<const double2*>(A.xin + o);
-            } else if (A.vold) {
-                // the previous step's increment as initial iterate (states have the grid's own row pitch)
-                const int gi = g.row0 + row;
-                if (gi >= 1 && gi <= g.N - 1) {
-                    const long long og = mo + (long long)row * g.ld + colj;
-                    if (ok0 && colj >= 1 && colj <= g.M - 1) vx.x = A.vstar[og] - A.vold[og];
-                    if (ok1 && colj + 1 <= g.M - 1) vx.y = A.vstar[og + 1] - A.vold[og + 1];
+        for (int k = 0; k < RPW; ++k) {
+            const int si = warp + DD_REG_WARPS * k;
+            if (pair_ok && si >= li0 && si < li1) {
+                const long long o = moR + (long long)(rbase + si) * A.ldR + colj;
+                dd_prefetch_l2(A.bb + o);
+                dd_prefetch_l2(A.aW + o);
+                if (!CONST_BAND) {
+                    dd_prefetch_l2(A.aE + o);
+                    dd_prefetch_l2(A.aS + o);
+                    dd_prefetch_l2(A.aN + o);
                 }
+                if (A.xin) dd_prefetch_l2(A.xin + o);
+            }
+            if (A.last_pass) {
+                const int a = warp + DD_REG_WARPS * k;
+                if (a < tr && lane * 2 < tc) dd_prefetch_l2(A.vstar + mo + (long long)(r0 + a) * g.ld + c0 + lane * 2);
             }
         }
-        // element .x is column sj0 (colour `flip`), .y is column sj0 + 1 (colour 1 - flip)
-        const double b0 = ok0 ? vb.x : 0.0, b1 = ok1 ? vb.y : 0.0, w0 = ok0 ? vw.x : 0.0, w1 = ok1 ? vw.y : 0.0;
-        cb[k][0] = flip ? b1 : b0;  cb[k][1] = flip ? b0 : b1;
-        cw[k][0] = flip ? w1 : w0;  cw[k][1] = flip ? w0 : w1;
-        if (!CONST_BAND) {
-            const double e0 = ok0 ? ve.x : 0.0, e1 = ok1 ? ve.y : 0.0, s0 = ok0 ? vs2.x : 0.0, s1 = ok1 ? vs2.y : 0.0;
-            const double n0 = ok0 ? vn.x : 0.0, n1 = ok1 ? vn.y : 0.0;
-            ce[k][0] = flip ? e1 : e0;  ce[k][1] = flip ? e0 : e1;
-            cs[k][0] = flip ? s1 : s0;  cs[k][1] = flip ? s0 : s1;
-            cn[k][0] = flip ? n1 : n0;  cn[k][1] = flip ? n0 : n1;
-        }
-        const double x0 = ok0 ? vx.x : 0.0, x1 = ok1 ? vx.y : 0.0;
-        sx[(flip ? 1 : 0) * plane + si * PW + lane] = x0;
-        sx[(flip ? 0 : 1) * plane + si * PW + lane] = x1;
     }
+    if (flip)
+        reg_load_cells<CONST_BAND, RPW, 1>(A, g, moR, mo, rbase, colj, pair_ok, li0, li1, lj0, lj1, lane, warp, cb, cw,
+                                           ce, cs, cn, sx);
+    else
+        reg_load_cells<CONST_BAND, RPW, 0>(A, g, moR, mo, rbase, colj, pair_ok, li0, li1, lj0, lj1, lane, warp, cb, cw,
+                                           ce, cs, cn, sx);
     // constant-band geometry factors of the thread's rows and of its two columns
     double rW[RPW], rE[RPW], cS2[2], cN2[2];
     if (CONST_BAND) {
@@ -504,34 +553,36 @@ __global__ void __launch_bounds__(DD_REG_WARPS * 32, 1) k_rbsor_reg(SolveArgs A)
                 A.xout[o + 1] = x1;
         }
     }
-    // (2) all threads, lanes along consecutive columns: v_new = v* + x with coalesced loads and stores
+    // (2) v_new = v* + x: warp w takes tile rows w, w + 16, ..., its lanes consecutive columns (coalesced);
+    //     all loads of v* are issued before the first store
     if (A.last_pass) {
-        const int ncell = tr * tc;
-        for (int base = threadIdx.x; base < ncell; base += 4 * DD_REG_WARPS * 32) {
-            double vsv[4];
-            long long ogv[4];
+        double vsv[RPW][2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int idx = base + u * DD_REG_WARPS * 32;
-                vsv[u] = 0.0;
-                ogv[u] = 0;
-                if (idx < ncell) {
-                    const int a = idx / tc, bcol = idx - a * tc;
-                    ogv[u] = mo + (long long)(r0 + a) * g.ld + (c0 + bcol);
-                    vsv[u] = A.vstar[ogv[u]];
-                }
+        for (int k = 0; k < RPW; ++k) {
+            const int a = warp + DD_REG_WARPS * k;
+            const long long rowoff = mo + (long long)(r0 + a) * g.ld + c0;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int bcol = lane + 32 * cc;
+                vsv[k][cc] = (a < tr && bcol < tc) ? A.vstar[rowoff + bcol] : 0.0;
             }
+        }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int idx = base + u * DD_REG_WARPS * 32;
-                if (idx >= ncell) continue;
-                const int a = idx / tc, bcol = idx - a * tc;
-                const int si = H + 1 + a, sj = H + 1 + bcol;
-                const double x = sx[((par0 + si + sj) & 1) * plane + si * PW + (sj >> 1)];
-                const bool inter = dd_is_interior(g, g.row0 + r0 + a, c0 + bcol);
-                const double vn = dd_newton_update(inter, vsv[u], x, A.zero_boundary);
-                A.vnew[ogv[u]] = vn;
-                vmax = nn_max(vmax, vn);
+        for (int k = 0; k < RPW; ++k) {
+            const int a = warp + DD_REG_WARPS * k;
+            const int si = H + 1 + a, gi = g.row0 + r0 + a;
+            const bool irow = gi > 0 && gi < g.N;
+            const long long rowoff = mo + (long long)(r0 + a) * g.ld + c0;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int bcol = lane + 32 * cc;
+                if (a < tr && bcol < tc) {
+                    const int sj = H + 1 + bcol, gj = c0 + bcol;
+                    const double x = sx[((par0 + si + sj) & 1) * plane + si * PW + (sj >> 1)];
+                    const double vn = dd_newton_update(irow && gj > 0 && gj < g.M, vsv[k][cc], x, A.zero_boundary);
+                    A.vnew[rowoff + bcol] = vn;
+                    vmax = nn_max(vmax, vn);
+                }
             }
         }
     }
