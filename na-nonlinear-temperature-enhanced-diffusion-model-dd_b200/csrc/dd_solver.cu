@@ -17,6 +17,16 @@
 // special casing is needed; outside the grid the staging pads with zeros.
 #include <cuda_pipeline.h>
 
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "dd_kernels.cuh"
 
 __device__ __forceinline__ void atomic_max_nn(double* addr, double v) {
@@ -67,6 +77,7 @@ struct SolveArgs {
     int own0, own1;  // local rows that are tiled (owned rows of a slab; all rows otherwise)
     int vr0, vr1;    // local rows holding valid assembled rows
     int sweeps, halo, tile_i, tile_j, tiles_i, tiles_j, last_pass;
+    int nblocks;  // tiles x members (the pipelined kernel walks them with a persistent grid)
 };
 
 extern __shared__ double dd_smem[];
@@ -324,6 +335,54 @@ __global__ void __launch_bounds__(512) k_rbsor_tile(SolveArgs A) {
 #define DD_REG_SJ 64
 #define DD_REG_PW 32
 
+// ---- bulk-copy (TMA, non-tensor form) pipeline of the persistent variant ------------------------------------
+// The coefficient rows of the NEXT tile are fetched into shared memory by cp.async.bulk while the current tile
+// sweeps: every staged row of a row array is one contiguous, 16-byte aligned segment (even pitch, even
+// first column).  One mbarrier (arrival count 1 + transaction bytes) per CTA; its phase flips once per tile.
+__device__ __forceinline__ unsigned dd_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dd_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dd_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void dd_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dd_smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void dd_mbar_wait(unsigned long long* bar, unsigned phase) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(dd_smem_u32(bar)), "r"(phase)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void dd_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     dd_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(dd_smem_u32(bar))
+                 : "memory");
+}
+
+// 2-D tiled TMA load: box (64 columns x SI rows) at (column c0, row c1) of a row array viewed as
+// [members * nrows][ldR]; out-of-range elements are zero-filled and still counted in the transaction bytes
+struct DDTileMaps {
+    CUtensorMap m[5];  // bb, aW, aE, aS, aN
+};
+__device__ __forceinline__ void dd_tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1,
+                                               unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+            "r"(dd_smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(dd_smem_u32(bar))
+        : "memory");
+}
+
 __device__ __forceinline__ void dd_prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -332,8 +391,9 @@ __device__ __forceinline__ void dd_prefetch_l2(const void* p) {
 // colour planes.  The two cells of a packed column are adjacent in memory and the row arrays have an even
 // pitch, so one aligned 16-byte load fetches both (cbase is even: tile_j even, H odd).  FLIP = colour of the
 // even column.  Cells outside the valid rows / the grid keep zero coefficients and a zero iterate.
-template <int CONST_BAND, int RPW, int FLIP>
-__device__ __forceinline__ void reg_load_cells(const SolveArgs& A, const DDGeom& g, long long moR, long long mo,
+template <int CONST_BAND, int RPW, int FLIP, int PIPE>
+__device__ __forceinline__ void reg_load_cells(const SolveArgs& A, const DDGeom& g, const double* buf, long long moR,
+                                               long long mo,
                                                int rbase, int colj, bool pair_ok, int li0, int li1, int lj0,
                                                int lj1, int lane, int warp, double (&cb)[RPW][2],
                                                double (&cw)[RPW][2], double (&ce)[RPW][2], double (&cs)[RPW][2],
@@ -350,12 +410,24 @@ __device__ __forceinline__ void reg_load_cells(const SolveArgs& A, const DDGeom&
         double2 vb = make_double2(0.0, 0.0), vw = vb, ve = vb, vs2 = vb, vn = vb, vx = vb;
         if (rowok) {
             const long long o = moR + (long long)row * A.ldR + colj;
-            vb = *reinterpret_cast<const double2*>(A.bb + o);
-            vw = *reinterpret_cast<const double2*>(A.aW + o);
-            if (!CONST_BAND) {
-                ve = *reinterpret_cast<const double2*>(A.aE + o);
-                vs2 = *reinterpret_cast<const double2*>(A.aS + o);
-                vn = *reinterpret_cast<const double2*>(A.aN + o);
+            if (PIPE) {
+                // staged by the bulk copies of the previous tile's iteration: [array][si][64 columns]
+                const double* q = buf + si * DD_REG_SJ + 2 * lane;
+                vb = *reinterpret_cast<const double2*>(q);
+                vw = *reinterpret_cast<const double2*>(q + SI * DD_REG_SJ);
+                if (!CONST_BAND) {
+                    ve = *reinterpret_cast<const double2*>(q + 2 * SI * DD_REG_SJ);
+                    vs2 = *reinterpret_cast<const double2*>(q + 3 * SI * DD_REG_SJ);
+                    vn = *reinterpret_cast<const double2*>(q + 4 * SI * DD_REG_SJ);
+                }
+            } else {
+                vb = *reinterpret_cast<const double2*>(A.bb + o);
+                vw = *reinterpret_cast<const double2*>(A.aW + o);
+                if (!CONST_BAND) {
+                    ve = *reinterpret_cast<const double2*>(A.aE + o);
+                    vs2 = *reinterpret_cast<const double2*>(A.aS + o);
+                    vn = *reinterpret_cast<const double2*>(A.aN + o);
+                }
             }
             if (A.xin) {
                 vx = *reinterpret_cast<const double2*>(A.xin + o);
@@ -385,27 +457,73 @@ __device__ __forceinline__ void reg_load_cells(const SolveArgs& A, const DDGeom&
     }
 }
 
-template <int CONST_BAND, int RPW>
-__global__ void __launch_bounds__(DD_REG_WARPS * 32, 1) k_rbsor_reg(SolveArgs A) {
-    const DDGeom& g = A.g;
+struct DDTileGeo {
+    int member, r0, c0, tr, tc, rbase, cbase, li0, li1;
+};
+
+template <int RPW>
+__device__ __forceinline__ DDTileGeo dd_tile_geo(const SolveArgs& A, int blk) {
+    constexpr int SI = DD_REG_WARPS * RPW;
+    DDTileGeo t;
     const int tiles = A.tiles_i * A.tiles_j;
-    const int member = blockIdx.x / tiles;
-    const int t = blockIdx.x - member * tiles;
-    const int ti = t / A.tiles_j, tj = t - ti * A.tiles_j;
+    t.member = blk / tiles;
+    const int q = blk - t.member * tiles;
+    const int ti = q / A.tiles_j, tj = q - ti * A.tiles_j;
+    t.r0 = A.own0 + ti * A.tile_i;
+    t.c0 = tj * A.tile_j;
+    t.tr = min(A.tile_i, A.own1 - t.r0);
+    t.tc = min(A.tile_j, A.g.M + 1 - t.c0);
+    t.rbase = t.r0 - A.halo - 1;
+    t.cbase = t.c0 - A.halo - 1;
+    // rows of the staged region that hold real data (smem coordinates, half-open)
+    t.li0 = max(1, A.vr0 - t.rbase);
+    t.li1 = min(min(SI - 1, A.vr1 - t.rbase), t.tr + 2 * A.halo + 1);
+    return t;
+}
+
+// Starts the TMA loads of tile `blk`'s coefficient boxes into `buf` ([array][si][64]): one elected thread arms
+// the barrier with the (constant) byte count and issues one instruction per array.
+template <int CONST_BAND, int RPW>
+__device__ __forceinline__ void dd_pipe_issue(const SolveArgs& A, const DDTileMaps& maps, int blk, double* buf,
+                                              unsigned long long* bar) {
+    constexpr int SI = DD_REG_WARPS * RPW, NARR = CONST_BAND ? 2 : 5;
+    if (threadIdx.x != 0) return;
+    const DDTileGeo t = dd_tile_geo<RPW>(A, blk);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of buf vs the async writes
+    dd_mbar_expect_tx(bar, (unsigned)(NARR * SI * DD_REG_SJ * sizeof(double)));
+    const int row = t.member * A.g.nrows + t.rbase;
+#pragma unroll
+    for (int a = 0; a < NARR; ++a) dd_tma_load_2d(buf + (size_t)a * SI * DD_REG_SJ, &maps.m[a], t.cbase, row, bar);
+}
+
+template <int CONST_BAND, int RPW, int PIPE>
+__global__ void __launch_bounds__(DD_REG_WARPS * 32, 1)
+k_rbsor_reg(const __grid_constant__ SolveArgs A, const __grid_constant__ DDTileMaps maps) {
+    const DDGeom& g = A.g;
     const int H = A.halo;
-    const int r0 = A.own0 + ti * A.tile_i, c0 = tj * A.tile_j;
-    const int tr = min(A.tile_i, A.own1 - r0), tc = min(A.tile_j, g.M + 1 - c0);
     constexpr int SI = DD_REG_WARPS * RPW, SJ = DD_REG_SJ, PW = DD_REG_PW, plane = SI * PW;
-    const int rbase = r0 - H - 1, cbase = c0 - H - 1;
+    constexpr int NARR = CONST_BAND ? 2 : 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* sx = dd_smem;             // [colour][si][pk]
+    double* buf = dd_smem + 2 * plane;  // PIPE: coefficient rows of one tile, [array][si][64]
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(buf + NARR * SI * SJ);
+    unsigned phase = 0;
+    if (PIPE) {
+        if (threadIdx.x == 0) dd_mbar_init(bar, 1);
+        __syncthreads();
+        if ((int)blockIdx.x < A.nblocks) dd_pipe_issue<CONST_BAND, RPW>(A, maps, blockIdx.x, buf, bar);
+    }
+    // PIPE: persistent grid, tile blk + gridDim.x is fetched while tile blk is swept; otherwise one tile per CTA
+    for (int blk = blockIdx.x; blk < A.nblocks; blk += (PIPE ? (int)gridDim.x : A.nblocks)) {
+    const DDTileGeo tg = dd_tile_geo<RPW>(A, blk);
+    const int member = tg.member, r0 = tg.r0, c0 = tg.c0, tr = tg.tr, tc = tg.tc, rbase = tg.rbase, cbase = tg.cbase;
     const int par0 = (g.row0 + rbase + cbase) & 1;
     const long long mo = member * g.mstride;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* sx = dd_smem;  // [colour][si][pk]
 #ifdef DD_SOLVER_TIMING
     long long tick_ = clock64();
 #endif
     // real data inside the staged region (smem coordinates, half-open)
-    const int li0 = max(1, A.vr0 - rbase), li1 = min(min(SI - 1, A.vr1 - rbase), tr + 2 * H + 1);
+    const int li0 = tg.li0, li1 = tg.li1;
     const int lj0 = max(1, -cbase), lj1 = min(min(SJ - 1, g.M + 1 - cbase), tc + 2 * H + 1);
 
     // ---- load: coefficients of the thread's own cells into registers, x into shared memory -----------
@@ -427,12 +545,14 @@ __global__ void __launch_bounds__(DD_REG_WARPS * 32, 1) k_rbsor_reg(SolveArgs A)
             const int si = warp + DD_REG_WARPS * k;
             if (pair_ok && si >= li0 && si < li1) {
                 const long long o = moR + (long long)(rbase + si) * A.ldR + colj;
-                dd_prefetch_l2(A.bb + o);
-                dd_prefetch_l2(A.aW + o);
-                if (!CONST_BAND) {
-                    dd_prefetch_l2(A.aE + o);
-                    dd_prefetch_l2(A.aS + o);
-                    dd_prefetch_l2(A.aN + o);
+                if (!PIPE) {
+                    dd_prefetch_l2(A.bb + o);
+                    dd_prefetch_l2(A.aW + o);
+                    if (!CONST_BAND) {
+                        dd_prefetch_l2(A.aE + o);
+                        dd_prefetch_l2(A.aS + o);
+                        dd_prefetch_l2(A.aN + o);
+                    }
                 }
                 if (A.xin) dd_prefetch_l2(A.xin + o);
             }
@@ -442,12 +562,17 @@ __global__ void __launch_bounds__(DD_REG_WARPS * 32, 1) k_rbsor_reg(SolveArgs A)
             }
         }
     }
+    const double rho = A.stats[member].rho;  // requested before waiting for the staged coefficients
+    if (PIPE) {
+        dd_mbar_wait(bar, phase);  // this tile's coefficient rows have landed in buf
+        phase ^= 1u;
+    }
     if (flip)
-        reg_load_cells<CONST_BAND, RPW, 1>(A, g, moR, mo, rbase, colj, pair_ok, li0, li1, lj0, lj1, lane, warp, cb, cw,
-                                           ce, cs, cn, sx);
+        reg_load_cells<CONST_BAND, RPW, 1, PIPE>(A, g, buf, moR, mo, rbase, colj, pair_ok, li0, li1, lj0, lj1, lane,
+                                                 warp, cb, cw, ce, cs, cn, sx);
     else
-        reg_load_cells<CONST_BAND, RPW, 0>(A, g, moR, mo, rbase, colj, pair_ok, li0, li1, lj0, lj1, lane, warp, cb, cw,
-                                           ce, cs, cn, sx);
+        reg_load_cells<CONST_BAND, RPW, 0, PIPE>(A, g, buf, moR, mo, rbase, colj, pair_ok, li0, li1, lj0, lj1, lane,
+                                                 warp, cb, cw, ce, cs, cn, sx);
     // constant-band geometry factors of the thread's rows and of its two columns
     double rW[RPW], rE[RPW], cS2[2], cN2[2];
     if (CONST_BAND) {
@@ -468,11 +593,12 @@ __global__ void __launch_bounds__(DD_REG_WARPS * 32, 1) k_rbsor_reg(SolveArgs A)
             cN2[o] = ok ? f * g.rkp[j] * g.rk[j + 1] : 0.0;
         }
     }
-    const double rho = A.stats[member].rho;
     double omega = 1.0;
     if (rho < 1.0) omega = 2.0 / (1.0 + sqrt(1.0 - rho * rho));
     DD_TICK(0);
     __syncthreads();
+    // buf has been consumed by every thread: fetch the next tile of this CTA while this one is swept
+    if (PIPE && blk + (int)gridDim.x < A.nblocks) dd_pipe_issue<CONST_BAND, RPW>(A, maps, blk + gridDim.x, buf, bar);
 
     // ---- sweeps ---------------------------------------------------------------------------------------
     for (int sw = 0; sw < A.sweeps; ++sw) {
@@ -613,6 +739,8 @@ __global__ void __launch_bounds__(DD_REG_WARPS * 32, 1) k_rbsor_reg(SolveArgs A)
 #ifdef DD_SOLVER_TIMING
     if (threadIdx.x == 0) atomicAdd(&dd_solver_cycles[3], 1ull);
 #endif
+    if (PIPE) __syncthreads();  // the x planes (and the statistics scratch in them) are reused by the next tile
+    }
 }
 
 #ifdef DD_SOLVER_TIMING
@@ -643,14 +771,74 @@ cudaError_t dd_launch_make_guess(const DDLaunch& L, const DDGeom& g, const DDRow
     return cudaGetLastError();
 }
 
+// dynamic shared memory of the register-resident kernel: x planes (+ coefficient staging buffer and barrier)
+static size_t dd_reg_smem_bytes(int const_band, int rpw, int pipe) {
+    const size_t si = (size_t)DD_REG_WARPS * rpw;
+    size_t bytes = 2 * si * DD_REG_PW * sizeof(double);
+    if (pipe) bytes += (size_t)(const_band ? 2 : 5) * si * DD_REG_SJ * sizeof(double) + 16;
+    return bytes;
+}
+
 cudaError_t dd_solver_configure() {
     cudaError_t e = cudaFuncSetAttribute(k_rbsor_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_rbsor_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_rbsor_reg<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    e = cudaFuncSetAttribute(k_rbsor_reg<1, 6, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_rbsor_reg<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    e = cudaFuncSetAttribute(k_rbsor_reg<1, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    if (e != cudaSuccess) return e;
+#define DD_CFG_PIPE(CB, RPW)                                                                                  \
+    e = cudaFuncSetAttribute(k_rbsor_reg<CB, RPW, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                             (int)dd_reg_smem_bytes(CB, RPW, 1));                                             \
+    if (e != cudaSuccess) return e;
+    DD_CFG_PIPE(1, 2) DD_CFG_PIPE(1, 3) DD_CFG_PIPE(1, 4) DD_CFG_PIPE(1, 6) DD_CFG_PIPE(1, 8)
+    DD_CFG_PIPE(0, 2) DD_CFG_PIPE(0, 3) DD_CFG_PIPE(0, 4)
+#undef DD_CFG_PIPE
+    return cudaSuccess;
+}
+
+// ---- tensor maps of the row arrays (host) ------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled dd_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_cuTensorMapEncodeTiled)p;
+    }
+    return fn;
+}
+
+// map of one row array [rows_total][ld] (doubles, even ld) with a box of 64 columns x box_rows rows
+static bool dd_tile_map(const double* base, int ld, long long rows_total, int box_rows, CUtensorMap* out) {
+    static std::mutex mu;
+    static std::map<std::tuple<const double*, int, long long, int>, CUtensorMap> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    const auto key = std::make_tuple(base, ld, rows_total, box_rows);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+        *out = it->second;
+        return true;
+    }
+    PFN_cuTensorMapEncodeTiled enc = dd_encode_fn();
+    if (!enc || (ld & 1) || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows_total};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+    const cuuint32_t box[2] = {(cuuint32_t)DD_REG_SJ, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    if (enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    if (cache.size() > 4096) cache.clear();  // freed and re-allocated work arrays leave stale keys behind
+    cache[key] = m;
+    *out = m;
+    return true;
 }
 
 cudaError_t dd_launch_solve_pass(const DDLaunch& L, const DDGeom& g, const DDMember* mem, const DDRows& R,
@@ -689,9 +877,37 @@ cudaError_t dd_launch_solve_pass(const DDLaunch& L, const DDGeom& g, const DDMem
     const long long nblocks = (long long)A.tiles_i * A.tiles_j * L.nmembers;
     if (nblocks <= 0 || nblocks > 2147483647LL) return cudaErrorInvalidConfiguration;
     if (P.rpw > 0) {
-        // register-resident kernel: 512 threads, x only in shared memory (2 colours x 16 rpw rows x 32 packed cols)
-        const size_t smem = (size_t)2 * DD_REG_WARPS * P.rpw * DD_REG_PW * sizeof(double);
-#define DD_LAUNCH_REG(CB, RPW) k_rbsor_reg<CB, RPW><<<(unsigned)nblocks, DD_REG_WARPS * 32, smem, L.stream>>>(A)
+        // register-resident kernel: 512 threads, x only in shared memory (2 colours x 16 rpw rows x 32 packed cols).
+        // With more tiles than SMs: persistent grid, the next tile's coefficient rows arrive by bulk copies
+        // while the current tile is swept (DD_SOLVER_PIPE=0 switches that off).
+        static int sm_count = 0;
+        if (sm_count == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0)
+                sm_count = 148;
+        }
+        static const bool pipe_off = getenv("DD_SOLVER_PIPE") && !strcmp(getenv("DD_SOLVER_PIPE"), "0");
+        // (measured: pays for the five-array systems; the constant-band T system stages too little to gain)
+        int pipe = (!pipe_off && nblocks > sm_count && !P.const_band) ? 1 : 0;
+        DDTileMaps maps;
+        memset(&maps, 0, sizeof(maps));
+        if (pipe) {
+            const double* arrs[5] = {R.bb, R.aW, R.aE, R.aS, R.aN};
+            const long long rows_total = (long long)L.nmembers * g.nrows;
+            for (int a = 0; a < (P.const_band ? 2 : 5) && pipe; ++a)
+                if (!dd_tile_map(arrs[a], R.ld, rows_total, DD_REG_WARPS * P.rpw, &maps.m[a])) pipe = 0;
+        }
+        const size_t smem = dd_reg_smem_bytes(P.const_band, P.rpw, pipe);
+        const unsigned grid = pipe ? (unsigned)sm_count : (unsigned)nblocks;
+        A.nblocks = (int)nblocks;
+#define DD_LAUNCH_REG(CB, RPW)                                                             \
+    do {                                                                                   \
+        if (pipe)                                                                          \
+            k_rbsor_reg<CB, RPW, 1><<<grid, DD_REG_WARPS * 32, smem, L.stream>>>(A, maps); \
+        else                                                                               \
+            k_rbsor_reg<CB, RPW, 0><<<grid, DD_REG_WARPS * 32, smem, L.stream>>>(A, maps); \
+    } while (0)
         if (P.const_band) {
             switch (P.rpw) {
                 case 2: DD_LAUNCH_REG(1, 2); break;
