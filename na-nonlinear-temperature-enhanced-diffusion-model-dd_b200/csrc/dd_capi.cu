@@ -906,7 +906,9 @@ static void plan_pass(const dd_batch* b, int sweeps_left, bool allow_last, bool 
         const int* rp = const_band ? rpw_cb : rpw_gen;
         const int nrp = const_band ? 5 : 3;
         const char* e_rpw = getenv("DD_RPW");
+        if (e_rpw && !*e_rpw) e_rpw = nullptr;
         const char* e_spp = getenv("DD_SWEEPS_PER_PASS");
+        if (e_spp && !*e_spp) e_spp = nullptr;  // empty = unset
         if (want_reg) {
             // whole member inside one staged region: no halo at all
             // (halo 1 instead of 0 keeps the staged origin on an even column for the 16-byte loads)
@@ -980,6 +982,7 @@ static void plan_pass(const dd_batch* b, int sweeps_left, bool allow_last, bool 
     const char* e_ti = getenv("DD_TILE_I");
     const char* e_sj = getenv("DD_STAGE_J");
     const char* e_sp = getenv("DD_SWEEPS_PER_PASS");
+    if (e_sp && !*e_sp) e_sp = nullptr;
     const char* e_th = getenv("DD_THREADS");
     double best = 1e300;
     DDSolvePlan bp = *P;
@@ -1023,8 +1026,10 @@ static void plan_pass(const dd_batch* b, int sweeps_left, bool allow_last, bool 
 }
 
 __global__ void k_summarise(const DDSolveStats* st, int nmem, const DDMember* mem, double tol, SolveSummary* out) {
-    // single block; one summary per solve
+    // one block per solve (blockIdx.x): statistics st[solve][member] -> out[solve]
     __shared__ double s_rho[256], s_ratio[256], s_res[256], s_bound[256];
+    st += (size_t)blockIdx.x * nmem;
+    out += blockIdx.x;
     double rho = 0.0, ratio = 0.0, res = 0.0, bound = 0.0;
     for (int m = threadIdx.x; m < nmem; m += blockDim.x) {
         if (!mem[m].active) continue;
@@ -1035,22 +1040,26 @@ __global__ void k_summarise(const DDSolveStats* st, int nmem, const DDMember* me
         const double allowed = tol * gap * s.vmax + 16.0 * eps * (s.bmax + s.xmax);
         double r = (allowed > 0.0) ? s.resid / allowed : (s.resid > 0.0 ? 1e300 : 0.0);
         if (s.resid != s.resid || s.rho != s.rho) r = 1e300;
-        rho = fmax(rho, s.rho);
-        if (s.rho != s.rho) rho = s.rho;
+        if (rho == rho) rho = (s.rho != s.rho) ? s.rho : fmax(rho, s.rho);  // a NaN ratio sticks
         ratio = fmax(ratio, r);
         res = fmax(res, s.resid);
         bound = fmax(bound, s.vmax > 0.0 ? s.resid / (gap * s.vmax) : 0.0);
     }
     s_rho[threadIdx.x] = rho; s_ratio[threadIdx.x] = ratio; s_res[threadIdx.x] = res; s_bound[threadIdx.x] = bound;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int k = 1; k < blockDim.x; ++k) {
-            if (s_rho[k] != s_rho[k]) rho = s_rho[k]; else rho = fmax(rho, s_rho[k]);
-            ratio = fmax(ratio, s_ratio[k]);
-            res = fmax(res, s_res[k]);
-            bound = fmax(bound, s_bound[k]);
+    for (int w = blockDim.x >> 1; w > 0; w >>= 1) {
+        if (threadIdx.x < w) {
+            const int k = threadIdx.x + w;
+            const double a = s_rho[threadIdx.x], c = s_rho[k];
+            s_rho[threadIdx.x] = (a != a) ? a : ((c != c) ? c : fmax(a, c));
+            s_ratio[threadIdx.x] = fmax(s_ratio[threadIdx.x], s_ratio[k]);
+            s_res[threadIdx.x] = fmax(s_res[threadIdx.x], s_res[k]);
+            s_bound[threadIdx.x] = fmax(s_bound[threadIdx.x], s_bound[k]);
         }
-        out->rho = rho; out->ratio = ratio; out->resid = res; out->bound = bound;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out->rho = s_rho[0]; out->ratio = s_ratio[0]; out->resid = s_res[0]; out->bound = s_bound[0];
     }
 }
 
@@ -1120,7 +1129,7 @@ static int launch_predictor(dd_batch* b, const DDStateC& s0, const DDPredictOut&
 
 static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const double* T1, const double* cl1,
                         const double* Y, double* vnew, const dd_pc_options& opt, int k, int* sweeps_used,
-                        int* passes_used, int what = 3, const double* vold = nullptr) {
+                        int* passes_used, int what = 3, const double* vold = nullptr, bool summarise = true) {
     dd_ctx* ctx = b->ctx;
     DDRows R;
     int rc;
@@ -1199,7 +1208,7 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
         }
         ++passes;
     }
-    {
+    if (summarise) {
         ProfScope ps_(ctx->stream, PC_SUMMARISE, 1);
         k_summarise<<<1, 256, 0, ctx->stream>>>(st, b->B, b->d_mem, opt.solve_tol, b->d_summary + k);
     }
@@ -1286,11 +1295,11 @@ static int pc_step_enqueue(dd_batch* b, int slot_in, int slot_out, const dd_pc_o
             // the marching predictor has already assembled the T system of the very first Newton step
             const int whatT = (fused_T && pc == 0 && nw == 0) ? 2 : 3;
             if ((rc = newton_solve(b, DD_T, u, nullptr, nullptr, po.YT, dst[0], opt, k++, &sweeps[0], &passes[0],
-                                   whatT, gs ? sout.v[DD_T] : nullptr)) != DD_OK) return rc;
+                                   whatT, gs ? sout.v[DD_T] : nullptr, false)) != DD_OK) return rc;
             if ((rc = newton_solve(b, DD_CL, u, dst[0], nullptr, po.Ycl, dst[1], opt, k++, &sweeps[1], &passes[1], 3,
-                                   gs ? sout.v[DD_CL] : nullptr)) != DD_OK) return rc;
+                                   gs ? sout.v[DD_CL] : nullptr, false)) != DD_OK) return rc;
             if ((rc = newton_solve(b, DD_CD, u, dst[0], dst[1], po.Ycd, dst[2], opt, k++, &sweeps[2], &passes[2], 3,
-                                   gs ? sout.v[DD_CD] : nullptr)) != DD_OK) return rc;
+                                   gs ? sout.v[DD_CD] : nullptr, false)) != DD_OK) return rc;
             for (int q = 0; q < 3; ++q) R.solve_sweeps.push_back(sweeps[q]);
             u.v[DD_T] = dst[0]; u.v[DD_CL] = dst[1]; u.v[DD_CD] = dst[2];
             pp ^= 1;
@@ -1317,6 +1326,12 @@ static int pc_step_enqueue(dd_batch* b, int slot_in, int slot_out, const dd_pc_o
                                     opt.consec_xs_rtol, b->d_itmax, b->d_itmin, b->d_used));
         u.v[DD_CP] = cpd; u.v[DD_CS] = csd;
     }
+    {
+        // summaries of all solves of the step in one launch (one block per solve)
+        ProfScope ps_(ctx->stream, PC_SUMMARISE, 1);
+        k_summarise<<<k, 256, 0, ctx->stream>>>(b->d_stats, b->B, b->d_mem, opt.solve_tol, b->d_summary);
+    }
+    CK(cudaGetLastError());
     // verification of every solve of this step: one small read-back, waited for in pc_step_finish
     CK(cudaMemcpyAsync(R.h_sums, b->d_summary, sizeof(SolveSummary) * k, cudaMemcpyDeviceToHost, ctx->stream));
     const bool track_used = opt.consec_xs_rtol > 0.0 && opt.num_newton_iterations > 0;

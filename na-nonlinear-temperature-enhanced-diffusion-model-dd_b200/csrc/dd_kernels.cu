@@ -951,11 +951,13 @@ __global__ void __launch_bounds__(DD_BLOCK, DD_MINB) k_cs_redo(DDGeom g, const D
                                                       const double* __restrict__ cd1, double* __restrict__ cs_out,
                                                       int cap, const int* __restrict__ used, int own0, int own1,
                                                       int bpm) {
+    // the common case first: the cap-iteration result already stored is the answer (whole block, one load)
+    if (used[blockIdx.x / bpm] >= cap) return;
     const NodeIdx n = node_index(g, own0, own1, bpm);
     if (!n.valid) return;
     const int u = used[n.member];
     const DDMember& mb = mem[n.member];
-    if (u >= cap || !mb.active) return;  // the cap-iteration result already stored is the answer
+    if (u >= cap || !mb.active) return;
     const long long mo = n.member * g.mstride;
     const long long o = mo + (long long)n.r * g.ld + n.j;
     double cp1, y, a;

@@ -1,5 +1,5 @@
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
-timeout 300 python scripts_solver_timing.py 2>&1 | tail -2
-timeout 300 python bench.py --steps 20 --warmup 10 --no-e2e --no-cpu-baseline 2>gpurun_out/bench_g3.err | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['config']['solver']['sweeps']); print({k:round(v['ms_per_step'],3) for k,v in d['roofline']['kernels'].items()})"
+for spp in "" 7 5 4; do
+DD_SWEEPS_PER_PASS=$spp timeout 300 python bench.py --steps 20 --warmup 10 --no-e2e --no-cpu-baseline 2>gpurun_out/bench_g3.err | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); k=d['roofline']['kernels']; print('spp=$spp', round(d['ms_per_step'],4), d['config']['solver']['sweeps'], d['config']['solver']['passes'], {n:round(k[n]['ms_per_step'],3) for n in k if 'rbsor' in n or 'cs_' in n})"
+done
 tail -3 gpurun_out/bench_g3.err
