@@ -199,6 +199,10 @@ int dd_error_norms(dd_batch* b, int slot, int slot_exact, const double* t, int n
 int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_out, const double* t0, const double* dt, int n_t,
                      const dd_pc_options* opt, double* summary, int* cs_iters);
 int dd_batch_set_plan(dd_batch* b, const int sweeps[3]);
+/* Gershgorin ratios (T, cl, cd) from which the solves derive their SOR relaxation factor instead of the ratio
+ * reduced on this device; NULL or values outside [0, 1) restore the default.  A slab mesh passes the all-reduced
+ * ratios of an earlier step here: every rank then relaxes identically without a collective before each solve. */
+int dd_batch_set_relax_rho(dd_batch* b, const double rho[3]);
 int dd_batch_get_plan(dd_batch* b, int sweeps[3]);
 int dd_sweeps_for_rho(double rho, int max_sweeps); /* SOR sweeps the planner uses for a Gershgorin ratio rho */
 int dd_next_plan(int cur, double rho, double ratio, int max_sweeps); /* next step's sweeps from this step's verified ratio */

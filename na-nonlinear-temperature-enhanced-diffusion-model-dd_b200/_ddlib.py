@@ -103,6 +103,7 @@ SIGNATURES = {
                                    _P(C.c_int)]),
     "dd_batch_set_plan": (C.c_int, [_vp, _P(C.c_int * 3)]),
     "dd_batch_get_plan": (C.c_int, [_vp, _P(C.c_int * 3)]),
+    "dd_batch_set_relax_rho": (C.c_int, [_vp, _P(C.c_double * 3)]),
     "dd_sweeps_for_rho": (C.c_int, [C.c_double, C.c_int]),
     "dd_next_plan": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int]),
     "dd_probe_math": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp]),

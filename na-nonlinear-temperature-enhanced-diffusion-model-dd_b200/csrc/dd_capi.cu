@@ -83,6 +83,7 @@ struct dd_batch {
         cudaEvent_t done = nullptr;
     } rec[2];
     int rec_cur;
+    double relax_rho[3];  // >= 0: ratio the solver derives omega from (slab meshes: the all-reduced one)
     bool prev_valid, use_guess, phase_fused_T;
     int prev_in, prev_out;
     double prev_dt, cur_dt;  // first member's step size (the increment scales with it)
@@ -312,6 +313,7 @@ extern "C" int dd_batch_create(dd_ctx* ctx, int N, int M, const double* x, const
     b->asm1 = (row0 + nrows == N + 1) ? nrows : nrows - 2;
     reset_ctl(b, true);
     b->prev_valid = b->use_guess = b->phase_fused_T = false;
+    b->relax_rho[0] = b->relax_rho[1] = b->relax_rho[2] = -1.0;
     b->prev_in = b->prev_out = -1;
     b->prev_dt = b->cur_dt = 0.0;
     b->rec_cur = 0;
@@ -1168,6 +1170,7 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
         DDSolvePlan P;
         memset(&P, 0, sizeof(P));
         plan_pass(b, left, true, var == DD_T, &P);
+        P.rho_fix = b->relax_rho[vi];
         if (P.sweeps <= 0) return fail(ctx, DD_ERR_INVALID, "no feasible solver tile");
         double* xout = nullptr;
         DDLaunch Lp = L;
@@ -1745,6 +1748,12 @@ extern "C" int dd_pc_residual(dd_batch* b, int var, int slot_state, const double
 extern "C" int dd_batch_set_plan(dd_batch* b, const int sweeps[3]) {
     if (!b || !sweeps) return DD_ERR_INVALID;
     for (int q = 0; q < 3; ++q) b->ctl[0].sweeps[q] = b->ctl[1].sweeps[q] = sweeps[q];
+    return DD_OK;
+}
+
+extern "C" int dd_batch_set_relax_rho(dd_batch* b, const double rho[3]) {
+    if (!b) return DD_ERR_INVALID;
+    for (int q = 0; q < 3; ++q) b->relax_rho[q] = (rho && rho[q] >= 0.0 && rho[q] < 1.0) ? rho[q] : -1.0;
     return DD_OK;
 }
 

@@ -40,6 +40,7 @@ struct DDSolvePlan {
     int const_band;  // T system: rows are (bb, dinv) + grid geometry instead of five stored bands
     int rpw;         // > 0: register-resident kernel with this many rows per warp (staged 16*rpw x 64)
     size_t smem_bytes;
+    double rho_fix;  // >= 0: Gershgorin ratio to derive the relaxation factor from (instead of the device statistic)
 };
 
 cudaError_t dd_solver_configure();  // opt-in to large dynamic shared memory (once per process)

@@ -78,6 +78,7 @@ struct SolveArgs {
     int vr0, vr1;    // local rows holding valid assembled rows
     int sweeps, halo, tile_i, tile_j, tiles_i, tiles_j, last_pass;
     int nblocks;  // tiles x members (the pipelined kernel walks them with a persistent grid)
+    double rho_fix;  // >= 0: use this Gershgorin ratio for omega (same on every rank of a slab mesh)
 };
 
 extern __shared__ double dd_smem[];
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(512) k_rbsor_tile(SolveArgs A) {
             colN[sj] = in ? f * g.rkp[j] * g.rk[j + 1] : 0.0;
         }
     }
-    const double rho = A.stats[member].rho;
+    const double rho = A.rho_fix >= 0.0 ? A.rho_fix : A.stats[member].rho;
     __pipeline_wait_prior(0);
     DD_TICK(0);
     // omega_opt of SOR for a consistently ordered matrix whose Jacobi spectral radius is <= rho
@@ -562,7 +563,7 @@ k_rbsor_reg(const __grid_constant__ SolveArgs A, const __grid_constant__ DDTileM
             }
         }
     }
-    const double rho = A.stats[member].rho;  // requested before waiting for the staged coefficients
+    const double rho = A.rho_fix >= 0.0 ? A.rho_fix : A.stats[member].rho;  // requested before waiting for the staged coefficients
     if (PIPE) {
         dd_mbar_wait(bar, phase);  // this tile's coefficient rows have landed in buf
         phase ^= 1u;
@@ -874,6 +875,7 @@ cudaError_t dd_launch_solve_pass(const DDLaunch& L, const DDGeom& g, const DDMem
     A.tiles_i = (L.own1 - L.own0 + P.tile_i - 1) / P.tile_i;
     A.tiles_j = (g.M + 1 + P.tile_j - 1) / P.tile_j;
     A.last_pass = P.last_pass;
+    A.rho_fix = P.rho_fix;
     const long long nblocks = (long long)A.tiles_i * A.tiles_j * L.nmembers;
     if (nblocks <= 0 || nblocks > 2147483647LL) return cudaErrorInvalidConfiguration;
     if (P.rpw > 0) {

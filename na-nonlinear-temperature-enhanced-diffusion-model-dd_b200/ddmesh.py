@@ -297,11 +297,20 @@ class SlabMesh:
                                                    C.byref(opt), None, None), f"step_pc_phase {k}")
         track = opt.consec_xs_rtol > 0.0 and opt.num_newton_iterations > 0
         phase(0)
+        # The SOR relaxation factor must be the same on every rank.  With a fixed sweep plan (bitwise
+        # reproducibility across decompositions) and on the first steps it comes from the current Gershgorin
+        # ratio, max-reduced before each solve; otherwise from the all-reduced ratios of the last verified step,
+        # which the host already holds (they move by O(dt) per step and convergence is verified anyway) --
+        # three collectives less on the critical path.
+        lag = opt.fixed_sweeps <= 0 and self._rho is not None and all(0.0 <= float(r) < 1.0 for r in self._rho)
+        arr = (C.c_double * 3)(*([float(r) for r in self._rho] if lag else [-1.0, -1.0, -1.0]))
+        for m in group:
+            m.batch.ctx.check(m.batch.lib.dd_batch_set_relax_rho(m.batch.handle, C.byref(arr)), "set_relax_rho")
         for k, var in ((1, "T"), (2, "cl"), (3, "cd")):
-            # assemble, make the Gershgorin ratio (hence the SOR relaxation factor) global, solve
-            phase(20 + k)
-            comm.allreduce([m._tensor("stats", m.batch.work_dev_ptr("solve_stats"), (3, 5))[k - 1, 0:1]
-                            for m in group], "max", group)
+            phase(20 + k)  # assemble (T: done by the predictor on wide grids)
+            if not lag:
+                comm.allreduce([m._tensor("stats", m.batch.work_dev_ptr("solve_stats"), (3, 5))[k - 1, 0:1]
+                                for m in group], "max", group)
             phase(30 + k)
             comm.exchange(group, slot_out, (var,))
         phase(4)
