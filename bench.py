@@ -49,7 +49,7 @@ KERNEL_BYTES = {"k_predict": 88, "k_assemble<T>": 40, "k_assemble<cl>": 80, "k_a
 def captured_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/), or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01c_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01e_traffic.json")) as f:
             t = json.load(f)
         return float(t["kernels"][kernel]["dram_bytes_per_launch"]), t["source"]
     except Exception:
@@ -73,27 +73,51 @@ def product_model():
 # clocks
 # ----------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region.  A helper process polls NVML every 2 ms
+    (the default run's timed region lasts tens of milliseconds -- too short for nvidia-smi's polling, and a
+    thread in this process would wait for the interpreter lock); the samples between begin() and stop() count."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+    CODE = (
+        "import sys, time\n"
+        "import pynvml as nv\n"
+        "nv.nvmlInit()\n"
+        "h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))\n"
+        "rs = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons\n"
+        "mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)\n"
+        "while True:\n"
+        "    print(time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), mx, int(rs(h)), flush=True)\n"
+        "    time.sleep(0.002)\n")
 
     def __init__(self, device):
-        self.device = device
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v for v in vis.split(",") if v.strip().isdigit()]
+        self.index = int(ids[device]) if device < len(ids) else device
+        self.p = self.f = None
+        self.t0 = self.t1 = None
 
     def start(self):
+        """spawn the poller and wait until it delivers (call before the warm-up)"""
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-i", str(self.device), "-lms", "100"], stdout=self.f,
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".clk", delete=False)
+            self.p = subprocess.Popen([sys.executable, "-c", self.CODE, str(self.index)], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
+            for _ in range(400):  # wait for the first sample (interpreter + NVML start-up), at most 20 s
+                if os.path.getsize(self.f.name) > 0 or self.p.poll() is not None:
+                    break
+                time.sleep(0.05)
         except Exception:
             self.p = None
 
+    def begin(self):
+        self.t0 = time.time()
+
     def stop(self):
+        self.t1 = time.time()
         if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock poller unavailable"], "samples": 0}
+        if self.t0 is None:
+            self.t0 = 0.0
+        time.sleep(0.01)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -101,22 +125,30 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, total = [], [], set(), 0
         for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
+            c = line.split()
+            if len(c) != 4:
                 continue
+            total += 1
             try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
+                ts, clk, cmax, mask = float(c[0]), float(c[1]), float(c[2]), int(c[3])
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                if val.lower().startswith("active"):
+            mx.append(cmax)
+            if ts < self.t0 or ts > self.t1:
+                continue
+            sm.append(clk)
+            for bit, name in self.REASONS.items():
+                if mask & bit:
                     reasons.add(name)
-        os.unlink(self.f.name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_total": total,
+                "source": "NVML polled every 2 ms by a helper process; samples inside the timed region"}
 
 
 # ----------------------------------------------------------------------------
@@ -204,9 +236,12 @@ def run_studies(args):
 
         def job(nsteps):
             return ens.run_for_errors(nsteps * dt, dt)
+        clocks = ClockSampler(local)
+        clocks.start()
         job(max(1, args.warmup))
         barrier()
         launches0 = lib.dd_launch_count()
+        clocks.begin()
         t0 = time.perf_counter()
         res = job(args.steps)
         torch.cuda.synchronize()
@@ -220,9 +255,12 @@ def run_studies(args):
         trials = sweep_trials()
         sw = ddensemble.RefinementSweep(p1mc.MMSCasePol, product_model(), trials, world=world, rank=rank,
                                         device=local)
+        clocks = ClockSampler(local)
+        clocks.start()
         sw.run_for_errors()
         barrier()
         launches0 = lib.dd_launch_count()
+        clocks.begin()
         t0 = time.perf_counter()
         res = sw.run_for_errors()
         torch.cuda.synchronize()
@@ -232,6 +270,7 @@ def run_studies(args):
         workload = ("pol_sweep: MMSCasePol spatial N=2..256 (dt=h^1.5) + temporal N=256 (4 dt) + eta sweep N=32 "
                     "(7 eta), Tf=0.01: 19 trials, batches by (grid, steps) on concurrent streams")
         extra = {"trials": len(trials), "overall_errors": [float(x) for x in merged["overall"]]}
+    clk = clocks.stop()
     launches = lib.dd_launch_count() - launches0
     if world > 1:
         t = torch.tensor([el], device="cuda", dtype=torch.float64)
@@ -246,7 +285,7 @@ def run_studies(args):
             "scaling": "weak" if args.workload == "ensemble" else "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": dict({"workload": workload, "timing": "host wall clock around whole "
                                                  "trials, device synchronised on both sides"}, **extra),
-            "clocks": None, "e2e": None, "gpu_launches": int(launches),
+            "clocks": clk, "e2e": None, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "whole step (SMEM/L2-resident grids: HBM is not the binding "
                          "roof for these sizes, SURVEY.md 8d)", "achieved": value / world * BYTES_PER_CELL_STEP / 1e9,
                          "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
@@ -302,16 +341,17 @@ def run_b200(args):
                 dist.barrier()
             torch.cuda.synchronize()
 
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
         for k in range(args.warmup):
             step(k)
         mesh.flush()
         barrier()
         launches0 = lib.dd_launch_count()
-        clocks = ClockSampler(local)
-        if rank == 0:
-            clocks.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        clocks.begin()
         e0.record(stream)
         for k in range(args.steps):
             step(args.warmup + k)

@@ -24,6 +24,8 @@ struct dd_ctx {
     bool own_stream;
     std::string err;
     int sm_count;
+    int nbatches = 0;   // batches alive on this context
+    bool dead = false;  // dd_ctx_destroy was called while batches were alive: freed with the last batch
 };
 
 struct SolveSummary {  // reduced over members on the device
@@ -245,11 +247,20 @@ extern "C" int dd_ctx_create(int device, void* cuda_stream, dd_ctx** out) {
     return DD_OK;
 }
 
-extern "C" int dd_ctx_destroy(dd_ctx* ctx) {
-    if (!ctx) return DD_OK;
+static void ctx_free(dd_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+// Handles may be released in any order (garbage-collected hosts do): a context outlives its batches.
+extern "C" int dd_ctx_destroy(dd_ctx* ctx) {
+    if (!ctx) return DD_OK;
+    if (ctx->nbatches > 0) {
+        ctx->dead = true;
+        return DD_OK;
+    }
+    ctx_free(ctx);
     return DD_OK;
 }
 
@@ -370,6 +381,7 @@ extern "C" int dd_batch_create(dd_ctx* ctx, int N, int M, const double* x, const
     CK(cudaMalloc((void**)&b->d_norm_partial, sizeof(double) * 8 * (size_t)b->norm_bpm * nmembers));
     CK(cudaMalloc((void**)&b->d_norm_out, sizeof(double) * 8 * nmembers));
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->nbatches += 1;
     *out = b;
     return DD_OK;
 }
@@ -390,7 +402,9 @@ extern "C" int dd_batch_destroy(dd_batch* b) {
     cudaFree(b->d_mem); cudaFree(b->d_t0); cudaFree(b->d_dt); cudaFree(b->d_stats); cudaFree(b->d_summary);
     cudaFree(b->d_itmax); cudaFree(b->d_itmin); cudaFree(b->d_used); cudaFree(b->d_norm_partial);
     cudaFree(b->d_norm_out);
+    dd_ctx* ctx = b->ctx;
     delete b;
+    if (--ctx->nbatches <= 0 && ctx->dead) ctx_free(ctx);
     return DD_OK;
 }
 

@@ -136,10 +136,27 @@ class TrajectoryEnsemble:
         if self.spec is None:
             raise ValueError(f"{mms_case_cls.__name__} has no device description (device_spec() is None)")
         self.last_stats: List[dict] = []
+        self._batches: Dict[Tuple[int, int], ddcore.Batch] = {}
 
     @property
     def nlocal(self) -> int:
         return self.last - self.first
+
+    def _batch(self, a: int, b: int):
+        """Device batch of the local members [a, b): created on first use, kept for later runs (allocating and
+        freeing gigabytes per run costs more than the stepping)."""
+        batch = self._batches.get((a, b))
+        if batch is None:
+            batch = ddcore.Batch(self.grid.x, self.grid.y, b - a, ctx=self.ctx, nslots=2)
+            batch.set_models([ddcore.model_struct(m, e) for m, e in zip(self.models[a:b], self.etas[a:b])])
+            batch.forcing_spec(self.spec)
+            self._batches[(a, b)] = batch
+        return batch
+
+    def close(self):
+        for batch in self._batches.values():
+            batch.close()
+        self._batches = {}
 
     def run_for_errors(self, Tf: float, dt, t0: float = 0.0) -> Dict[str, np.ndarray]:
         """Every local member from the exact state at t0 to Tf; dt scalar or (nmembers,) with a common number
@@ -156,21 +173,16 @@ class TrajectoryEnsemble:
         self.last_stats = []
         for a in range(0, self.nlocal, self.chunk):
             b = min(a + self.chunk, self.nlocal)
-            batch = ddcore.Batch(self.grid.x, self.grid.y, b - a, ctx=self.ctx, nslots=2)
-            try:
-                batch.set_models([ddcore.model_struct(m, e) for m, e in zip(self.models[a:b], self.etas[a:b])])
-                batch.forcing_spec(self.spec)
-                batch.fill_exact(0, t0)
-                dts = dt_used[a:b] if len(sd) > 1 else dt_used[a:a + 1]
-                if self.integrator == "pc":
-                    _, norms, st = batch.run_pc(0, 1, t0, dts, nsteps, self.opt, norms=True)
-                    self.last_stats.append(st)
-                else:
-                    _, norms = batch.run_feuler(0, 1, t0, dts, nsteps, norms=True)
-                res = combined_error_norms(norms, dt_used[a:b])
-                overall[a:b], per_var[a:b] = res["overall"], res["per_var"]
-            finally:
-                batch.close()
+            batch = self._batch(a, b)
+            batch.fill_exact(0, t0)
+            dts = dt_used[a:b] if len(sd) > 1 else dt_used[a:a + 1]
+            if self.integrator == "pc":
+                _, norms, st = batch.run_pc(0, 1, t0, dts, nsteps, self.opt, norms=True)
+                self.last_stats.append(st)
+            else:
+                _, norms = batch.run_feuler(0, 1, t0, dts, nsteps, norms=True)
+            res = combined_error_norms(norms, dt_used[a:b])
+            overall[a:b], per_var[a:b] = res["overall"], res["per_var"]
         return dict(overall=overall, per_var=per_var, dt_used=np.array(dt_used), nsteps=nsteps)
 
     def gather(self, local: np.ndarray, dist=None, device=None) -> np.ndarray:
@@ -218,24 +230,30 @@ class RefinementSweep:
     def _run_group(self, g) -> List[Tuple[int, float, np.ndarray]]:
         N, M, nsteps = g["key"]
         ts = [self.trials[k] for k in g["members"]]
-        grid = self.make_grid(N, M)
-        ctx = Context(self.device)  # own stream
-        batch = ddcore.Batch(grid.x, grid.y, len(ts), ctx=ctx, nslots=2)
-        try:
+        if "batch" not in g:  # context (own stream), batch and forcing tables are kept for later runs
+            grid = self.make_grid(N, M)
+            ctx = Context(self.device)
+            batch = ddcore.Batch(grid.x, grid.y, len(ts), ctx=ctx, nslots=2)
             batch.set_models([ddcore.model_struct(self.model, t["eta"]) for t in ts])
             spec = self.case_cls(grid=grid, model=self.model).device_spec()
             if spec is None:
+                batch.close()
                 raise ValueError(f"{self.case_cls.__name__} has no device description")
             batch.forcing_spec(spec)
-            t0 = np.array([t["t0"] for t in ts])
-            batch.fill_exact(0, t0)
-            dts = np.array([t["dt_used"] for t in ts])
-            _, norms, _ = batch.run_pc(0, 1, t0, dts, nsteps, self.opt, norms=True)
-            res = combined_error_norms(norms, dts)
-            return [(k, float(res["overall"][q]), res["per_var"][q]) for q, k in enumerate(g["members"])]
-        finally:
-            batch.close()
-            ctx.close()
+            g["ctx"], g["batch"] = ctx, batch
+        batch = g["batch"]
+        t0 = np.array([t["t0"] for t in ts])
+        batch.fill_exact(0, t0)
+        dts = np.array([t["dt_used"] for t in ts])
+        _, norms, _ = batch.run_pc(0, 1, t0, dts, nsteps, self.opt, norms=True)
+        res = combined_error_norms(norms, dts)
+        return [(k, float(res["overall"][q]), res["per_var"][q]) for q, k in enumerate(g["members"])]
+
+    def close(self):
+        for g in self.groups:
+            if "batch" in g:
+                g.pop("batch").close()
+                g.pop("ctx").close()
 
     def run_for_errors(self) -> Dict[str, np.ndarray]:
         """Runs this rank's groups; returns overall (ntrials,), per_var (ntrials, 5) with NaN for trials owned

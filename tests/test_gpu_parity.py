@@ -500,3 +500,20 @@ def test_deferred_verification_slab_emulation(dd):
         got = {v: np.concatenate([m.owned(nsteps % 3)[v] for m in meshes]) for v in VARS}
         for v in VARS:
             assert rel_err(got[v], getattr(s, v)) <= TOL, (sabotage, v)
+
+
+def test_handles_may_be_released_in_any_order(dd):
+    """A garbage-collected host drops contexts and batches in arbitrary order: destroying the context first
+    must not pull the stream from under a live batch."""
+    from _ddlib import Context
+    ddcore, p1 = dd["ddcore"], dd["p1"]
+    grid = p1.make_uniform_grid(8, 8)
+    ctx = Context(0)
+    b = ddcore.Batch(grid.x, grid.y, 1, ctx=ctx)
+    b.forcing_none()
+    ctx.close()              # context first ...
+    b.close()                # ... then the batch (frees the context with it)
+    ctx2 = Context(0)
+    b2 = ddcore.Batch(grid.x, grid.y, 1, ctx=ctx2)
+    b2.close()
+    ctx2.close()
