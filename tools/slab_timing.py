@@ -1,6 +1,6 @@
 """Development probe: where a slab step spends its time at N ranks (sync after every part)."""
 import os, sys, time, collections
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "na-nonlinear-temperature-enhanced-diffusion-model-dd_b200"))
 import numpy as np, torch, torch.distributed as dist
 import bench, ddcore, ddmesh

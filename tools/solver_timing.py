@@ -1,6 +1,6 @@
 """development aid: per-phase cycles of the tile solver (library built with -DDD_SOLVER_TIMING)"""
 import ctypes as C, os, sys
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "na-nonlinear-temperature-enhanced-diffusion-model-dd_b200")]
 os.environ["DD_LIB"] = os.path.join(ROOT, "na-nonlinear-temperature-enhanced-diffusion-model-dd_b200", "libdd_b200_timing.so")
 import torch
