@@ -272,6 +272,23 @@ struct DDSpatial {
 };
 
 DD_HD void dd_spatial_separable(const DDTables& tb, int i, int j, bool want_q, DDSpatial* sp) {
+    if (tb.nprof == 1) {
+        // one spatial profile shared by all five variables (MMSCasePol, SlowlyChangingPeaks): no selection logic
+        double sXY = 0.0, sX1Y = 0.0, sXY1 = 0.0, sLap = 0.0;
+        for (int r = 0; r < tb.nterms; ++r) {
+            const int oi = r * tb.nx + i, oj = r * tb.ny + j;
+            const double X0 = tb.X[0][0][oi], X1 = tb.X[0][1][oi], X2 = tb.X[0][2][oi];
+            const double Y0 = tb.Y[0][0][oj], Y1 = tb.Y[0][1][oj], Y2 = tb.Y[0][2][oj];
+            sXY += X0 * Y0;
+            sX1Y += X1 * Y0;
+            sXY1 += X0 * Y1;
+            sLap += X2 * Y0 + X0 * Y2;
+        }
+#pragma unroll
+        for (int v = 0; v < DD_NVAR; ++v) {
+            sp->S[v] = sXY; sp->Sx[v] = sX1Y; sp->Sy[v] = sXY1; sp->Sl[v] = sLap;
+        }
+    } else {
     double pS[DD_NVAR], pSx[DD_NVAR], pSy[DD_NVAR], pSl[DD_NVAR];
 #pragma unroll
     for (int p = 0; p < DD_NVAR; ++p) {
@@ -297,6 +314,7 @@ DD_HD void dd_spatial_separable(const DDTables& tb, int i, int j, bool want_q, D
         for (int p = 1; p < DD_NVAR; ++p)
             if (q == p) { a = pS[p]; bx = pSx[p]; by = pSy[p]; l = pSl[p]; }
         sp->S[v] = a; sp->Sx[v] = bx; sp->Sy[v] = by; sp->Sl[v] = l;
+    }
     }
     sp->Q1 = sp->Q2 = sp->Q3 = 0.0;
     if (want_q) {
