@@ -432,13 +432,14 @@ k_predict_march(DDGeom g, const DDMember* __restrict__ mem, DDForcingArrays A, D
                 const double FT0 = m.DT * lap - m.K3 * C.cp * C.T;
                 const double Fcl0 = (rhp * (E.cl - W.cl) + rkp * (Nf.cl - S.cl)) - rhp * (eadv - wadv) -
                                     m.K4 * C.cp * (C.cl + 1.0);
-                const double Fcd0 = (rhp * (E.cd - W.cd) + rkp * (Nf.cd - S.cd)) + dd_reaction(m, C.cl, C.cd, csC);
+                const double react0 = dd_reaction(m, C.cl, C.cd, csC);
+                const double Fcd0 = (rhp * (E.cd - W.cd) + rkp * (Nf.cd - S.cd)) + react0;
                 const double YT = dt * (src.fT0 + FT0) + 2.0 * C.T;
                 const double cp1p = dd_predict_cp(m, dt, C.cp, C.T, C.cl, src.fcp0, src.fcp1);
                 out.Ycl[o] = dt * (src.fcl0 + Fcl0) + 2.0 * C.cl;
                 out.Ycd[o] = dt * (src.fcd0 + Fcd0) + 2.0 * C.cd;
                 out.cp1p[o] = cp1p;
-                out.cs1p[o] = dd_predict_cs(m, dt, csC, C.cl, C.cd, src.fcs0, src.fcs1);
+                out.cs1p[o] = dd_predict_cs_r(m, dt, csC, C.cl, C.cd, src.fcs0, src.fcs1, react0);
                 if (store_YT) out.YT[o] = YT;  // only later Newton steps / the class-level pieces read it
                 if (FUSE_T) {
                     const double sumc = m.DT * (rhp * g.rh[i] + rhp * g.rh[i + 1] + cS + cN);

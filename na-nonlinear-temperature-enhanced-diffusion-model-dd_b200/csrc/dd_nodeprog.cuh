@@ -48,8 +48,9 @@ DD_HD void dd_node_F(const DDGeom& g, const DDMember& mb, const DDForcing& F, co
     Fout[DD_CP] = src.fcp + dd_Fcp_int(m, cp.c, T.c, cl.c);
     Fout[DD_T] = src.fT + dd_FT_int(m, q, T, cp.c);
     Fout[DD_CL] = src.fcl + dd_Fcl_int(m, q, dd_faces_Dl(m, cp), T, cl, cp.c);
-    Fout[DD_CD] = src.fcd + dd_Fcd_int(m, q, dd_faces_Dd(m, cp, T), cd, cl.c, cs);
-    Fout[DD_CS] = src.fcs - dd_reaction(m, cl.c, cd.c, cs);
+    const double react = dd_reaction(m, cl.c, cd.c, cs);  // once for Fcd and Fcs
+    Fout[DD_CD] = src.fcd + (dd_div_flux(q, dd_faces_Dd(m, cp, T), cd) + react);
+    Fout[DD_CS] = src.fcs - react;
 }
 
 // forward Euler (reference ForwardEulerIntegrator.step, src/prob1base.py:2889-2903):
@@ -106,9 +107,10 @@ DD_HD void dd_node_predict(const DDGeom& g, const DDMember& mb, const DDForcing&
     const double cs = s.v[DD_CS][o];
     out.YT[o] = dt * (s0.fT + dd_FT_int(m, q, T, cp.c)) + 2.0 * T.c;
     out.Ycl[o] = dt * (s0.fcl + dd_Fcl_int(m, q, dd_faces_Dl(m, cp), T, cl, cp.c)) + 2.0 * cl.c;
-    out.Ycd[o] = dt * (s0.fcd + dd_Fcd_int(m, q, dd_faces_Dd(m, cp, T), cd, cl.c, cs)) + 2.0 * cd.c;
+    const double react0 = dd_reaction(m, cl.c, cd.c, cs);
+    out.Ycd[o] = dt * (s0.fcd + (dd_div_flux(q, dd_faces_Dd(m, cp, T), cd) + react0)) + 2.0 * cd.c;
     out.cp1p[o] = dd_predict_cp(m, dt, cp.c, T.c, cl.c, s0.fcp, s1.fcp);
-    out.cs1p[o] = dd_predict_cs(m, dt, cs, cl.c, cd.c, s0.fcs, s1.fcs);
+    out.cs1p[o] = dd_predict_cs_r(m, dt, cs, cl.c, cd.c, s0.fcs, s1.fcs, react0);
 }
 
 // ---------------------------------------------------------------------------

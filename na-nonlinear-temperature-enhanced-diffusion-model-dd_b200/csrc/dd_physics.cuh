@@ -384,17 +384,18 @@ DD_HD double dd_src_fcl(const DDModel& m, const DDExact& e) {
                           m.K4 * e.u[DD_CP] * cl1);
 }
 
-DD_HD double dd_src_fcd(const DDModel& m, const DDExact& e) {
+// (Hcs = H_eta(cs): evaluated once by the caller for fcd and fcs)
+DD_HD double dd_src_fcd(const DDModel& m, const DDExact& e, double Hcs) {
     double dT;
     const double Dd = dd_Dd_dT(m, e.u[DD_CP], e.u[DD_T], &dT);
     const double dC = -m.phi_d * Dd;
     return e.ut[DD_CD] - ((dC * e.ux[DD_CP] + dT * e.ux[DD_T]) * e.ux[DD_CD] +
                           (dC * e.uy[DD_CP] + dT * e.uy[DD_T]) * e.uy[DD_CD] + Dd * e.lap[DD_CD] +
-                          m.Kd * (m.Sd - e.u[DD_CD]) * (e.u[DD_CL] + 1.0) * dd_H(e.u[DD_CS], m.eta));
+                          m.Kd * (m.Sd - e.u[DD_CD]) * (e.u[DD_CL] + 1.0) * Hcs);
 }
 
-DD_HD double dd_src_fcs(const DDModel& m, const DDExact& e) {
-    return e.ut[DD_CS] + m.Kd * (1.0 + e.u[DD_CL]) * (m.Sd - e.u[DD_CD]) * dd_H(e.u[DD_CS], m.eta);
+DD_HD double dd_src_fcs(const DDModel& m, const DDExact& e, double Hcs) {
+    return e.ut[DD_CS] + m.Kd * (1.0 + e.u[DD_CL]) * (m.Sd - e.u[DD_CD]) * Hcs;
 }
 
 // 3x3 Gauss-Legendre cell average of fcp_ptwise = dt cp + cp (K1 (1+cl) + K2 T)
@@ -465,8 +466,9 @@ DD_HD DDSrc dd_sources(const DDForcing& F, const DDMember& mb, const DDSpatial& 
             dd_exact_expsin(mb.m, F.tab, tc, i, j, &e);
         s.fT = dd_src_fT(mb.m, e);
         s.fcl = dd_src_fcl(mb.m, e);
-        s.fcd = dd_src_fcd(mb.m, e);
-        s.fcs = dd_src_fcs(mb.m, e);
+        const double Hcs = dd_H(e.u[DD_CS], mb.m.eta);
+        s.fcd = dd_src_fcd(mb.m, e, Hcs);
+        s.fcs = dd_src_fcs(mb.m, e, Hcs);
         if (interior && want_cp) {
             s.fcp = (MODE == DD_FORCING_SEPARABLE) ? dd_fcp_avg_separable(mb.m, sp, tc)
                                                    : dd_fcp_avg_expsin(mb.m, F.tab, tc, i, j);
@@ -576,6 +578,15 @@ DD_HD double dd_predict_cp(const DDModel& m, double dt, double cp0, double T0, d
 }
 
 // Heun predictor for cs (reference initial_cs_pred 3631-3645), interior node
+// (react0 = dd_reaction(m, cl0, cd0, cs0), which the caller needs for Fcd as well)
+DD_HD double dd_predict_cs_r(const DDModel& m, double dt, double cs0, double cl0, double cd0, double fcs0, double fcs1,
+                             double react0) {
+    const double F0 = fcs0 - react0;
+    const double star = cs0 + dt * F0;
+    const double Fs = fcs1 - dd_reaction(m, cl0, cd0, star);
+    return cs0 + (0.5 * dt) * (F0 + Fs);
+}
+
 DD_HD double dd_predict_cs(const DDModel& m, double dt, double cs0, double cl0, double cd0, double fcs0, double fcs1) {
     const double F0 = fcs0 - dd_reaction(m, cl0, cd0, cs0);
     const double star = cs0 + dt * F0;
