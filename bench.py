@@ -40,7 +40,9 @@ BYTES_PER_CELL_STEP = 280.0  # PC-RegH step, p = q = 1
 POL = dict(K1=1e-3, K2=1e-3, K3=1e-3, K4=1e-3, DT=1e-3, Dl_max=8.01e-4, phi_l=1e-5, gamma_T=1e-9, Kd=1e-2, Sd=1.0,
            Dd_max=2.46e-6, phi_d=1e-5, r_sp=5e-2, T_ref=300.0)
 ETA = 50.0
-# algorithmic bytes per node and launch of each kernel class ("kernels")
+# algorithmic bytes per node and launch of each kernel class ("kernels").  The classes are those of the
+# library's event profile (dd_profile_read): "k_rbsor_tile<v>" = all solver passes of variable v (kernel
+# k_rbsor_reg<...> unless DD_SOLVER=smem), "k_predict" = k_predict_march or k_predict, "k_assemble<v>" likewise.
 KERNEL_BYTES = {"k_predict": 88, "k_assemble<T>": 40, "k_assemble<cl>": 80, "k_assemble<cd>": 104,
                 "k_rbsor_tile<T>": 32, "k_rbsor_tile<cl>": 56, "k_rbsor_tile<cd>": 56, "k_correct": 80,
                 "k_feuler": 80, "k_eval_sources": 40}
@@ -51,7 +53,8 @@ def captured_traffic(kernel):
     try:
         with open(os.path.join(ROOT, "profiles", "r01e_traffic.json")) as f:
             t = json.load(f)
-        return float(t["kernels"][kernel]["dram_bytes_per_launch"]), t["source"]
+        k = t["kernels"][kernel]
+        return float(k["dram_bytes_per_launch"]), t["source"] + "; kernel " + k["ncu_kernel"]
     except Exception:
         return None, None
 
