@@ -117,3 +117,40 @@ def test_ensemble_with_member_constants_matches_oracle(mods):
     e = ens.TrajectoryEnsemble(grid, mods["CASES"]["scp_fast1e1"], models[0], [etas[0]] * 3)
     res = e.run_for_errors(Tf, dt)
     assert close(res["overall"], [want[0, 0]] * 3)
+
+
+# Published in the reference's notebooks (cell 9 outputs): overall error per spatial level
+# N = 2 .. 256 at dt = h^1.5, Tf = 0.01, eta = 50, and the observed rates printed beneath them.
+NOTEBOOK_SPATIAL = {
+    "expsin": ([1.942652829989e-05, 5.197056624911e-06, 1.322695968641e-06, 3.372248813359e-07,
+                8.344194130557e-08, 2.052209700229e-08, 5.119616858484e-09, 1.278782670173e-09], 5e-11,
+               [1.877, 1.975, 1.957, 2.012, 2.030, 2.004]),
+    "pol": ([4.93452e-05, 1.59616e-05, 4.28269e-06, 1.08800e-06, 2.75006e-07, 6.96085e-08, 1.74802e-08,
+             4.38284e-09], 5e-6, [None, None, None, None, None, 1.993]),
+}
+NOTEBOOK_MODEL = {
+    "expsin": dict(K1=1e-3, K2=1e-3, K3=1e-3, K4=1e-3, DT=1e-3, Dl_max=1e-5, phi_l=1e-5, gamma_T=1e-9, Kd=1e-2,
+                   Sd=1.0, Dd_max=1e-6, phi_d=1e-5, r_sp=5e-2, T_ref=300.0, kind=2),
+    "pol": dict(K1=1e-3, K2=1e-3, K3=1e-3, K4=1e-3, DT=1e-3, Dl_max=8.01e-4, phi_l=1e-5, gamma_T=1e-9, Kd=1e-2,
+                Sd=1.0, Dd_max=2.46e-6, phi_d=1e-5, r_sp=5e-2, T_ref=300.0, kind=2),
+}
+
+
+@pytest.mark.parametrize("case", ["expsin", "pol"])
+def test_notebook_spatial_study_numbers_and_orders(mods, case):
+    """The full spatial study of the notebooks (eight levels up to N = 256, launched as one sweep): the published
+    error values and observed convergence orders are reproduced."""
+    errors, rtol, rates = NOTEBOOK_SPATIAL[case]
+    model = mods["product_model"](NOTEBOOK_MODEL[case])
+    trials = [dict(N=n, dt=(1.0 / n) ** 1.5, Tf=0.01, eta=50.0) for n in (2, 4, 8, 16, 32, 64, 128, 256)]
+    sw = mods["ens"].RefinementSweep(mods["CASES"][case], model, trials)
+    got = sw.run_for_errors()["overall"]
+    sw.close()
+    # the error norm is a difference of nearly equal O(1) fields: a few ulps of the fields (2e-15) on top of the
+    # digits the notebook prints
+    assert np.all(np.abs(got - np.array(errors)) <= rtol * np.array(errors) + 2e-15), (got, errors)
+    mods["cvg"].VERBOSE = False
+    got_rates = [r for r, status in mods["cvg"].calculate_observed_rates(list(got), 2.0)]
+    for g, want in zip(got_rates, rates):
+        if want is not None:
+            assert abs(g - want) <= 6e-4, (got_rates, rates)   # printed with three decimals
