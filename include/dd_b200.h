@@ -36,7 +36,9 @@ enum dd_status {
     DD_ERR_INVALID = -1,       /* bad argument (the reference raises AssertionError, e.g. dt <= 0: src/prob1base.py:3118) */
     DD_ERR_CUDA = -2,          /* CUDA runtime error */
     DD_ERR_NOT_CONVERGED = -3, /* a Newton linear solve missed its residual bound */
-    DD_ERR_NO_DEVICE = -4      /* no CUDA device: there is no CPU fallback */
+    DD_ERR_NO_DEVICE = -4,     /* no CUDA device: there is no CPU fallback */
+    DD_ERR_DOMAIN = -5         /* HCsTriple cs corrector: 2 - dt Kd (Sd - cd1)(1 + cl1) below its positivity threshold
+                                  (the reference raises ValueError, src/prob1base.py:3410-3413) */
 };
 
 enum dd_var { DD_VAR_CP = 0, DD_VAR_T = 1, DD_VAR_CL = 2, DD_VAR_CD = 3, DD_VAR_CS = 4 };
@@ -64,7 +66,10 @@ typedef struct dd_model {
     double K1, K2, K3, K4, DT, Dl_max, phi_l, gamma_T, Kd, Sd, Dd_max, phi_d, phi_T, r_sp, T_ref;
     double eta;   /* regularisation factor of H_eta, src/prob1base.py:3452-3466 */
     int kind;     /* 1 = DefaultModel01, 2 = DefaultModel02 (Dd uses T + T_ref), src/prob1base.py:71-217 */
-    int _pad;
+    int reaction; /* cs/cd interaction Kd (Sd - cd)(1 + cl) F2(cs): 0 = RegHCsTriple, F2 = H_eta(cs) (3553-3593);
+                     1 = CsTriple, F2 = cs (2842-2876); 2 = HCsTriple, F2 = (cs > 0) (3303-3340).  The cs
+                     predictor / corrector follow the matching integrator class (3152-3219, 3343-3430, 3596-3702);
+                     for 1 and 2 the corrector is a closed form: pass num_newton_iterations = 0 */
 } dd_model;
 
 /* options of the predictor-corrector step: the constructor arguments of

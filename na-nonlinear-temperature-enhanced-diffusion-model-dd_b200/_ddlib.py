@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DD_LIB", os.path.join(_HERE, "libdd_b200.so"))  # DD_LIB: development override
 
-DD_OK, DD_ERR_INVALID, DD_ERR_CUDA, DD_ERR_NOT_CONVERGED, DD_ERR_NO_DEVICE = 0, -1, -2, -3, -4
+DD_OK, DD_ERR_INVALID, DD_ERR_CUDA, DD_ERR_NOT_CONVERGED, DD_ERR_NO_DEVICE, DD_ERR_DOMAIN = 0, -1, -2, -3, -4, -5
 VAR_INDEX = {"cp": 0, "T": 1, "cl": 2, "cd": 3, "cs": 4}
 VARS = ("cp", "T", "cl", "cd", "cs")
 MODE_NONE, MODE_ARRAYS, MODE_SEPARABLE, MODE_EXPSIN = 0, 1, 2, 3
@@ -33,7 +33,7 @@ class DDNotConverged(RuntimeError):
 class dd_model(C.Structure):
     _fields_ = [(n, C.c_double) for n in
                 ("K1", "K2", "K3", "K4", "DT", "Dl_max", "phi_l", "gamma_T", "Kd", "Sd", "Dd_max", "phi_d",
-                 "phi_T", "r_sp", "T_ref", "eta")] + [("kind", C.c_int), ("_pad", C.c_int)]
+                 "phi_T", "r_sp", "T_ref", "eta")] + [("kind", C.c_int), ("reaction", C.c_int)]
 
 
 class dd_pc_options(C.Structure):
@@ -184,6 +184,8 @@ class Context:
         if rc == DD_ERR_INVALID:
             # the reference signals bad arguments (dt <= 0, shape mismatch) with AssertionError
             raise AssertionError(f"{what}: {msg or 'invalid argument'}")
+        if rc == DD_ERR_DOMAIN:
+            raise ValueError(msg)  # the reference's HCsTriple corrector raises ValueError (src/prob1base.py:3410)
         if rc == DD_ERR_NOT_CONVERGED:
             raise DDNotConverged(f"{what}: {msg}")
         raise DDLibraryError(f"{what}: status {rc}: {msg}")

@@ -51,6 +51,7 @@ struct dd_batch {
     SolveSummary* d_summary;  // [nsolve_cap]
     double *d_itmax, *d_itmin;
     int* d_used;
+    int* d_flags;  // per member: bit 0 = HCsTriple corrector hit its positivity threshold
     int cs_cap_alloc;
     double *d_norm_partial, *d_norm_out;
     int norm_bpm;
@@ -81,6 +82,7 @@ struct dd_batch {
         std::vector<int> solve_sweeps;   // sweeps used by each solve of the step
         SolveSummary* h_sums = nullptr;  // pinned [cap_sums]
         int* h_used = nullptr;           // pinned [B]
+        int* h_flags = nullptr;          // pinned [B]
         int cap_sums = 0;
         cudaEvent_t done = nullptr;
     } rec[2];
@@ -303,6 +305,8 @@ static void model_to_dev(const dd_model& s, DDModel* d) {
     d->phi_d = s.phi_d; d->phi_T = s.phi_T; d->r_sp = s.r_sp;
     d->T_shift = (s.kind == 2) ? s.T_ref : 0.0;
     d->eta = s.eta;
+    d->react = (s.reaction == 1) ? DD_REACT_CS : (s.reaction == 2 ? DD_REACT_H : DD_REACT_REGH);
+    d->_pad = 0;
 }
 
 extern "C" int dd_batch_create(dd_ctx* ctx, int N, int M, const double* x, const double* y, int nmembers, int row0,
@@ -377,6 +381,8 @@ extern "C" int dd_batch_create(dd_ctx* ctx, int N, int M, const double* x, const
     CK(cudaMalloc((void**)&b->d_dt, sizeof(double) * nmembers));
     b->nsolve_cap = 0; b->d_stats = nullptr; b->d_summary = nullptr;
     b->d_itmax = b->d_itmin = nullptr; b->d_used = nullptr; b->cs_cap_alloc = 0;
+    CK(cudaMalloc((void**)&b->d_flags, sizeof(int) * nmembers));
+    CK(cudaMemsetAsync(b->d_flags, 0, sizeof(int) * nmembers, ctx->stream));
     b->norm_bpm = dd_norm_blocks_per_member(g);
     CK(cudaMalloc((void**)&b->d_norm_partial, sizeof(double) * 8 * (size_t)b->norm_bpm * nmembers));
     CK(cudaMalloc((void**)&b->d_norm_out, sizeof(double) * 8 * nmembers));
@@ -397,11 +403,13 @@ extern "C" int dd_batch_destroy(dd_batch* b) {
     for (auto& r : b->rec) {
         if (r.h_sums) cudaFreeHost(r.h_sums);
         if (r.h_used) cudaFreeHost(r.h_used);
+        if (r.h_flags) cudaFreeHost(r.h_flags);
         if (r.done) cudaEventDestroy(r.done);
     }
     cudaFree(b->d_mem); cudaFree(b->d_t0); cudaFree(b->d_dt); cudaFree(b->d_stats); cudaFree(b->d_summary);
     cudaFree(b->d_itmax); cudaFree(b->d_itmin); cudaFree(b->d_used); cudaFree(b->d_norm_partial);
     cudaFree(b->d_norm_out);
+    cudaFree(b->d_flags);
     dd_ctx* ctx = b->ctx;
     delete b;
     if (--ctx->nbatches <= 0 && ctx->dead) ctx_free(ctx);
@@ -1265,6 +1273,7 @@ static int rec_prepare(dd_batch* b, dd_batch::StepRec& R, int nsolves) {
         R.cap_sums = nsolves;
     }
     if (!R.h_used) CK(cudaMallocHost((void**)&R.h_used, sizeof(int) * b->B));
+    if (!R.h_flags) CK(cudaMallocHost((void**)&R.h_flags, sizeof(int) * b->B));
     if (!R.done) CK(cudaEventCreateWithFlags(&R.done, cudaEventDisableTiming));
     return DD_OK;
 }
@@ -1277,6 +1286,7 @@ static int pc_step_enqueue(dd_batch* b, int slot_in, int slot_out, const dd_pc_o
     if ((rc = ensure_solve_slots(b, 3 * P * Q)) != DD_OK) return rc;
     if ((rc = rec_prepare(b, R, 3 * P * Q)) != DD_OK) return rc;
     R.solve_sweeps.clear();
+    CK(cudaMemsetAsync(b->d_flags, 0, sizeof(int) * b->B, ctx->stream));
     DDPredictOut po;
     if ((rc = get_work(b, "cp1p", &po.cp1p)) != DD_OK) return rc;
     if ((rc = get_work(b, "cs1p", &po.cs1p)) != DD_OK) return rc;
@@ -1336,7 +1346,7 @@ static int pc_step_enqueue(dd_batch* b, int slot_in, int slot_out, const dd_pc_o
         }
         CKP(PC_CORRECT, 1,
             dd_launch_correct(Lall, b->smode, b->g, b->d_mem, b->sF, s0, u.v[DD_T], u.v[DD_CL], u.v[DD_CD], cpd, csd,
-                              cap, track ? opt.consec_xs_rtol : 0.0, b->d_itmax, b->d_itmin));
+                              cap, track ? opt.consec_xs_rtol : 0.0, b->d_itmax, b->d_itmin, b->d_flags));
         if (track)
             CKP(PC_CS_FINISH, 2,
                 dd_launch_cs_finish(Lall, b->smode, b->g, b->d_mem, b->sF, s0, u.v[DD_CL], u.v[DD_CD], csd, cap,
@@ -1354,6 +1364,7 @@ static int pc_step_enqueue(dd_batch* b, int slot_in, int slot_out, const dd_pc_o
     const bool track_used = opt.consec_xs_rtol > 0.0 && opt.num_newton_iterations > 0;
     if (track_used)
         CK(cudaMemcpyAsync(R.h_used, b->d_used, sizeof(int) * b->B, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(R.h_flags, b->d_flags, sizeof(int) * b->B, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaEventRecord(R.done, ctx->stream));
     R.active = true;
     R.slot_in = slot_in;
@@ -1373,6 +1384,10 @@ static int pc_step_finish(dd_batch* b, dd_batch::StepRec& R, dd_step_stats* stat
     dd_ctx* ctx = b->ctx;
     CK(cudaEventSynchronize(R.done));
     R.active = false;
+    for (int m = 0; m < b->B; ++m)
+        if (b->h_mem[m].active && (R.h_flags[m] & 1))
+            return fail(ctx, DD_ERR_DOMAIN,
+                        "Denominator 2 - dt Kd (Sd - Cd1) (1 + Cl1) below positiveness treshold.");
     const dd_pc_options& opt = R.opt;
     const int k = R.nsolves;
     const bool guess = R.guess;
@@ -1714,8 +1729,9 @@ extern "C" int dd_pc_correct(dd_batch* b, int slot0, int slot_new, const double*
             k_cs_arm<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(b->d_itmax, b->d_itmin, n);
         }
     }
+    CK(cudaMemsetAsync(b->d_flags, 0, sizeof(int) * b->B, ctx->stream));
     CK(dd_launch_correct(L, b->smode, b->g, b->d_mem, b->sF, s0, nw.v[DD_T], nw.v[DD_CL], nw.v[DD_CD], nw.v[DD_CP],
-                         nw.v[DD_CS], cap, track ? opt.consec_xs_rtol : 0.0, b->d_itmax, b->d_itmin));
+                         nw.v[DD_CS], cap, track ? opt.consec_xs_rtol : 0.0, b->d_itmax, b->d_itmin, b->d_flags));
     if (track)
         CK(dd_launch_cs_finish(L, b->smode, b->g, b->d_mem, b->sF, s0, nw.v[DD_CL], nw.v[DD_CD], nw.v[DD_CS], cap,
                                opt.consec_xs_rtol, b->d_itmax, b->d_itmin, b->d_used));
@@ -1726,7 +1742,12 @@ extern "C" int dd_pc_correct(dd_batch* b, int slot0, int slot_new, const double*
             for (int m = 0; m < b->B; ++m) cs_iters_out[m] = cap;
         }
     }
+    std::vector<int> flags(b->B);
+    CK(cudaMemcpyAsync(flags.data(), b->d_flags, sizeof(int) * b->B, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    for (int m = 0; m < b->B; ++m)
+        if (b->h_mem[m].active && (flags[m] & 1))
+            return fail(ctx, DD_ERR_DOMAIN, "Denominator 2 - dt Kd (Sd - Cd1) (1 + Cl1) below positiveness treshold.");
     return DD_OK;
 }
 
@@ -1842,7 +1863,7 @@ extern "C" int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_ou
             CKP(PC_CORRECT, 1,
                 dd_launch_correct(launch_of(b, ROWS_ALL), b->smode, b->g, b->d_mem, b->sF, s0, sout.v[DD_T],
                                   sout.v[DD_CL], sout.v[DD_CD], sout.v[DD_CP], sout.v[DD_CS], cap,
-                                  track ? opt.consec_xs_rtol : 0.0, b->d_itmax, b->d_itmin));
+                                  track ? opt.consec_xs_rtol : 0.0, b->d_itmax, b->d_itmin, b->d_flags));
             return DD_OK;
         case 6:
             // as 5 without the read-back: the driver reduces "summary" / "cs_used" on the device itself

@@ -456,7 +456,7 @@ k_predict_march(DDGeom g, const DDMember* __restrict__ mem, DDForcingArrays A, D
                 out.Ycl[o] = dt * src.fcl0 + 2.0 * C.cl;
                 out.Ycd[o] = dt * src.fcd0 + 2.0 * C.cd;
                 out.cp1p[o] = C.cp + 0.5 * dt * (src.fcp0 + src.fcp1);
-                out.cs1p[o] = csC * 0.0;
+                out.cs1p[o] = (m.react == DD_REACT_CS) ? csC : csC * 0.0;
                 if (FUSE_T) {
                     R.bb[oR] = 0.0;
                     R.aW[oR] = 0.0;
@@ -795,7 +795,7 @@ k_assemble_cd_march(DDGeom g, const DDMember* __restrict__ mem, const double* __
                 const double rhp = g.rhp[i];
                 const double W = DdW * (rhp * g.rh[i]), E = DdE * (rhp * g.rh[i + 1]);
                 const double S = DdS * q.cS, Nn = DdN * q.cN;
-                const double KH = m.Kd * dd_H(csc, m.eta);
+                const double KH = m.Kd * dd_F2(m, csc);
                 const double Cc = -(W + E + S + Nn) - KH * (clc + 1.0);
                 const double Fcd = fc + (rhp * (flE - flW) + q.rkp * (flN - flS)) + (m.Sd - C.v) * (clc + 1.0) * KH;
                 const double JT = rhp * (-jtW + jtE) + q.rkp * (-jtS + jtN);
@@ -848,8 +848,8 @@ __global__ void __launch_bounds__(DD_BLOCK) k_correct(DDGeom g, const DDMember* 
                                                       const double* __restrict__ cl1,
                                                       const double* __restrict__ cd1, double* __restrict__ cp_out,
                                                       double* __restrict__ cs_out, int cap, double rtol,
-                                                      double* it_max, double* it_min, int own0, int own1,
-                                                      int bpm) {
+                                                      double* it_max, double* it_min, int* flags, int own0,
+                                                      int own1, int bpm) {
     // per-iteration block statistics of the reference's global exit test (max |dx|, min |x|):
     // warp shuffles + shared-memory atomics, flushed to global memory once per block
     __shared__ unsigned long long sh_max[DD_CS_SMEM_CAP], sh_min[DD_CS_SMEM_CAP];
@@ -872,9 +872,20 @@ __global__ void __launch_bounds__(DD_BLOCK) k_correct(DDGeom g, const DDMember* 
         const long long mo = n.member * g.mstride;
         o = mo + (long long)n.r * g.ld + n.j;
         inter = dd_is_interior(g, g.row0 + n.r, n.j);
-        dd_node_correct_prepare<MODE>(g, mb, F, s0, T1, cl1, cd1, mo, n.r, n.j, &cp1, &y, &a);
+        double fcs0, fcs1;
+        dd_node_correct_prepare<MODE>(g, mb, F, s0, T1, cl1, cd1, mo, n.r, n.j, &cp1, &y, &a, &fcs0, &fcs1);
         x = s0.v[DD_CS][o];
         cp_out[o] = cp1;
+        if (mb.m.react != DD_REACT_REGH) {
+            // CsTriple / HCsTriple: closed-form corrector, no iterations (the caller passes cap = 0)
+            int bad = 0;
+            x = dd_node_correct_cs_closed(g, mb, s0, cl1, cd1, mo, n.r, n.j, fcs0, fcs1, &bad);
+            if (bad) atomicOr(&flags[n.member], 1);
+            cs_out[o] = x;
+            return;
+        }
+    } else if (mem[n.member].m.react != DD_REACT_REGH) {
+        return;
     }
     const double eta = mb.m.eta;
     const int lane = threadIdx.x & 31;
@@ -914,11 +925,11 @@ __global__ void __launch_bounds__(DD_BLOCK) k_correct(DDGeom g, const DDMember* 
 cudaError_t dd_launch_correct(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,
                               const DDForcing& F, const DDStateC& s0, const double* T1, const double* cl1,
                               const double* cd1, double* cp_out, double* cs_out, int cap, double rtol,
-                              double* it_max, double* it_min) {
+                              double* it_max, double* it_min, int* flags) {
     const int bpm = blocks_per_member(g, L);
     DD_DISPATCH_MODE(mode, (k_correct<MODE><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(
-                               g, mem, F, s0, T1, cl1, cd1, cp_out, cs_out, cap, rtol, it_max, it_min, L.own0,
-                               L.own1, bpm)));
+                               g, mem, F, s0, T1, cl1, cd1, cp_out, cs_out, cap, rtol, it_max, it_min, flags,
+                               L.own0, L.own1, bpm)));
     return cudaGetLastError();
 }
 

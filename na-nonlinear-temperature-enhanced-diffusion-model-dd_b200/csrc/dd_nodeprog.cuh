@@ -94,7 +94,9 @@ DD_HD void dd_node_predict(const DDGeom& g, const DDMember& mb, const DDForcing&
             cpb = cpb + 0.5 * dt * (s0.fcp + s1b.fcp);
         }
         out.cp1p[o] = cpb;
-        out.cs1p[o] = s.v[DD_CS][o] * 0.0;
+        // cs: Fcs carries the mask, so the Heun predictor keeps cs0 on the boundary; the RegH / H integrators
+        // then multiply by the mask (3644, 3391), the CsTriple one does not (3175-3189)
+        out.cs1p[o] = (mb.m.react == DD_REACT_CS) ? s.v[DD_CS][o] : s.v[DD_CS][o] * 0.0;
         return;
     }
     const DDSrc s1 = dd_sources<MODE>(F, mb, sp, 1, i, j, o, inter, true);
@@ -243,7 +245,8 @@ DD_HD double dd_newton_update(bool interior, double vstar, double x, int zero_bo
 template <int MODE>
 DD_HD void dd_node_correct_prepare(const DDGeom& g, const DDMember& mb, const DDForcing& F, const DDStateC& s0,
                                    const double* T1, const double* cl1, const double* cd1, long long mo, int r,
-                                   int j, double* cp1, double* y, double* a) {
+                                   int j, double* cp1, double* y, double* a, double* fcs0 = nullptr,
+                                   double* fcs1 = nullptr) {
     const int i = g.row0 + r;
     const long long o = mo + (long long)r * g.ld + j;
     const bool inter = dd_is_interior(g, i, j);
@@ -256,4 +259,21 @@ DD_HD void dd_node_correct_prepare(const DDGeom& g, const DDMember& mb, const DD
                                  q1.fcp)
                  : 0.0;
     dd_cs_ya(m, mb.dt, s0.v[DD_CS][o], s0.v[DD_CL][o], s0.v[DD_CD][o], cl1[o], cd1[o], q0.fcs, q1.fcs, y, a);
+    if (fcs0) *fcs0 = q0.fcs;
+    if (fcs1) *fcs1 = q1.fcs;
+}
+
+// cs corrector of the closed-form variants (CsTriple, HCsTriple) at a node; see dd_physics.cuh
+DD_HD double dd_node_correct_cs_closed(const DDGeom& g, const DDMember& mb, const DDStateC& s0, const double* cl1,
+                                       const double* cd1, long long mo, int r, int j, double fcs0, double fcs1,
+                                       int* bad) {
+    const long long o = mo + (long long)r * g.ld + j;
+    const bool inter = dd_is_interior(g, g.row0 + r, j);
+    const DDModel& m = mb.m;
+    if (m.react == DD_REACT_CS)
+        return inter ? dd_correct_cs_cstriple(m, mb.dt, s0.v[DD_CS][o], s0.v[DD_CL][o], s0.v[DD_CD][o], cl1[o],
+                                              cd1[o], fcs0, fcs1)
+                     : 0.0;
+    return dd_correct_cs_hcstriple(m, mb.dt, s0.v[DD_CS][o], s0.v[DD_CL][o], s0.v[DD_CD][o], cl1[o], cd1[o], fcs0,
+                                   fcs1, inter, bad);
 }

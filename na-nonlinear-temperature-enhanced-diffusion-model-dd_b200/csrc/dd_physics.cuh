@@ -86,6 +86,13 @@ DD_HD double dd_Dd_dT(const DDModel& m, double cp, double T, double* dT) {
 
 DD_HD double dd_H(double x, double eta) { return dd_rcp(1.0 + dd_exp(-eta * x)); }
 
+// F2(cs) of the cs/cd interaction (cscd_reaction_cs / Kd of the reference's three field classes)
+DD_HD double dd_F2(const DDModel& m, double cs) {
+    if (m.react == DD_REACT_CS) return cs;
+    if (m.react == DD_REACT_H) return cs > 0.0 ? 1.0 : 0.0;
+    return dd_H(cs, m.eta);
+}
+
 // ---------------------------------------------------------------------------
 // stencil helpers
 // ---------------------------------------------------------------------------
@@ -171,7 +178,7 @@ DD_HD double dd_div_flux(const DDNodeGeo& q, const DDFaces& a, const DDSten& u) 
 // ---------------------------------------------------------------------------
 
 DD_HD double dd_reaction(const DDModel& m, double cl, double cd, double cs) {
-    return (m.Sd - cd) * (cl + 1.0) * (m.Kd * dd_H(cs, m.eta));
+    return (m.Sd - cd) * (cl + 1.0) * (m.Kd * dd_F2(m, cs));
 }
 
 DD_HD double dd_Fcp_int(const DDModel& m, double cp, double T, double cl) {
@@ -466,7 +473,7 @@ DD_HD DDSrc dd_sources(const DDForcing& F, const DDMember& mb, const DDSpatial& 
             dd_exact_expsin(mb.m, F.tab, tc, i, j, &e);
         s.fT = dd_src_fT(mb.m, e);
         s.fcl = dd_src_fcl(mb.m, e);
-        const double Hcs = dd_H(e.u[DD_CS], mb.m.eta);
+        const double Hcs = dd_F2(mb.m, e.u[DD_CS]);
         s.fcd = dd_src_fcd(mb.m, e, Hcs);
         s.fcs = dd_src_fcs(mb.m, e, Hcs);
         if (interior && want_cp) {
@@ -552,7 +559,7 @@ DD_HD DDRow dd_row_cd(const DDModel& m, const DDNodeGeo& q, double dt, const DDS
     DDFaces dT;
     const DDFaces Dd = dd_faces_Dd_dT(m, cps, Ts, &dT);
     const double W = Dd.w * q.cW, E = Dd.e * q.cE, S = Dd.s * q.cS, Nn = Dd.n * q.cN;
-    const double KH = m.Kd * dd_H(css, m.eta);
+    const double KH = m.Kd * dd_F2(m, css);
     const double C = -(W + E + S + Nn) - KH * (cls + 1.0);
     const double Fcd = fcd1 + dd_div_flux(q, Dd, cds) + (m.Sd - cds.c) * (cls + 1.0) * KH;
     const double gxw = ((cds.c - cds.w) * q.rhW) * dT.w, gxe = ((cds.e - cds.c) * q.rhE) * dT.e;
@@ -609,6 +616,32 @@ DD_HD void dd_cs_ya(const DDModel& m, double dt, double cs0, double cl0, double 
                     double fcs0, double fcs1, double* y, double* a) {
     *y = 2.0 * cs0 - dt * m.Kd * (m.Sd - cd0) * (cl0 + 1.0) * dd_H(cs0, m.eta) + dt * (fcs0 + fcs1);
     *a = dt * m.Kd * (m.Sd - cd1) * (cl1 + 1.0);
+}
+
+// closed-form cs correctors of the other two field variants (the regularised one iterates, see below)
+// CsTriple (reference corrector_cs_step 3191-3219): trapezoidal rule solved for cs1, interior node
+DD_HD double dd_correct_cs_cstriple(const DDModel& m, double dt, double cs0, double cl0, double cd0, double cl1,
+                                    double cd1, double fcs0, double fcs1) {
+    const double a0 = -m.Kd * (m.Sd - cd0) * (1.0 + cl0);
+    const double a1 = -m.Kd * (m.Sd - cd1) * (1.0 + cl1);
+    const double num = (1.0 + (dt / 2.0) * a0) * cs0 + (dt / 2.0) * (fcs0 + fcs1);
+    return num * dd_rcp(1.0 - (dt / 2.0) * a1);
+}
+
+// HCsTriple (reference corrector_cs_step 3393-3430), any node: Y0 = 2 cs0 + dt Fcs(u0, t0) + dt fcs(t1);
+// cs1 = Y0 / (2 - dt R1) where Y0 > tol, Y0 / 2 where Y0 < -tol, else 0; times the boundary mask.
+// *bad is set when 2 - dt Kd (Sd - cd1)(1 + cl1) < tol (the reference raises ValueError if that holds anywhere).
+DD_HD double dd_correct_cs_hcstriple(const DDModel& m, double dt, double cs0, double cl0, double cd0, double cl1,
+                                     double cd1, double fcs0, double fcs1, bool interior, int* bad) {
+    const double tol = 2.220446049250313e-16 * 100.0;
+    const double dY1 = 2.0 - dt * ((m.Sd - cd1) * (1.0 + cl1) * m.Kd);
+    if (dY1 < tol) *bad = 1;
+    const double Fcs0 = interior ? fcs0 - dd_reaction(m, cl0, cd0, cs0) : (fcs0 - 0.0) * 0.0;
+    const double Y0 = 2.0 * cs0 + dt * Fcs0 + dt * fcs1;
+    double r = 0.0;
+    if (Y0 > tol) r = Y0 / dY1;
+    else if (Y0 < -tol) r = Y0 / 2.0;
+    return r * (interior ? 1.0 : 0.0);
 }
 
 // one Newton update (reference _newton_iterations 3654-3663); returns dx

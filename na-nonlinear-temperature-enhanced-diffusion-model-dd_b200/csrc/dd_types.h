@@ -39,6 +39,14 @@ struct DDModel {
     double K1, K2, K3, K4, DT, Dl_max, phi_l, gamma_T, Kd, Sd, Dd_max, phi_d, phi_T, r_sp;
     double T_shift;  // T_ref for DefaultModel02 (src/prob1base.py:205-217), 0 for DefaultModel01
     double eta;
+    int react, _pad;  // DD_REACT_*: which F2(cs) the cs/cd interaction uses
+};
+
+// [Cs-Cd-int] = Kd (Sd - cd)(1 + cl) F2(cs): the three field variants of the reference
+enum {
+    DD_REACT_REGH = 0,  // F2 = H_eta(cs)   RegHCsTriple, src/prob1base.py:3553-3593
+    DD_REACT_CS = 1,    // F2 = cs          CsTriple,     src/prob1base.py:2842-2876
+    DD_REACT_H = 2      // F2 = (cs > 0)    HCsTriple,    src/prob1base.py:3303-3340
 };
 
 // Per-member, per-time-slot scalars of the manufactured solution

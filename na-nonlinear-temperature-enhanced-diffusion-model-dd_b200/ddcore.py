@@ -123,15 +123,19 @@ def pc_options(num_pc_steps=1, num_newton_steps=1, num_newton_iterations=5, cons
     return o
 
 
-def model_struct(model, eta: float) -> dd_model:
+REACTIONS = {"regh": 0, "cs": 1, "h": 2}  # F2(cs) = H_eta(cs) | cs | (cs > 0): RegHCsTriple, CsTriple, HCsTriple
+
+
+def model_struct(model, eta: float, reaction="regh") -> dd_model:
     """dd_model from any object with the ModelConsts attributes (reference src/prob1base.py:28-45).
-    `kind` comes from `model.dd_kind` (2 for DefaultModel02, else 1)."""
+    `kind` comes from `model.dd_kind` (2 for DefaultModel02, else 1); `reaction` selects the field variant."""
     m = dd_model()
     for n in ("K1", "K2", "K3", "K4", "DT", "Dl_max", "phi_l", "gamma_T", "Kd", "Sd", "Dd_max", "phi_d", "phi_T",
               "r_sp", "T_ref"):
         setattr(m, n, float(getattr(model, n)))
     m.eta = float(eta)
     m.kind = int(getattr(model, "dd_kind", 1))
+    m.reaction = REACTIONS[reaction] if isinstance(reaction, str) else int(reaction)
     return m
 
 
@@ -183,9 +187,9 @@ class Batch:
         arr = (dd_model * len(models))(*models)
         self.ctx.check(self.lib.dd_batch_set_models(self.handle, first, len(models), arr), "set_models")
 
-    def set_model(self, model, eta: float):
+    def set_model(self, model, eta: float, reaction="regh"):
         """same model for every member"""
-        self.set_models([model_struct(model, eta)] * self.B)
+        self.set_models([model_struct(model, eta, reaction)] * self.B)
 
     def set_active(self, active: Sequence[int], first: int = 0):
         a = (C.c_int * len(active))(*[int(v) for v in active])

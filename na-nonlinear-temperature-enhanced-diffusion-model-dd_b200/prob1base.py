@@ -673,19 +673,25 @@ def heaviside_regularized(x, regularization_factor: float):
 # the device cannot evaluate the manufactured solution itself.
 # ----------------------------------------------------------------------------
 
-class ForcingTerms_RegHCsTriple(ForcingTermsBase):
-    def __init__(self, *, mms_case: MMSCaseBase, model: DefaultModel01, regularization_factor: float):
+class ForcingTerms_CsTriple(ForcingTermsBase):
+    """MMS sources of the field with [Cs-Cd-int] = Kd (Sd - cd)(1 + cl) cs (reference :2296-2425).  The other
+    two variants only differ in F2(cs) (`_F2`)."""
+
+    dd_reaction = "cs"
+
+    def __init__(self, *, mms_case: MMSCaseBase, model: DefaultModel01):
         self._mms_case = mms_case
         self._model = model
-        self._regularization_factor = regularization_factor
 
     mms_case = property(lambda self: self._mms_case)
     model = property(lambda self: self._model)
-    regularization_factor = property(lambda self: self._regularization_factor)
 
     @property
     def grid(self):
         return self._mms_case.grid
+
+    def _F2(self, cs):
+        return cs
 
     def fcp_ptwise(self, t, xx, yy):
         c, m = self.mms_case, self.model
@@ -714,7 +720,7 @@ class ForcingTerms_RegHCsTriple(ForcingTermsBase):
         c, m = self.mms_case, self.model
         cp, T = c.cp(t, xx, yy), c.T(t, xx, yy)
         dC, dT = m.Dd(cp, T, d=(1, 0)), m.Dd(cp, T, d=(0, 1))
-        H = heaviside_regularized(c.cs(t, xx, yy), self.regularization_factor)
+        H = self._F2(c.cs(t, xx, yy))
         return c.dt_cd(t, xx, yy) - (
             (dC * c.dx_cp(t, xx, yy) + dT * c.dx_T(t, xx, yy)) * c.dx_cd(t, xx, yy)
             + (dC * c.dy_cp(t, xx, yy) + dT * c.dy_T(t, xx, yy)) * c.dy_cd(t, xx, yy)
@@ -723,7 +729,40 @@ class ForcingTerms_RegHCsTriple(ForcingTermsBase):
 
     def fcs(self, t, xx, yy):
         c, m = self.mms_case, self.model
-        H = heaviside_regularized(c.cs(t, xx, yy), self.regularization_factor)
+        H = self._F2(c.cs(t, xx, yy))
+        return c.dt_cs(t, xx, yy) - (-m.Kd * H * (1 + c.cl(t, xx, yy)) * (m.Sd - c.cd(t, xx, yy)))
+
+
+class ForcingTerms_HCsTriple(ForcingTerms_CsTriple):
+    """F2(cs) = (cs > 0) (reference :3222-3300)."""
+
+    dd_reaction = "h"
+
+    def __init__(self, *, mms_case: MMSCaseBase, model: DefaultModel01):
+        super().__init__(mms_case=mms_case, model=model)
+        self.cs3_forcing_terms = ForcingTerms_CsTriple(mms_case=mms_case, model=model)
+
+    def _F2(self, cs):
+        return cs > 0
+
+
+class ForcingTerms_RegHCsTriple(ForcingTerms_CsTriple):
+    """F2(cs) = H_eta(cs) (reference :3473-3551)."""
+
+    dd_reaction = "regh"
+
+    def __init__(self, *, mms_case: MMSCaseBase, model: DefaultModel01, regularization_factor: float):
+        super().__init__(mms_case=mms_case, model=model)
+        self._regularization_factor = regularization_factor
+
+    regularization_factor = property(lambda self: self._regularization_factor)
+
+    def _F2(self, cs):
+        return heaviside_regularized(cs, self.regularization_factor)
+
+    def fcs(self, t, xx, yy):  # factor order of the reference's RegH class (:3538-3551)
+        c, m = self.mms_case, self.model
+        H = self._F2(c.cs(t, xx, yy))
         return c.dt_cs(t, xx, yy) - (-m.Kd * (1 + c.cl(t, xx, yy)) * (m.Sd - c.cd(t, xx, yy)) * H)
 
 
@@ -734,8 +773,8 @@ class ForcingTerms_RegHCsTriple(ForcingTermsBase):
 _FORCING_NAMES = ("fcp", "fT", "fcl", "fcd", "fcs")
 
 
-def _model_signature(model, eta):
-    return tuple(float(getattr(model, n)) for n in ModelConsts._fields[2:]) + (float(eta), model.dd_kind)
+def _model_signature(model, eta, reaction):
+    return tuple(float(getattr(model, n)) for n in ModelConsts._fields[2:]) + (float(eta), model.dd_kind, reaction)
 
 
 class _DeviceBinding:
@@ -763,9 +802,9 @@ class _DeviceBinding:
         """Upload model constants and select the forcing mode.  Returns True when the device evaluates
         the sources itself, False when the host has to (ARRAYS mode)."""
         b, fld = self.batch, self.field
-        sig = _model_signature(fld.model, fld.regularization_factor)
+        sig = _model_signature(fld.model, fld.regularization_factor, fld.dd_reaction)
         if getattr(b, "_model_sig", None) != sig:
-            b.set_model(fld.model, fld.regularization_factor)
+            b.set_model(fld.model, fld.regularization_factor, fld.dd_reaction)
             b._model_sig = sig
         o = self._owner()
         if isinstance(o, NoForcingTerms):
@@ -773,9 +812,9 @@ class _DeviceBinding:
                 b.forcing_none()
                 b._spec_owner = None
             return True
-        if (type(o) is ForcingTerms_RegHCsTriple and o.model is fld.model
-                and float(o.regularization_factor) == float(fld.regularization_factor)
-                and type(o).fcp is ForcingTerms_RegHCsTriple.fcp):
+        if (type(o) in (ForcingTerms_RegHCsTriple, ForcingTerms_CsTriple, ForcingTerms_HCsTriple)
+                and o.model is fld.model and o.dd_reaction == fld.dd_reaction
+                and float(getattr(o, "regularization_factor", 0.0)) == float(fld.regularization_factor)):
             spec = o.mms_case.device_spec() if hasattr(o.mms_case, "device_spec") else None
             if spec is not None and o.mms_case.model is fld.model:
                 if getattr(b, "_spec_owner", None) is not spec:
@@ -806,8 +845,10 @@ class SemiDiscreteFieldBase(ABC):
 class SemiDiscreteField_RegHCsTriple(SemiDiscreteFieldBase):
     """[Cs-Cd-int] = Kd (Sd - cd)(1 + cl) H_eta(cs).  F*(state, t) run on the device."""
 
+    dd_reaction = "regh"
+
     def __init__(self, *, grid: Grid, model: DefaultModel01, forcing_terms: ForcingTermsBase,
-                 regularization_factor: float):
+                 regularization_factor: float = 0.0):
         self._model = model
         self._grid = grid
         self._regularization_factor = regularization_factor
@@ -866,6 +907,30 @@ class SemiDiscreteField_RegHCsTriple(SemiDiscreteFieldBase):
 
     def Fcs(self, at_t, t):
         return self._all_F(at_t, t)["cs"]
+
+
+class SemiDiscreteField_CsTriple(SemiDiscreteField_RegHCsTriple):
+    """[Cs-Cd-int] = Kd (Sd - cd)(1 + cl) cs (reference :2842-2876); same kernels, F2(cs) = cs."""
+
+    dd_reaction = "cs"
+
+    def __init__(self, *, grid: Grid, model: DefaultModel01, forcing_terms: ForcingTermsBase):
+        super().__init__(grid=grid, model=model, forcing_terms=forcing_terms, regularization_factor=0.0)
+
+    def cscd_reaction_cs(self, cs):
+        return self.model.Kd * cs
+
+
+class SemiDiscreteField_HCsTriple(SemiDiscreteField_RegHCsTriple):
+    """[Cs-Cd-int] = Kd (Sd - cd)(1 + cl) H(cs), H(cs) = (cs > 0) (reference :3303-3340)."""
+
+    dd_reaction = "h"
+
+    def __init__(self, *, grid: Grid, model: DefaultModel01, forcing_terms: ForcingTermsBase):
+        super().__init__(grid=grid, model=model, forcing_terms=forcing_terms, regularization_factor=0.0)
+
+    def cscd_reaction_cs(self, cs):
+        return self.model.Kd * (cs > 0)
 
 
 # ----------------------------------------------------------------------------
@@ -1049,3 +1114,21 @@ class P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_RegHCsTriple(P_ModifiedEuler_
         out = dict(self.last_residual)
         self.last_residual = saved
         return out
+
+
+class P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_CsTriple(P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_RegHCsTriple):
+    """The same predictor-corrector / Newton step for the CsTriple field (reference :3152-3219): Heun cs
+    predictor without boundary mask, closed-form trapezoidal cs corrector (no Newton iterations)."""
+
+    def __init__(self, semi_discrete_field, *, num_pc_steps=1, num_newton_steps=1):
+        super().__init__(semi_discrete_field, num_pc_steps=num_pc_steps, num_newton_steps=num_newton_steps,
+                         regularization_factor=0.0, num_newton_iterations=0, consec_xs_rtol=0.0)
+
+
+class P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_HCsTriple(P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_RegHCsTriple):
+    """... for the HCsTriple field (reference :3343-3430): masked Heun cs predictor, piecewise closed-form cs
+    corrector; raises ValueError when 2 - dt Kd (Sd - cd1)(1 + cl1) is not safely positive."""
+
+    def __init__(self, semi_discrete_field, *, num_pc_steps=1, num_newton_steps=1):
+        super().__init__(semi_discrete_field, num_pc_steps=num_pc_steps, num_newton_steps=num_newton_steps,
+                         regularization_factor=0.0, num_newton_iterations=0, consec_xs_rtol=0.0)

@@ -109,6 +109,21 @@ def scenarios():
                   levels=[dict(N=32, M=32, dt=1e-2 / 2 ** k) for k in range(4)], integrator="pc", pc={}))
     S.append(dict(name="trial_fe_pol", kind="trial", case="pol", model=dict(NOTEBOOK["pol"], kind=2), eta=50.0,
                   Tf=0.01, levels=[dict(N=8, M=8, dt=1e-3), dict(N=8, M=8, dt=5e-4)], integrator="fe", pc={}))
+    # F. the CsTriple and HCsTriple field variants (src/prob1base.py:2842-2876, 3152-3430): same stencils, other
+    #    F2(cs) and closed-form cs correctors
+    for variant in ("cs", "h"):
+        for case in ("pol", "expsin"):
+            for integ in ("pc", "fe"):
+                S.append(dict(name=f"steps_{variant}triple_{case}_12x9_{integ}", kind="steps", case=case,
+                              variant=variant, model=dict(_consts_for(case), kind=2), grid=dict(N=12, M=9),
+                              eta=50.0, dt=(1.0 / 12) ** 1.5 if integ == "pc" else 1e-3, t0=0.0, nsteps=3,
+                              integrator=integ, init="exact", pc={}))
+        S.append(dict(name=f"random_nonuniform_{variant}triple_pc22", kind="steps", case=None, variant=variant,
+                      model=dict(STRESS, kind=2), grid=dict(N=6, M=5, nonuniform=True), eta=7.0, dt=0.03, t0=0.1,
+                      nsteps=2, integrator="pc", init="random", pc=dict(num_pc_steps=2, num_newton_steps=2)))
+        S.append(dict(name=f"random_uniform_{variant}triple_pol_forcing", kind="steps", case="pol", variant=variant,
+                      model=dict(STRESS, kind=2), grid=dict(N=7, M=9), eta=20.0, dt=0.02, t0=0.0, nsteps=2,
+                      integrator="pc", init="random", pc={}))
     # E. the convergence-study driver (src/cvg_studies_base.py): observed rates with their status strings and one
     #    small spatial + temporal study (the driver's constructor convention has no regularisation factor, so the
     #    RegHCsTriple classes are passed as functools.partial objects)
@@ -175,13 +190,21 @@ def run_steps(d):
     grid = p1.Grid(x, y)
     model = ref_model(p1, d["model"])
     eta = d["eta"]
+    variant = d.get("variant", "regh")
+    forcing_cls, field_cls, integ_cls = {
+        "regh": (p1.ForcingTerms_RegHCsTriple, p1.SemiDiscreteField_RegHCsTriple,
+                 p1.P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_RegHCsTriple),
+        "cs": (p1.ForcingTerms_CsTriple, p1.SemiDiscreteField_CsTriple,
+               p1.P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_CsTriple),
+        "h": (p1.ForcingTerms_HCsTriple, p1.SemiDiscreteField_HCsTriple,
+              p1.P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_HCsTriple)}[variant]
+    extra = dict(regularization_factor=eta) if variant == "regh" else {}
     if d["case"] is not None:
         case = ref_case_cls(p1mc, d["case"])(grid=grid, model=model)
-        forcing = p1.ForcingTerms_RegHCsTriple(mms_case=case, model=model, regularization_factor=eta)
+        forcing = forcing_cls(mms_case=case, model=model, **extra)
     else:
         case, forcing = None, p1.NoForcingTerms(grid)
-    field = p1.SemiDiscreteField_RegHCsTriple(grid=grid, model=model, forcing_terms=forcing,
-                                              regularization_factor=eta)
+    field = field_cls(grid=grid, model=model, forcing_terms=forcing, **extra)
     if d["init"] == "exact":
         s = p1.state_from_mms_when(mms_case=case, t=d["t0"], grid=grid)
     else:
@@ -195,16 +218,16 @@ def run_steps(d):
         out["F0_" + v] = F(s, t)
     counts = []
     if d["integrator"] == "pc":
-        integ = p1.P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_RegHCsTriple(
-            field, regularization_factor=eta, **d["pc"])
+        integ = integ_cls(field, **extra, **d["pc"])
         calls = [0]
-        orig = integ._predictor_equation
+        if variant == "regh":
+            orig = integ._predictor_equation
 
-        def counting(*a, **k):
-            calls[0] += 1
-            return orig(*a, **k)
+            def counting(*a, **k):
+                calls[0] += 1
+                return orig(*a, **k)
 
-        integ._predictor_equation = counting
+            integ._predictor_equation = counting
     else:
         integ = p1.ForwardEulerIntegrator(field)
     keep_all = d.get("keep", "all") == "all"

@@ -16,7 +16,7 @@ from __future__ import annotations
 import numpy as np
 import sympy
 
-from .ddoracle import OGrid, OModel, heaviside_reg
+from .ddoracle import OGrid, OModel, heaviside_reg, reaction_F2
 
 # same assumptions as src/prob1base.py:1164
 t_s, x_s, y_s = sympy.symbols("t x y", negative=False, real=True)
@@ -157,10 +157,10 @@ class OForcing:
     def fcd(self, t):
         c, m, X, Y = self.c, self.m, self.g.xx, self.g.yy
         dtcd, diff = self._cd_parts(t)
-        H = heaviside_reg(c.cs(t, X, Y), self.eta)
+        H = reaction_F2(c.cs(t, X, Y), m, self.eta)  # H_eta(cs) | cs | (cs > 0): 3503-3551 | 2380-2413 | 3254-3286
         return dtcd - (diff + m.Kd * (m.Sd - c.cd(t, X, Y)) * (c.cl(t, X, Y) + 1) * H)
 
     def fcs(self, t):
         c, m, X, Y = self.c, self.m, self.g.xx, self.g.yy
-        H = heaviside_reg(c.cs(t, X, Y), self.eta)
+        H = reaction_F2(c.cs(t, X, Y), m, self.eta)
         return c.dt_cs(t, X, Y) - (-m.Kd * (1 + c.cl(t, X, Y)) * (m.Sd - c.cd(t, X, Y)) * H)

@@ -60,8 +60,9 @@ static void setup(const HSProblem& P, HSCtx& c, double t0, double dt) {
     const double* q = P.model;
     m.K1 = q[0]; m.K2 = q[1]; m.K3 = q[2]; m.K4 = q[3]; m.DT = q[4]; m.Dl_max = q[5]; m.phi_l = q[6];
     m.gamma_T = q[7]; m.Kd = q[8]; m.Sd = q[9]; m.Dd_max = q[10]; m.phi_d = q[11]; m.phi_T = q[12]; m.r_sp = q[13];
-    m.T_shift = (P.kind == 2) ? q[14] : 0.0;
+    m.T_shift = (P.kind % 10 == 2) ? q[14] : 0.0;  // kind = model kind + 10 * reaction kind
     m.eta = q[15];
+    m.react = P.kind / 10;
     c.mb.active = 1;
     c.mb.t0 = t0; c.mb.dt = dt;
     for (int v = 0; v < 5; ++v) { c.mb.phi_kind[v] = P.phi_kind[v]; for (int s = 0; s < 4; ++s) c.mb.phi_p[v][s] = P.phi_p[v][s]; }
@@ -217,7 +218,20 @@ extern "C" int hs_pc_step(const HSProblem* P, const double* const in[5], double*
                 cpc[p] = cp1; ys[p] = yy; as[p] = aa; xs[p] = in[DD_CS][p];
             }
         int used = 0;
-        for (int it = 0; it < cap; ++it) {
+        const bool closed = c.mb.m.react != DD_REACT_REGH;
+        if (closed) {
+            // CsTriple / HCsTriple: closed-form corrector (sources read again through the prepare routine)
+            for (int r = 0; r <= P->N; ++r)
+                for (int j = 0; j <= P->M; ++j) {
+                    const size_t p = (size_t)r * g.ld + j;
+                    double cp1, yy, aa, f0, f1;
+                    HS_MODE(P->mode, (dd_node_correct_prepare<MODE>(g, c.mb, c.F, s0, u.v[DD_T], u.v[DD_CL], u.v[DD_CD], 0, r, j, &cp1, &yy, &aa, &f0, &f1)));
+                    int bad = 0;
+                    xs[p] = dd_node_correct_cs_closed(g, c.mb, s0, u.v[DD_CL], u.v[DD_CD], 0, r, j, f0, f1, &bad);
+                    if (bad) return -5;
+                }
+        }
+        for (int it = 0; it < (closed ? 0 : cap); ++it) {
             double mx = 0.0, mn = INFINITY;
             bool nan = false;
             for (size_t p = 0; p < n; ++p) {
@@ -236,7 +250,7 @@ extern "C" int hs_pc_step(const HSProblem* P, const double* const in[5], double*
         for (int r = 0; r <= P->N; ++r)
             for (int j = 0; j <= P->M; ++j) {
                 const size_t p = (size_t)r * g.ld + j;
-                csc[p] = xs[p] * (dd_is_interior(g, r, j) ? 1.0 : 0.0);
+                csc[p] = closed ? xs[p] : xs[p] * (dd_is_interior(g, r, j) ? 1.0 : 0.0);
             }
         cp1p = cpc; cs1p = csc;
         u.v[DD_CP] = cp1p.data(); u.v[DD_CS] = cs1p.data();

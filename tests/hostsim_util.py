@@ -61,7 +61,7 @@ def ptr(a):
 class Problem:
     """Holds an HSProblem and keeps the arrays it points to alive."""
 
-    def __init__(self, x, y, model, eta, spec=None, t0=0.0, dt=1.0, arrays=None):
+    def __init__(self, x, y, model, eta, spec=None, t0=0.0, dt=1.0, arrays=None, reaction="regh"):
         import ddcore
         from _ddlib import MODE_ARRAYS, MODE_EXPSIN, MODE_NONE, MODE_SEPARABLE
         self.keep = []
@@ -74,7 +74,7 @@ class Problem:
         for k, n in enumerate(names):
             P.model[k] = float(getattr(model, n))
         P.model[15] = float(eta)
-        P.kind = int(getattr(model, "dd_kind", getattr(model, "kind", 1)))
+        P.kind = int(getattr(model, "dd_kind", getattr(model, "kind", 1))) + 10 * {"regh": 0, "cs": 1, "h": 2}[reaction]
         P.nterms = 1
         px, py = ddcore.quadrature_points(self.x), ddcore.quadrature_points(self.y)
         if arrays is not None:

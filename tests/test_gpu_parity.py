@@ -29,7 +29,7 @@ def make_batch(dd, desc, z, nmembers=1):
     model = dd["product_model"](desc["model"])
     grid = p1.Grid(z["x"], z["y"])
     b = ddcore.Batch(grid.x, grid.y, nmembers)
-    b.set_model(model, desc["eta"])
+    b.set_model(model, desc["eta"], desc.get("variant", "regh"))
     if desc["case"] is not None:
         case = dd["CASES"][desc["case"]](grid=grid, model=model)
         b.forcing_spec(case.device_spec())
@@ -38,7 +38,9 @@ def make_batch(dd, desc, z, nmembers=1):
     return b, model, grid
 
 
-def pc_opts(dd, pc, **kw):
+def pc_opts(dd, pc, variant="regh", **kw):
+    if variant != "regh":  # CsTriple / HCsTriple: closed-form cs corrector, no Newton iterations
+        pc = dict(pc, num_newton_iterations=0, consec_xs_rtol=0.0)
     return dd["ddcore"].pc_options(num_pc_steps=pc.get("num_pc_steps", 1), num_newton_steps=pc.get("num_newton_steps", 1),
                                    num_newton_iterations=pc.get("num_newton_iterations", 5),
                                    consec_xs_rtol=pc.get("consec_xs_rtol", 1e-6), **kw)
@@ -63,7 +65,7 @@ def test_steps_match_reference(dd, name):
     cur, nxt = 0, 1
     for n in range(desc["nsteps"]):
         if desc["integrator"] == "pc":
-            st = b.step_pc(cur, nxt, t, dt, pc_opts(dd, desc["pc"]))
+            st = b.step_pc(cur, nxt, t, dt, pc_opts(dd, desc["pc"], desc.get("variant", "regh")))
             per_step = desc["pc"].get("num_pc_steps", 1)
             # the fixture counts calls over all pc steps; the last corrector's count is what stats report
             assert st["cs_newton_iters"] * per_step >= int(z["cs_newton_calls_per_step"][n]) or per_step > 1
@@ -517,3 +519,40 @@ def test_handles_may_be_released_in_any_order(dd):
     b2 = ddcore.Batch(grid.x, grid.y, 1, ctx=ctx2)
     b2.close()
     ctx2.close()
+
+
+@pytest.mark.parametrize("variant", ["cs", "h"])
+def test_field_variants_through_the_class_api(dd, variant):
+    """CsTriple / HCsTriple (reference src/prob1base.py:2842-2876, 3152-3430) through the reference-facing
+    classes: F(state, t), one step and the corrector pieces against the reference's fixture."""
+    p1 = dd["p1"]
+    name = f"random_uniform_{variant}triple_pol_forcing"
+    desc, z = load_fixture(name)
+    model = dd["product_model"](desc["model"])
+    grid = p1.Grid(z["x"], z["y"])
+    case = dd["CASES"][desc["case"]](grid=grid, model=model)
+    fcls, fldcls, icls = {
+        "cs": (p1.ForcingTerms_CsTriple, p1.SemiDiscreteField_CsTriple,
+               p1.P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_CsTriple),
+        "h": (p1.ForcingTerms_HCsTriple, p1.SemiDiscreteField_HCsTriple,
+              p1.P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_HCsTriple)}[variant]
+    forcing = fcls(mms_case=case, model=model)
+    field = fldcls(grid=grid, model=model, forcing_terms=forcing)
+    integ = icls(field)
+    s = p1.StateVars(*[z["init_" + v] for v in VARS], model=model, hh=grid.hh, kk=grid.kk)
+    t, dt = desc["t0"], desc["dt"]
+    for v, F in zip(VARS, (field.Fcp, field.FT, field.Fcl, field.Fcd, field.Fcs)):
+        assert rel_err(F(s, t), z["F0_" + v]) <= TOL, f"F0_{v}"
+    for n in range(desc["nsteps"]):
+        s = integ.step(s, t0=t, dt=dt)
+        t += dt
+        for v in VARS:
+            assert rel_err(getattr(s, v), z[f"step{n + 1}_{v}"]) <= TOL, (n, v)
+    for v in ("T", "cl", "cd"):
+        scale = max(np.max(np.abs(z[f"step{desc['nsteps']}_{v}"])), 1e-300)
+        assert np.max(np.abs(integ.last_residual[v] - z["resid_" + v])) <= 1e-11 * scale
+    if variant == "h":
+        # the reference's positivity guard: a huge step makes 2 - dt Kd (Sd - cd1)(1 + cl1) negative
+        with pytest.raises(ValueError):
+            integ.corrector_cs_step(None, np.full(grid.full_shape, 50.0), np.full(grid.full_shape, -50.0),
+                                    at_t0=s, t0=t, dt=10.0)

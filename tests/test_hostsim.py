@@ -39,7 +39,8 @@ def make_problem(desc, z, t0, dt):
         case = CASES[desc["case"]](grid=grid, model=model)
         spec = case.device_spec()
         assert spec is not None
-    return hs.Problem(z["x"], z["y"], model, desc["eta"], spec, t0, dt), model, grid
+    return hs.Problem(z["x"], z["y"], model, desc["eta"], spec, t0, dt,
+                      reaction=desc.get("variant", "regh")), model, grid
 
 
 @pytest.mark.parametrize("name", fixture_names(kind="steps"))

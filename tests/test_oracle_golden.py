@@ -17,7 +17,7 @@ FIELD_TOL = 1e-12
 
 def _setup(desc, z):
     g = OGrid(z["x"], z["y"])
-    m = oracle_model(desc["model"])
+    m = oracle_model(desc["model"]).with_changes(reaction=desc.get("variant", "regh"))
     if desc["case"] is not None:
         case = make_case(desc["case"], m)
         forcing = OForcing(case, m, desc["eta"], g)
@@ -48,7 +48,7 @@ def test_steps_match_reference(name):
     if stepper:
         per_step = desc["pc"].get("num_pc_steps", 1)
         got = np.array(stepper.cs_newton_iters).reshape(-1, per_step).sum(axis=1)
-        assert np.array_equal(got, z["cs_newton_calls_per_step"])
+        assert np.array_equal(got, z["cs_newton_calls_per_step"])  # 0 for the closed-form cs correctors
         for v in ("T", "cl", "cd"):
             scale = max(np.max(np.abs(z[f"step{desc['nsteps']}_{v}"])), 1e-300)
             assert np.max(np.abs(stepper.last_residual[v] - z["resid_" + v])) <= 1e-11 * scale
