@@ -52,6 +52,7 @@ struct dd_batch {
     double *d_itmax, *d_itmin;
     int* d_used;
     int* d_flags;  // per member: bit 0 = HCsTriple corrector hit its positivity threshold
+    bool has_variants;  // some member uses the CsTriple / HCsTriple reaction
     int cs_cap_alloc;
     double *d_norm_partial, *d_norm_out;
     int norm_bpm;
@@ -381,6 +382,7 @@ extern "C" int dd_batch_create(dd_ctx* ctx, int N, int M, const double* x, const
     CK(cudaMalloc((void**)&b->d_dt, sizeof(double) * nmembers));
     b->nsolve_cap = 0; b->d_stats = nullptr; b->d_summary = nullptr;
     b->d_itmax = b->d_itmin = nullptr; b->d_used = nullptr; b->cs_cap_alloc = 0;
+    b->has_variants = false;
     CK(cudaMalloc((void**)&b->d_flags, sizeof(int) * nmembers));
     CK(cudaMemsetAsync(b->d_flags, 0, sizeof(int) * nmembers, ctx->stream));
     b->norm_bpm = dd_norm_blocks_per_member(g);
@@ -433,6 +435,9 @@ extern "C" int dd_batch_set_models(dd_batch* b, int first, int count, const dd_m
     if (!b || !models || first < 0 || count < 1 || first + count > b->B) return DD_ERR_INVALID;
     { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
     for (int k = 0; k < count; ++k) model_to_dev(models[k], &b->h_mem[first + k].m);
+    b->has_variants = false;
+    for (int m = 0; m < b->B; ++m)
+        if (b->h_mem[m].m.react != DD_REACT_REGH) b->has_variants = true;
     reset_ctl(b, true);
     return push_members(b, first, count);
 }
@@ -1346,7 +1351,7 @@ static int pc_step_enqueue(dd_batch* b, int slot_in, int slot_out, const dd_pc_o
         }
         CKP(PC_CORRECT, 1,
             dd_launch_correct(Lall, b->smode, b->g, b->d_mem, b->sF, s0, u.v[DD_T], u.v[DD_CL], u.v[DD_CD], cpd, csd,
-                              cap, track ? opt.consec_xs_rtol : 0.0, b->d_itmax, b->d_itmin, b->d_flags));
+                              cap, track ? opt.consec_xs_rtol : 0.0, b->d_itmax, b->d_itmin, b->has_variants ? b->d_flags : nullptr));
         if (track)
             CKP(PC_CS_FINISH, 2,
                 dd_launch_cs_finish(Lall, b->smode, b->g, b->d_mem, b->sF, s0, u.v[DD_CL], u.v[DD_CD], csd, cap,
@@ -1731,7 +1736,7 @@ extern "C" int dd_pc_correct(dd_batch* b, int slot0, int slot_new, const double*
     }
     CK(cudaMemsetAsync(b->d_flags, 0, sizeof(int) * b->B, ctx->stream));
     CK(dd_launch_correct(L, b->smode, b->g, b->d_mem, b->sF, s0, nw.v[DD_T], nw.v[DD_CL], nw.v[DD_CD], nw.v[DD_CP],
-                         nw.v[DD_CS], cap, track ? opt.consec_xs_rtol : 0.0, b->d_itmax, b->d_itmin, b->d_flags));
+                         nw.v[DD_CS], cap, track ? opt.consec_xs_rtol : 0.0, b->d_itmax, b->d_itmin, b->has_variants ? b->d_flags : nullptr));
     if (track)
         CK(dd_launch_cs_finish(L, b->smode, b->g, b->d_mem, b->sF, s0, nw.v[DD_CL], nw.v[DD_CD], nw.v[DD_CS], cap,
                                opt.consec_xs_rtol, b->d_itmax, b->d_itmin, b->d_used));
@@ -1863,7 +1868,7 @@ extern "C" int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_ou
             CKP(PC_CORRECT, 1,
                 dd_launch_correct(launch_of(b, ROWS_ALL), b->smode, b->g, b->d_mem, b->sF, s0, sout.v[DD_T],
                                   sout.v[DD_CL], sout.v[DD_CD], sout.v[DD_CP], sout.v[DD_CS], cap,
-                                  track ? opt.consec_xs_rtol : 0.0, b->d_itmax, b->d_itmin, b->d_flags));
+                                  track ? opt.consec_xs_rtol : 0.0, b->d_itmax, b->d_itmin, b->has_variants ? b->d_flags : nullptr));
             return DD_OK;
         case 6:
             // as 5 without the read-back: the driver reduces "summary" / "cs_used" on the device itself

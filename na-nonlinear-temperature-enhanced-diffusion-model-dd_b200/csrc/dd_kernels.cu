@@ -842,7 +842,9 @@ cudaError_t dd_launch_assemble_march(const DDLaunch& L, int mode, int var, const
 // ---------------------------------------------------------------------------
 #define DD_CS_SMEM_CAP 1024  // per-iteration statistics staged in shared memory up to this many iterations
 
-template <int MODE>
+// VARIANTS = false: every member is a RegHCsTriple one (the iteration below); true: members may use the
+// closed-form cs correctors of CsTriple / HCsTriple (kept out of the common instantiation: it costs registers)
+template <int MODE, bool VARIANTS>
 __global__ void __launch_bounds__(DD_BLOCK) k_correct(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
                                                       DDStateC s0, const double* __restrict__ T1,
                                                       const double* __restrict__ cl1,
@@ -872,11 +874,14 @@ __global__ void __launch_bounds__(DD_BLOCK) k_correct(DDGeom g, const DDMember* 
         const long long mo = n.member * g.mstride;
         o = mo + (long long)n.r * g.ld + n.j;
         inter = dd_is_interior(g, g.row0 + n.r, n.j);
-        double fcs0, fcs1;
-        dd_node_correct_prepare<MODE>(g, mb, F, s0, T1, cl1, cd1, mo, n.r, n.j, &cp1, &y, &a, &fcs0, &fcs1);
+        double fcs0 = 0.0, fcs1 = 0.0;
+        if (VARIANTS)
+            dd_node_correct_prepare<MODE>(g, mb, F, s0, T1, cl1, cd1, mo, n.r, n.j, &cp1, &y, &a, &fcs0, &fcs1);
+        else
+            dd_node_correct_prepare<MODE>(g, mb, F, s0, T1, cl1, cd1, mo, n.r, n.j, &cp1, &y, &a);
         x = s0.v[DD_CS][o];
         cp_out[o] = cp1;
-        if (mb.m.react != DD_REACT_REGH) {
+        if (VARIANTS && mb.m.react != DD_REACT_REGH) {
             // CsTriple / HCsTriple: closed-form corrector, no iterations (the caller passes cap = 0)
             int bad = 0;
             x = dd_node_correct_cs_closed(g, mb, s0, cl1, cd1, mo, n.r, n.j, fcs0, fcs1, &bad);
@@ -884,7 +889,7 @@ __global__ void __launch_bounds__(DD_BLOCK) k_correct(DDGeom g, const DDMember* 
             cs_out[o] = x;
             return;
         }
-    } else if (mem[n.member].m.react != DD_REACT_REGH) {
+    } else if (VARIANTS && mem[n.member].m.react != DD_REACT_REGH) {
         return;
     }
     const double eta = mb.m.eta;
@@ -927,9 +932,15 @@ cudaError_t dd_launch_correct(const DDLaunch& L, int mode, const DDGeom& g, cons
                               const double* cd1, double* cp_out, double* cs_out, int cap, double rtol,
                               double* it_max, double* it_min, int* flags) {
     const int bpm = blocks_per_member(g, L);
-    DD_DISPATCH_MODE(mode, (k_correct<MODE><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(
-                               g, mem, F, s0, T1, cl1, cd1, cp_out, cs_out, cap, rtol, it_max, it_min, flags,
-                               L.own0, L.own1, bpm)));
+    if (flags) {
+        DD_DISPATCH_MODE(mode, (k_correct<MODE, true><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(
+                                   g, mem, F, s0, T1, cl1, cd1, cp_out, cs_out, cap, rtol, it_max, it_min, flags,
+                                   L.own0, L.own1, bpm)));
+    } else {
+        DD_DISPATCH_MODE(mode, (k_correct<MODE, false><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(
+                                   g, mem, F, s0, T1, cl1, cd1, cp_out, cs_out, cap, rtol, it_max, it_min, flags,
+                                   L.own0, L.own1, bpm)));
+    }
     return cudaGetLastError();
 }
 

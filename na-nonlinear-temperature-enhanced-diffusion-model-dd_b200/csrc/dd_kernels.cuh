@@ -66,7 +66,8 @@ cudaError_t dd_launch_make_guess(const DDLaunch& L, const DDGeom& g, const DDRow
 cudaError_t dd_launch_correct(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,
                               const DDForcing& F, const DDStateC& s0, const double* T1, const double* cl1,
                               const double* cd1, double* cp_out, double* cs_out, int cap, double rtol,
-                              double* it_max, double* it_min, int* flags);
+                              double* it_max, double* it_min,
+                              int* flags /* null: every member is RegHCsTriple; else per-member error flags */);
 
 cudaError_t dd_launch_cs_finish(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,
                                 const DDForcing& F, const DDStateC& s0, const double* cl1, const double* cd1,

@@ -88,9 +88,8 @@ DD_HD double dd_H(double x, double eta) { return dd_rcp(1.0 + dd_exp(-eta * x));
 
 // F2(cs) of the cs/cd interaction (cscd_reaction_cs / Kd of the reference's three field classes)
 DD_HD double dd_F2(const DDModel& m, double cs) {
-    if (m.react == DD_REACT_CS) return cs;
-    if (m.react == DD_REACT_H) return cs > 0.0 ? 1.0 : 0.0;
-    return dd_H(cs, m.eta);
+    if (m.react == DD_REACT_REGH) return dd_H(cs, m.eta);  // the common case first
+    return (m.react == DD_REACT_CS) ? cs : (cs > 0.0 ? 1.0 : 0.0);
 }
 
 // ---------------------------------------------------------------------------
