@@ -485,6 +485,15 @@ def separable_terms(expr, t_var=t_sym, x_var=x_sym, y_var=y_sym):
 
 def separable_factors(expr, t_var=t_sym, x_var=x_sym, y_var=y_sym):
     """(f(t), X(x), Y(y)) with expr == f X Y, or None when it is not a single product."""
+    e = _split_abs_products(sympy.factor_terms(sympy.sympify(expr)))
+    if e != 0:
+        # a product such as x (1 - x) y (1 - y) splits as it stands (expanding it would give four terms)
+        ft, rest = e.as_independent(x_var, y_var, as_Add=False)
+        if not rest.has(t_var):
+            for cand in (rest, sympy.factor(rest)):
+                gx, hy = cand.as_independent(y_var, as_Add=False)
+                if not gx.has(y_var) and not hy.has(x_var):
+                    return ft, gx, hy
     st = separable_terms(expr, t_var, x_var, y_var)
     if st is None or len(st[1]) != 1:
         return None

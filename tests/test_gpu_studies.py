@@ -154,3 +154,46 @@ def test_notebook_spatial_study_numbers_and_orders(mods, case):
     for g, want in zip(got_rates, rates):
         if want is not None:
             assert abs(g - want) <= 6e-4, (got_rates, rates)   # printed with three decimals
+
+
+def _library_cases():
+    import inspect
+    import prob1_mms_cases as cases
+    import prob1base as p1
+    return [n for n, cls in inspect.getmembers(cases, inspect.isclass)
+            if issubclass(cls, p1.MMSCaseBase) and cls.__module__ == cases.__name__ and not n.startswith("_")
+            and n != "MMSCaseNonFullySmoothPol"]
+
+
+@pytest.mark.parametrize("name", _library_cases())
+def test_every_library_case_device_forcing_equals_host_forcing(mods, name):
+    """Each MMS case of the library, two PC steps: sources evaluated on the device from the case's tables /
+    closed form vs the same step with the sources evaluated by the host callables (the reference's formulas)
+    and uploaded.  Pins all device descriptions, not only the four cases that have reference fixtures."""
+    import prob1_mms_cases as cases
+    p1 = mods["p1"]
+    model = mods["product_model"](NOTEBOOK_MODEL["pol"])
+    grid = p1.make_uniform_grid(14, 11)
+    eta, t0, dt = 50.0, 0.05, 2e-3
+    case = getattr(cases, name)(grid=grid, model=model)
+    out = []
+    for host_sources in (False, True):
+        forcing = p1.ForcingTerms_RegHCsTriple(mms_case=case, model=model, regularization_factor=eta)
+        field = p1.SemiDiscreteField_RegHCsTriple(grid=grid, model=model, forcing_terms=forcing,
+                                                  regularization_factor=eta)
+        if host_sources:
+            field.fcs = lambda t, xx, yy, f=forcing: f.fcs(t, xx, yy)   # a rebound callable: generic (array) path
+        integ = p1.P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_RegHCsTriple(field, regularization_factor=eta)
+        s = p1.state_from_mms_when(mms_case=case, t=t0, grid=grid)
+        t = t0
+        for _ in range(2):
+            s = integ.step(s, t0=t, dt=dt)
+            t += dt
+        out.append((s, field.binding().batch.mode))
+    import ddcore
+    assert out[0][1] in (ddcore.MODE_SEPARABLE, ddcore.MODE_EXPSIN) and out[1][1] == ddcore.MODE_ARRAYS, name
+    everything = max(np.max(np.abs(getattr(out[1][0], v))) for v in VARS)
+    for v in VARS:
+        a, b = getattr(out[0][0], v), getattr(out[1][0], v)
+        # (fields that are identically zero analytically hold rounding noise of the sources only)
+        assert np.max(np.abs(a - b)) <= 1e-12 * np.max(np.abs(b)) + 1e-16 * everything, (name, v)
