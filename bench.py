@@ -51,7 +51,7 @@ KERNEL_BYTES = {"k_predict": 88, "k_assemble<T>": 40, "k_assemble<cl>": 80, "k_a
 def captured_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/), or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01e_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01f_traffic.json")) as f:
             t = json.load(f)
         k = t["kernels"][kernel]
         return float(k["dram_bytes_per_launch"]), t["source"] + "; kernel " + k["ncu_kernel"]
