@@ -146,9 +146,9 @@ def test_notebook_spatial_study_numbers_and_orders(mods, case):
     sw = mods["ens"].RefinementSweep(mods["CASES"][case], model, trials)
     got = sw.run_for_errors()["overall"]
     sw.close()
-    # the error norm is a difference of nearly equal O(1) fields: a few ulps of the fields (2e-15) on top of the
-    # digits the notebook prints
-    assert np.all(np.abs(got - np.array(errors)) <= rtol * np.array(errors) + 2e-15), (got, errors)
+    # the error norm is a difference of nearly equal O(1) fields: some ulps of the fields (1e-14: it moves with
+    # the number of solver sweeps) on top of the digits the notebook prints
+    assert np.all(np.abs(got - np.array(errors)) <= rtol * np.array(errors) + 1e-14), (got, errors)
     mods["cvg"].VERBOSE = False
     got_rates = [r for r, status in mods["cvg"].calculate_observed_rates(list(got), 2.0)]
     for g, want in zip(got_rates, rates):
