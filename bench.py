@@ -321,6 +321,8 @@ def run_b200(args):
         if args.workload == "mesh":
             mesh, dt, cells = mesh_setup(world, rank, ctx)
             opt = ddcore.pc_options()
+            if os.environ.get("DD_BENCH_NOTRACK"):  # development probe: cost of the cs exit-test statistics
+                opt = ddcore.pc_options(consec_xs_rtol=0.0)
 
             clock = {"t": 0.0}
 
