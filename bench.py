@@ -331,7 +331,10 @@ def run_b200(args):
                 # the t1 sources of a step are then bitwise the t0 sources of the next one
                 # verification is deferred by one step (three rotating slots): the host enqueues step k + 1
                 # before it reads the convergence summaries of step k; flush() settles the last one
-                mesh.step_pc(k % 3, (k + 1) % 3, clock["t"], dt, opt, defer=not args.sync_steps)
+                if args.integrator == "feuler":
+                    mesh.step_feuler(k % 3, (k + 1) % 3, clock["t"], dt)  # ForwardEulerIntegrator.step (80 B/cell-step)
+                else:
+                    mesh.step_pc(k % 3, (k + 1) % 3, clock["t"], dt, opt, defer=not args.sync_steps)
                 clock["t"] += dt
             workload = (f"pol_mesh: MMSCasePol, {MESH_ROWS_PER_GPU} rows/GPU x {MESH_COLS} cols of the N=M=8192 "
                         f"unit-square mesh (h=k=1/8192, dt=h^1.5), slab decomposition along i")
@@ -399,7 +402,10 @@ def run_b200(args):
             def pipeline(m, pin, pout, nsteps):
                 for k in range(nsteps):
                     m.batch.upload(0, pin)
-                    m.step_pc(0, 1, k * dt, dt, opt)
+                    if args.integrator == "feuler":
+                        m.step_feuler(0, 1, k * dt, dt)
+                    else:
+                        m.step_pc(0, 1, k * dt, dt, opt)
                     m.batch.download_into(1, pout)
 
             if world == 1 and not args.e2e_single:
@@ -454,20 +460,22 @@ def run_b200(args):
     achieved = alg_per_launch / (tms / tcount * 1e-3) / 1e9
     total_prof = sum(v[0] for v in prof.values())
     traffic, traffic_src = captured_traffic(tname)
+    step_bytes = 80.0 if args.integrator == "feuler" else BYTES_PER_CELL_STEP
     roof = {"bound": "hbm", "kernel": tname, "achieved": achieved, "peak": peak, "peak_kind": peak_kind,
             "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
             "algorithmic_bytes_per_launch": alg_per_launch, "launches_per_step": lps,
             "launch_ms": tms / tcount, "share_of_step": tms / total_prof,
-            "step": {"bytes_per_cell_step": BYTES_PER_CELL_STEP,
-                     "achieved": value / world * BYTES_PER_CELL_STEP / 1e9,
-                     "frac": value / world * BYTES_PER_CELL_STEP / 1e9 / peak},
+            "step": {"bytes_per_cell_step": step_bytes,
+                     "achieved": value / world * step_bytes / 1e9,
+                     "frac": value / world * step_bytes / 1e9 / peak},
             "kernels": {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
                         for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": dict({"workload": workload, "integrator": "PC RegHCsTriple p=q=1, 5 cs-Newton iterations",
+        "config": dict({"workload": workload, "integrator": ("forward Euler (all five fields, all nodes)" if args.integrator == "feuler"
+                                       else "PC RegHCsTriple p=q=1, 5 cs-Newton iterations"),
                         "eta": ETA, "forcing": "fused MMS (separable tables)", "solver": stats}, **extra_cfg),
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
     }
@@ -563,6 +571,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="mesh", choices=["mesh", "ensemble", "sweep"])
     ap.add_argument("--members", type=int, default=12500, help="ensemble workload: members per GPU")
+    ap.add_argument("--integrator", default="pc", choices=["pc", "feuler"],
+                    help="mesh workload: the predictor-corrector step (headline) or the forward-Euler step")
     ap.add_argument("--sync-steps", action="store_true", help="verify every step before enqueuing the next one")
     ap.add_argument("--no-e2e", dest="e2e", action="store_false")
     ap.add_argument("--e2e-single", action="store_true", help="e2e with one trajectory (no duplex overlap)")

@@ -197,8 +197,13 @@ __global__ void __launch_bounds__(DD_BLOCK) k_eval_sources(DDGeom g, const DDMem
         default: return cudaErrorInvalidValue;                     \
     }
 
+bool dd_predict_march_ok(const DDGeom& g, const DDLaunch& L, int mode);
+static cudaError_t launch_feuler_march(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,
+                                       const DDForcing& F, const DDStateC& in, const DDState& out);
+
 cudaError_t dd_launch_feuler(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem, const DDForcing& F,
                              const DDStateC& in, const DDState& out) {
+    if (dd_predict_march_ok(g, L, mode)) return launch_feuler_march(L, mode, g, mem, F, in, out);
     const int bpm = blocks_per_member(g, L);
     DD_DISPATCH_MODE(mode, (k_feuler<MODE><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(g, mem, F, in, out, L.own0,
                                                                                       L.own1, bpm)));
@@ -478,6 +483,105 @@ k_predict_march(DDGeom g, const DDMember* __restrict__ mem, DDForcingArrays A, D
     }
 }
 
+// Forward Euler in the same marching form (ForwardEulerIntegrator.step, reference src/prob1base.py:2889-2903):
+// u1 = u0 + dt F(u0, t0) on every node of the row range, boundary nodes included (there F is the source alone,
+// Fcs = 0); the face fluxes are those of the predictor.
+__global__ void __launch_bounds__(DD_MARCH_WARPS * 32, DD_MARCH_MINB)
+k_feuler_march(DDGeom g, const DDMember* __restrict__ mem, DDForcingArrays A, DDStateC s, DDState out, int r0, int r1,
+               int nwc, int wcb, int nrb) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int bid = blockIdx.x;
+    const int member = bid / (wcb * nrb);
+    bid -= member * (wcb * nrb);
+    const int rbk = bid / wcb, cbk = bid - rbk * wcb;
+    const DDMember& mb = mem[member];
+    if (!mb.active) return;
+    const int wc = cbk * (blockDim.x >> 5) + warp;
+    if (wc >= nwc) return;
+    const DDModel& m = mb.m;
+    const double dt = mb.dt;
+    const int j = wc * 31 + lane - 1;
+    const int ra = r0 + rbk * DD_MARCH_ROWS, rz = min(ra + DD_MARCH_ROWS, r1);
+    const bool col = j >= 0 && j <= g.M;
+    const bool owner = lane >= 1 && col;
+    const bool jint = j >= 1 && j <= g.M - 1;
+    const bool colN = j >= 0 && j + 1 <= g.M;
+    const long long mo = member * g.mstride;
+    double rkp = 0.0, rkN = 0.0;
+    if (colN) rkN = g.rk[j + 1];
+    if (jint) rkp = g.rkp[j];
+    const long long oa = mo + (long long)ra * g.ld + j;
+    DDMarchCell P = dd_march_load(s, oa - g.ld, col && ra - 1 >= 0);
+    DDMarchCell C = dd_march_load(s, oa, col);
+    DDMarchCell N = dd_march_load(s, oa + g.ld, col && ra + 1 < g.nrows);
+    DDMarchCell Cn = dd_march_load(s, oa + 1, colN);
+    double csC = col ? __ldg(s.v[DD_CS] + oa) : 0.0;
+    double f[DD_NVAR];
+#pragma unroll
+    for (int v = 0; v < DD_NVAR; ++v) f[v] = owner ? dd_ldg0(A.f[v][0], oa) : 0.0;
+    DDMarchFace W = {0.0, 0.0, 0.0};
+    double wadv = 0.0;
+    {
+        const int i = g.row0 + ra;
+        if (jint && i >= 1 && i <= g.N - 1) {
+            W = dd_march_face(m, P, C, g.rh[i]);
+            wadv = 0.5 * (m.gamma_T * C.T * (C.cl + 1.0) + m.gamma_T * P.T * (P.cl + 1.0));
+        }
+    }
+    DD_MARCH_LOOP
+    for (int r = ra; r < rz; ++r) {
+        const int i = g.row0 + r;
+        const long long o = mo + (long long)r * g.ld + j;
+        const bool nxt = r + 1 < rz;
+        const DDMarchCell NN = dd_march_load(s, o + 2LL * g.ld, col && nxt && r + 2 < g.nrows);
+        const DDMarchCell Nn = dd_march_load(s, o + g.ld + 1, colN && nxt);
+        const double csN = (col && nxt) ? __ldg(s.v[DD_CS] + o + g.ld) : 0.0;
+        double fN[DD_NVAR];
+#pragma unroll
+        for (int v = 0; v < DD_NVAR; ++v) fN[v] = (owner && nxt) ? dd_ldg0(A.f[v][0], o + g.ld) : 0.0;
+        const bool irow = i >= 1 && i <= g.N - 1;
+        DDMarchFace E = {0.0, 0.0, 0.0};
+        double eadv = 0.0;
+        if (jint && i >= 0 && i <= g.N - 1 && r + 1 < g.nrows) {
+            E = dd_march_face(m, C, N, g.rh[i + 1]);
+            eadv = 0.5 * (m.gamma_T * N.T * (N.cl + 1.0) + m.gamma_T * C.T * (C.cl + 1.0));
+        }
+        DDMarchFace Nf = {0.0, 0.0, 0.0};
+        if (irow && colN) Nf = dd_march_face(m, C, Cn, rkN);
+        DDMarchFace S;
+        S.T = __shfl_up_sync(0xffffffffu, Nf.T, 1);
+        S.cl = __shfl_up_sync(0xffffffffu, Nf.cl, 1);
+        S.cd = __shfl_up_sync(0xffffffffu, Nf.cd, 1);
+        if (owner) {
+            double Fcp = f[DD_CP], FT = f[DD_T], Fcl = f[DD_CL], Fcd = f[DD_CD], Fcs = (f[DD_CS] - 0.0) * 0.0;
+            if (irow && jint) {
+                const double rhp = g.rhp[i];
+                const double react = dd_reaction(m, C.cl, C.cd, csC);
+                Fcp = f[DD_CP] + dd_Fcp_int(m, C.cp, C.T, C.cl);
+                FT = f[DD_T] + (m.DT * (rhp * (E.T - W.T) + rkp * (Nf.T - S.T)) - m.K3 * C.cp * C.T);
+                Fcl = f[DD_CL] + ((rhp * (E.cl - W.cl) + rkp * (Nf.cl - S.cl)) - rhp * (eadv - wadv) -
+                                  m.K4 * C.cp * (C.cl + 1.0));
+                Fcd = f[DD_CD] + ((rhp * (E.cd - W.cd) + rkp * (Nf.cd - S.cd)) + react);
+                Fcs = f[DD_CS] - react;
+            }
+            out.v[DD_CP][o] = C.cp + dt * Fcp;
+            out.v[DD_T][o] = C.T + dt * FT;
+            out.v[DD_CL][o] = C.cl + dt * Fcl;
+            out.v[DD_CD][o] = C.cd + dt * Fcd;
+            out.v[DD_CS][o] = csC + dt * Fcs;
+        }
+        W = E;
+        wadv = eadv;
+        P = C;
+        C = N;
+        N = NN;
+        Cn = Nn;
+        csC = csN;
+#pragma unroll
+        for (int v = 0; v < DD_NVAR; ++v) f[v] = fN[v];
+    }
+}
+
 bool dd_predict_march_ok(const DDGeom& g, const DDLaunch& L, int mode) {
     static const bool off = getenv("DD_NO_MARCH") != nullptr;
     return !off && (mode == DD_FORCING_ARRAYS || mode == DD_FORCING_NONE) && g.M + 1 >= 4 * 31 &&
@@ -506,6 +610,21 @@ cudaError_t dd_launch_predict_march(const DDLaunch& L, int mode, const DDGeom& g
         k_predict_march<false><<<(unsigned)nblocks, wpb * 32, 0, L.stream>>>(g, mem, A, in, out, R, stats, L.own0,
                                                                               L.own1, nwc, wcb, nrb, 1);
     }
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_feuler_march(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,
+                                       const DDForcing& F, const DDStateC& in, const DDState& out) {
+    DDForcingArrays A;
+    memset(&A, 0, sizeof(A));
+    if (mode == DD_FORCING_ARRAYS) A = F.arr;
+    const int nwc = (g.M + 1 + 30) / 31;
+    const int wpb = nwc < DD_MARCH_WARPS ? nwc : DD_MARCH_WARPS;
+    const int wcb = (nwc + wpb - 1) / wpb;
+    const int nrb = (L.own1 - L.own0 + DD_MARCH_ROWS - 1) / DD_MARCH_ROWS;
+    const long long nblocks = (long long)wcb * nrb * L.nmembers;
+    if (nblocks <= 0 || nblocks > 2147483647LL) return cudaErrorInvalidConfiguration;
+    k_feuler_march<<<(unsigned)nblocks, wpb * 32, 0, L.stream>>>(g, mem, A, in, out, L.own0, L.own1, nwc, wcb, nrb);
     return cudaGetLastError();
 }
 
