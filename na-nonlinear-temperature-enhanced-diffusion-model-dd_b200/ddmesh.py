@@ -360,7 +360,8 @@ class SlabMesh:
         for m in self.group:
             m._rho, m.last_stats = s[:, 0], stats
         if ok:
-            nxt = [max(self.batch.lib.dd_next_plan(int(p), float(r), float(q), opt.max_sweeps), f)
+            # (a negative ratio marks a system that was NaN / Inf on entry: nothing to learn from it)
+            nxt = [max(self.batch.lib.dd_next_plan(int(p), float(r), float(q), opt.max_sweeps), f) if q >= 0.0 else p
                    for p, r, q, f in zip(plan, s[:, 0], s[:, 1], ctl["floor"])]
             for m in self.group:
                 m._ctl[mode]["plan"] = nxt

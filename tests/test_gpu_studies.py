@@ -197,3 +197,29 @@ def test_every_library_case_device_forcing_equals_host_forcing(mods, name):
         a, b = getattr(out[0][0], v), getattr(out[1][0], v)
         # (fields that are identically zero analytically hold rounding noise of the sources only)
         assert np.max(np.abs(a - b)) <= 1e-12 * np.max(np.abs(b)) + 1e-16 * everything, (name, v)
+
+
+def test_blown_up_trial_propagates_nan_like_the_reference(mods):
+    """SlowlyChangingPeaks_Fast1e1 at dt = 1 (the reference's temporal study starts there and prints an overall
+    error of 0.0): cs overflows to NaN in the first step, cd follows, cp / T / cl stay
+    finite.  The reference's direct solves return NaN and `max(0.0, nan)` keeps 0.0; the device path must do the
+    same - no NOT_CONVERGED for systems that are NaN on entry - and agree on the finite variables."""
+    from oracle import NOTEBOOK_CONSTS, OForcing, OGrid, make_case, run_trial
+    p1 = mods["p1"]
+    om = NOTEBOOK_CONSTS["pol"]
+    N, Tf, dt, eta = 32, 10.0, 1.0, 50.0
+    grid = p1.make_uniform_grid(N, N)
+    og = OGrid(np.array(grid.x), np.array(grid.y))
+    oc = make_case("scp_fast1e1", om)
+    with np.errstate(all="ignore"):
+        want = run_trial(oc, og, om, eta, OForcing(oc, om, eta, og), Tf=Tf, dt=dt)
+    assert want["overall"] == 0.0 and want["per_var"]["cs"] == 0.0     # the fixture really blows up
+    model = mods["product_model"](NOTEBOOK_MODEL["pol"])
+    sw = mods["ens"].RefinementSweep(mods["CASES"]["scp_fast1e1"], model, [dict(N=N, dt=dt, Tf=Tf, eta=eta)])
+    got = sw.run_for_errors()
+    sw.close()
+    assert got["overall"][0] == 0.0
+    gv = got["per_var"][0]
+    wv = np.array([want["per_var"][v] for v in VARS])
+    assert gv[4] == 0.0
+    assert np.all(np.abs(gv - wv) <= 1e-9 * np.abs(wv)), (gv, wv)
