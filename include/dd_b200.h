@@ -48,7 +48,9 @@ enum dd_forcing_mode {
     DD_MODE_NONE = 0,      /* NoForcingTerms, src/prob1base.py:852-869 */
     DD_MODE_ARRAYS = 1,    /* caller evaluates fcp..fcs and uploads them (any ForcingTermsBase) */
     DD_MODE_SEPARABLE = 2, /* u_v = phi_v(t) X_v(x) Y_v(y): fused evaluation from 1-D tables */
-    DD_MODE_EXPSIN = 3     /* MMSCaseExpSin closed form, src/prob1_mms_cases.py:296-337 */
+    DD_MODE_EXPSIN = 3,    /* MMSCaseExpSin closed form, src/prob1_mms_cases.py:296-337 */
+    DD_MODE_PROGRAM = 4    /* any MMSCaseSymbolic: sources and exact solution from a generated kernel
+                              (dd_b200_program.h), src/prob1base.py:1226-1280 */
 };
 
 /* time profiles phi_v(t) of DD_MODE_SEPARABLE */
@@ -61,16 +63,8 @@ enum dd_phi_kind {
     DD_PHI_K_HOST = 5    /* p = phi(t0), phi'(t0), phi(t1), phi'(t1): refreshed by the caller before each step */
 };
 
-/* ModelConsts (src/prob1base.py:28-45) + model kind + eta; one per member */
-typedef struct dd_model {
-    double K1, K2, K3, K4, DT, Dl_max, phi_l, gamma_T, Kd, Sd, Dd_max, phi_d, phi_T, r_sp, T_ref;
-    double eta;   /* regularisation factor of H_eta, src/prob1base.py:3452-3466 */
-    int kind;     /* 1 = DefaultModel01, 2 = DefaultModel02 (Dd uses T + T_ref), src/prob1base.py:71-217 */
-    int reaction; /* cs/cd interaction Kd (Sd - cd)(1 + cl) F2(cs): 0 = RegHCsTriple, F2 = H_eta(cs) (3553-3593);
-                     1 = CsTriple, F2 = cs (2842-2876); 2 = HCsTriple, F2 = (cs > 0) (3303-3340).  The cs
-                     predictor / corrector follow the matching integrator class (3152-3219, 3343-3430, 3596-3702);
-                     for 1 and 2 the corrector is a closed form: pass num_newton_iterations = 0 */
-} dd_model;
+/* dd_model, dd_program_member, dd_program_args: shared with generated forcing programs */
+#include "dd_b200_program.h"
 
 /* options of the predictor-corrector step: the constructor arguments of
  * P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_RegHCsTriple (src/prob1base.py:3612-3629) */
@@ -132,6 +126,12 @@ int dd_forcing_expsin(dd_batch* b, const double* sx, const double* cx, const dou
                       const double* sxq, const double* syq);
 /* host-evaluated sources for the next step: f[v][slot] (slot 0: t0, slot 1: t0+dt), NULL = zero */
 int dd_forcing_arrays(dd_batch* b, int member, const double* const f[5][2]);
+/* generated forcing: `image` is a cubin or PTX image (NVRTC output for sm_100a) that defines the kernel
+ * `dd_program` of dd_b200_program.h; xq / yq: Gauss abscissae of the dual cells, 3 per node ((N+1)*3, (M+1)*3
+ * doubles, src/prob1base.py:538-570).  Replaces the per-step host evaluation of MMSCaseSymbolic's lambdified
+ * expressions (src/prob1base.py:1226-1280) and of the ForcingTerms object built on them. */
+int dd_forcing_program(dd_batch* b, const void* image, unsigned long long image_bytes, const double* xq,
+                       const double* yq);
 
 /* ---- state slots ------------------------------------------------------- */
 int dd_state_upload(dd_batch* b, int slot, int member, const double* const fields[5] /* NULL entries skipped */);

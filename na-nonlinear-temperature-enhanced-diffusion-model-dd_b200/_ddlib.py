@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("DD_LIB", os.path.join(_HERE, "libdd_b200.so"))  # DD_
 DD_OK, DD_ERR_INVALID, DD_ERR_CUDA, DD_ERR_NOT_CONVERGED, DD_ERR_NO_DEVICE, DD_ERR_DOMAIN = 0, -1, -2, -3, -4, -5
 VAR_INDEX = {"cp": 0, "T": 1, "cl": 2, "cd": 3, "cs": 4}
 VARS = ("cp", "T", "cl", "cd", "cs")
-MODE_NONE, MODE_ARRAYS, MODE_SEPARABLE, MODE_EXPSIN = 0, 1, 2, 3
+MODE_NONE, MODE_ARRAYS, MODE_SEPARABLE, MODE_EXPSIN, MODE_PROGRAM = 0, 1, 2, 3, 4
 PHI_INV1PT, PHI_EXP, PHI_LINEAR, PHI_OSC, PHI_CONST, PHI_HOST = 0, 1, 2, 3, 4, 5
 
 
@@ -34,6 +34,20 @@ class dd_model(C.Structure):
     _fields_ = [(n, C.c_double) for n in
                 ("K1", "K2", "K3", "K4", "DT", "Dl_max", "phi_l", "gamma_T", "Kd", "Sd", "Dd_max", "phi_d",
                  "phi_T", "r_sp", "T_ref", "eta")] + [("kind", C.c_int), ("reaction", C.c_int)]
+
+
+class dd_program_member(C.Structure):
+    """include/dd_b200_program.h"""
+    _fields_ = [("model", dd_model), ("t", C.c_double * 2), ("active", C.c_int), ("_pad", C.c_int)]
+
+
+class dd_program_args(C.Structure):
+    """include/dd_b200_program.h"""
+    _fields_ = [("x", C.POINTER(C.c_double)), ("y", C.POINTER(C.c_double)), ("xq", C.POINTER(C.c_double)),
+                ("yq", C.POINTER(C.c_double)), ("members", C.POINTER(dd_program_member)),
+                ("out", C.POINTER(C.c_double) * 5), ("mstride", C.c_longlong), ("N", C.c_int), ("M", C.c_int),
+                ("row0", C.c_int), ("nrows", C.c_int), ("ld", C.c_int), ("nmembers", C.c_int), ("what", C.c_int),
+                ("tslot", C.c_int)]
 
 
 class dd_pc_options(C.Structure):
@@ -76,6 +90,7 @@ SIGNATURES = {
     "dd_forcing_set_phi": (C.c_int, [_vp, C.c_int, C.c_int, _P(C.c_int), _dp]),
     "dd_forcing_expsin": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "dd_forcing_arrays": (C.c_int, [_vp, C.c_int, _P(_dp * 2 * 5)]),
+    "dd_forcing_program": (C.c_int, [_vp, C.c_char_p, C.c_ulonglong, _dp, _dp]),
     "dd_state_upload": (C.c_int, [_vp, C.c_int, C.c_int, _P(_dp * 5)]),
     "dd_state_download": (C.c_int, [_vp, C.c_int, C.c_int, _P(_dp * 5)]),
     "dd_state_fill_exact": (C.c_int, [_vp, C.c_int, _dp, C.c_int]),

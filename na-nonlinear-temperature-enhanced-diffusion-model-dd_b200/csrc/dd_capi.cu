@@ -43,6 +43,11 @@ struct dd_batch {
     int mode;
     DDForcing F;
     std::vector<double*> table_dev;
+    // DD_FORCING_PROGRAM: the loaded image, its kernel, what it is launched with
+    cudaLibrary_t prog_lib = nullptr;
+    cudaKernel_t prog_kernel = nullptr;
+    dd_program_member* d_prog_mem = nullptr;
+    const double *d_prog_xq = nullptr, *d_prog_yq = nullptr;
     std::vector<std::vector<double*>> slots;  // [slot][var]
     std::map<std::string, double*> work;
     double *d_t0, *d_dt;
@@ -99,6 +104,7 @@ struct dd_batch {
 };
 
 static int flush_pending(dd_batch* b, dd_step_stats* stats, int* have);  // verifies a deferred step
+static void free_tables(dd_batch* b);
 
 static void reset_ctl(dd_batch* b, bool all) {
     for (int m = 0; m < 2; ++m)
@@ -399,7 +405,8 @@ extern "C" int dd_batch_destroy(dd_batch* b) {
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
     for (double* p : b->geo_dev) cudaFree(p);
-    for (double* p : b->table_dev) cudaFree(p);
+    free_tables(b);
+    cudaFree(b->d_prog_mem);
     for (auto& s : b->slots) for (double* p : s) cudaFree(p);
     for (auto& kv : b->work) cudaFree(kv.second);
     for (auto& r : b->rec) {
@@ -456,6 +463,10 @@ static void free_tables(dd_batch* b) {
     for (double* p : b->table_dev) cudaFree(p);
     b->table_dev.clear();
     memset(&b->F.tab, 0, sizeof(b->F.tab));
+    if (b->prog_lib) cudaLibraryUnload(b->prog_lib);
+    b->prog_lib = nullptr;
+    b->prog_kernel = nullptr;
+    b->d_prog_xq = b->d_prog_yq = nullptr;
 }
 
 static int up_table(dd_batch* b, const double* h, size_t n, const double** dst) {
@@ -553,6 +564,83 @@ extern "C" int dd_forcing_expsin(dd_batch* b, const double* sx, const double* cx
     b->F.tab.nx = b->N + 1;
     b->F.tab.ny = b->M + 1;
     b->mode = DD_FORCING_EXPSIN;
+    return DD_OK;
+}
+
+// ---------------------------------------------------------------------------
+// generated forcing (include/dd_b200_program.h)
+// ---------------------------------------------------------------------------
+__global__ void k_pack_program_members(const DDMember* mem, dd_program_member* out, int nmem) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nmem) return;
+    const DDMember& mb = mem[m];
+    dd_program_member o;
+    o.model.K1 = mb.m.K1; o.model.K2 = mb.m.K2; o.model.K3 = mb.m.K3; o.model.K4 = mb.m.K4;
+    o.model.DT = mb.m.DT; o.model.Dl_max = mb.m.Dl_max; o.model.phi_l = mb.m.phi_l; o.model.gamma_T = mb.m.gamma_T;
+    o.model.Kd = mb.m.Kd; o.model.Sd = mb.m.Sd; o.model.Dd_max = mb.m.Dd_max; o.model.phi_d = mb.m.phi_d;
+    o.model.phi_T = mb.m.phi_T; o.model.r_sp = mb.m.r_sp; o.model.T_ref = mb.m.T_shift;
+    o.model.eta = mb.m.eta; o.model.kind = 2; o.model.reaction = mb.m.react;
+    o.t[0] = mb.t0;
+    o.t[1] = mb.t0 + mb.dt;
+    o.active = mb.active;
+    o._pad = 0;
+    out[m] = o;
+}
+
+// one launch of the program: `what` into the five arrays of `out`, at the members' current t0 (tslot 0) or
+// t0 + dt (tslot 1); rows: all local rows
+static int launch_program(dd_batch* b, int what, int tslot, const DDState& out) {
+    dd_ctx* ctx = b->ctx;
+    if (!b->prog_kernel) return fail(ctx, DD_ERR_INVALID, "no forcing program loaded");
+    if (b->B > 65535 || b->nrows > 65535) return fail(ctx, DD_ERR_INVALID, "forcing program: more than 65535 members or rows");
+    k_pack_program_members<<<(b->B + 127) / 128, 128, 0, ctx->stream>>>(b->d_mem, b->d_prog_mem, b->B);
+    CK(cudaGetLastError());
+    dd_program_args a;
+    memset(&a, 0, sizeof(a));
+    a.x = b->g.x; a.y = b->g.y; a.xq = b->d_prog_xq; a.yq = b->d_prog_yq;
+    a.members = b->d_prog_mem;
+    for (int v = 0; v < DD_NVAR; ++v) a.out[v] = out.v[v];
+    a.mstride = b->g.mstride;
+    a.N = b->N; a.M = b->M; a.row0 = b->row0; a.nrows = b->nrows; a.ld = b->g.ld; a.nmembers = b->B;
+    a.what = what; a.tslot = tslot;
+    void* params[1] = {&a};
+    const dim3 grid((unsigned)((b->M + 1 + 127) / 128), (unsigned)b->nrows, (unsigned)b->B);
+    const int phase = what == DD_PROGRAM_SOURCES ? PC_SOURCES : PC_OTHER;
+    CKP(phase, 2, cudaLaunchKernel((const void*)b->prog_kernel, grid, dim3(128, 1, 1), params, 0, ctx->stream));
+    return DD_OK;
+}
+
+extern "C" int dd_forcing_program(dd_batch* b, const void* image, unsigned long long image_bytes, const double* xq,
+                                  const double* yq) {
+    if (!b || !image || image_bytes == 0 || !xq || !yq) return DD_ERR_INVALID;
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    { const int rcf_ = flush_pending(b, nullptr, nullptr); if (rcf_ != DD_OK) return rcf_; }
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_tables(b);
+    b->mode = DD_FORCING_NONE;
+    // the loader keeps no reference to `image` after the call (it is copied into the library object)
+    cudaLibrary_t lib = nullptr;
+    cudaError_t e = cudaLibraryLoadData(&lib, image, nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, DD_ERR_INVALID, (std::string("forcing program: image rejected: ") + cudaGetErrorString(e)).c_str());
+    }
+    cudaKernel_t k = nullptr;
+    e = cudaLibraryGetKernel(&k, lib, "dd_program");
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaLibraryUnload(lib);
+        return fail(ctx, DD_ERR_INVALID, "forcing program: the image does not define the kernel dd_program");
+    }
+    b->prog_lib = lib;
+    b->prog_kernel = k;
+    int rc;
+    if ((rc = up_table(b, xq, (size_t)(b->N + 1) * 3, &b->d_prog_xq)) != DD_OK) return rc;
+    if ((rc = up_table(b, yq, (size_t)(b->M + 1) * 3, &b->d_prog_yq)) != DD_OK) return rc;
+    if (!b->d_prog_mem) CK(cudaMalloc((void**)&b->d_prog_mem, sizeof(dd_program_member) * b->B));
+    CK(cudaStreamSynchronize(ctx->stream));
+    b->mode = DD_FORCING_PROGRAM;
     return DD_OK;
 }
 
@@ -740,7 +828,8 @@ static int set_times(dd_batch* b, const double* t0, const double* dt, int n_t) {
 static int stage_sources(dd_batch* b, double t0, double dt, bool times_uniform, bool need_slot1,
                          int* carry = nullptr) {
     dd_ctx* ctx = b->ctx;
-    if ((b->mode != DD_FORCING_SEPARABLE && b->mode != DD_FORCING_EXPSIN) || b->fused_sources) {
+    const bool program = b->mode == DD_FORCING_PROGRAM;
+    if (!program && ((b->mode != DD_FORCING_SEPARABLE && b->mode != DD_FORCING_EXPSIN) || b->fused_sources)) {
         b->smode = b->mode;
         b->sF = b->F;
         return DD_OK;
@@ -763,7 +852,11 @@ static int stage_sources(dd_batch* b, double t0, double dt, bool times_uniform, 
         if (need_slot1 && b->src_has[0] && b->src_time[0] == t1) s0 = 1;  // keep a set that already holds t1
         DDState out;
         for (int v = 0; v < DD_NVAR; ++v) out.v[v] = b->src_set[s0][v];
-        CKP(PC_SOURCES, 1, dd_launch_eval_sources(launch_of(b, ROWS_ALL), b->mode, b->g, b->d_mem, b->F, out, 0));
+        if (program) {
+            if ((rc = launch_program(b, DD_PROGRAM_SOURCES, 0, out)) != DD_OK) return rc;
+        } else {
+            CKP(PC_SOURCES, 1, dd_launch_eval_sources(launch_of(b, ROWS_ALL), b->mode, b->g, b->d_mem, b->F, out, 0));
+        }
         b->src_has[s0] = times_uniform;
         b->src_time[s0] = t0;
     }
@@ -771,7 +864,11 @@ static int stage_sources(dd_batch* b, double t0, double dt, bool times_uniform, 
     if (need_slot1 && !(b->src_has[s1] && b->src_time[s1] == t1)) {
         DDState out;
         for (int v = 0; v < DD_NVAR; ++v) out.v[v] = b->src_set[s1][v];
-        CKP(PC_SOURCES, 1, dd_launch_eval_sources(launch_of(b, ROWS_ALL), b->mode, b->g, b->d_mem, b->F, out, 1));
+        if (program) {
+            if ((rc = launch_program(b, DD_PROGRAM_SOURCES, 1, out)) != DD_OK) return rc;
+        } else {
+            CKP(PC_SOURCES, 1, dd_launch_eval_sources(launch_of(b, ROWS_ALL), b->mode, b->g, b->d_mem, b->F, out, 1));
+        }
         b->src_has[s1] = times_uniform;
         b->src_time[s1] = t1;
     }
@@ -794,7 +891,11 @@ extern "C" int dd_state_fill_exact(dd_batch* b, int slot, const double* t, int n
     int rc = set_times(b, t, one.data(), n_t);
     if (rc != DD_OK) return rc;
     b->prev_valid = false;
-    CKP(PC_OTHER, 1, dd_launch_fill_exact(launch_of(b, ROWS_ALL), b->mode, b->g, b->d_mem, b->F, mstate(b, slot)));
+    if (b->mode == DD_FORCING_PROGRAM) {
+        if ((rc = launch_program(b, DD_PROGRAM_EXACT, 0, mstate(b, slot))) != DD_OK) return rc;
+    } else {
+        CKP(PC_OTHER, 1, dd_launch_fill_exact(launch_of(b, ROWS_ALL), b->mode, b->g, b->d_mem, b->F, mstate(b, slot)));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     return DD_OK;
 }
@@ -825,7 +926,12 @@ extern "C" int dd_eval_fields(dd_batch* b, int slot_in, int slot_out, const doub
     std::vector<double> one(n_t, 1.0);
     int rc = set_times(b, t, one.data(), n_t);
     if (rc != DD_OK) return rc;
-    CKP(PC_OTHER, 1, dd_launch_fields(launch_of(b), b->mode, b->g, b->d_mem, b->F, cstate(b, slot_in), mstate(b, slot_out), 0));
+    if (b->mode == DD_FORCING_PROGRAM) {
+        if ((rc = stage_sources(b, t[0], 1.0, n_t == 1, false)) != DD_OK) return rc;
+        CKP(PC_OTHER, 1, dd_launch_fields(launch_of(b), b->smode, b->g, b->d_mem, b->sF, cstate(b, slot_in), mstate(b, slot_out), 0));
+    } else {
+        CKP(PC_OTHER, 1, dd_launch_fields(launch_of(b), b->mode, b->g, b->d_mem, b->F, cstate(b, slot_in), mstate(b, slot_out), 0));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     return DD_OK;
 }
@@ -834,8 +940,21 @@ static int norms_async(dd_batch* b, int slot, int slot_exact, double* out_host) 
     dd_ctx* ctx = b->ctx;
     DDStateC ex;
     if (slot_exact >= 0) ex = cstate(b, slot_exact);
+    bool have_exact = slot_exact >= 0;
+    if (!have_exact && b->mode == DD_FORCING_PROGRAM) {
+        // the program writes the exact solution at the members' current time into scratch fields
+        static const char* names[DD_NVAR] = {"exact_cp", "exact_T", "exact_cl", "exact_cd", "exact_cs"};
+        DDState scratch;
+        int rc;
+        for (int v = 0; v < DD_NVAR; ++v) {
+            if ((rc = get_work(b, names[v], &scratch.v[v])) != DD_OK) return rc;
+            ex.v[v] = scratch.v[v];
+        }
+        if ((rc = launch_program(b, DD_PROGRAM_EXACT, 0, scratch)) != DD_OK) return rc;
+        have_exact = true;
+    }
     CKP(PC_NORMS, 2, dd_launch_error_norms(launch_of(b, ROWS_OWNED), b->mode, b->g, b->d_mem, b->F, cstate(b, slot),
-                                           slot_exact >= 0 ? &ex : nullptr, b->d_norm_partial, b->norm_bpm,
+                                           have_exact ? &ex : nullptr, b->d_norm_partial, b->norm_bpm,
                                            b->d_norm_out));
     CK(cudaMemcpyAsync(out_host, b->d_norm_out, sizeof(double) * 8 * b->B, cudaMemcpyDeviceToHost, ctx->stream));
     return DD_OK;

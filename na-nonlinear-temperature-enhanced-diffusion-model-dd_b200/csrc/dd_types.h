@@ -19,7 +19,9 @@ enum DDForcingMode {
     DD_FORCING_NONE = 0,       // NoForcingTerms (reference src/prob1base.py:852-869)
     DD_FORCING_ARRAYS = 1,     // host-evaluated source fields uploaded per step
     DD_FORCING_SEPARABLE = 2,  // u_v = phi_v(t) X_v(x) Y_v(y): 1-D tables + time profile
-    DD_FORCING_EXPSIN = 3      // MMSCaseExpSin closed form (reference src/prob1_mms_cases.py:296-337)
+    DD_FORCING_EXPSIN = 3,     // MMSCaseExpSin closed form (reference src/prob1_mms_cases.py:296-337)
+    DD_FORCING_PROGRAM = 4     // generated kernel (include/dd_b200_program.h); host-level mode only: the step kernels
+                               // see its output as ARRAYS
 };
 
 enum DDPhiKind {

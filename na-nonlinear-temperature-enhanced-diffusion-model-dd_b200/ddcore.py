@@ -16,7 +16,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 from _ddlib import DDNotConverged  # noqa: F401
-from _ddlib import (DD_OK, MODE_ARRAYS, MODE_EXPSIN, MODE_NONE, MODE_SEPARABLE, PHI_CONST, PHI_EXP, PHI_HOST,
+from _ddlib import (DD_OK, MODE_ARRAYS, MODE_EXPSIN, MODE_NONE, MODE_PROGRAM, MODE_SEPARABLE, PHI_CONST, PHI_EXP, PHI_HOST,
                     PHI_INV1PT, PHI_LINEAR, PHI_OSC, VARS, Context, as_f64, dd_model, dd_pc_options,
                     dd_step_stats, dptr, _dp, _vp)
 
@@ -242,6 +242,14 @@ class Batch:
                                                      C.byref(YQ), C.byref(kinds), C.byref(pp)),
                        "forcing_separable")
         self.mode, self.spec = MODE_SEPARABLE, spec
+
+    def forcing_program(self, program):
+        """Select generated forcing: `program` is a ddprogram.ProgramSpec (NVRTC image of the case's expressions)."""
+        xq = as_f64(quadrature_points(self.x).reshape(-1))
+        yq = as_f64(quadrature_points(self.y).reshape(-1))
+        self.ctx.check(self.lib.dd_forcing_program(self.handle, program.image, len(program.image), dptr(xq),
+                                                   dptr(yq)), "forcing_program")
+        self.mode, self.spec = MODE_PROGRAM, program
 
     def refresh_host_phi(self, t0: float, dt: float):
         """phi kinds evaluated on the host need their four values renewed for each (t0, dt)."""

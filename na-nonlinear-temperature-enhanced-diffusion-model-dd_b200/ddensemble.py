@@ -48,6 +48,21 @@ def _builtin_sum(terms: Sequence[np.ndarray]) -> np.ndarray:
         return np.where((comp != 0.0) & np.isfinite(comp), total + comp, total)
 
 
+def _device_description(case):
+    """Table description of the case's exact solution, else its generated program (arbitrary SymPy cases)."""
+    spec = case.device_spec()
+    if spec is None and hasattr(case, "device_program"):
+        spec = case.device_program()
+    return spec
+
+
+def _select_forcing(batch, spec):
+    if hasattr(spec, "image"):
+        batch.forcing_program(spec)
+    else:
+        batch.forcing_spec(spec)
+
+
 def combined_error_norms(norms: np.ndarray, dt) -> Dict[str, np.ndarray]:
     """Combined max-integral error norms of B members at once.
 
@@ -132,7 +147,7 @@ class TrajectoryEnsemble:
         # shared constants (per-member constants enter the sources on the device)
         self.case = mms_case_cls(grid=grid, model=self.models[0] if self.models else models[0],
                                  **(mms_case_params or {}))
-        self.spec = self.case.device_spec()
+        self.spec = _device_description(self.case)
         if self.spec is None:
             raise ValueError(f"{mms_case_cls.__name__} has no device description (device_spec() is None)")
         self.last_stats: List[dict] = []
@@ -149,7 +164,7 @@ class TrajectoryEnsemble:
         if batch is None:
             batch = ddcore.Batch(self.grid.x, self.grid.y, b - a, ctx=self.ctx, nslots=2)
             batch.set_models([ddcore.model_struct(m, e) for m, e in zip(self.models[a:b], self.etas[a:b])])
-            batch.forcing_spec(self.spec)
+            _select_forcing(batch, self.spec)
             self._batches[(a, b)] = batch
         return batch
 
@@ -235,11 +250,11 @@ class RefinementSweep:
             ctx = Context(self.device)
             batch = ddcore.Batch(grid.x, grid.y, len(ts), ctx=ctx, nslots=2)
             batch.set_models([ddcore.model_struct(self.model, t["eta"]) for t in ts])
-            spec = self.case_cls(grid=grid, model=self.model).device_spec()
+            spec = _device_description(self.case_cls(grid=grid, model=self.model))
             if spec is None:
                 batch.close()
                 raise ValueError(f"{self.case_cls.__name__} has no device description")
-            batch.forcing_spec(spec)
+            _select_forcing(batch, spec)
             g["ctx"], g["batch"] = ctx, batch
         batch = g["batch"]
         t0 = np.array([t["t0"] for t in ts])

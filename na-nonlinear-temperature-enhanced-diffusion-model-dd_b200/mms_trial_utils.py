@@ -103,7 +103,7 @@ def _device_trial(grid, integrator, case, initial_state, t0, dt, num_steps, vari
     if not bind.configure(t0, dt):
         return None
     b = bind.batch
-    if b.mode not in (ddcore.MODE_SEPARABLE, ddcore.MODE_EXPSIN):
+    if b.mode not in (ddcore.MODE_SEPARABLE, ddcore.MODE_EXPSIN, ddcore.MODE_PROGRAM):
         return None
     owner = bind._owner()
     if owner is None or getattr(owner, "mms_case", None) is not case:

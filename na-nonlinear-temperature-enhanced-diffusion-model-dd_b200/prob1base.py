@@ -526,6 +526,16 @@ class MMSCaseSymbolic(MMSCaseBase):
             self._spec = self._derive_separable_spec()
         return self._spec
 
+    def device_program(self):
+        """Generated forcing program (ddprogram.ProgramSpec) for expressions that are not separable: the five
+        expressions and their derivatives printed as CUDA C and compiled with NVRTC (the device counterpart of
+        the reference's lambdify, :1226-1280).  None when the expressions cannot be printed."""
+        if getattr(self, "_program", False) is False:
+            import ddprogram
+            t_var, x_var, y_var = self._vars3
+            self._program = ddprogram.program_for(self._exprs, t_var, x_var, y_var)
+        return self._program
+
     def _derive_separable_spec(self):
         t_var, x_var, y_var = self._vars3
         try:
@@ -829,6 +839,13 @@ class _DeviceBinding:
                 if getattr(b, "_spec_owner", None) is not spec:
                     b.forcing_spec(spec, t0, dt)
                     b._spec_owner = spec
+                return True
+            prog = (o.mms_case.device_program() if spec is None and hasattr(o.mms_case, "device_program")
+                    else None)
+            if prog is not None and o.mms_case.model is fld.model:
+                if getattr(b, "_spec_owner", None) is not prog:
+                    b.forcing_program(prog)
+                    b._spec_owner = prog
                 return True
         # generic path: evaluate the caller's source callables on the host and upload them
         g = fld.grid
