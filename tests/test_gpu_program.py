@@ -68,7 +68,9 @@ def test_program_steps_equal_host_forcing_steps(env, integrator):
     for n in ("Fcp", "FT", "Fcl", "Fcd", "Fcs"):
         a, b = getattr(field, n)(s, t0), getattr(field_h, n)(s, t0)
         assert np.max(np.abs(a - b)) <= 1e-12 * max(np.max(np.abs(b)), 1e-3), n
+    assert field.binding().configure(t0, dt)          # the grid's batch is shared: back from ARRAYS to the program
     b = field.binding().batch
+    assert b.mode == ddcore.MODE_PROGRAM
     b.fill_exact(1, t0 + 0.125)
     ex = b.download(1)
     for v in VARS:
@@ -137,7 +139,7 @@ def test_program_sweep_ensemble_and_slabs(env):
     N, M, t0, dt = 150, 40, 0.05, 2e-4
     grid = p1.make_uniform_grid(N, M)
     prog = env["Case"](grid=grid, model=model).device_program()
-    opts = env["ddcore"].pc_options(fixed_sweeps=5)
+    opts = env["ddcore"].pc_options(fixed_sweeps=4)
     meshes = ddmesh.SlabMesh.local_group(grid.x, grid.y, 3, halo=12)
     for m in meshes:
         m.batch.set_model(model, 50.0)
