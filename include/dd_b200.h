@@ -163,6 +163,15 @@ int dd_run_pc(dd_batch* b, int slot_a, int slot_b, const double* t0, const doubl
               const dd_pc_options* opt, double* norms_out, dd_step_stats* stats);
 int dd_run_feuler(dd_batch* b, int slot_a, int slot_b, const double* t0, const double* dt, int n_t, int nsteps,
                   double* norms_out);
+/* the same run loops with the per-step norms kept on the device and combined there: combined[m][6] = the
+ * combined max-integral error norm of member m over all variables (calculate_combined_error_norm,
+ * src/mms_trial_utils.py:15-53) and the per-variable figures cp, T, cl, cd, cs of NumericalErrorSummary
+ * (src/mms_trial_utils.py:150-190), bit for bit what the reference's Python arithmetic gives on the same norms
+ * (builtin sum(), trapezoid, `max(0.0, nan)` keeps 0.0).  Only 6 doubles per member cross PCIe. */
+int dd_run_pc_errors(dd_batch* b, int slot_a, int slot_b, const double* t0, const double* dt, int n_t, int nsteps,
+                     const dd_pc_options* opt, double* combined /* nmembers*6 */, dd_step_stats* stats);
+int dd_run_feuler_errors(dd_batch* b, int slot_a, int slot_b, const double* t0, const double* dt, int n_t, int nsteps,
+                         double* combined /* nmembers*6 */);
 void dd_pc_options_default(dd_pc_options* opt);
 
 /* ---- pieces of the step, for the class-level API and its tests ---------- */

@@ -106,6 +106,9 @@ SIGNATURES = {
     "dd_run_pc": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, _P(dd_pc_options), _dp,
                             _P(dd_step_stats)]),
     "dd_run_feuler": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, _dp]),
+    "dd_run_pc_errors": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, _P(dd_pc_options), _dp,
+                                   _P(dd_step_stats)]),
+    "dd_run_feuler_errors": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, _dp]),
     "dd_pc_options_default": (None, [_P(dd_pc_options)]),
     "dd_eval_fields": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int]),
     "dd_pc_predict": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int]),

@@ -61,6 +61,9 @@ struct dd_batch {
     int cs_cap_alloc;
     double *d_norm_partial, *d_norm_out;
     int norm_bpm;
+    double* d_series = nullptr;    // norm series of a run kept on the device (dd_run_*_errors)
+    size_t series_cap = 0;
+    double* d_combined = nullptr;  // [B][6]
     // staged sources: the MMS sources of a time level are evaluated once (k_eval_sources) into one of two
     // sets of five arrays and the step kernels read them in ARRAYS mode; the t1 set of a step is the t0
     // set of the next one.  smode / sF is what the step kernels are launched with.
@@ -418,6 +421,7 @@ extern "C" int dd_batch_destroy(dd_batch* b) {
     cudaFree(b->d_mem); cudaFree(b->d_t0); cudaFree(b->d_dt); cudaFree(b->d_stats); cudaFree(b->d_summary);
     cudaFree(b->d_itmax); cudaFree(b->d_itmin); cudaFree(b->d_used); cudaFree(b->d_norm_partial);
     cudaFree(b->d_norm_out);
+    cudaFree(b->d_series); cudaFree(b->d_combined);
     cudaFree(b->d_flags);
     dd_ctx* ctx = b->ctx;
     delete b;
@@ -936,7 +940,8 @@ extern "C" int dd_eval_fields(dd_batch* b, int slot_in, int slot_out, const doub
     return DD_OK;
 }
 
-static int norms_async(dd_batch* b, int slot, int slot_exact, double* out_host) {
+// error norms of `slot` into out_host (through b->d_norm_out) or, when out_dev is given, into that device buffer
+static int norms_async(dd_batch* b, int slot, int slot_exact, double* out_host, double* out_dev = nullptr) {
     dd_ctx* ctx = b->ctx;
     DDStateC ex;
     if (slot_exact >= 0) ex = cstate(b, slot_exact);
@@ -955,8 +960,9 @@ static int norms_async(dd_batch* b, int slot, int slot_exact, double* out_host) 
     }
     CKP(PC_NORMS, 2, dd_launch_error_norms(launch_of(b, ROWS_OWNED), b->mode, b->g, b->d_mem, b->F, cstate(b, slot),
                                            have_exact ? &ex : nullptr, b->d_norm_partial, b->norm_bpm,
-                                           b->d_norm_out));
-    CK(cudaMemcpyAsync(out_host, b->d_norm_out, sizeof(double) * 8 * b->B, cudaMemcpyDeviceToHost, ctx->stream));
+                                           out_dev ? out_dev : b->d_norm_out));
+    if (!out_dev)
+        CK(cudaMemcpyAsync(out_host, b->d_norm_out, sizeof(double) * 8 * b->B, cudaMemcpyDeviceToHost, ctx->stream));
     return DD_OK;
 }
 
@@ -1715,8 +1721,77 @@ extern "C" int dd_step_pc_deferred(dd_batch* b, int slot_in, int slot_out, const
     return DD_OK;
 }
 
-extern "C" int dd_run_pc(dd_batch* b, int slot_a, int slot_b, const double* t0, const double* dt, int n_t, int nsteps,
-                         const dd_pc_options* opt_in, double* norms_out, dd_step_stats* stats) {
+// ---------------------------------------------------------------------------
+// combined max-integral error norms on the device (calculate_combined_error_norm, reference
+// src/mms_trial_utils.py:15-53, and the per-variable figures of NumericalErrorSummary, :150-190), from the
+// per-step norms the run loop left in `series` [(nsteps + 1)][B][8] = H2[cp, T, cl, cd, cs], P2[T, cl, cd]:
+//   sup_k ( sum_v H2_v(t_k) + trapezoid_0^{t_k} sum_w P2_w ),  then the square root.
+// The arithmetic repeats the reference's Python operation by operation (explicit _rn intrinsics: no
+// contraction): the builtin sum() with its Neumaier compensation, `0.5 * dt * (a + b)`, and a maximum that a
+// NaN never replaces (`max(0.0, nan)`).  out[m][6] = overall, cp, T, cl, cd, cs.
+// ---------------------------------------------------------------------------
+__device__ double py_sum(const double* y, int n) {
+    double total = 0.0, comp = 0.0;
+    for (int k = 0; k < n; ++k) {
+        const double t = __dadd_rn(total, y[k]);
+        if (fabs(total) >= fabs(y[k])) comp = __dadd_rn(comp, __dadd_rn(__dsub_rn(total, t), y[k]));
+        else comp = __dadd_rn(comp, __dadd_rn(__dsub_rn(y[k], t), total));
+        total = t;
+    }
+    if (comp != 0.0 && isfinite(comp)) total = __dadd_rn(total, comp);
+    return total;
+}
+
+__global__ void k_combine_errors(const double* __restrict__ series, int K, int B, const double* __restrict__ dt,
+                                 int n_t, double* __restrict__ out) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= B) return;
+    const double half_dt = __dmul_rn(0.5, dt[n_t == 1 ? 0 : m]);
+    double best[6], run[6], prev[6];
+    for (int q = 0; q < 6; ++q) best[q] = run[q] = prev[q] = 0.0;
+    for (int k = 0; k < K; ++k) {
+        const double* r = series + ((size_t)k * B + m) * 8;
+        double H[5], P[3];
+        for (int v = 0; v < 5; ++v) H[v] = r[v];
+        for (int v = 0; v < 3; ++v) P[v] = r[5 + v];
+        const double hsq[6] = {py_sum(H, 5), H[0], H[1], H[2], H[3], H[4]};
+        const double ig[6] = {py_sum(P, 3), 0.0, P[0], P[1], P[2], 0.0};
+        for (int q = 0; q < 6; ++q) {
+            if (k > 0) run[q] = __dadd_rn(run[q], __dmul_rn(half_dt, __dadd_rn(prev[q], ig[q])));
+            const double val = __dadd_rn(hsq[q], run[q]);
+            if (val > best[q]) best[q] = val;
+            prev[q] = ig[q];
+        }
+    }
+    for (int q = 0; q < 6; ++q) out[(size_t)m * 6 + q] = __dsqrt_rn(best[q]);
+}
+
+// device buffer for the norm series of a run ((nsteps + 1) * B * 8 doubles) and the combined figures (B * 6)
+static int ensure_series(dd_batch* b, int nsteps) {
+    dd_ctx* ctx = b->ctx;
+    const size_t need = (size_t)(nsteps + 1) * b->B * 8;
+    if (need > b->series_cap) {
+        if (b->d_series) CK(cudaFree(b->d_series));
+        b->d_series = nullptr;
+        b->series_cap = 0;
+        CK(cudaMalloc((void**)&b->d_series, need * sizeof(double)));
+        b->series_cap = need;
+    }
+    if (!b->d_combined) CK(cudaMalloc((void**)&b->d_combined, sizeof(double) * 6 * b->B));
+    return DD_OK;
+}
+
+static int combine_async(dd_batch* b, int nsteps, int n_t, double* combined_host) {
+    dd_ctx* ctx = b->ctx;
+    k_combine_errors<<<(b->B + 127) / 128, 128, 0, ctx->stream>>>(b->d_series, nsteps + 1, b->B, b->d_dt, n_t,
+                                                                  b->d_combined);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(combined_host, b->d_combined, sizeof(double) * 6 * b->B, cudaMemcpyDeviceToHost, ctx->stream));
+    return DD_OK;
+}
+
+static int run_pc_loop(dd_batch* b, int slot_a, int slot_b, const double* t0, const double* dt, int n_t, int nsteps,
+                       const dd_pc_options* opt_in, double* norms_out, double* combined_out, dd_step_stats* stats) {
     if (!b || !slot_ok(b, slot_a) || !slot_ok(b, slot_b) || slot_a == slot_b || nsteps < 0) return DD_ERR_INVALID;
     dd_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
@@ -1728,7 +1803,10 @@ extern "C" int dd_run_pc(dd_batch* b, int slot_a, int slot_b, const double* t0, 
     if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
     int cur = slot_a, nxt = slot_b;
     const size_t nstride = (size_t)8 * b->B;
-    if (norms_out && (rc = norms_async(b, cur, -1, norms_out)) != DD_OK) return rc;
+    if (combined_out && (rc = ensure_series(b, nsteps)) != DD_OK) return rc;
+    const bool want = norms_out || combined_out;
+    double* const ser = combined_out ? b->d_series : nullptr;  // the series stays on the device
+    if (want && (rc = norms_async(b, cur, -1, norms_out, ser)) != DD_OK) return rc;
     double th = t0[0];  // host mirror of the device-side time advance (same IEEE additions)
     int carry = -1;
     for (int s = 0; s < nsteps; ++s) {
@@ -1736,15 +1814,28 @@ extern "C" int dd_run_pc(dd_batch* b, int slot_a, int slot_b, const double* t0, 
         th = th + dt[0];
         if ((rc = pc_step_retry(b, cur, nxt, opt, stats)) != DD_OK) return rc;
         CKP(PC_TIME, 1, dd_launch_time_coefs(launch_of(b), b->mode, b->d_mem, b->d_t0, b->d_dt, n_t, 1));
-        if (norms_out && (rc = norms_async(b, nxt, -1, norms_out + (s + 1) * nstride)) != DD_OK) return rc;
+        if (want && (rc = norms_async(b, nxt, -1, norms_out ? norms_out + (s + 1) * nstride : nullptr,
+                                      ser ? ser + (s + 1) * nstride : nullptr)) != DD_OK) return rc;
         const int tmp = cur; cur = nxt; nxt = tmp;
     }
+    if (combined_out && (rc = combine_async(b, nsteps, n_t, combined_out)) != DD_OK) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     return DD_OK;
 }
 
-extern "C" int dd_run_feuler(dd_batch* b, int slot_a, int slot_b, const double* t0, const double* dt, int n_t,
-                             int nsteps, double* norms_out) {
+extern "C" int dd_run_pc(dd_batch* b, int slot_a, int slot_b, const double* t0, const double* dt, int n_t, int nsteps,
+                         const dd_pc_options* opt_in, double* norms_out, dd_step_stats* stats) {
+    return run_pc_loop(b, slot_a, slot_b, t0, dt, n_t, nsteps, opt_in, norms_out, nullptr, stats);
+}
+
+extern "C" int dd_run_pc_errors(dd_batch* b, int slot_a, int slot_b, const double* t0, const double* dt, int n_t,
+                                int nsteps, const dd_pc_options* opt_in, double* combined_out, dd_step_stats* stats) {
+    if (!combined_out) return DD_ERR_INVALID;
+    return run_pc_loop(b, slot_a, slot_b, t0, dt, n_t, nsteps, opt_in, nullptr, combined_out, stats);
+}
+
+static int run_feuler_loop(dd_batch* b, int slot_a, int slot_b, const double* t0, const double* dt, int n_t,
+                           int nsteps, double* norms_out, double* combined_out) {
     if (!b || !slot_ok(b, slot_a) || !slot_ok(b, slot_b) || slot_a == slot_b || nsteps < 0) return DD_ERR_INVALID;
     b->prev_valid = false;
     dd_ctx* ctx = b->ctx;
@@ -1754,19 +1845,36 @@ extern "C" int dd_run_feuler(dd_batch* b, int slot_a, int slot_b, const double* 
     if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
     int cur = slot_a, nxt = slot_b;
     const size_t nstride = (size_t)8 * b->B;
-    if (norms_out && (rc = norms_async(b, cur, -1, norms_out)) != DD_OK) return rc;
+    if (combined_out && (rc = ensure_series(b, nsteps)) != DD_OK) return rc;
+    const bool want = norms_out || combined_out;
+    double* const ser = combined_out ? b->d_series : nullptr;
+    if (want && (rc = norms_async(b, cur, -1, norms_out, ser)) != DD_OK) return rc;
     double th = t0[0];
     for (int s = 0; s < nsteps; ++s) {
         if ((rc = stage_sources(b, th, dt[0], n_t == 1, false)) != DD_OK) return rc;
         th = th + dt[0];
         CKP(PC_FEULER, 1, dd_launch_feuler(launch_of(b), b->smode, b->g, b->d_mem, b->sF, cstate(b, cur), mstate(b, nxt)));
         CKP(PC_TIME, 1, dd_launch_time_coefs(launch_of(b), b->mode, b->d_mem, b->d_t0, b->d_dt, n_t, 1));
-        if (norms_out && (rc = norms_async(b, nxt, -1, norms_out + (s + 1) * nstride)) != DD_OK) return rc;
+        if (want && (rc = norms_async(b, nxt, -1, norms_out ? norms_out + (s + 1) * nstride : nullptr,
+                                      ser ? ser + (s + 1) * nstride : nullptr)) != DD_OK) return rc;
         const int tmp = cur; cur = nxt; nxt = tmp;
     }
+    if (combined_out && (rc = combine_async(b, nsteps, n_t, combined_out)) != DD_OK) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     return DD_OK;
 }
+
+extern "C" int dd_run_feuler(dd_batch* b, int slot_a, int slot_b, const double* t0, const double* dt, int n_t,
+                             int nsteps, double* norms_out) {
+    return run_feuler_loop(b, slot_a, slot_b, t0, dt, n_t, nsteps, norms_out, nullptr);
+}
+
+extern "C" int dd_run_feuler_errors(dd_batch* b, int slot_a, int slot_b, const double* t0, const double* dt, int n_t,
+                                    int nsteps, double* combined_out) {
+    if (!combined_out) return DD_ERR_INVALID;
+    return run_feuler_loop(b, slot_a, slot_b, t0, dt, n_t, nsteps, nullptr, combined_out);
+}
+
 
 // ---------------------------------------------------------------------------
 // pieces of the step (class-level API)

@@ -394,6 +394,27 @@ class Batch:
                                           dptr(out) if norms else None, C.byref(st)), "run_pc")
         return (slot_a if nsteps % 2 == 0 else slot_b), out, st.as_dict()
 
+    def run_errors(self, slot_a: int, slot_b: int, t0, dt, nsteps: int, opt: Optional[dd_pc_options] = None,
+                   integrator: str = "pc"):
+        """nsteps steps with the error norms of every step taken and combined on the device: returns
+        dict(overall (B,), per_var (B, 5)) = the combined max-integral norms of the reference
+        (src/mms_trial_utils.py:15-53, 150-190) and, for "pc", the step statistics."""
+        t0, dt, n = self._times(t0, dt)
+        if self.mode == MODE_SEPARABLE and any(p.kind == "host" for p in self.spec.phi):
+            raise ValueError("run_errors needs device-evaluable time profiles (phi kind != host)")
+        out = np.zeros((self.B, 6))
+        st = None
+        if integrator == "pc":
+            opt = opt or pc_options()
+            st = dd_step_stats()
+            self.ctx.check(self.lib.dd_run_pc_errors(self.handle, slot_a, slot_b, dptr(t0), dptr(dt), n, nsteps,
+                                                     C.byref(opt), dptr(out), C.byref(st)), "run_pc_errors")
+            st = st.as_dict()
+        else:
+            self.ctx.check(self.lib.dd_run_feuler_errors(self.handle, slot_a, slot_b, dptr(t0), dptr(dt), n, nsteps,
+                                                         dptr(out)), "run_feuler_errors")
+        return dict(overall=out[:, 0].copy(), per_var=out[:, 1:].copy()), st
+
     def run_feuler(self, slot_a: int, slot_b: int, t0, dt, nsteps: int, norms: bool = False):
         t0, dt, n = self._times(t0, dt)
         if self.mode == MODE_SEPARABLE and any(p.kind == "host" for p in self.spec.phi):

@@ -73,7 +73,8 @@ def combined_error_norms(norms: np.ndarray, dt) -> Dict[str, np.ndarray]:
     norms = np.asarray(norms, dtype=np.float64)
     K, B, _ = norms.shape
     dt = np.broadcast_to(np.asarray(dt, dtype=np.float64), (B,))
-    h2, p2 = norms[:, :, :5], norms[:, :, 5:]
+    planes = np.ascontiguousarray(np.moveaxis(norms, 2, 0))  # (8, K, B): one contiguous plane per quantity
+    h2, p2 = planes[:5], planes[5:]
 
     def sup(hsq, integrand):
         best = np.zeros(B)
@@ -86,13 +87,13 @@ def combined_error_norms(norms: np.ndarray, dt) -> Dict[str, np.ndarray]:
         return np.sqrt(best)
 
     # the reference adds the variables with the builtin sum(), which compensates (Neumaier) since Python 3.12
-    hs = _builtin_sum([h2[:, :, v] for v in range(5)])
-    ig = _builtin_sum([p2[:, :, v] for v in range(3)])
+    hs = _builtin_sum([h2[v] for v in range(5)])
+    ig = _builtin_sum([p2[v] for v in range(3)])
     overall = sup(hs, ig)
     per_var = np.zeros((B, 5))
     zero = np.zeros((K, B))
     for v in range(5):
-        per_var[:, v] = sup(h2[:, :, v], p2[:, :, v - 1] if 1 <= v <= 3 else zero)
+        per_var[:, v] = sup(h2[v], p2[v - 1] if 1 <= v <= 3 else zero)
     return dict(overall=overall, per_var=per_var)
 
 
@@ -191,12 +192,10 @@ class TrajectoryEnsemble:
             batch = self._batch(a, b)
             batch.fill_exact(0, t0)
             dts = dt_used[a:b] if len(sd) > 1 else dt_used[a:a + 1]
-            if self.integrator == "pc":
-                _, norms, st = batch.run_pc(0, 1, t0, dts, nsteps, self.opt, norms=True)
+            # time loop, per-step norms and their combination all on the device: 6 doubles per member come back
+            res, st = batch.run_errors(0, 1, t0, dts, nsteps, self.opt, integrator=self.integrator)
+            if st is not None:
                 self.last_stats.append(st)
-            else:
-                _, norms = batch.run_feuler(0, 1, t0, dts, nsteps, norms=True)
-            res = combined_error_norms(norms, dt_used[a:b])
             overall[a:b], per_var[a:b] = res["overall"], res["per_var"]
         return dict(overall=overall, per_var=per_var, dt_used=np.array(dt_used), nsteps=nsteps)
 
@@ -260,8 +259,7 @@ class RefinementSweep:
         t0 = np.array([t["t0"] for t in ts])
         batch.fill_exact(0, t0)
         dts = np.array([t["dt_used"] for t in ts])
-        _, norms, _ = batch.run_pc(0, 1, t0, dts, nsteps, self.opt, norms=True)
-        res = combined_error_norms(norms, dts)
+        res, _ = batch.run_errors(0, 1, t0, dts, nsteps, self.opt)
         return [(k, float(res["overall"][q]), res["per_var"][q]) for q, k in enumerate(g["members"])]
 
     def close(self):

@@ -223,3 +223,43 @@ def test_blown_up_trial_propagates_nan_like_the_reference(mods):
     wv = np.array([want["per_var"][v] for v in VARS])
     assert gv[4] == 0.0
     assert np.all(np.abs(gv - wv) <= 1e-9 * np.abs(wv)), (gv, wv)
+
+
+def test_device_combined_norms_equal_the_python_arithmetic_bit_for_bit(mods):
+    """dd_run_pc_errors / dd_run_feuler_errors keep the per-step norms on the device and combine them there; the
+    result must be what the reference's Python arithmetic (builtin sum(), trapezoid, max that skips NaN) gives on
+    the same norms - compared exactly, on a healthy ensemble with per-member dt and on the blown-up trial."""
+    import ddcore
+    p1, ens = mods["p1"], mods["ens"]
+    model = mods["product_model"](NOTEBOOK_MODEL["pol"])
+    rng = np.random.default_rng(7)
+    for N, B, Tf, dts, etas in ((12, 7, 0.004, 0.004 / 8 * rng.uniform(0.9, 1.0, 7), 10.0 ** rng.uniform(1, 3, 7)),
+                                (32, 2, 10.0, np.array([1.0, 1.0]), np.array([50.0, 20.0]))):
+        grid = p1.make_uniform_grid(N, N)
+        nsteps = int(np.ceil(Tf / dts[0]))
+        dt_used = np.full(B, Tf / nsteps) if N == 32 else dts
+        b = ddcore.Batch(grid.x, grid.y, B)
+        b.set_models([ddcore.model_struct(model, float(e)) for e in etas])
+        b.forcing_spec(mods["CASES"]["scp_fast1e1"](grid=grid, model=model).device_spec())
+        # a fixed sweep count makes two runs of the same trial produce the same fields bit for bit (the adaptive
+        # plan learns between runs); the blown-up trial needs the adaptive plan and is compared to rounding level
+        opt = ddcore.pc_options(fixed_sweeps=8) if N == 12 else ddcore.pc_options()
+        for integrator in ("pc", "feuler"):
+            b.fill_exact(0, 0.0)
+            if integrator == "pc":
+                _, norms, _ = b.run_pc(0, 1, 0.0, dt_used, nsteps, opt, norms=True)
+            else:
+                _, norms = b.run_feuler(0, 1, 0.0, dt_used, nsteps, norms=True)
+            want = ens.combined_error_norms(norms, dt_used)
+            b.fill_exact(0, 0.0)
+            got, _ = b.run_errors(0, 1, 0.0, dt_used, nsteps, opt, integrator=integrator)
+            if N == 12 or integrator == "feuler":
+                assert np.array_equal(got["overall"], want["overall"]), (N, integrator, got["overall"], want["overall"])
+                assert np.array_equal(got["per_var"], want["per_var"]), (N, integrator)
+            else:
+                assert np.array_equal(got["overall"] == 0, want["overall"] == 0)
+                assert np.array_equal(got["per_var"] == 0, want["per_var"] == 0)
+                assert np.allclose(got["per_var"], want["per_var"], rtol=1e-9, atol=0)
+            if N == 32 and integrator == "pc":
+                assert np.isnan(norms).any() and got["overall"][0] == 0.0        # the blow-up really is in this run
+        b.close()
