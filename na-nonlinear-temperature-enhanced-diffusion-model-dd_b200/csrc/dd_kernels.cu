@@ -1133,13 +1133,15 @@ __global__ void __launch_bounds__(DD_BLOCK, DD_MINB) k_error_partial(DDGeom g, c
                                                             double* __restrict__ partial, int own0, int own1,
                                                             int bpm) {
     __shared__ double sh[8][DD_BLOCK / 32];
+    __shared__ double se[FROM_ARRAY ? 1 : 3][FROM_ARRAY ? 1 : DD_BLOCK];
     const NodeIdx n = node_index(g, own0, own1, bpm);
     const DDMember& mb = mem[n.member];
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double e[DD_NVAR], ew[DD_NVAR], es[DD_NVAR];
+    for (int v = 0; v < DD_NVAR; ++v) e[v] = ew[v] = es[v] = 0.0;
     if (n.valid) {
         const int i = g.row0 + n.r, j = n.j;
         const long long o = n.member * g.mstride + (long long)n.r * g.ld + j;
-        double e[DD_NVAR], ew[DD_NVAR], es[DD_NVAR];
         const bool need_w = i >= 1 && j >= 1 && j <= g.M - 1;  // D-x at (i,j), i = 1..N, j interior
         const bool need_s = j >= 1 && i >= 1 && i <= g.N - 1;
         if (FROM_ARRAY) {
@@ -1152,13 +1154,38 @@ __global__ void __launch_bounds__(DD_BLOCK, DD_MINB) k_error_partial(DDGeom g, c
             double u[DD_NVAR];
             dd_exact_values<MODE>(F, mb, 0, i, j, u);
             for (int v = 0; v < DD_NVAR; ++v) e[v] = s.v[v][o] - u[v];
+        }
+    }
+    if (!FROM_ARRAY) {
+        // The errors at (i-1, j) and (i, j-1) are those of threads t - (M+1) and t - 1 (nodes are numbered row
+        // by row within a member): taken from shared memory when that thread is in this block, evaluated here
+        // otherwise -- the same expression on the same operands either way.
+        for (int q = 0; q < 3; ++q) se[q][threadIdx.x] = n.valid ? e[DD_T + q] : 0.0;
+        __syncthreads();
+    }
+    if (n.valid) {
+        const int i = g.row0 + n.r, j = n.j;
+        const long long o = n.member * g.mstride + (long long)n.r * g.ld + j;
+        const bool need_w = i >= 1 && j >= 1 && j <= g.M - 1;
+        const bool need_s = j >= 1 && i >= 1 && i <= g.N - 1;
+        if (!FROM_ARRAY) {
+            double u[DD_NVAR];
+            const int tw = (int)threadIdx.x - (g.M + 1), ts = (int)threadIdx.x - 1;
             if (need_w) {
-                dd_exact_values<MODE>(F, mb, 0, i - 1, j, u);
-                for (int v = 0; v < DD_NVAR; ++v) ew[v] = s.v[v][o - g.ld] - u[v];
+                if (tw >= 0 && n.r > own0) {
+                    for (int q = 0; q < 3; ++q) ew[DD_T + q] = se[q][tw];
+                } else {
+                    dd_exact_values<MODE>(F, mb, 0, i - 1, j, u);
+                    for (int v = 0; v < DD_NVAR; ++v) ew[v] = s.v[v][o - g.ld] - u[v];
+                }
             }
             if (need_s) {
-                dd_exact_values<MODE>(F, mb, 0, i, j - 1, u);
-                for (int v = 0; v < DD_NVAR; ++v) es[v] = s.v[v][o - 1] - u[v];
+                if (ts >= 0) {
+                    for (int q = 0; q < 3; ++q) es[DD_T + q] = se[q][ts];
+                } else {
+                    dd_exact_values<MODE>(F, mb, 0, i, j - 1, u);
+                    for (int v = 0; v < DD_NVAR; ++v) es[v] = s.v[v][o - 1] - u[v];
+                }
             }
         }
         if (dd_is_interior(g, i, j)) {
