@@ -61,9 +61,8 @@ struct dd_batch {
     int cs_cap_alloc;
     double *d_norm_partial, *d_norm_out;
     int norm_bpm;
-    double* d_series = nullptr;    // norm series of a run kept on the device (dd_run_*_errors)
-    size_t series_cap = 0;
-    double* d_combined = nullptr;  // [B][6]
+    double* d_combine_state = nullptr;  // dd_run_*_errors: running best / integral / last integrand, [B][18]
+    double* d_combined = nullptr;       // [B][6]
     // staged sources: the MMS sources of a time level are evaluated once (k_eval_sources) into one of two
     // sets of five arrays and the step kernels read them in ARRAYS mode; the t1 set of a step is the t0
     // set of the next one.  smode / sF is what the step kernels are launched with.
@@ -421,7 +420,7 @@ extern "C" int dd_batch_destroy(dd_batch* b) {
     cudaFree(b->d_mem); cudaFree(b->d_t0); cudaFree(b->d_dt); cudaFree(b->d_stats); cudaFree(b->d_summary);
     cudaFree(b->d_itmax); cudaFree(b->d_itmin); cudaFree(b->d_used); cudaFree(b->d_norm_partial);
     cudaFree(b->d_norm_out);
-    cudaFree(b->d_series); cudaFree(b->d_combined);
+    cudaFree(b->d_combine_state); cudaFree(b->d_combined);
     cudaFree(b->d_flags);
     dd_ctx* ctx = b->ctx;
     delete b;
@@ -1724,7 +1723,7 @@ extern "C" int dd_step_pc_deferred(dd_batch* b, int slot_in, int slot_out, const
 // ---------------------------------------------------------------------------
 // combined max-integral error norms on the device (calculate_combined_error_norm, reference
 // src/mms_trial_utils.py:15-53, and the per-variable figures of NumericalErrorSummary, :150-190), from the
-// per-step norms the run loop left in `series` [(nsteps + 1)][B][8] = H2[cp, T, cl, cd, cs], P2[T, cl, cd]:
+// per-step norms [B][8] = H2[cp, T, cl, cd, cs], P2[T, cl, cd], folded in after every step:
 //   sup_k ( sum_v H2_v(t_k) + trapezoid_0^{t_k} sum_w P2_w ),  then the square root.
 // The arithmetic repeats the reference's Python operation by operation (explicit _rn intrinsics: no
 // contraction): the builtin sum() with its Neumaier compensation, `0.5 * dt * (a + b)`, and a maximum that a
@@ -1742,49 +1741,57 @@ __device__ double py_sum(const double* y, int n) {
     return total;
 }
 
-__global__ void k_combine_errors(const double* __restrict__ series, int K, int B, const double* __restrict__ dt,
-                                 int n_t, double* __restrict__ out) {
+// running state per member: best[6], run[6], prev[6] (updated after every step: the norm series is never stored)
+__global__ void k_combine_update(const double* __restrict__ norms, int B, const double* __restrict__ dt, int n_t,
+                                 int first, double* __restrict__ state) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= B) return;
     const double half_dt = __dmul_rn(0.5, dt[n_t == 1 ? 0 : m]);
-    double best[6], run[6], prev[6];
-    for (int q = 0; q < 6; ++q) best[q] = run[q] = prev[q] = 0.0;
-    for (int k = 0; k < K; ++k) {
-        const double* r = series + ((size_t)k * B + m) * 8;
-        double H[5], P[3];
-        for (int v = 0; v < 5; ++v) H[v] = r[v];
-        for (int v = 0; v < 3; ++v) P[v] = r[5 + v];
-        const double hsq[6] = {py_sum(H, 5), H[0], H[1], H[2], H[3], H[4]};
-        const double ig[6] = {py_sum(P, 3), 0.0, P[0], P[1], P[2], 0.0};
-        for (int q = 0; q < 6; ++q) {
-            if (k > 0) run[q] = __dadd_rn(run[q], __dmul_rn(half_dt, __dadd_rn(prev[q], ig[q])));
-            const double val = __dadd_rn(hsq[q], run[q]);
-            if (val > best[q]) best[q] = val;
-            prev[q] = ig[q];
-        }
+    const double* r = norms + (size_t)m * 8;
+    double* st = state + (size_t)m * 18;
+    double H[5], P[3];
+    for (int v = 0; v < 5; ++v) H[v] = r[v];
+    for (int v = 0; v < 3; ++v) P[v] = r[5 + v];
+    const double hsq[6] = {py_sum(H, 5), H[0], H[1], H[2], H[3], H[4]};
+    const double ig[6] = {py_sum(P, 3), 0.0, P[0], P[1], P[2], 0.0};
+    for (int q = 0; q < 6; ++q) {
+        double best = first ? 0.0 : st[q], run = first ? 0.0 : st[6 + q];
+        if (!first) run = __dadd_rn(run, __dmul_rn(half_dt, __dadd_rn(st[12 + q], ig[q])));
+        const double val = __dadd_rn(hsq[q], run);
+        if (val > best) best = val;
+        st[q] = best;
+        st[6 + q] = run;
+        st[12 + q] = ig[q];
     }
-    for (int q = 0; q < 6; ++q) out[(size_t)m * 6 + q] = __dsqrt_rn(best[q]);
 }
 
-// device buffer for the norm series of a run ((nsteps + 1) * B * 8 doubles) and the combined figures (B * 6)
-static int ensure_series(dd_batch* b, int nsteps) {
+__global__ void k_combine_final(const double* __restrict__ state, int B, double* __restrict__ out) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= B) return;
+    for (int q = 0; q < 6; ++q) out[(size_t)m * 6 + q] = __dsqrt_rn(state[(size_t)m * 18 + q]);
+}
+
+static int ensure_combine(dd_batch* b) {
     dd_ctx* ctx = b->ctx;
-    const size_t need = (size_t)(nsteps + 1) * b->B * 8;
-    if (need > b->series_cap) {
-        if (b->d_series) CK(cudaFree(b->d_series));
-        b->d_series = nullptr;
-        b->series_cap = 0;
-        CK(cudaMalloc((void**)&b->d_series, need * sizeof(double)));
-        b->series_cap = need;
-    }
+    if (!b->d_combine_state) CK(cudaMalloc((void**)&b->d_combine_state, sizeof(double) * 18 * b->B));
     if (!b->d_combined) CK(cudaMalloc((void**)&b->d_combined, sizeof(double) * 6 * b->B));
     return DD_OK;
 }
 
-static int combine_async(dd_batch* b, int nsteps, int n_t, double* combined_host) {
+// error norms of `slot` at the members' current time, folded into the running combination
+static int norms_combine_async(dd_batch* b, int slot, int n_t, bool first) {
     dd_ctx* ctx = b->ctx;
-    k_combine_errors<<<(b->B + 127) / 128, 128, 0, ctx->stream>>>(b->d_series, nsteps + 1, b->B, b->d_dt, n_t,
-                                                                  b->d_combined);
+    int rc = norms_async(b, slot, -1, nullptr, b->d_norm_out);
+    if (rc != DD_OK) return rc;
+    k_combine_update<<<(b->B + 127) / 128, 128, 0, ctx->stream>>>(b->d_norm_out, b->B, b->d_dt, n_t, first ? 1 : 0,
+                                                                  b->d_combine_state);
+    CK(cudaGetLastError());
+    return DD_OK;
+}
+
+static int combine_async(dd_batch* b, double* combined_host) {
+    dd_ctx* ctx = b->ctx;
+    k_combine_final<<<(b->B + 127) / 128, 128, 0, ctx->stream>>>(b->d_combine_state, b->B, b->d_combined);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(combined_host, b->d_combined, sizeof(double) * 6 * b->B, cudaMemcpyDeviceToHost, ctx->stream));
     return DD_OK;
@@ -1803,10 +1810,9 @@ static int run_pc_loop(dd_batch* b, int slot_a, int slot_b, const double* t0, co
     if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
     int cur = slot_a, nxt = slot_b;
     const size_t nstride = (size_t)8 * b->B;
-    if (combined_out && (rc = ensure_series(b, nsteps)) != DD_OK) return rc;
-    const bool want = norms_out || combined_out;
-    double* const ser = combined_out ? b->d_series : nullptr;  // the series stays on the device
-    if (want && (rc = norms_async(b, cur, -1, norms_out, ser)) != DD_OK) return rc;
+    if (combined_out && (rc = ensure_combine(b)) != DD_OK) return rc;
+    if (norms_out && (rc = norms_async(b, cur, -1, norms_out)) != DD_OK) return rc;
+    if (combined_out && (rc = norms_combine_async(b, cur, n_t, true)) != DD_OK) return rc;
     double th = t0[0];  // host mirror of the device-side time advance (same IEEE additions)
     int carry = -1;
     for (int s = 0; s < nsteps; ++s) {
@@ -1814,11 +1820,11 @@ static int run_pc_loop(dd_batch* b, int slot_a, int slot_b, const double* t0, co
         th = th + dt[0];
         if ((rc = pc_step_retry(b, cur, nxt, opt, stats)) != DD_OK) return rc;
         CKP(PC_TIME, 1, dd_launch_time_coefs(launch_of(b), b->mode, b->d_mem, b->d_t0, b->d_dt, n_t, 1));
-        if (want && (rc = norms_async(b, nxt, -1, norms_out ? norms_out + (s + 1) * nstride : nullptr,
-                                      ser ? ser + (s + 1) * nstride : nullptr)) != DD_OK) return rc;
+        if (norms_out && (rc = norms_async(b, nxt, -1, norms_out + (s + 1) * nstride)) != DD_OK) return rc;
+        if (combined_out && (rc = norms_combine_async(b, nxt, n_t, false)) != DD_OK) return rc;
         const int tmp = cur; cur = nxt; nxt = tmp;
     }
-    if (combined_out && (rc = combine_async(b, nsteps, n_t, combined_out)) != DD_OK) return rc;
+    if (combined_out && (rc = combine_async(b, combined_out)) != DD_OK) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     return DD_OK;
 }
@@ -1845,21 +1851,20 @@ static int run_feuler_loop(dd_batch* b, int slot_a, int slot_b, const double* t0
     if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
     int cur = slot_a, nxt = slot_b;
     const size_t nstride = (size_t)8 * b->B;
-    if (combined_out && (rc = ensure_series(b, nsteps)) != DD_OK) return rc;
-    const bool want = norms_out || combined_out;
-    double* const ser = combined_out ? b->d_series : nullptr;
-    if (want && (rc = norms_async(b, cur, -1, norms_out, ser)) != DD_OK) return rc;
+    if (combined_out && (rc = ensure_combine(b)) != DD_OK) return rc;
+    if (norms_out && (rc = norms_async(b, cur, -1, norms_out)) != DD_OK) return rc;
+    if (combined_out && (rc = norms_combine_async(b, cur, n_t, true)) != DD_OK) return rc;
     double th = t0[0];
     for (int s = 0; s < nsteps; ++s) {
         if ((rc = stage_sources(b, th, dt[0], n_t == 1, false)) != DD_OK) return rc;
         th = th + dt[0];
         CKP(PC_FEULER, 1, dd_launch_feuler(launch_of(b), b->smode, b->g, b->d_mem, b->sF, cstate(b, cur), mstate(b, nxt)));
         CKP(PC_TIME, 1, dd_launch_time_coefs(launch_of(b), b->mode, b->d_mem, b->d_t0, b->d_dt, n_t, 1));
-        if (want && (rc = norms_async(b, nxt, -1, norms_out ? norms_out + (s + 1) * nstride : nullptr,
-                                      ser ? ser + (s + 1) * nstride : nullptr)) != DD_OK) return rc;
+        if (norms_out && (rc = norms_async(b, nxt, -1, norms_out + (s + 1) * nstride)) != DD_OK) return rc;
+        if (combined_out && (rc = norms_combine_async(b, nxt, n_t, false)) != DD_OK) return rc;
         const int tmp = cur; cur = nxt; nxt = tmp;
     }
-    if (combined_out && (rc = combine_async(b, nsteps, n_t, combined_out)) != DD_OK) return rc;
+    if (combined_out && (rc = combine_async(b, combined_out)) != DD_OK) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     return DD_OK;
 }
