@@ -147,3 +147,30 @@ def test_separable_cases_keep_their_tables_and_unprintable_cases_have_no_program
     f = sympy.Function("mystery")
     bad = dict(nonseparable_exprs(), cs_sym_expr=f(x * y + t))
     assert ddprogram.program_for({k[:-9]: v for k, v in bad.items()}, t, x, y) is None
+
+
+def test_dirac_and_sign_follow_the_reference_lambdify_rules(tmp_path):
+    """|x - 1/2| with a grid node exactly on the kink: the Laplacian holds 2 DiracDelta(x - 1/2), which the
+    reference's lambdify evaluates as (|arg| < 1e-13 ? 1 : 0) (src/prob1base.py:1226-1247), and the gradient holds
+    sign(x - 1/2) = 0 there.  The generated program must give the same sources as the host callables."""
+    grid = p1.make_uniform_grid(8, 6)
+    model = product_model(MODEL)
+    ex = dict(nonseparable_exprs(),
+              T_sym_expr=1 + sympy.Abs(x - sympy.Rational(1, 2)) * (1 + y * t) / 5,
+              cd_sym_expr=sympy.exp(-t) * sympy.Abs(y - sympy.Rational(1, 2)) * sympy.cos(x * y) / 2)
+    case = p1.MMSCaseSymbolic(grid=grid, model=model, **ex)
+    assert case.device_spec() is None
+    src = ddprogram.generate_source(case._exprs, t, x, y)
+    assert "dd_dirac(" in src and "dd_sign(" in src
+    (tmp_path / "prog.c").write_text(src)
+    subprocess.run(["gcc", "-std=c99", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"),
+                    "-o", str(tmp_path / "prog.so"), str(tmp_path / "prog.c"), "-lm"], check=True)
+    lib = C.CDLL(str(tmp_path / "prog.so"))
+    forcing = p1.ForcingTerms_RegHCsTriple(mms_case=case, model=model, regularization_factor=50.0)
+    got = run_host(lib, grid, [member(model, 50.0, "regh", 0.2, 0.25)], 0, 0)
+    want = [getattr(forcing, n)(0.2, grid.xx, grid.yy) for n in ("fcp", "fT", "fcl", "fcd", "fcs")]
+    for g, w, n in zip(got, want, "cp T cl cd cs".split()):
+        assert np.max(np.abs(g[0] - w)) <= 2e-14 * max(1.0, np.max(np.abs(w))), n
+    # the delta really contributes on the kink line (and only there)
+    lapT = case.lap_T(0.2, grid.xx, grid.yy)
+    assert np.all(lapT[4, :] != 0) and np.all(lapT[3, :] == 0)
