@@ -12,7 +12,8 @@
  *
  * The image (cubin or PTX) must define
  *     extern "C" __global__ void dd_program(dd_program_args a);
- * launched with block (128,1,1) and grid (ceil((M+1)/128), nrows, nmembers): thread (j, r, m) owns node
+ * launched with block (128,1,1) and grid (ceil((M+1)/128), nrows, nmembers) -- hence at most 65535 rows and 65535
+ * members per batch in this mode (dd_forcing_program batches beyond that are refused at launch): thread (j, r, m) owns node
  * (row0 + r, j) of member m and writes a.out[v][m * mstride + r * ld + j] for v = cp, T, cl, cd, cs:
  *   what == DD_PROGRAM_SOURCES: the five MMS sources at time members[m].t[tslot] (fcp: 3x3 Gauss average over
  *                               the dual cell at interior nodes, 0 on the boundary, src/prob1base.py:493-598);
