@@ -14,6 +14,7 @@
 
 #include "../../include/dd_b200.h"
 #include "dd_kernels.cuh"
+#include "dd_combine.cuh"
 #include "dd_tables_host.h"
 
 #define DD_VERSION_STR "dd_b200 0.1 (sm_100a)"
@@ -1721,48 +1722,14 @@ extern "C" int dd_step_pc_deferred(dd_batch* b, int slot_in, int slot_out, const
 }
 
 // ---------------------------------------------------------------------------
-// combined max-integral error norms on the device (calculate_combined_error_norm, reference
-// src/mms_trial_utils.py:15-53, and the per-variable figures of NumericalErrorSummary, :150-190), from the
-// per-step norms [B][8] = H2[cp, T, cl, cd, cs], P2[T, cl, cd], folded in after every step:
-//   sup_k ( sum_v H2_v(t_k) + trapezoid_0^{t_k} sum_w P2_w ),  then the square root.
-// The arithmetic repeats the reference's Python operation by operation (explicit _rn intrinsics: no
-// contraction): the builtin sum() with its Neumaier compensation, `0.5 * dt * (a + b)`, and a maximum that a
-// NaN never replaces (`max(0.0, nan)`).  out[m][6] = overall, cp, T, cl, cd, cs.
+// combined max-integral error norms on the device (csrc/dd_combine.cuh): running state per member, updated
+// after every step -- the norm series is never stored.  out[m][6] = overall, cp, T, cl, cd, cs.
 // ---------------------------------------------------------------------------
-__device__ double py_sum(const double* y, int n) {
-    double total = 0.0, comp = 0.0;
-    for (int k = 0; k < n; ++k) {
-        const double t = __dadd_rn(total, y[k]);
-        if (fabs(total) >= fabs(y[k])) comp = __dadd_rn(comp, __dadd_rn(__dsub_rn(total, t), y[k]));
-        else comp = __dadd_rn(comp, __dadd_rn(__dsub_rn(y[k], t), total));
-        total = t;
-    }
-    if (comp != 0.0 && isfinite(comp)) total = __dadd_rn(total, comp);
-    return total;
-}
-
-// running state per member: best[6], run[6], prev[6] (updated after every step: the norm series is never stored)
 __global__ void k_combine_update(const double* __restrict__ norms, int B, const double* __restrict__ dt, int n_t,
                                  int first, double* __restrict__ state) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= B) return;
-    const double half_dt = __dmul_rn(0.5, dt[n_t == 1 ? 0 : m]);
-    const double* r = norms + (size_t)m * 8;
-    double* st = state + (size_t)m * 18;
-    double H[5], P[3];
-    for (int v = 0; v < 5; ++v) H[v] = r[v];
-    for (int v = 0; v < 3; ++v) P[v] = r[5 + v];
-    const double hsq[6] = {py_sum(H, 5), H[0], H[1], H[2], H[3], H[4]};
-    const double ig[6] = {py_sum(P, 3), 0.0, P[0], P[1], P[2], 0.0};
-    for (int q = 0; q < 6; ++q) {
-        double best = first ? 0.0 : st[q], run = first ? 0.0 : st[6 + q];
-        if (!first) run = __dadd_rn(run, __dmul_rn(half_dt, __dadd_rn(st[12 + q], ig[q])));
-        const double val = __dadd_rn(hsq[q], run);
-        if (val > best) best = val;
-        st[q] = best;
-        st[6 + q] = run;
-        st[12 + q] = ig[q];
-    }
+    dd_combine_fold(norms + (size_t)m * 8, dt[n_t == 1 ? 0 : m], first, state + (size_t)m * 18);
 }
 
 __global__ void k_combine_final(const double* __restrict__ state, int B, double* __restrict__ out) {

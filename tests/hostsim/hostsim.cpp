@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "dd_nodeprog.cuh"
+#include "dd_combine.cuh"
 #include "dd_tables_host.h"
 
 struct HSProblem {
@@ -258,6 +259,19 @@ extern "C" int hs_pc_step(const HSProblem* P, const double* const in[5], double*
     for (size_t p = 0; p < n; ++p) {
         out[DD_CP][p] = cp1p[p]; out[DD_T][p] = u.v[DD_T][p]; out[DD_CL][p] = u.v[DD_CL][p];
         out[DD_CD][p] = u.v[DD_CD][p]; out[DD_CS][p] = cs1p[p];
+    }
+    return 0;
+}
+
+
+// combined error norms of B members from a norm series [K][B][8] (the arithmetic of k_combine_update /
+// k_combine_final): out[B][6]
+extern "C" int hs_combine(const double* series, int K, int B, const double* dt, int n_t, double* out) {
+    std::vector<double> st(18);
+    for (int m = 0; m < B; ++m) {
+        for (int k = 0; k < K; ++k)
+            dd_combine_fold(series + ((size_t)k * B + m) * 8, dt[n_t == 1 ? 0 : m], k == 0, st.data());
+        for (int q = 0; q < 6; ++q) out[(size_t)m * 6 + q] = sqrt(st[q]);
     }
     return 0;
 }

@@ -30,7 +30,7 @@ class HSProblem(C.Structure):
 def build():
     os.makedirs(BUILD, exist_ok=True)
     src = os.path.join(HERE, "hostsim", "hostsim.cpp")
-    deps = [src] + [os.path.join(CSRC, f) for f in ("dd_types.h", "dd_physics.cuh", "dd_nodeprog.cuh")]
+    deps = [src] + [os.path.join(CSRC, f) for f in ("dd_types.h", "dd_physics.cuh", "dd_nodeprog.cuh", "dd_combine.cuh")]
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-I", CSRC,
@@ -45,7 +45,7 @@ def lib():
     global _lib
     if _lib is None:
         _lib = C.CDLL(build())
-        for n in ("hs_fields", "hs_feuler", "hs_exact", "hs_pc_step"):
+        for n in ("hs_fields", "hs_feuler", "hs_exact", "hs_pc_step", "hs_combine"):
             getattr(_lib, n).restype = C.c_int
     return _lib
 

@@ -55,6 +55,43 @@ def test_vectorised_combined_norm_equals_scalar_one():
             assert a == b or (np.isnan(a) and np.isnan(b)), (m, name, a, b)
 
 
+def test_device_combination_arithmetic_equals_python_on_the_host():
+    """csrc/dd_combine.cuh (what k_combine_update / k_combine_final run after every step of dd_run_*_errors),
+    compiled for the host: bit for bit the scalar Python arithmetic, on magnitudes spread over many decades (so
+    that the Neumaier correction of sum() matters), with NaN, Inf and all-zero members."""
+    import ctypes as C
+    import ddensemble
+    import hostsim_util as hu
+    import mms_trial_utils as mtu
+    rng = np.random.default_rng(11)
+    K, B = 23, 40
+    norms = rng.random((K, B, 8)) * 10.0 ** rng.integers(-18, 2, (K, B, 8))
+    norms[7:, 3, 4] = np.nan
+    norms[5, 4, 6] = np.nan
+    norms[9:, 6, 2] = np.inf
+    norms[:, 8, :] = 0.0
+    norms[0, 9, :] = 0.0
+    dt = rng.random(B) * 1e-2 + 1e-4
+    out = np.zeros((B, 6))
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    series = np.ascontiguousarray(norms)
+    assert hu.lib().hs_combine(dp(series), K, B, dp(dt), B, dp(out)) == 0
+    res = ddensemble.combined_error_norms(norms, dt)
+    assert np.array_equal(out[:, 0], res["overall"], equal_nan=True)
+    assert np.array_equal(out[:, 1:], res["per_var"], equal_nan=True)
+    names, integral = list(mtu.VARS), ["T", "cl", "cd"]
+    for m in (0, 3, 4, 6, 8, 9):
+        ser = mtu._series_from_norms(np.arange(K) * dt[m], norms[:, m, :], names, integral)
+        want = mtu.NumericalErrorSummary(dt[m], ser, names, integral)
+        assert out[m, 0] == want.overall_combined_error or (np.isnan(out[m, 0]) and np.isnan(want.overall_combined_error))
+    # one dt for all members
+    one = np.array([dt[0]])
+    out1 = np.zeros((B, 6))
+    assert hu.lib().hs_combine(dp(series), K, B, dp(one), 1, dp(out1)) == 0
+    res1 = ddensemble.combined_error_norms(norms, dt[0])
+    assert np.array_equal(out1[:, 0], res1["overall"], equal_nan=True)
+
+
 def test_steps_and_dt_follow_the_trial_rule():
     import ddensemble
     assert ddensemble.steps_and_dt(0.01, (1 / 256) ** 1.5) == (41, 0.01 / 41)
