@@ -580,6 +580,90 @@ for _v in VARS:
 
 
 # ----------------------------------------------------------------------------
+# MMS case from plain callables (reference :895-1155): derivatives by second-order finite differences.
+# Host-only by nature (the solution is an opaque Python function): its forcing goes through the ARRAYS mode.
+# ----------------------------------------------------------------------------
+
+# (offsets in units of eps, integer weights, divisor as a function of eps) of the second-order difference
+# formulas; summed left to right so that the rounding is that of the reference's written-out expressions
+_FD_FIRST = {"center": ((1, -1), (1, -1), lambda e: 2 * e),
+             "forward": ((0, 1, 2), (-3, 4, -1), lambda e: 2 * e),
+             "backward": ((0, -1, -2), (3, -4, 1), lambda e: 2 * e)}
+_FD_SECOND = {"center": ((1, 0, -1), (1, -2, 1), lambda e: e * e),
+              "forward": ((0, 1, 2, 3), (2, -5, 4, -1), lambda e: e * e),
+              "backward": ((0, -1, -2, -3), (2, -5, 4, -1), lambda e: e * e)}
+
+
+def pack_analytical_txy_with_o2fdm_derivatives(fn, *, default_eps: float = 1e-6, time_stepping: str = "center"):
+    """`fn(t, x, y)` -> `g(t, x, y, *, d=(dt, dx, dy), op=None, small_eps=None)`: derivatives of combined order
+    <= 2 by second-order finite differences of step eps (one-sided in t for "forward" / "backward"), and
+    `op="laplacian"` (or "lap") for the five-point Laplacian.  Same interface and formulas as the reference's
+    helper (:895-1031)."""
+    if time_stepping not in _FD_FIRST:
+        raise ValueError("Invalid time stepping strategy")
+
+    def line(t, x, y, axis, table, eps):
+        offsets, weights, divisor = table
+        acc = None
+        for off, w in zip(offsets, weights):
+            s = off * eps
+            term = fn(t + s if axis == 0 else t, x + s if axis == 1 else x, y + s if axis == 2 else y)
+            if abs(w) != 1:
+                term = abs(w) * term
+            acc = (term if w > 0 else -term) if acc is None else (acc + term if w > 0 else acc - term)
+        return acc / divisor(eps)
+
+    def enhanced(t, x, y, *, d=(0, 0, 0), op=None, small_eps=None):
+        eps = small_eps or default_eps
+        if op is not None:
+            if op.lower() not in ("laplacian", "lap"):
+                raise ValueError(f"Unknown operator: {op}. Use 'laplacian'/'lap'")
+            return (fn(t, x + eps, y) + fn(t, x - eps, y) + fn(t, x, y + eps) + fn(t, x, y - eps)
+                    - 4 * fn(t, x, y)) / (eps * eps)
+        nt, nx, ny = d
+        if any(k not in (0, 1, 2) for k in (nt, nx, ny)):
+            raise ValueError("Individual derivatives must be 0, 1, or 2")
+        if nt + nx + ny > 2:
+            raise ValueError("Combined derivative order must be 0, 1, or 2")
+        if nt:  # (a time derivative takes precedence over spatial ones, as in the reference)
+            return line(t, x, y, 0, (_FD_FIRST if nt == 1 else _FD_SECOND)[time_stepping], eps)
+        if nx == 1 and ny == 1:
+            return (fn(t, x + eps, y + eps) - fn(t, x + eps, y - eps) - fn(t, x - eps, y + eps)
+                    + fn(t, x - eps, y - eps)) / (4 * eps * eps)
+        if nx:
+            return line(t, x, y, 1, (_FD_FIRST if nx == 1 else _FD_SECOND)["center"], eps)
+        if ny:
+            return line(t, x, y, 2, (_FD_FIRST if ny == 1 else _FD_SECOND)["center"], eps)
+        return fn(t, x, y)
+
+    return enhanced
+
+
+class MMSCaseFromAnalytic(MMSCaseBase):
+    """Exact solution given as five Python callables `f(t, xx, yy)` (reference :1034-1155); the derivatives the
+    forcing needs come from `pack_analytical_txy_with_o2fdm_derivatives`."""
+
+    def __init__(self, model, *, grid, cp_base, T_base, cl_base, cd_base, cs_base):
+        super().__init__(grid, model)
+        self.cp_ex, self.T_ex, self.cl_ex, self.cd_ex, self.cs_ex = (
+            pack_analytical_txy_with_o2fdm_derivatives(f) for f in (cp_base, T_base, cl_base, cd_base, cs_base))
+
+
+def _make_analytic_method(var, kw):
+    def method(self, t, xx, yy):
+        return getattr(self, var + "_ex")(t, xx, yy, **kw)
+    return method
+
+
+for _v in VARS:
+    setattr(MMSCaseFromAnalytic, _v, _make_analytic_method(_v, {}))
+    for _k, _d in (("dt", (1, 0, 0)), ("dx", (0, 1, 0)), ("dy", (0, 0, 1))):
+        setattr(MMSCaseFromAnalytic, f"{_k}_{_v}", _make_analytic_method(_v, {"d": _d}))
+for _v in ("T", "cl", "cd"):
+    setattr(MMSCaseFromAnalytic, f"lap_{_v}", _make_analytic_method(_v, {"op": "lap"}))
+
+
+# ----------------------------------------------------------------------------
 # state (reference src/prob1base.py:1913-2085)
 # ----------------------------------------------------------------------------
 

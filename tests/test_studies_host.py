@@ -213,3 +213,49 @@ def test_reference_study_modules_load_on_this_core():
             assert theirs.device_spec() is not None, name
     trial = ref_mtu.MMSTrial  # constructing it needs a device (state upload); the class itself resolves
     assert callable(trial)
+
+
+def test_analytic_case_finite_differences_and_errors():
+    """MMSCaseFromAnalytic / pack_analytical_txy_with_o2fdm_derivatives (reference src/prob1base.py:895-1155):
+    second-order differences against exact derivatives, the precedence and error rules of the interface, and a
+    host forcing object built on such a case against the same solution given symbolically."""
+    import sympy
+    import prob1base as p1
+    from test_hostsim import product_model
+    from test_program_codegen import MODEL
+    t, x, y = p1.t_sym, p1.x_sym, p1.y_sym
+    expr = sympy.exp(-t) * sympy.sin(2 * x + y * t) + x * y ** 2
+    f = sympy.lambdify([t, x, y], expr, "numpy")
+    X, Y = np.meshgrid(np.linspace(0.1, 0.9, 6), np.linspace(0.2, 0.8, 5), indexing="ij")
+    exact = lambda d: sympy.lambdify([t, x, y], sympy.diff(expr, *([t] * d[0] + [x] * d[1] + [y] * d[2])), "numpy")(0.3, X, Y)
+    for ts in ("center", "forward", "backward"):
+        g = p1.pack_analytical_txy_with_o2fdm_derivatives(f, default_eps=1e-4, time_stepping=ts)
+        assert np.array_equal(g(0.3, X, Y), f(0.3, X, Y))
+        for d in ((1, 0, 0), (2, 0, 0), (0, 1, 0), (0, 2, 0), (0, 0, 1), (0, 0, 2), (0, 1, 1)):
+            assert np.max(np.abs(g(0.3, X, Y, d=d) - exact(d))) <= 2e-6, (ts, d)   # O(eps^2) + rounding / eps^2
+        assert np.max(np.abs(g(0.3, X, Y, op="Laplacian") - exact((0, 2, 0)) - exact((0, 0, 2)))) <= 2e-6
+        assert np.array_equal(g(0.3, X, Y, d=(1, 1, 0)), g(0.3, X, Y, d=(1, 0, 0)))   # a time derivative wins
+        assert np.max(np.abs(g(0.3, X, Y, d=(0, 1, 0), small_eps=1e-3) - exact((0, 1, 0)))) <= 1e-5
+    g = p1.pack_analytical_txy_with_o2fdm_derivatives(f)
+    for bad in (dict(op="grad"), dict(d=(3, 0, 0)), dict(d=(0, 2, 1))):
+        with pytest.raises(ValueError):
+            g(0.3, X, Y, **bad)
+    with pytest.raises(ValueError):
+        p1.pack_analytical_txy_with_o2fdm_derivatives(f, time_stepping="sideways")
+    # a case from callables next to the same case from expressions
+    grid = p1.make_uniform_grid(6, 5)
+    model = product_model(MODEL)
+    exprs = dict(cp=sympy.exp(-t) * x * (1 - x) * y * (1 - y), T=1 + sympy.sin(x + y + t) / 10, cl=sympy.cos(x * y + t) / 3,
+                 cd=sympy.exp(-t - x) / 2, cs=sympy.sin(sympy.pi * x) * sympy.cos(t) / 4)
+    sym = p1.MMSCaseSymbolic(grid=grid, model=model, **{k + "_sym_expr": v for k, v in exprs.items()})
+    ana = p1.MMSCaseFromAnalytic(model, grid=grid, **{k + "_base": sympy.lambdify([t, x, y], v, "numpy")
+                                                      for k, v in exprs.items()})
+    assert ana.device_spec() is None and ana.grid is grid and ana.model is model
+    for name in ("cp", "dt_cs", "dx_T", "dy_cl", "lap_cd", "lap_T", "dx_cp"):
+        a, b = getattr(ana, name)(0.2, grid.xx, grid.yy), getattr(sym, name)(0.2, grid.xx, grid.yy)
+        assert np.max(np.abs(a - b)) <= 5e-3 * max(1.0, np.max(np.abs(b))), name   # eps = 1e-6: rounding / eps^2 ~ 1e-3
+    fa = p1.ForcingTerms_RegHCsTriple(mms_case=ana, model=model, regularization_factor=50.0)
+    fs = p1.ForcingTerms_RegHCsTriple(mms_case=sym, model=model, regularization_factor=50.0)
+    for name in ("fcp", "fT", "fcl", "fcd", "fcs"):
+        a, b = getattr(fa, name)(0.2, grid.xx, grid.yy), getattr(fs, name)(0.2, grid.xx, grid.yy)
+        assert np.max(np.abs(a - b)) <= 1e-6 * max(1.0, np.max(np.abs(b))) + 1e-6, name
