@@ -134,10 +134,35 @@ def scenarios():
                               [1.0, 2.0, 1.5], [1.0, 1.0, 0.5], [0.5, 0.25, 0.3], [3.0, 2.0, 2.0 - 1e-17, 1.0],
                               [0.0, 0.0, 0.0], [1.0, 0.1, 0.01, 0.001], [1.0, 0.5, 0.25]],
                   rate_factors=[2.0, 2.0, 2.0, 2.0, 2.0, 2.0, 2.0, 10.0, 3.0]))
+    # the finite-difference helper behind MMSCaseFromAnalytic
+    S.append(dict(name="analytic_fd", kind="analytic", nx=7, ny=5, t=0.3))
     return S
 
 
 # ----------------------------------------------------------------------------
+
+ANALYTIC_DERIVS = [(0, 0, 0), (1, 0, 0), (2, 0, 0), (0, 1, 0), (0, 2, 0), (0, 0, 1), (0, 0, 2), (0, 1, 1), (1, 1, 0)]
+
+
+def analytic_fn(t, x, y):
+    """the callable differentiated by the `analytic` fixture (the test restates it)"""
+    return np.exp(-t) * np.sin(2 * x + y * t) + x * y ** 2
+
+
+def run_analytic(d):
+    """pack_analytical_txy_with_o2fdm_derivatives of the live reference (src/prob1base.py:895-1031): every
+    derivative selector, the Laplacian and a caller-chosen step, for the three time-stepping strategies."""
+    p1, _, _ = _ref()
+    X, Y = np.meshgrid(np.linspace(0, 1, d["nx"]), np.linspace(0, 1, d["ny"]), indexing="ij")
+    out = {"X": X, "Y": Y}
+    for ts in ("center", "forward", "backward"):
+        g = p1.pack_analytical_txy_with_o2fdm_derivatives(analytic_fn, time_stepping=ts)
+        for dd in ANALYTIC_DERIVS:
+            out[f"{ts}_d{dd[0]}{dd[1]}{dd[2]}"] = g(d["t"], X, Y, d=dd)
+        out[f"{ts}_lap"] = g(d["t"], X, Y, op="lap")
+        out[f"{ts}_d020_eps1e-4"] = g(d["t"], X, Y, d=(0, 2, 0), small_eps=1e-4)
+    return out
+
 
 def make_xy(gd):
     N, M = gd["N"], gd["M"]
@@ -319,7 +344,7 @@ def main():
         if args.only and args.only not in d["name"]:
             continue
         print("scenario", d["name"], flush=True)
-        arrays = {"steps": run_steps, "trial": run_trial, "cvg": run_cvg}[d["kind"]](d)
+        arrays = {"steps": run_steps, "trial": run_trial, "cvg": run_cvg, "analytic": run_analytic}[d["kind"]](d)
         np.savez_compressed(os.path.join(OUT_DIR, d["name"] + ".npz"),
                             __desc__=np.array(json.dumps(d)), __meta__=np.array(json.dumps(meta)), **arrays)
 

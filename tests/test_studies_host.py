@@ -259,3 +259,27 @@ def test_analytic_case_finite_differences_and_errors():
     for name in ("fcp", "fT", "fcl", "fcd", "fcs"):
         a, b = getattr(fa, name)(0.2, grid.xx, grid.yy), getattr(fs, name)(0.2, grid.xx, grid.yy)
         assert np.max(np.abs(a - b)) <= 1e-6 * max(1.0, np.max(np.abs(b))) + 1e-6, name
+
+
+def test_analytic_helper_equals_the_reference_bit_for_bit():
+    """tests/golden/analytic_fd.npz holds the outputs of the live reference's finite-difference helper
+    (oracle/make_golden.py, `run_analytic`) for the callable restated below."""
+    import prob1base as p1
+    from golden_util import load_fixture
+    desc, z = load_fixture("analytic_fd")
+    fn = lambda t, x, y: np.exp(-t) * np.sin(2 * x + y * t) + x * y ** 2
+    X, Y, t = z["X"], z["Y"], desc["t"]
+    checked = 0
+    for ts in ("center", "forward", "backward"):
+        g = p1.pack_analytical_txy_with_o2fdm_derivatives(fn, time_stepping=ts)
+        for key in [k for k in z.files if k.startswith(ts + "_")]:
+            sel = key[len(ts) + 1:]
+            if sel == "lap":
+                got = g(t, X, Y, op="lap")
+            elif sel.endswith("_eps1e-4"):
+                got = g(t, X, Y, d=(0, 2, 0), small_eps=1e-4)
+            else:
+                got = g(t, X, Y, d=tuple(int(c) for c in sel[1:]))
+            assert np.array_equal(got, z[key]), key
+            checked += 1
+    assert checked == 33
