@@ -250,7 +250,7 @@ extern "C" int dd_ctx_create(int device, void* cuda_stream, dd_ctx** out) {
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     ctx->sm_count = prop.multiProcessorCount;
-    if (dd_solver_configure() != cudaSuccess) {
+    if (dd_solver_configure() != cudaSuccess || dd_wave_configure() != cudaSuccess) {
         cudaGetLastError();
         delete ctx;
         return DD_ERR_CUDA;
@@ -1323,10 +1323,22 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
     // on the physical boundary do not shrink.
     int v0 = b->asm0, v1 = b->asm1;
     const bool lo_edge = (b->row0 == 0), hi_edge = (b->row0 + b->nrows == b->N + 1);
+    // wide grids: wavefront kernel (rows marched once per pass, no row halo); the previous step's increment as
+    // initial iterate is only known to the tile kernels
+    const bool wave = dd_wave_ok(b->g, L) && !vold;
     while (left > 0) {
         DDSolvePlan P;
         memset(&P, 0, sizeof(P));
-        plan_pass(b, left, true, var == DD_T, &P);
+        if (wave) {
+            // as many sweeps per pass as the ring of the widest fitting kernel variant holds
+            const int cap_all = dd_wave_max_sweeps(var == DD_T), cap_wide = 7;
+            P.sweeps = left <= cap_all ? left : cap_wide;
+            P.last_pass = P.sweeps == left ? 1 : 0;
+            P.const_band = var == DD_T ? 1 : 0;
+            P.halo = 2 * P.sweeps + 1;
+        } else {
+            plan_pass(b, left, true, var == DD_T, &P);
+        }
         P.rho_fix = b->relax_rho[vi];
         if (P.sweeps <= 0) return fail(ctx, DD_ERR_INVALID, "no feasible solver tile");
         double* xout = nullptr;
@@ -1358,8 +1370,13 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
             xin = x0;
             vo = nullptr;
         }
-        CKP(PC_SOLVE_T + (var - DD_T), 1,
-            dd_launch_solve_pass(Lp, b->g, b->d_mem, R, xin, vo, xout, vstar, vnew, var == DD_T ? 1 : 0, st, P));
+        if (wave)
+            CKP(PC_SOLVE_T + (var - DD_T), 1,
+                dd_launch_solve_wave(Lp, b->g, b->d_mem, R, xin, xout, vstar, vnew, var == DD_T ? 1 : 0, st,
+                                     P.const_band, P.sweeps, P.last_pass, P.rho_fix));
+        else
+            CKP(PC_SOLVE_T + (var - DD_T), 1,
+                dd_launch_solve_pass(Lp, b->g, b->d_mem, R, xin, vo, xout, vstar, vnew, var == DD_T ? 1 : 0, st, P));
         left -= P.sweeps;
         xin = xout;
         if (!P.last_pass) {

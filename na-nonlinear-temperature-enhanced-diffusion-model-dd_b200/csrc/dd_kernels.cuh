@@ -45,6 +45,15 @@ struct DDSolvePlan {
 
 cudaError_t dd_solver_configure();  // opt-in to large dynamic shared memory (once per process)
 
+// wavefront solver (dd_wave.cu): one pass of `sweeps` red-black SOR sweeps marching down column strips; wide grids
+cudaError_t dd_wave_configure();
+bool dd_wave_ok(const DDGeom& g, const DDLaunch& L);
+int dd_wave_max_sweeps(int const_band);
+cudaError_t dd_launch_solve_wave(const DDLaunch& L, const DDGeom& g, const DDMember* mem, const DDRows& R,
+                                 const double* xin, double* xout, const double* vstar, double* vnew,
+                                 int zero_boundary, DDSolveStats* stats, int const_band, int sweeps, int last_pass,
+                                 double rho_fix);
+
 // marching form of the predictor (sources as arrays or none, wide grids); fuse_T also assembles the
 // constant-band T system of the first Newton step into R.bb / R.aW and the Gershgorin ratio into stats
 bool dd_predict_march_ok(const DDGeom& g, const DDLaunch& L, int mode);

@@ -28,6 +28,7 @@
 #include <cudaTypedefs.h>
 
 #include "dd_kernels.cuh"
+#include "dd_sor.cuh"
 
 __device__ __forceinline__ void atomic_max_nn(double* addr, double v) {
     atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(fabs(v)));
@@ -243,12 +244,12 @@ __global__ void __launch_bounds__(512) k_rbsor_tile(SolveArgs A) {
                     if (CONST_BAND) {
                         const int sj = 2 * pk + ((colour + par0 + si) & 1);
                         const int sic = on[u] ? si : 0, sjc = on[u] ? sj : 0;
-                        gs = bv[u] + wv[u] * (rowW[sic] * xw[u] + rowE[sic] * xe[u] + colS[sjc] * xs[u] +
-                                              colN[sjc] * xn[u]);
+                        gs = dd_sor_gsT(bv[u], wv[u], rowW[sic], rowE[sic], colS[sjc], colN[sjc], xw[u], xe[u], xs[u],
+                                        xn[u]);
                     } else {
-                        gs = bv[u] + wv[u] * xw[u] + ev[u] * xe[u] + sv[u] * xs[u] + nv[u] * xn[u];
+                        gs = dd_sor_gs5(bv[u], wv[u], ev[u], sv[u], nv[u], xw[u], xe[u], xs[u], xn[u]);
                     }
-                    if (on[u]) dd_smem[o_xc + si * PW + pk] = xv[u] + omega * (gs - xv[u]);
+                    if (on[u]) dd_smem[o_xc + si * PW + pk] = dd_sor_relax(xv[u], gs, omega);
                 }
             }
         }
@@ -289,11 +290,11 @@ __global__ void __launch_bounds__(512) k_rbsor_tile(SolveArgs A) {
                 const double bbv = Bb.c(col)[p];
                 double res;
                 if (CONST_BAND)
-                    res = bbv + AW.c(col)[p] * (rowW[si] * xo[p - PW] + rowE[si] * xo[p + PW] +
-                                                colS[sj] * xo[p - 1 + o] + colN[sj] * xo[p + o]) - x;
+                    res = dd_sor_gsT(bbv, AW.c(col)[p], rowW[si], rowE[si], colS[sj], colN[sj], xo[p - PW], xo[p + PW],
+                                     xo[p - 1 + o], xo[p + o]) - x;
                 else
-                    res = bbv + AW.c(col)[p] * xo[p - PW] + AE.c(col)[p] * xo[p + PW] +
-                          AS.c(col)[p] * xo[p - 1 + o] + AN.c(col)[p] * xo[p + o] - x;
+                    res = dd_sor_gs5(bbv, AW.c(col)[p], AE.c(col)[p], AS.c(col)[p], AN.c(col)[p], xo[p - PW], xo[p + PW],
+                                     xo[p - 1 + o], xo[p + o]) - x;
                 const bool inter = dd_is_interior(g, g.row0 + r, j);
                 const double vn = dd_newton_update(inter, vs[u], x, A.zero_boundary);
                 A.vnew[ogs[u]] = vn;
@@ -626,11 +627,11 @@ k_rbsor_reg(const __grid_constant__ SolveArgs A, const __grid_constant__ DDTileM
             const double xv = xc[p];
             double gs;
             if (CONST_BAND)
-                gs = cb[k][c] + cw[k][c] * (rW[k] * xw + rE[k] * xe + (o ? cS2[1] : cS2[0]) * xs +
-                                            (o ? cN2[1] : cN2[0]) * xn);
+                gs = dd_sor_gsT(cb[k][c], cw[k][c], rW[k], rE[k], (o ? cS2[1] : cS2[0]), (o ? cN2[1] : cN2[0]), xw, xe,
+                                xs, xn);
             else
-                gs = cb[k][c] + cw[k][c] * xw + ce[k][c] * xe + cs[k][c] * xs + cn[k][c] * xn;
-            xnew[k] = xv + omega * (gs - xv);
+                gs = dd_sor_gs5(cb[k][c], cw[k][c], ce[k][c], cs[k][c], cn[k][c], xw, xe, xs, xn);
+            xnew[k] = dd_sor_relax(xv, gs, omega);
         }
 #pragma unroll
         for (int k = 0; k < RPW; ++k) xc[(warp + DD_REG_WARPS * k) * PW + lane] = xnew[k];
@@ -658,10 +659,10 @@ k_rbsor_reg(const __grid_constant__ SolveArgs A, const __grid_constant__ DDTileM
                 const double xw = xo[p - PW], xe = xo[p + PW], xs = xo[p + o - 1], xn = xo[p + o];
                 double res;
                 if (CONST_BAND)
-                    res = cb[k][c] + cw[k][c] * (rW[k] * xw + rE[k] * xe + (o ? cS2[1] : cS2[0]) * xs +
-                                                 (o ? cN2[1] : cN2[0]) * xn) - x;
+                    res = dd_sor_gsT(cb[k][c], cw[k][c], rW[k], rE[k], (o ? cS2[1] : cS2[0]), (o ? cN2[1] : cN2[0]), xw,
+                                     xe, xs, xn) - x;
                 else
-                    res = cb[k][c] + cw[k][c] * xw + ce[k][c] * xe + cs[k][c] * xs + cn[k][c] * xn - x;
+                    res = dd_sor_gs5(cb[k][c], cw[k][c], ce[k][c], cs[k][c], cn[k][c], xw, xe, xs, xn) - x;
                 rmax = nn_max(rmax, res);
                 xmax = nn_max(xmax, x);
                 bmax = nn_max(bmax, cb[k][c]);

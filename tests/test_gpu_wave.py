@@ -1,0 +1,110 @@
+"""GPU tests of the wavefront solver and of the marching kernels at the sizes where they are used
+(M + 1 >= 124): bitwise against the tile kernels, and against the oracle for the cases the reference's
+studies use plus a non-uniform grid, DefaultModel01, repeated Newton / PC steps and a time step large enough
+to need several solver passes."""
+import os
+
+import numpy as np
+import pytest
+
+from golden_util import VARS, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def dd():
+    import ddcore
+    import prob1base as p1
+    from test_hostsim import CASES, product_model
+    return dict(ddcore=ddcore, p1=p1, CASES=CASES, product_model=product_model)
+
+
+def _model_dict(om):
+    return dict(K1=om.K1, K2=om.K2, K3=om.K3, K4=om.K4, DT=om.DT, Dl_max=om.Dl_max, phi_l=om.phi_l,
+                gamma_T=om.gamma_T, Kd=om.Kd, Sd=om.Sd, Dd_max=om.Dd_max, phi_d=om.phi_d, r_sp=om.r_sp,
+                T_ref=om.T_ref, kind=om.kind)
+
+
+def _batch(dd, case, om, x, y, eta):
+    p1, ddcore = dd["p1"], dd["ddcore"]
+    model = dd["product_model"](_model_dict(om))
+    grid = p1.Grid(x, y)
+    b = ddcore.Batch(grid.x, grid.y, 1)
+    b.set_model(model, eta)
+    b.forcing_spec(dd["CASES"][case](grid=grid, model=model).device_spec())
+    return b
+
+
+@pytest.mark.parametrize("N,M,sweeps", [(150, 260, 7), (97, 131, 3), (64, 520, 11)])
+def test_wave_solver_equals_tile_solver_bitwise(dd, N, M, sweeps):
+    """Same global red-black iteration, same arithmetic (dd_sor.cuh): the wavefront kernel and the register-tile
+    kernel give identical fields for equal sweep counts."""
+    from oracle import NOTEBOOK_CONSTS
+    om = NOTEBOOK_CONSTS["pol"]
+    x, y = np.linspace(0, 1, N + 1) ** 1.05, np.linspace(0, 1, M + 1)
+    opts = dd["ddcore"].pc_options(fixed_sweeps=sweeps)
+    out = {}
+    for mode in ("wave", "tile"):
+        if mode == "tile":
+            os.environ["DD_NO_WAVE"] = "1"
+        try:
+            b = _batch(dd, "pol", om, x, y, 50.0)
+            b.fill_exact(0, 0.1)
+            st = b.step_pc(0, 1, 0.1, 3e-4, opts)
+            out[mode] = (b.download(1), st)
+            b.close()
+        finally:
+            os.environ.pop("DD_NO_WAVE", None)
+    for v in VARS:
+        assert np.array_equal(out["wave"][0][v], out["tile"][0][v]), v
+    assert out["wave"][1]["resid"] == out["tile"][1]["resid"]
+
+
+MARCH_CASES = [
+    # id, case, constants, N, M, grid power, model kind, pc steps, newton steps, dt (None: h^1.5)
+    ("expsin", "expsin", "expsin", 130, 140, 1.0, 2, 1, 1, None),
+    ("nfsp_h1h2", "nfsp_h1h2", "pol", 128, 130, 1.0, 2, 1, 1, None),
+    ("pol_nonuniform", "pol", "pol", 140, 150, 1.1, 2, 1, 1, None),
+    ("scp_nonuniform_pc22", "scp_fast1e1", "pol", 126, 135, 1.15, 2, 2, 2, None),
+    ("pol_model01", "pol", "pol", 125, 125, 1.0, 1, 1, 1, None),
+    ("pol_pc22", "pol", "pol", 128, 128, 1.0, 2, 2, 2, None),
+    ("scp_bigdt", "scp_fast1e1", "pol", 128, 140, 1.0, 2, 1, 1, 2e-2),
+]
+
+
+@pytest.mark.parametrize("cid,case,consts,N,M,power,kind,P,Q,dt", MARCH_CASES, ids=[c[0] for c in MARCH_CASES])
+def test_marching_sizes_match_oracle(dd, cid, case, consts, N, M, power, kind, P, Q, dt):
+    from oracle import NOTEBOOK_CONSTS, OForcing, OGrid, PCStepper, exact_state, feuler_step, make_case
+    ddcore = dd["ddcore"]
+    om = NOTEBOOK_CONSTS[consts].with_changes(kind=kind)
+    eta, t0 = 50.0, 0.1
+    dt = (1.0 / max(N, M)) ** 1.5 if dt is None else dt
+    x, y = np.linspace(0, 1, N + 1) ** power, np.linspace(0, 1, M + 1) ** (2.0 - power if power != 1.0 else 1.0)
+    og = OGrid(x, y)
+    oc = make_case(case, om)
+    of = OForcing(oc, om, eta, og)
+    s0 = exact_state(oc, t0, og)
+    stepper = PCStepper(og, om, eta, of, num_pc_steps=P, num_newton_steps=Q, keep_residuals=False)
+    ref1 = stepper.step(s0, t0, dt)
+    ref2 = stepper.step(ref1, t0 + dt, dt)
+    ref_fe = feuler_step(s0, t0, dt, og, om, eta, of)
+    b = _batch(dd, case, om, x, y, eta)
+    b.upload(0, s0.fields())
+    opts = ddcore.pc_options(num_pc_steps=P, num_newton_steps=Q)
+    st1 = b.step_pc(0, 1, t0, dt, opts)
+    got1 = b.download(1)
+    st2 = b.step_pc(1, 2, t0 + dt, dt, opts)
+    got2 = b.download(2)
+    b.step_feuler(0, 2, t0, dt)
+    got_fe = b.download(2)
+    for v in VARS:
+        assert rel_err(got1[v], getattr(ref1, v)) <= TOL, (v, st1)
+        assert rel_err(got2[v], getattr(ref2, v)) <= TOL, (v, st2)
+        assert rel_err(got_fe[v], getattr(ref_fe, v)) <= TOL, v
+    assert st1["cs_newton_iters"] == stepper.cs_newton_iters[0]
+    assert max(st2["bound"]) <= 5e-13
+    if cid == "scp_bigdt":
+        assert max(st2["passes"]) >= 1 and max(st2["sweeps"]) >= 8, st2
+    b.close()
