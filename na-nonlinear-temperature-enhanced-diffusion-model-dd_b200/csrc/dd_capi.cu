@@ -1323,15 +1323,16 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
     // on the physical boundary do not shrink.
     int v0 = b->asm0, v1 = b->asm1;
     const bool lo_edge = (b->row0 == 0), hi_edge = (b->row0 + b->nrows == b->N + 1);
-    // wide grids: wavefront kernel (rows marched once per pass, no row halo); the previous step's increment as
-    // initial iterate is only known to the tile kernels
-    const bool wave = dd_wave_ok(b->g, L) && !vold;
+    // opt-in on wide grids: wavefront kernel (rows marched once per pass, no row halo); the previous step's
+    // increment as initial iterate is only known to the tile kernels
+    const bool wave = dd_wave_ok(b->g, L, var) && !vold;
     while (left > 0) {
         DDSolvePlan P;
         memset(&P, 0, sizeof(P));
         if (wave) {
             // as many sweeps per pass as the ring of the widest fitting kernel variant holds
-            const int cap_all = dd_wave_max_sweeps(var == DD_T), cap_wide = 7;
+            int cap_all = 0, cap_wide = 0;
+            dd_wave_max_sweeps(var == DD_T, &cap_all, &cap_wide);
             P.sweeps = left <= cap_all ? left : cap_wide;
             P.last_pass = P.sweeps == left ? 1 : 0;
             P.const_band = var == DD_T ? 1 : 0;

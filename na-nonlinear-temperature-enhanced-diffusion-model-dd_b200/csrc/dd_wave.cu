@@ -26,58 +26,73 @@ __device__ __forceinline__ void wave_atomic_max_nn(double* addr, double v) {
 
 template <int CB, int C, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) k_sor_wave(const __grid_constant__ WaveArgs A) {
-    constexpr int W = 64 * C;
-    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int W = 64 * C, PWP = 32 * C + 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwo = A.nwo, D = 2 * nwo, S4 = 4 * A.sweeps;
+    const int nx = D * 2 * PWP;  // doubles of the x ring
+    const bool owner = warp < nwo;
     WaveSmem sm;
-    sm.x = dd_wsmem;
-    sm.vs = sm.x + (size_t)2 * nwarps * W;
-    sm.scol = sm.vs + DD_WAVE_VS * W;
+    dd_wave_smem_carve(sm, dd_wsmem, (unsigned)__cvta_generic_to_shared(dd_wsmem), CB, C, nwo);
+    unsigned* scratch = dd_wave_scratch(sm);
     long long f0 = (long long)blockIdx.x * A.flat_per_cta;
     const long long f1 = f0 + A.flat_per_cta < A.flat_total ? f0 + A.flat_per_cta : A.flat_total;
     WaveRegs<CB, C> R;
+    WaveEpi E;
     while (f0 < f1) {
         const WaveSeg sg = dd_wave_segment(A, f0, f1);
         f0 += sg.r1 - sg.r0;
         const DDMember& mb = A.mem[sg.member];
         if (!mb.active) continue;
-        for (int k = threadIdx.x; k < 2 * nwarps * W; k += blockDim.x) sm.x[k] = 0.0;
+        for (int k = threadIdx.x; k < nx; k += blockDim.x) dd_wsmem[k] = 0.0;
         const double fT = mb.dt * mb.m.DT;
         if (CB) {
             for (int sj = threadIdx.x; sj < W; sj += blockDim.x) {
                 const int j = sg.cbase + sj;
                 const bool in = j >= 1 && j <= A.g.M - 1;
-                sm.scol[sj] = in ? fT * A.g.rkp[j] * A.g.rk[j] : 0.0;
-                sm.scol[W + sj] = in ? fT * A.g.rkp[j] * A.g.rk[j + 1] : 0.0;
+                dd_wsmem[nx + sj] = in ? fT * A.g.rkp[j] * A.g.rk[j] : 0.0;
+                dd_wsmem[nx + W + sj] = in ? fT * A.g.rkp[j] * A.g.rk[j + 1] : 0.0;
             }
         }
         const double rho = A.rho_fix >= 0.0 ? A.rho_fix : A.stats[sg.member].rho;
         double omega = 1.0;
         if (rho < 1.0) omega = 2.0 / (1.0 + sqrt(1.0 - rho * rho));
-        dd_wave_init_thread<CB, C>(R, warp);
+        if (owner)
+            dd_wave_init_thread<CB, C>(A, sg, R, sm, warp, lane);
+        else
+            dd_wave_epi_init(A, sg, E, sm, warp - nwo, lane, C);
         __syncthreads();
         const int nsteps = dd_wave_steps(A, sg);
-        for (int t = 0; t < nsteps; ++t) {
-            dd_wave_thread_step<CB, C>(A, sg, R, sm, warp, lane, nwarps, omega, fT);
-            __syncthreads();
+        if (owner) {
+            for (int t = 0; t < nsteps; ++t) {
+                dd_wave_thread_step<CB, C>(A, sg, R, sm, lane, D, S4, omega, fT);
+                __syncthreads();
+            }
+        } else {
+            for (int t = 0; t < nsteps; ++t) {
+                dd_wave_epi_step<C>(A, sg, E, sm, t - 2 - DD_WAVE_LS - S4);
+                __syncthreads();
+            }
         }
         if (A.last_pass) {
-            // one atomic per quantity and march (the staging ring is free now: scratch for the CTA reduction)
-            const double r0 = wave_warp_max_nn(R.rmax), r1 = wave_warp_max_nn(R.xmax), r2 = wave_warp_max_nn(R.vmax),
-                         r3 = wave_warp_max_nn(R.bmax);
+            // one atomic per quantity and march: resid, |x|, |v_new|, |bb| (high words, see dd_wave_hi)
+            const unsigned h0 = __reduce_max_sync(0xffffffffu, owner ? R.hr : 0u);
+            const unsigned h1 = __reduce_max_sync(0xffffffffu, owner ? 0u : E.hx);
+            const unsigned h2 = __reduce_max_sync(0xffffffffu, owner ? 0u : E.hv);
+            const unsigned h3 = __reduce_max_sync(0xffffffffu, owner ? R.hb : 0u);
             if (lane == 0) {
-                sm.vs[warp * 4 + 0] = r0;
-                sm.vs[warp * 4 + 1] = r1;
-                sm.vs[warp * 4 + 2] = r2;
-                sm.vs[warp * 4 + 3] = r3;
+                scratch[warp * 4 + 0] = h0;
+                scratch[warp * 4 + 1] = h1;
+                scratch[warp * 4 + 2] = h2;
+                scratch[warp * 4 + 3] = h3;
             }
             __syncthreads();
             if (threadIdx.x < 4) {
-                double m = 0.0;
-                for (int w = 0; w < nwarps; ++w) m = dd_nn_max(m, sm.vs[w * 4 + threadIdx.x]);
+                unsigned m = 0u;
+                for (int w = 0; w < nwo + DD_WAVE_NE; ++w) m = max(m, scratch[w * 4 + threadIdx.x]);
                 DDSolveStats* st = A.stats + sg.member;
                 double* dst = threadIdx.x == 0 ? &st->resid : threadIdx.x == 1 ? &st->xmax
                             : threadIdx.x == 2 ? &st->vmax : &st->bmax;
-                wave_atomic_max_nn(dst, m);
+                wave_atomic_max_nn(dst, dd_wave_from_hi(m, threadIdx.x == 0));
             }
         }
         __syncthreads();
@@ -85,46 +100,68 @@ __global__ void __launch_bounds__(MAXT, 1) k_sor_wave(const __grid_constant__ Wa
 }
 
 // ---- kernel variants: (const band, chunks per lane, thread limit) ------------------------------------------------
-// Registers bound the CTA: 65536 / threads per thread, and a thread holds 8 C (const band) or 20 C doubles of
-// coefficients (thread counts in multiples of 128: registers are allotted per four warps).  The ring needs
-// D = 2 * warps >= 4 S + 4 slots, which limits the sweeps of one pass.
+// Registers bound the CTA: 65536 / threads per thread (allotted per four warps), and an owner thread holds 8 C
+// (const band) or 20 C doubles of coefficients.  The ring needs D = 2 * (owner warps) >= 4 S + 4 slots, which
+// limits the sweeps of one pass; DD_WAVE_NE epilogue warps come on top.
 struct WaveVariant {
     int cb, C, maxt;
     const void* fn;
 };
 static const WaveVariant kVariants[] = {
-    {1, 4, 512, (const void*)k_sor_wave<1, 4, 512>},  // T, up to 7 sweeps per pass
-    {1, 3, 640, (const void*)k_sor_wave<1, 3, 640>},  // T, up to 9
-    {1, 2, 768, (const void*)k_sor_wave<1, 2, 768>},  // T, up to 11
-    {0, 2, 512, (const void*)k_sor_wave<0, 2, 512>},  // cl / cd, up to 7
-    {0, 1, 768, (const void*)k_sor_wave<0, 1, 768>},  // cl / cd, up to 11
+    {1, 3, 640, (const void*)k_sor_wave<1, 3, 640>},  // T, up to 7 sweeps per pass
+    {1, 2, 640, (const void*)k_sor_wave<1, 2, 640>},
+    {1, 2, 896, (const void*)k_sor_wave<1, 2, 896>},  // T, up to 11
+    {0, 2, 384, (const void*)k_sor_wave<0, 2, 384>},  // cl / cd, up to 3
+    {0, 2, 512, (const void*)k_sor_wave<0, 2, 512>},  // cl / cd, up to 5
+    {0, 1, 768, (const void*)k_sor_wave<0, 1, 768>},  // cl / cd, up to 9
 };
 
-static int wave_warps_for(int sweeps) { return 2 * sweeps + 2; }  // ring of D = 2 * warps >= 4 S + 4 slots
+static int wave_owner_warps_for(int sweeps) { return 2 * sweeps + 2; }  // ring of D = 2 * warps >= 4 S + 4 slots
 
 cudaError_t dd_wave_configure() {
     for (const WaveVariant& v : kVariants) {
-        const size_t smem = dd_wave_smem_doubles(v.C, v.maxt / 32) * sizeof(double);
+        const size_t smem = dd_wave_smem_doubles(v.cb, v.C, v.maxt / 32 - DD_WAVE_NE) * sizeof(double);
         cudaError_t e = cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
 }
 
-// largest number of sweeps one pass of the widest fitting variant can take
-int dd_wave_max_sweeps(int const_band) {
-    int best = 0;
+// largest number of sweeps one pass can take: (any variant, the widest variant)
+void dd_wave_max_sweeps(int const_band, int* any, int* wide) {
+    *any = *wide = 0;
+    int wideC = 0;
     for (const WaveVariant& v : kVariants)
         if (v.cb == const_band) {
-            const int s = (2 * (v.maxt / 32) - 4) / 4;
-            if (s > best) best = s;
+            const int s = (2 * (v.maxt / 32 - DD_WAVE_NE) - 4) / 4;
+            if (s > *any) *any = s;
+            if (v.C > wideC || (v.C == wideC && s > *wide)) {
+                wideC = v.C;
+                *wide = s;
+            }
         }
-    return best;
 }
 
-bool dd_wave_ok(const DDGeom& g, const DDLaunch& L) {
-    const char* off = getenv("DD_NO_WAVE");  // read per call: the tests switch kernels inside one process
-    return !(off && *off && *off != '0') && g.M + 1 >= 4 * 31 && L.own1 - L.own0 >= 16;
+// Opt-in (DD_WAVE=1, or a list of variables "T,cl,cd"): measured on B200 at 8193 x 1025 nodes the wavefront kernel
+// only matches the register-tile kernels (T 0.47 vs 0.40 ms, cl 0.31 vs 0.35, cd 0.23 vs 0.21; profiles/README.md):
+// its steps are lock-step sequences of a shared-memory phase, an fp64 phase and a barrier that cannot overlap.
+bool dd_wave_ok(const DDGeom& g, const DDLaunch& L, int var) {
+    const char* on = getenv("DD_WAVE");  // read per call: the tests switch kernels inside one process
+    if (!on || !*on || *on == '0') return false;
+    if (*on != '1') {
+        static const char* names[3] = {"T", "cl", "cd"};
+        const char* n = names[var - DD_T];
+        const char* hit = strstr(on, n);
+        // "cl" and "cd" both start with c: compare whole tokens
+        bool found = false;
+        while (hit) {
+            const char after = hit[strlen(n)];
+            if ((hit == on || hit[-1] == ',') && (after == 0 || after == ',')) found = true;
+            hit = strstr(hit + 1, n);
+        }
+        if (!found) return false;
+    }
+    return g.M + 1 >= 4 * 31 && L.own1 - L.own0 >= 16;
 }
 
 cudaError_t dd_launch_solve_wave(const DDLaunch& L, const DDGeom& g, const DDMember* mem, const DDRows& R,
@@ -132,10 +169,11 @@ cudaError_t dd_launch_solve_wave(const DDLaunch& L, const DDGeom& g, const DDMem
                                  int zero_boundary, DDSolveStats* stats, int const_band, int sweeps, int last_pass,
                                  double rho_fix) {
     if (sweeps < 1) return cudaErrorInvalidValue;
-    const int nw = wave_warps_for(sweeps);
+    const int nwo = wave_owner_warps_for(sweeps), nw = nwo + DD_WAVE_NE;
     const WaveVariant* v = nullptr;
+    const char* wantC = getenv(const_band ? "DD_WAVE_C_T" : "DD_WAVE_C");  // development: force the strip width
     for (const WaveVariant& c : kVariants)
-        if (c.cb == (const_band ? 1 : 0) && nw * 32 <= c.maxt) {
+        if (c.cb == (const_band ? 1 : 0) && nw * 32 <= c.maxt && !(wantC && *wantC && atoi(wantC) != c.C)) {
             v = &c;
             break;
         }
@@ -162,16 +200,17 @@ cudaError_t dd_launch_solve_wave(const DDLaunch& L, const DDGeom& g, const DDMem
     A.mstrideR = R.mstride;
     A.own0 = L.own0; A.own1 = L.own1; A.vr0 = L.vr0; A.vr1 = L.vr1;
     A.sweeps = sweeps;
-    A.halo = 2 * sweeps + 1;
+    A.halo = 2 * sweeps + 2;
     A.last_pass = last_pass;
-    A.tj = 64 * v->C - 2 * A.halo - 2;
-    if (A.tj < 2) return cudaErrorInvalidValue;
+    A.tj = 64 * v->C - 2 * A.halo;
+    A.nwo = nwo;
+    if (A.tj < 2 || A.tj > 32 * DD_WAVE_NE * DD_WAVE_EV) return cudaErrorInvalidValue;
     A.nstrips = (g.M + 1 + A.tj - 1) / A.tj;
     A.flat_total = (long long)L.nmembers * A.nstrips * (L.own1 - L.own0);
     A.rho_fix = rho_fix;
     // one CTA per SM (or several when registers and shared memory allow), each marching an equal share of the
     // rows of all strips laid end to end; a share is never shorter than a few pipeline depths
-    const size_t smem = dd_wave_smem_doubles(v->C, nw) * sizeof(double);
+    const size_t smem = dd_wave_smem_doubles(v->cb, v->C, nwo) * sizeof(double);
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v->fn, nw * 32, smem) != cudaSuccess || per_sm < 1)
         per_sm = 1;

@@ -28,7 +28,7 @@ struct WSProblem {
 
 template <int CB, int C>
 static void run(WSProblem& P) {
-    constexpr int W = 64 * C;
+    constexpr int W = 64 * C, PWP = 32 * C + 2;
     DDMember mb;
     memset(&mb, 0, sizeof(mb));
     mb.active = 1;
@@ -51,58 +51,67 @@ static void run(WSProblem& P) {
     A.mstrideR = (long long)P.nrows * P.ldR;
     A.own0 = P.own0; A.own1 = P.own1; A.vr0 = P.vr0; A.vr1 = P.vr1;
     A.sweeps = P.sweeps;
-    A.halo = 2 * P.sweeps + 1;
+    A.halo = 2 * P.sweeps + 2;
     A.last_pass = P.last_pass;
-    A.tj = W - 2 * A.halo - 2;
+    A.tj = W - 2 * A.halo;
     A.nstrips = (P.M + 1 + A.tj - 1) / A.tj;
+    A.nwo = P.nwarps;
     A.flat_total = (long long)A.nstrips * (P.own1 - P.own0);
     A.flat_per_cta = (A.flat_total + P.nctas - 1) / P.nctas;
     A.rho_fix = -1.0;
-    const int nwarps = P.nwarps, nthreads = 32 * nwarps;
-    std::vector<double> smem(dd_wave_smem_doubles(C, nwarps));
-    std::vector<WaveRegs<CB, C>> regs(nthreads);
-    double rmax = 0, xmax = 0, vmax = 0, bmax = 0;
+    const int nwo = P.nwarps, D = 2 * nwo, S4 = 4 * P.sweeps;
+    const int nthreads = 32 * (nwo + DD_WAVE_NE);
+    std::vector<double> smem(dd_wave_smem_doubles(CB, C, nwo));
+    std::vector<WaveRegs<CB, C>> regs(32 * nwo);
+    std::vector<WaveEpi> epi(32 * DD_WAVE_NE);
+    unsigned hr = 0, hx = 0, hv = 0, hb = 0;
     P.steps = 0;
+    const size_t nx = (size_t)D * 2 * PWP;
     for (int cta = 0; cta < P.nctas; ++cta) {
         WaveSmem sm;
-        sm.x = smem.data();
-        sm.vs = sm.x + (size_t)2 * nwarps * W;
-        sm.scol = sm.vs + DD_WAVE_VS * W;
+        dd_wave_smem_carve(sm, smem.data(), 0u, CB, C, nwo);
         long long f0 = (long long)cta * A.flat_per_cta;
         const long long f1 = f0 + A.flat_per_cta < A.flat_total ? f0 + A.flat_per_cta : A.flat_total;
         while (f0 < f1) {
             const WaveSeg sg = dd_wave_segment(A, f0, f1);
             f0 += sg.r1 - sg.r0;
-            for (size_t k = 0; k < (size_t)2 * nwarps * W; ++k) sm.x[k] = 0.0;
-            // poison the staging ring: a finish that reads a value nobody requested must show up
-            for (int k = 0; k < DD_WAVE_VS * W; ++k) sm.vs[k] = NAN;
+            for (size_t k = 0; k < nx; ++k) smem[k] = 0.0;
             const double fT = mb.dt * mb.m.DT;
             if (CB)
                 for (int sj = 0; sj < W; ++sj) {
                     const int j = sg.cbase + sj;
                     const bool in = j >= 1 && j <= P.M - 1;
-                    sm.scol[sj] = in ? fT * P.rkp[j] * P.rk[j] : 0.0;
-                    sm.scol[W + sj] = in ? fT * P.rkp[j] * P.rk[j + 1] : 0.0;
+                    smem[nx + sj] = in ? fT * P.rkp[j] * P.rk[j] : 0.0;
+                    smem[nx + W + sj] = in ? fT * P.rkp[j] * P.rk[j + 1] : 0.0;
                 }
             double omega = 1.0;
             if (P.rho < 1.0) omega = 2.0 / (1.0 + sqrt(1.0 - P.rho * P.rho));
-            for (int t = 0; t < nthreads; ++t) dd_wave_init_thread<CB, C>(regs[t], t >> 5);
+            for (int t = 0; t < 32 * nwo; ++t) dd_wave_init_thread<CB, C>(A, sg, regs[t], sm, t >> 5, t & 31);
+            for (int t = 0; t < 32 * DD_WAVE_NE; ++t) dd_wave_epi_init(A, sg, epi[t], sm, t >> 5, t & 31, C);
+            // poison the staging rings: a value nobody requested must show up
+            for (size_t k = nx + 2 * W; k < smem.size(); ++k) smem[k] = NAN;
             const int nsteps = dd_wave_steps(A, sg);
             P.steps += nsteps;
             for (int s = 0; s < nsteps; ++s)
                 for (int tt = 0; tt < nthreads; ++tt) {
                     const int t = P.order ? nthreads - 1 - tt : tt;
-                    dd_wave_thread_step<CB, C>(A, sg, regs[t], sm, t >> 5, t & 31, nwarps, omega, fT);
+                    if (t < 32 * nwo)
+                        dd_wave_thread_step<CB, C>(A, sg, regs[t], sm, t & 31, D, S4, omega, fT);
+                    else
+                        dd_wave_epi_step<C>(A, sg, epi[t - 32 * nwo], sm, s - 2 - DD_WAVE_LS - S4);
                 }
-            for (int t = 0; t < nthreads; ++t) {
-                rmax = dd_nn_max(rmax, regs[t].rmax);
-                xmax = dd_nn_max(xmax, regs[t].xmax);
-                vmax = dd_nn_max(vmax, regs[t].vmax);
-                bmax = dd_nn_max(bmax, regs[t].bmax);
+            for (int t = 0; t < 32 * nwo; ++t) {
+                hr = regs[t].hr > hr ? regs[t].hr : hr;
+                hb = regs[t].hb > hb ? regs[t].hb : hb;
+            }
+            for (auto& e : epi) {
+                hx = e.hx > hx ? e.hx : hx;
+                hv = e.hv > hv ? e.hv : hv;
             }
         }
     }
-    P.stats[0] = rmax; P.stats[1] = xmax; P.stats[2] = vmax; P.stats[3] = bmax;
+    P.stats[0] = dd_wave_from_hi(hr, true); P.stats[1] = dd_wave_from_hi(hx, false);
+    P.stats[2] = dd_wave_from_hi(hv, false); P.stats[3] = dd_wave_from_hi(hb, false);
 }
 
 extern "C" int ws_wave(WSProblem* P) {
@@ -145,8 +154,9 @@ extern "C" int ws_reference(WSProblem* P, double* x) {
                     const size_t p = (size_t)i * ldR + j;
                     x[p] = dd_sor_relax(x[p], gs(i, j), omega);
                 }
-    double rmax = 0, xmax = 0, vmax = 0, bmax = 0;
-    if (P->vnew)
+    unsigned hr = 0, hx = 0, hv = 0, hb = 0;
+    auto up = [](unsigned& m, double v) { const unsigned h = dd_wave_hi(v); m = h > m ? h : m; };
+    if (P->vnew && P->last_pass)
         for (int i = P->own0; i < P->own1; ++i)
             for (int j = 0; j <= M; ++j) {
                 const size_t p = (size_t)i * ldR + j;
@@ -154,11 +164,12 @@ extern "C" int ws_reference(WSProblem* P, double* x) {
                 const bool inter = gi > 0 && gi < P->N && j > 0 && j < M;
                 const double vn = dd_newton_update(inter, P->vstar[(size_t)i * P->ld + j], x[p], P->zero_boundary);
                 P->vnew[(size_t)i * P->ld + j] = vn;
-                rmax = dd_nn_max(rmax, gs(i, j) - x[p]);
-                xmax = dd_nn_max(xmax, x[p]);
-                vmax = dd_nn_max(vmax, vn);
-                bmax = dd_nn_max(bmax, P->bb[p]);
+                up(hr, gs(i, j) - x[p]);
+                up(hx, x[p]);
+                up(hv, vn);
+                up(hb, P->bb[p]);
             }
-    P->stats[0] = rmax; P->stats[1] = xmax; P->stats[2] = vmax; P->stats[3] = bmax;
+    P->stats[0] = dd_wave_from_hi(hr, true); P->stats[1] = dd_wave_from_hi(hx, false);
+    P->stats[2] = dd_wave_from_hi(hv, false); P->stats[3] = dd_wave_from_hi(hb, false);
     return 0;
 }

@@ -47,8 +47,8 @@ def test_wave_solver_equals_tile_solver_bitwise(dd, N, M, sweeps):
     opts = dd["ddcore"].pc_options(fixed_sweeps=sweeps)
     out = {}
     for mode in ("wave", "tile"):
-        if mode == "tile":
-            os.environ["DD_NO_WAVE"] = "1"
+        if mode == "wave":
+            os.environ["DD_WAVE"] = "1"
         try:
             b = _batch(dd, "pol", om, x, y, 50.0)
             b.fill_exact(0, 0.1)
@@ -56,10 +56,12 @@ def test_wave_solver_equals_tile_solver_bitwise(dd, N, M, sweeps):
             out[mode] = (b.download(1), st)
             b.close()
         finally:
-            os.environ.pop("DD_NO_WAVE", None)
+            os.environ.pop("DD_WAVE", None)
     for v in VARS:
         assert np.array_equal(out["wave"][0][v], out["tile"][0][v]), v
-    assert out["wave"][1]["resid"] == out["tile"][1]["resid"]
+    # the wavefront kernel keeps its statistics as high words (residual rounded up by at most 2^-20 relative)
+    for a, b in zip(out["wave"][1]["resid"], out["tile"][1]["resid"]):
+        assert b <= a <= b * (1 + 2e-6) + 1e-300, (a, b)
 
 
 MARCH_CASES = [
@@ -74,8 +76,17 @@ MARCH_CASES = [
 ]
 
 
+@pytest.fixture(params=["tile", "wave"])
+def solver(request):
+    """Both solvers of the wide-grid regime: the register-tile kernels (default) and the wavefront kernel."""
+    if request.param == "wave":
+        os.environ["DD_WAVE"] = "1"
+    yield request.param
+    os.environ.pop("DD_WAVE", None)
+
+
 @pytest.mark.parametrize("cid,case,consts,N,M,power,kind,P,Q,dt", MARCH_CASES, ids=[c[0] for c in MARCH_CASES])
-def test_marching_sizes_match_oracle(dd, cid, case, consts, N, M, power, kind, P, Q, dt):
+def test_marching_sizes_match_oracle(dd, solver, cid, case, consts, N, M, power, kind, P, Q, dt):
     from oracle import NOTEBOOK_CONSTS, OForcing, OGrid, PCStepper, exact_state, feuler_step, make_case
     ddcore = dd["ddcore"]
     om = NOTEBOOK_CONSTS[consts].with_changes(kind=kind)
