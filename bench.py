@@ -13,11 +13,13 @@ exactly that config), slab-decomposed along i with halo exchange over NCCL.  Oth
 One JSON line on rank 0.  `value` = cell-steps/s with state resident in HBM, timed with CUDA events on
 the launching stream (max over ranks); `e2e` = the same step through Batch.upload / step_pc / download
 with pinned HOST buffers; `roofline` = dominant kernel vs the measured HBM peak; `cpu_baseline` = the
-oracle port (NumPy + SuperLU) on the host cores.
+unmodified reference (baseline/_ref, staged by tools/stage_reference.sh; else the oracle port) on the host cores;
+`check` = error norms of the timed state and, on several GPUs, slab-vs-whole-mesh digests.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import statistics
@@ -46,17 +48,40 @@ ETA = 50.0
 KERNEL_BYTES = {"k_predict": 88, "k_assemble<T>": 40, "k_assemble<cl>": 80, "k_assemble<cd>": 104,
                 "k_rbsor_tile<T>": 32, "k_rbsor_tile<cl>": 56, "k_rbsor_tile<cd>": 56, "k_correct": 80,
                 "k_feuler": 80, "k_eval_sources": 40}
+# CUDA kernels behind the profile classes on the mesh workload (wide grid, staged sources); the solver's variant is
+# asked from the library after the run (dd_solver_kernel_name)
+KERNEL_NAMES = {"k_predict": "k_predict_march<true>", "k_assemble<cl>": "k_assemble_cl_march",
+                "k_assemble<cd>": "k_assemble_cd_march", "k_correct": "k_correct<ARRAYS, false>",
+                "k_eval_sources": "k_eval_sources<SEPARABLE>", "k_feuler": "k_feuler_march",
+                "k_cs_decide+k_cs_redo": "k_cs_decide, k_cs_redo<ARRAYS>", "k_time_coefs": "k_time_coefs",
+                "k_summarise": "k_summarise"}
+PROFILE_TAG = "r02"  # profiles/<tag>_traffic.json, <tag>_fp64.json: the ncu captures the static figures come from
 
 
 def captured_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/), or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01f_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", PROFILE_TAG + "_traffic.json")) as f:
             t = json.load(f)
         k = t["kernels"][kernel]
         return float(k["dram_bytes_per_launch"]), t["source"] + "; kernel " + k["ncu_kernel"]
     except Exception:
         return None, None
+
+
+def captured_fp64():
+    """fp64 flops per step (2 DFMA + DADD + DMUL thread instructions, predicated on) of the whole PC step from the
+    committed ncu capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", PROFILE_TAG + "_fp64.json")) as f:
+            t = json.load(f)
+        return float(t["flops_per_step"]), float(t["dfma_per_step"]), t["source"]
+    except Exception:
+        return None, None, None
+
+
+def step_bytes_of(args):
+    return 80.0 if args.integrator == "feuler" else BYTES_PER_CELL_STEP
 
 
 def measured_peak():
@@ -220,7 +245,6 @@ def run_studies(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = load_library()
 
@@ -296,6 +320,63 @@ def run_studies(args):
     _emit(line)
 
 
+def field_digest(torch, mesh, slot, r0, r1):
+    """Order-independent 64-bit digests (sum of the bit patterns, mod 2^64) of local rows [r0, r1) of the five fields."""
+    out = []
+    for v in ("cp", "T", "cl", "cd", "cs"):
+        t = mesh.field(slot, v)[r0:r1]
+        out.append(t.contiguous().view(torch.int64).sum())
+    return torch.stack(out)
+
+
+def mesh_check(args, torch, dist, world, rank, local, mesh, dt, slot, t_now):
+    """(a) H- and p-norms of (state - exact) after the timed steps, all-reduced over the ranks;
+    (b) world > 1: two PC steps from the exact state at a fixed sweep plan on the slabs and, on rank 0, on the
+    undecomposed mesh: the slabs' owned rows must be bit-identical to the corresponding rows of the whole mesh."""
+    import ddcore
+    import ddmesh
+    from _ddlib import Context
+    e = mesh.error_norms(slot, t_now)
+    out = {"err_H": float(np.sqrt(np.sum(e[:5]))), "err_P": float(np.sqrt(np.sum(e[5:]))),
+           "what": "discrete H and p norms of (state - exact MMS state) after the timed steps, all ranks"}
+    if world == 1 or args.integrator != "pc":
+        return out
+    fixed = ddcore.pc_options(fixed_sweeps=8)
+    mesh.fill_exact(0, 0.0)
+    for k in range(2):
+        mesh.step_pc(k % 3, (k + 1) % 3, k * dt, dt, fixed)
+    p = mesh.part
+    mine = field_digest(torch, mesh, 2, p["own0"], p["own1"])
+    gathered = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    if rank == 0:
+        whole = ddmesh.SlabMesh(mesh.x, mesh.y, world=1, rank=0, ctx=Context(local), nslots=3)
+        whole.torch = torch
+        whole.batch.set_model(product_model(), ETA)
+        whole.batch.forcing_spec(mesh_case_spec())
+        whole.fill_exact(0, 0.0)
+        for k in range(2):
+            whole.step_pc(k % 3, (k + 1) % 3, k * dt, dt, fixed)
+        whole.batch.ctx.synchronize()
+        equal = True
+        for r in range(world):
+            a, b = ddmesh.shard_members(len(mesh.x), world, r)
+            ref = field_digest(torch, whole, 2, a, b)
+            equal = equal and bool(torch.equal(ref, gathered[r]))
+        out["slabs_equal_whole_mesh"] = equal
+        out["digest"] = ("2 PC steps from the exact state, 8 sweeps per solve: 64-bit sums of the bit patterns of "
+                         "each rank's owned rows (5 fields) == those of the same rows of an undecomposed run on rank 0")
+        whole.batch.close()
+    return out
+
+
+def mesh_case_spec():
+    import prob1_mms_cases as p1mc
+    import prob1base as p1
+    case = p1mc.MMSCasePol(grid=p1.Grid(np.array([0.0, 0.5, 1.0]), np.array([0.0, 0.5, 1.0])), model=product_model())
+    return case.device_spec()
+
+
 def run_b200(args):
     if args.workload != "mesh":
         return run_studies(args)
@@ -311,8 +392,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its banner on stdout; this program prints one JSON line
+        # (NCCL's INFO log goes to this process's C-level stdout, which main() has pointed at stderr: the one JSON
+        # line is written to the saved original descriptor)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.Stream(device=local)
     lib = load_library()
@@ -384,6 +465,20 @@ def run_b200(args):
         barrier()
         prof = profile_read(True)
         lib.dd_profile_enable(0)
+        solver_kernels = {v: lib.dd_solver_kernel_name(k).decode() for k, v in ((1, "T"), (2, "cl"), (3, "cd"))}
+
+        # correctness of what was just timed: error norms of the state against the exact
+        # manufactured solution, and -- on more than one GPU -- a digest of the slabs against an undecomposed run
+        check = None
+        if args.check:
+            check = mesh_check(args, torch, dist if world > 1 else None, world, rank, local, mesh, dt,
+                               (args.warmup + 2 * args.steps) % 3, clock["t"])
+            barrier()
+        fp64_peak = None
+        if rank == 0:
+            tf = C.c_double(0.0)
+            ctx.check(lib.dd_probe_fp64(ctx.handle, 30.0, C.byref(tf)), "probe_fp64")
+            fp64_peak = float(tf.value)
 
         # end to end through the host-buffer API (rank-local slab): H2D 5 fields, step, D2H 5 fields, every step
         e2e = None
@@ -461,7 +556,24 @@ def run_b200(args):
     total_prof = sum(v[0] for v in prof.values())
     traffic, traffic_src = captured_traffic(tname)
     step_bytes = 80.0 if args.integrator == "feuler" else BYTES_PER_CELL_STEP
-    roof = {"bound": "hbm", "kernel": tname, "achieved": achieved, "peak": peak, "peak_kind": peak_kind,
+    knames = dict(KERNEL_NAMES)
+    for v in ("T", "cl", "cd"):
+        knames["k_rbsor_tile<%s>" % v] = solver_kernels.get(v, "")
+    if "k_predict" in prof and "k_assemble<T>" in prof:
+        knames["k_predict"] = "k_predict_march<false>"
+    flops_step, dfma_step, fp64_src = captured_fp64()
+    fp64 = None
+    if fp64_peak and flops_step and args.integrator == "pc":
+        # the capture counts thread instructions of one rank's step (1025 x 8193 nodes); time = this run's step
+        ach = flops_step / (ms / args.steps * 1e-3) / 1e12
+        fp64 = {"achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+                "flops_per_step": flops_step, "dfma_per_step": dfma_step, "source": fp64_src,
+                "peak_source": "dd_probe_fp64: 8 independent FMA chains per thread, 2 x 1024 threads per SM, "
+                               "CUDA events, best of 3, this run"}
+    hbm_frac = value / world * step_bytes_of(args) / 1e9 / peak
+    bound = "fp64" if (fp64 and fp64["frac"] > hbm_frac) else "hbm"
+    roof = {"bound": bound, "kernel": knames.get(tname, tname), "kernel_class": tname, "achieved": achieved,
+            "peak": peak, "peak_kind": peak_kind, "fp64": fp64, "kernel_names": knames,
             "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
             "algorithmic_bytes_per_launch": alg_per_launch, "launches_per_step": lps,
             "launch_ms": tms / tcount, "share_of_step": tms / total_prof,
@@ -477,7 +589,7 @@ def run_b200(args):
         "config": dict({"workload": workload, "integrator": ("forward Euler (all five fields, all nodes)" if args.integrator == "feuler"
                                        else "PC RegHCsTriple p=q=1, 5 cs-Newton iterations"),
                         "eta": ETA, "forcing": "fused MMS (separable tables)", "solver": stats}, **extra_cfg),
-        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "check": check,
     }
     if world == 1 and args.cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(threads=1, steps=2, warmup=1)
@@ -485,10 +597,39 @@ def run_b200(args):
 
 
 # ----------------------------------------------------------------------------
-# CPU side: the oracle port (NumPy + SciPy SuperLU), test infrastructure used here only as the
-# timed baseline
+# CPU side.  The UNMODIFIED reference (staged by tools/stage_reference.sh into the git-ignored baseline/_ref/, which
+# travels to the GPU box) is timed when it is there: kind "reference".  Otherwise the oracle port (NumPy + SciPy
+# SuperLU, test infrastructure, used here only as the timed baseline): kind "port".
 # ----------------------------------------------------------------------------
-CPU_SAMPLE_N = 256
+CPU_SAMPLE_N = 256   # oracle port
+REF_SAMPLE_N = 128   # live reference: 2 s per step and core at this size (8 s at 256)
+REF_DIR = os.path.join(ROOT, "baseline", "_ref", "src")
+
+REF_WORKER = r"""
+import sys, time, json
+import numpy as np
+import prob1base as p1
+import prob1_mms_cases as cases
+N, steps, warmup, eta = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), float(sys.argv[4])
+consts = json.loads(sys.argv[5])
+assert "_ref" in p1.__file__, p1.__file__
+mc = p1.ModelConsts(R0=p1.R0, Ea=p1.Ea, phi_T=p1.Ea / p1.R0, **consts)
+model = p1.DefaultModel02(mc)
+grid = p1.make_uniform_grid(N, N)
+case = cases.MMSCasePol(grid=grid, model=model)
+forcing = p1.ForcingTerms_RegHCsTriple(mms_case=case, model=model, regularization_factor=eta)
+field = p1.SemiDiscreteField_RegHCsTriple(grid=grid, model=model, forcing_terms=forcing, regularization_factor=eta)
+integ = p1.P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_RegHCsTriple(field, regularization_factor=eta)
+state = p1.state_from_mms_when(mms_case=case, t=0.0, grid=grid)
+dt = (1.0 / N) ** 1.5
+t = 0.0
+for _ in range(warmup):
+    state = integ.step(state, t0=t, dt=dt); t += dt
+t0 = time.perf_counter()
+for _ in range(steps):
+    state = integ.step(state, t0=t, dt=dt); t += dt
+print(json.dumps({"seconds": time.perf_counter() - t0, "finite": bool(np.isfinite(state.T).all())}))
+"""
 
 
 def _cpu_worker(job):
@@ -513,7 +654,35 @@ def _cpu_worker(job):
     return time.perf_counter() - t0
 
 
+def reference_baseline(threads: int, steps: int, warmup: int):
+    """`threads` independent trajectories of the live reference, one fresh interpreter per core (the reference is
+    single-threaded: NumPy element-wise work + serial SuperLU), module search path = baseline/_ref/src only."""
+    env = dict(os.environ, PYTHONPATH=REF_DIR, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    cmd = [sys.executable, "-c", REF_WORKER, str(REF_SAMPLE_N), str(steps), str(warmup), str(ETA), json.dumps(POL)]
+    procs = [subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=REF_DIR)
+             for _ in range(threads)]
+    el = []
+    for pr in procs:
+        out, err = pr.communicate(timeout=1200)
+        if pr.returncode != 0:
+            raise RuntimeError("reference worker failed: " + err[-500:])
+        el.append(json.loads(out.strip().splitlines()[-1])["seconds"])
+    cells = REF_SAMPLE_N * REF_SAMPLE_N * steps
+    value = sum(cells / e for e in el)
+    return {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
+            "sample": (f"the unmodified reference (baseline/_ref/src, staged from /root/reference by "
+                       f"tools/stage_reference.sh): P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_RegHCsTriple.step, "
+                       f"MMSCasePol N=M={REF_SAMPLE_N}, dt=h^1.5, {steps} steps per worker after {warmup} warm-up, "
+                       f"{threads} independent trajectories (one interpreter per core; the reference is single-threaded)"),
+            "host_cpus": os.cpu_count(), "s_per_step": max(el) / steps}
+
+
 def cpu_baseline(threads: int, steps: int, warmup: int):
+    if os.path.isdir(REF_DIR):
+        try:
+            return reference_baseline(threads, steps, warmup)
+        except Exception as e:  # a broken staging must not take the bench line down: say so and time the port
+            sys.stderr.write(f"reference baseline failed ({e}); timing the oracle port instead\n")
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     if threads <= 1:
@@ -537,10 +706,11 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     steps = max(1, min(args.steps, 4))
     base = cpu_baseline(threads=threads, steps=steps, warmup=min(args.warmup, 1))
+    n = REF_SAMPLE_N if base["kind"] == "reference" else CPU_SAMPLE_N
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": base["s_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "pol_mesh (bounded sample: N=M=256 per core, same case, constants, eta, "
+            "config": {"workload": f"pol_mesh (bounded sample: N=M={n} per core, same case, constants, eta, "
                                    "dt rule and integrator settings as the CUDA arm)"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -577,6 +747,8 @@ def main():
     ap.add_argument("--no-e2e", dest="e2e", action="store_false")
     ap.add_argument("--e2e-single", action="store_true", help="e2e with one trajectory (no duplex overlap)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-check", dest="check", action="store_false",
+                    help="skip the correctness check of the timed state (error norms; slab digests on > 1 GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -227,6 +227,12 @@ int dd_profile_enable(int on);                  /* bracket every launch group wi
 int dd_profile_read(const char** names, double* ms, long long* count, int reset); /* returns #classes (<= 16) */
 
 int dd_probe_math(dd_ctx* ctx, int n, const double* in, double* out_exp, double* out_rcp); /* accuracy probe of the inline device exp / 1/x */
+/* fp64 roof of the device, measured: every SM runs chains of independent double-precision fused multiply-adds for
+   about `ms_target` milliseconds (CUDA events on the context's stream); *tflops = 2 * FMAs / time.  The PC step is
+   bound by fp64 issue rather than by HBM, bench.py reports it against this number. */
+int dd_probe_fp64(dd_ctx* ctx, double ms_target, double* tflops);
+/* name of the CUDA kernel the last solve of variable `var` (1 = T, 2 = cl, 3 = cd) was launched with */
+const char* dd_solver_kernel_name(int var);
 
 #ifdef __cplusplus
 }

@@ -125,6 +125,8 @@ SIGNATURES = {
     "dd_sweeps_for_rho": (C.c_int, [C.c_double, C.c_int]),
     "dd_next_plan": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int]),
     "dd_probe_math": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp]),
+    "dd_probe_fp64": (C.c_int, [_vp, C.c_double, _dp]),
+    "dd_solver_kernel_name": (C.c_char_p, [C.c_int]),
     "dd_launch_count": (C.c_longlong, []),
     "dd_profile_enable": (C.c_int, [C.c_int]),
     "dd_profile_read": (C.c_int, [_P(C.c_char_p), _dp, _P(C.c_longlong), C.c_int]),

@@ -727,14 +727,15 @@ extern "C" int dd_work_dev_ptr(dd_batch* b, const char* name, void** ptr) {
     if (!b || !name || !ptr) return DD_ERR_INVALID;
     if (!strcmp(name, "solve_stats")) {
         // DDSolveStats[3][nmembers] of the phased step: 5 doubles each, rho first (all-reduced by the slab driver)
-        int rc0 = ensure_solve_slots(b, 3);
+        int rc0 = ensure_solve_slots(b, 4);
         if (rc0 != DD_OK) return rc0;
         *ptr = b->d_stats;
         return DD_OK;
     }
     if (!strcmp(name, "summary")) {
-        // SolveSummary[3] of the phased step: rho, ratio, resid, bound per solve (all-reduced by the slab driver)
-        int rc0 = ensure_solve_slots(b, 3);
+        // SolveSummary[4] of the phased step: rho, ratio, resid, bound per solve, then a row whose first entry is the
+        // corrector's domain-error flag (all-reduced by the slab driver)
+        int rc0 = ensure_solve_slots(b, 4);
         if (rc0 != DD_OK) return rc0;
         *ptr = b->d_summary;
         return DD_OK;
@@ -1222,6 +1223,17 @@ __global__ void k_summarise(const DDSolveStats* st, int nmem, const DDMember* me
     }
 }
 
+__global__ void k_flags_to_summary(const int* flags, const DDMember* mem, int nmem, SolveSummary* out) {
+    int any = 0;
+    for (int m = threadIdx.x; m < nmem; m += 32)
+        if (mem[m].active && (flags[m] & 1)) any = 1;
+    any = __any_sync(0xffffffffu, any);
+    if (threadIdx.x == 0) {
+        out->rho = any ? 1.0 : 0.0;
+        out->ratio = out->resid = out->bound = 0.0;
+    }
+}
+
 static int ensure_solve_slots(dd_batch* b, int n) {
     dd_ctx* ctx = b->ctx;
     if (n <= b->nsolve_cap) return DD_OK;
@@ -1378,6 +1390,7 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
         else
             CKP(PC_SOLVE_T + (var - DD_T), 1,
                 dd_launch_solve_pass(Lp, b->g, b->d_mem, R, xin, vo, xout, vstar, vnew, var == DD_T ? 1 : 0, st, P));
+        dd_note_solver_kernel(var, dd_last_solver_kernel());
         left -= P.sweeps;
         xin = xout;
         if (!P.last_pass) {
@@ -2043,7 +2056,7 @@ extern "C" int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_ou
     if (rc != DD_OK) return rc;
     if (opt.num_pc_steps != 1 || opt.num_newton_steps != 1)
         return fail(ctx, DD_ERR_INVALID, "phased step supports num_pc_steps = num_newton_steps = 1");
-    if ((rc = ensure_solve_slots(b, 3)) != DD_OK) return rc;
+    if ((rc = ensure_solve_slots(b, 4)) != DD_OK) return rc;  // three solves + the row the domain flag is filed in
     DDPredictOut po;
     if ((rc = get_work(b, "cp1p", &po.cp1p)) != DD_OK) return rc;
     if ((rc = get_work(b, "cs1p", &po.cs1p)) != DD_OK) return rc;
@@ -2060,6 +2073,7 @@ extern "C" int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_ou
     int sw = 0, pa = 0;
     switch (phase) {
         case 0:
+            CK(cudaMemsetAsync(b->d_flags, 0, sizeof(int) * b->B, ctx->stream));
             if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
             if ((rc = stage_sources(b, t0[0], dt[0], n_t == 1, true)) != DD_OK) return rc;
             if ((rc = launch_predictor(b, s0, po, &b->phase_fused_T, false)) != DD_OK) return rc;
@@ -2099,6 +2113,10 @@ extern "C" int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_ou
                     dd_launch_cs_finish(launch_of(b, ROWS_ALL), b->smode, b->g, b->d_mem, b->sF, s0, sout.v[DD_CL],
                                         sout.v[DD_CD], sout.v[DD_CS], cap, opt.consec_xs_rtol, b->d_itmax,
                                         b->d_itmin, b->d_used));
+            // the domain-error flags of the corrector (HCsTriple: 2 - dt R1 not positive) ride in row 3 of the
+            // summaries, which the slab driver max-reduces over the ranks
+            k_flags_to_summary<<<1, 32, 0, ctx->stream>>>(b->d_flags, b->d_mem, b->B, b->d_summary + 3);
+            CK(cudaGetLastError());
             record_step(b, slot_in, slot_out);
             return DD_OK;
         case 5: {
@@ -2109,6 +2127,8 @@ extern "C" int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_ou
                                         b->d_itmin, b->d_used));
             SolveSummary sums[3];
             CK(cudaMemcpyAsync(sums, b->d_summary, sizeof(sums), cudaMemcpyDeviceToHost, ctx->stream));
+            std::vector<int> hflags(b->B, 0);
+            CK(cudaMemcpyAsync(hflags.data(), b->d_flags, sizeof(int) * b->B, cudaMemcpyDeviceToHost, ctx->stream));
             int used0 = cap;
             if (track && cs_iters) CK(cudaMemcpyAsync(&used0, b->d_used, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
@@ -2120,6 +2140,10 @@ extern "C" int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_ou
                     summary[q * 4 + 3] = sums[q].bound;
                 }
             if (cs_iters) *cs_iters = used0;
+            for (int m = 0; m < b->B; ++m)
+                if (b->h_mem[m].active && (hflags[m] & 1))
+                    return fail(ctx, DD_ERR_DOMAIN,
+                                "Denominator 2 - dt Kd (Sd - Cd1) (1 + Cl1) below positiveness treshold.");
             record_step(b, slot_in, slot_out);
             return DD_OK;
         }
@@ -2142,4 +2166,49 @@ extern "C" int dd_probe_math(dd_ctx* ctx, int n, const double* in, double* out_e
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(d);
     return DD_OK;
+}
+
+// fp64 roof of the device (see include/dd_b200.h)
+extern "C" int dd_probe_fp64(dd_ctx* ctx, double ms_target, double* tflops) {
+    if (!ctx || !tflops || !(ms_target > 0.0)) return DD_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    double* sink = nullptr;
+    CK(cudaMalloc((void**)&sink, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int sm = ctx->sm_count > 0 ? ctx->sm_count : 148;
+    const int blocks = 2 * sm;  // two 1024-thread CTAs per SM: all 64 warps resident
+    int iters = 2000;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(e0, ctx->stream));
+        CK(dd_launch_probe_fp64(ctx->stream, sink, blocks, iters));
+        CK(cudaEventRecord(e1, ctx->stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8.0 * 16.0 * (double)iters * 1024.0 * (double)blocks;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;  // the first round sizes the loop
+        if (ms > 0.f) {
+            const double scale = ms_target / ms;
+            iters = (int)fmin(2e6, fmax(100.0, iters * scale));
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *tflops = best;
+    return DD_OK;
+}
+
+static char g_solver_kernel[3][64] = {"", "", ""};
+void dd_note_solver_kernel(int var, const char* name) {
+    if (var < DD_T || var > DD_CD) return;
+    snprintf(g_solver_kernel[var - DD_T], sizeof(g_solver_kernel[0]), "%s", name);
+}
+extern "C" const char* dd_solver_kernel_name(int var) {
+    if (var < DD_T || var > DD_CD) return "";
+    return g_solver_kernel[var - DD_T];
 }

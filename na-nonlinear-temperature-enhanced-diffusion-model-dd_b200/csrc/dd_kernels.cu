@@ -1274,3 +1274,27 @@ cudaError_t dd_launch_probe_math(cudaStream_t st, const double* in, double* out_
     k_probe_math<<<(n + 255) / 256, 256, 0, st>>>(in, out_exp, out_rcp, n);
     return cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------
+// fp64 roof probe (measurement only): 8 independent chains of dependent fused multiply-adds per thread keep the
+// double-precision pipe full; 2 * 8 * 16 * iters flops per thread
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_probe_fp64(double* sink, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0,
+           a6 = a0 + 6.0, a7 = a0 + 7.0;
+    const double m = 1.0 - 1e-9, c = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 12345.678) sink[0] = s;  // never true: keeps the chains alive
+}
+
+cudaError_t dd_launch_probe_fp64(cudaStream_t st, double* sink, int blocks, int iters) {
+    k_probe_fp64<<<blocks, 1024, 0, st>>>(sink, iters);
+    return cudaGetLastError();
+}

@@ -104,3 +104,10 @@ cudaError_t dd_launch_eval_sources(const DDLaunch& L, int mode, const DDGeom& g,
                                    const DDForcing& F, const DDState& out, int slot);
 
 cudaError_t dd_launch_probe_math(cudaStream_t st, const double* in, double* out_exp, double* out_rcp, int n);
+// fp64 roof probe: `iters` rounds of 8 independent FMA chains x 16 per thread, one 1024-thread CTA per SM slot
+cudaError_t dd_launch_probe_fp64(cudaStream_t st, double* sink, int blocks, int iters);
+
+// name of the kernel variant the last solve of a variable used (bench.py's roofline names the real kernel)
+void dd_note_solver_kernel(int var, const char* name);
+void dd_set_last_solver_kernel(const char* fmt, int a, int b, int c);
+const char* dd_last_solver_kernel();

@@ -17,6 +17,7 @@
 // special casing is needed; outside the grid the staging pads with zeros.
 #include <cuda_pipeline.h>
 
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -843,6 +844,10 @@ static bool dd_tile_map(const double* base, int ld, long long rows_total, int bo
     return true;
 }
 
+static thread_local char g_last_kernel[64] = "";
+void dd_set_last_solver_kernel(const char* fmt, int a, int b, int c) { snprintf(g_last_kernel, sizeof(g_last_kernel), fmt, a, b, c); }
+const char* dd_last_solver_kernel() { return g_last_kernel; }
+
 cudaError_t dd_launch_solve_pass(const DDLaunch& L, const DDGeom& g, const DDMember* mem, const DDRows& R,
                                  const double* xin, const double* vold,
                                  double* xout, const double* vstar, double* vnew, int zero_boundary,
@@ -904,6 +909,7 @@ cudaError_t dd_launch_solve_pass(const DDLaunch& L, const DDGeom& g, const DDMem
         const size_t smem = dd_reg_smem_bytes(P.const_band, P.rpw, pipe);
         const unsigned grid = pipe ? (unsigned)sm_count : (unsigned)nblocks;
         A.nblocks = (int)nblocks;
+        dd_set_last_solver_kernel("k_rbsor_reg<%d, %d, %d>", P.const_band, P.rpw, pipe);
 #define DD_LAUNCH_REG(CB, RPW)                                                             \
     do {                                                                                   \
         if (pipe)                                                                          \
@@ -930,8 +936,10 @@ cudaError_t dd_launch_solve_pass(const DDLaunch& L, const DDGeom& g, const DDMem
         }
 #undef DD_LAUNCH_REG
     } else if (P.const_band) {
+        dd_set_last_solver_kernel("k_rbsor_tile<%d>", 1, 0, 0);
         k_rbsor_tile<1><<<(unsigned)nblocks, P.threads, P.smem_bytes, L.stream>>>(A);
     } else {
+        dd_set_last_solver_kernel("k_rbsor_tile<%d>", 0, 0, 0);
         k_rbsor_tile<0><<<(unsigned)nblocks, P.threads, P.smem_bytes, L.stream>>>(A);
     }
     return cudaGetLastError();

@@ -220,6 +220,7 @@ cudaError_t dd_launch_solve_wave(const DDLaunch& L, const DDGeom& g, const DDMem
     if (ctas < 1) ctas = 1;
     A.flat_per_cta = (A.flat_total + ctas - 1) / ctas;
     ctas = (A.flat_total + A.flat_per_cta - 1) / A.flat_per_cta;
+    dd_set_last_solver_kernel("k_sor_wave<%d, %d, %d>", v->cb, v->C, v->maxt);
     void* args[] = {&A};
     return cudaLaunchKernel(v->fn, dim3((unsigned)ctas), dim3((unsigned)(nw * 32)), args, smem, L.stream);
 }

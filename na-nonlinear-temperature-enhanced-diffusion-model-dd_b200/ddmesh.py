@@ -157,6 +157,13 @@ class SlabMesh:
         self.x, self.y = as_f64(x), as_f64(y)
         self.world, self.rank = world, rank
         self.G = halo if world > 1 else 0
+        if world > 1:
+            # every rank sends G of its OWN rows to each neighbour: a slab thinner than the halo would send stale
+            # halo rows (and post a different size than its neighbour expects)
+            thin = min(b - a for a, b in (shard_members(len(self.x), world, r) for r in range(world)))
+            if thin < self.G:
+                raise ValueError(f"SlabMesh: {len(self.x)} rows over {world} ranks leaves a rank with {thin} rows, "
+                                 f"fewer than the halo of {self.G}; use fewer ranks or a shallower halo")
         self.part = slab_rows(len(self.x), world, rank, self.G)
         p = self.part
         self.batch = ddcore.Batch(self.x, self.y, 1, ctx=ctx, nslots=nslots, row0=p["row0"], nrows=p["nrows"],
@@ -191,9 +198,13 @@ class SlabMesh:
 
     # -- torch views of device fields ---------------------------------------------
     def _tensor(self, key, ptr, shape=None, dtype="<f8"):
+        # keyed on the address and shape as well: the library re-allocates some buffers (statistics, cs iteration
+        # arrays) when they have to grow, and a view cached by name alone would then point at freed memory
+        shape = tuple(shape or self.batch.shape)
+        key = (key, int(ptr), shape, dtype)
         t = self._tensors.get(key)
         if t is None:
-            t = self.torch.as_tensor(_DevArray(ptr, shape or self.batch.shape, dtype), device="cuda")
+            t = self.torch.as_tensor(_DevArray(ptr, shape, dtype), device="cuda")
             self._tensors[key] = t
         return t
 
@@ -322,7 +333,8 @@ class SlabMesh:
                            group)
         phase(6)
         with _Ordered(group, torch):
-            summ = [m._tensor("summary", m.batch.work_dev_ptr("summary"), (3, 4)) for m in group]
+            # rows 0..2: the three solves; row 3, column 0: the step's domain-error flag (HCsTriple corrector)
+            summ = [m._tensor("summary", m.batch.work_dev_ptr("summary"), (4, 4)) for m in group]
             red = [torch.nan_to_num(t, nan=1e300) for t in summ]
         comm.allreduce(red, "max", group)
         with _Ordered(group, torch):
@@ -340,7 +352,7 @@ class SlabMesh:
         """Two alternating sets of pinned read-back buffers (one step may be pending while the next is enqueued)."""
         torch = self.torch
         if not hasattr(self, "_hostbuf"):
-            self._hostbuf = [dict(summary=torch.zeros((3, 4), dtype=torch.float64).pin_memory(),
+            self._hostbuf = [dict(summary=torch.zeros((4, 4), dtype=torch.float64).pin_memory(),
                                   used=torch.zeros((1,), dtype=torch.int32).pin_memory()) for _ in range(2)]
             self._hostsel = 0
         self._hostsel ^= 1
@@ -351,7 +363,10 @@ class SlabMesh:
         rec["done"].synchronize()
         opt, plan, mode = rec["opt"], rec["plan"], rec["mode"]
         ctl = self._ctl[mode]
-        s = rec["host"]["summary"].numpy().copy()
+        s4 = rec["host"]["summary"].numpy().copy()
+        if s4[3, 0] > 0.0:  # same condition, same exception as the reference (src/prob1base.py:3417-3420)
+            raise ValueError("Denominator 2 - dt Kd (Sd - Cd1) (1 + Cl1) below positiveness treshold.")
+        s = s4[:3]
         iters = int(rec["host"]["used"][0]) if rec["track"] else int(opt.num_newton_iterations)
         stats = dict(sweeps=list(plan), guess=mode, rho=[float(x) for x in s[:, 0]],
                      resid=[float(x) for x in s[:, 2]], bound=[float(x) for x in s[:, 3]],

@@ -67,7 +67,9 @@ class DefaultModel01:
             setattr(self, k, v)
 
     def with_changes(self, **kwargs):
-        out = type(self)(ModelConsts(**{k: getattr(self, k) for k in ModelConsts._fields}))
+        # always a DefaultModel01, like the reference (:76-82): DefaultModel02(...).copy() drops the T_ref shift
+        # of Dd, and tests/test_spatial_isolated_T_accuracy.py:407-409 of the reference relies on it
+        out = DefaultModel01(ModelConsts(**{k: getattr(self, k) for k in ModelConsts._fields}))
         for k, v in kwargs.items():
             setattr(out, k, v)
         return out
@@ -995,6 +997,30 @@ class SemiDiscreteField_RegHCsTriple(SemiDiscreteFieldBase):
         return ((self.model.Sd - state.cd) * (state.cl + 1) * self.cscd_reaction_cs(state.cs)
                 * self.grid.null_bd_mask)
 
+    # derivative of the reaction term at (i, j) with respect to T, cl, cd at (i + a, j + b): a product of affine
+    # factors, so only the node itself contributes (host helpers of the reference's API, :2511-2597; the device
+    # kernels carry the same factors inside the cd Jacobian rows)
+    def _del_reaction(self, state: StateVars, a, b, wrt: str):
+        assert a in (-1, 0, 1) and b in (-1, 0, 1) and (a == 0 or b == 0)
+        if a != 0 or b != 0:
+            return self.grid.make_full0()
+        coef = {"T": self.cscd_reaction_T(), "cl": self.cscd_reaction_cl(), "cd": self.cscd_reaction_cd()}
+        if coef[wrt][0] == 0.0:
+            return self.grid.make_full0()
+        out = self.cscd_reaction_cp(state.cp) * self.cscd_reaction_cs(state.cs) * self.grid.null_bd_mask
+        for v, (slope, shift) in coef.items():
+            out = out * (slope if v == wrt else slope * getattr(state, v) + shift)
+        return out
+
+    def delT_ab_cscd_reaction_ij(self, state: StateVars, *, a, b):
+        return self._del_reaction(state, a, b, "T")
+
+    def delcl_ab_cscd_reaction_ij(self, state: StateVars, *, a, b):
+        return self._del_reaction(state, a, b, "cl")
+
+    def delcd_ab_cscd_reaction_ij(self, state: StateVars, *, a, b):
+        return self._del_reaction(state, a, b, "cd")
+
     def _all_F(self, at_t: StateVars, t: float) -> Dict[str, np.ndarray]:
         bind = self.binding()
         bind.configure(t, 1.0)
@@ -1146,13 +1172,32 @@ class P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_RegHCsTriple(P_ModifiedEuler_
         return out
 
     # -- pieces (called directly by the reference's tests) --------------------------
+    _cs_pred_masked = True  # RegHCsTriple / HCsTriple multiply the predicted cs by the boundary mask, CsTriple does not
+
+    def _user_F(self, name: str) -> bool:
+        """True when `semi_discrete_field.<name>` is user code (a subclass override or a rebound attribute, as the
+        reference's tests do with mock fields): an opaque Python callable cannot run on the device, the piece is
+        then evaluated with it on the host exactly as the reference composes it."""
+        f = self.semi_discrete_field
+        return name in vars(f) or getattr(type(f), name, None) is not getattr(SemiDiscreteField_RegHCsTriple, name)
+
+    def _heun(self, F, at_t, t, dt, var):
+        F0 = F(at_t, t)
+        star = at_t.with_changes(**{var: getattr(at_t, var) + dt * F0})
+        return getattr(at_t, var) + (0.5 * dt) * (F0 + F(star, t + dt))
+
     def initial_cp_pred(self, at_t, t, *, dt):
+        if self._user_F("Fcp"):
+            return self._heun(self.semi_discrete_field.Fcp, at_t, t, dt, "cp")
         b = self._bind(t, dt)
         b.upload(0, at_t.fields())
         b.pc_predict(0, t, dt)
         return b.work_download("cp1p")
 
     def initial_cs_pred(self, at_t, t, *, dt):
+        if self._user_F("Fcs"):
+            cs1 = self._heun(self.semi_discrete_field.Fcs, at_t, t, dt, "cs")
+            return cs1 * self._grid.null_bd_mask if self._cs_pred_masked else cs1
         b = self._bind(t, dt)
         b.upload(0, at_t.fields())
         b.pc_predict(0, t, dt)
@@ -1166,8 +1211,8 @@ class P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_RegHCsTriple(P_ModifiedEuler_
         self.last_cs_newton_iterations = int(iters[0])
         return b.download(1, which=("cp", "cs"))
 
-    def corrector_cp_step(self, T1, cl1, _cd1_ignored, *, at_t0, t0, dt):
-        cd1 = _cd1_ignored if _cd1_ignored is not None else at_t0.cd
+    def corrector_cp_step(self, T1, cl1, _cd1_ignroed, *, at_t0, t0, dt):  # (parameter name as in the reference, :2967)
+        cd1 = _cd1_ignroed if _cd1_ignroed is not None else at_t0.cd
         return self._correct(T1, cl1, cd1, at_t0, t0, dt)["cp"]
 
     def corrector_cs_step(self, _T1_ignored, cl1, cd1, *, at_t0, t0, dt):
@@ -1230,6 +1275,8 @@ class P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_CsTriple(P_ModifiedEuler_C_Tr
     """The same predictor-corrector / Newton step for the CsTriple field (reference :3152-3219): Heun cs
     predictor without boundary mask, closed-form trapezoidal cs corrector (no Newton iterations)."""
 
+    _cs_pred_masked = False
+
     def __init__(self, semi_discrete_field, *, num_pc_steps=1, num_newton_steps=1):
         super().__init__(semi_discrete_field, num_pc_steps=num_pc_steps, num_newton_steps=num_newton_steps,
                          regularization_factor=0.0, num_newton_iterations=0, consec_xs_rtol=0.0)
@@ -1242,3 +1289,20 @@ class P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_HCsTriple(P_ModifiedEuler_C_T
     def __init__(self, semi_discrete_field, *, num_pc_steps=1, num_newton_steps=1):
         super().__init__(semi_discrete_field, num_pc_steps=num_pc_steps, num_newton_steps=num_newton_steps,
                          regularization_factor=0.0, num_newton_iterations=0, consec_xs_rtol=0.0)
+
+    def corrector_cs_step(self, _T1_ignored, cl1, cd1, *, at_t0, t0, dt):
+        if not self._user_F("Fcs"):
+            return super().corrector_cs_step(_T1_ignored, cl1, cd1, at_t0=at_t0, t0=t0, dt=dt)
+        # a user-supplied Fcs (reference tests mock it): the same piecewise closed form on the host (:3393-3430) --
+        # Y0 = 2 cs0 + dt Fcs(u0, t0) + dt fcs(t1); cs1 = Y0 / (2 - dt R1) where Y0 > 0, Y0 / 2 where Y0 < 0
+        field, g, m = self.semi_discrete_field, self._grid, self._model
+        tol = np.finfo(float).eps * 100
+        denom = 2 - dt * ((m.Sd - cd1) * (1 + cl1) * m.Kd)
+        if np.any(denom < tol):
+            raise ValueError("Denominator 2 - \u0394t Kd (Sd - Cd1) (1 + Cl1) below positiveness treshold.")
+        Y0 = 2 * at_t0.cs + dt * field.Fcs(at_t0, t0) + dt * field.fcs(t0 + dt, g.xx, g.yy)
+        cs1 = g.make_full0()
+        pos, neg = Y0 > tol, Y0 < -tol
+        cs1[pos] = Y0[pos] / denom[pos]
+        cs1[neg] = Y0[neg] / 2.0
+        return cs1 * g.null_bd_mask

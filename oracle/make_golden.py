@@ -52,6 +52,20 @@ def _consts_for(case):
     return NOTEBOOK["expsin"] if case in ("expsin", "nfsp_h1h2", "nfsp_h2h2", "nfsp_h2h3") else NOTEBOOK["pol"]
 
 
+NONSEP_MODEL = dict(K1=1e-3, K2=2e-3, K3=1.5e-3, K4=1e-3, DT=1e-3, Dl_max=8.01e-4, phi_l=1e-5, gamma_T=1e-3, Kd=1e-2,
+                    Sd=1.0, Dd_max=2.46e-6, phi_d=1e-5, r_sp=5e-2, T_ref=300.0, kind=2)
+
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from oracle.mms import nonsep_exprs  # noqa: E402  (one definition for the oracle and for the reference run)
+
+
+def nonsep_expr_strings():
+    import sympy
+    t, x, y = sympy.symbols("t x y")
+    return {k: str(v) for k, v in nonsep_exprs(t, x, y).items()}
+
+
 def scenarios():
     S = []
     # A. MMS per-step fields, uniform grids, notebook constants
@@ -134,6 +148,12 @@ def scenarios():
                               [1.0, 2.0, 1.5], [1.0, 1.0, 0.5], [0.5, 0.25, 0.3], [3.0, 2.0, 2.0 - 1e-17, 1.0],
                               [0.0, 0.0, 0.0], [1.0, 0.1, 0.01, 0.001], [1.0, 0.5, 0.25]],
                   rate_factors=[2.0, 2.0, 2.0, 2.0, 2.0, 2.0, 2.0, 10.0, 3.0]))
+    # G. a manufactured solution that is NOT a sum of separable terms (MMSCaseSymbolic on the expressions of
+    #    tests/test_program_codegen.py:nonseparable_exprs): pins the generated forcing programs to the reference
+    for integ in ("pc", "fe"):
+        S.append(dict(name=f"steps_nonsep_14x11_{integ}", kind="steps", case="nonsep", model=dict(NONSEP_MODEL),
+                      grid=dict(N=14, M=11, nonuniform=True), eta=50.0, dt=2e-3 if integ == "pc" else 1e-3, t0=0.05,
+                      nsteps=3, integrator=integ, init="exact", pc={}, exprs=nonsep_expr_strings()))
     # the finite-difference helper behind MMSCaseFromAnalytic
     S.append(dict(name="analytic_fd", kind="analytic", nx=7, ny=5, t=0.3))
     return S
@@ -224,7 +244,11 @@ def run_steps(d):
         "h": (p1.ForcingTerms_HCsTriple, p1.SemiDiscreteField_HCsTriple,
               p1.P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_HCsTriple)}[variant]
     extra = dict(regularization_factor=eta) if variant == "regh" else {}
-    if d["case"] is not None:
+    if d["case"] == "nonsep":
+        ex = nonsep_exprs(p1.t_sym, p1.x_sym, p1.y_sym)
+        case = p1.MMSCaseSymbolic(grid=grid, model=model, **{k + "_sym_expr": v for k, v in ex.items()})
+        forcing = forcing_cls(mms_case=case, model=model, **extra)
+    elif d["case"] is not None:
         case = ref_case_cls(p1mc, d["case"])(grid=grid, model=model)
         forcing = forcing_cls(mms_case=case, model=model, **extra)
     else:

@@ -69,6 +69,16 @@ def _same(e):
     return {v: e for v in ("cp", "T", "cl", "cd", "cs")}
 
 
+def nonsep_exprs(t, x, y):
+    """A manufactured solution none of whose variables is a product f(t) X(x) Y(y); cs changes sign and has a kink
+    (the expressions of tests/test_program_codegen.py:nonseparable_exprs, which the device runs from a generated
+    forcing program; oracle/make_golden.py feeds the same ones to the reference's MMSCaseSymbolic)."""
+    return dict(cp=sympy.exp(-t * x * y) / 2, T=1 + sympy.sin(sympy.pi * x * y + t) / 10,
+                cl=sympy.cos(x + y * t) / 3, cd=sympy.exp(-(x - y) ** 2 - t) / 2,
+                cs=(sympy.sin(sympy.pi * (x + y * t)) * sympy.exp(-t) - sympy.Rational(1, 5)
+                    + sympy.Abs(x - sympy.Rational(1, 2)) ** sympy.Rational(21, 10)))
+
+
 def make_case(name: str, model: OModel, **kw) -> OCase:
     x, y, t = x_s, y_s, t_s
     if name == "pol":  # src/prob1_mms_cases.py:258-264
@@ -86,6 +96,8 @@ def make_case(name: str, model: OModel, **kw) -> OCase:
         base = sympy.Abs((x - theta) * (y - theta))
         g_of = {"cp": gam[0], "cs": gam[0], "T": gam[1], "cl": gam[1], "cd": gam[1]}
         return OCase({v: common * base ** g_of[v] for v in g_of})
+    if name == "nonsep":  # test-local MMSCaseSymbolic of tests/test_program_codegen.py (no library class)
+        return OCase(nonsep_exprs(t, x, y))
     if name == "expsin":  # src/prob1_mms_cases.py:296-337
         pi = sympy.pi
         W = sympy.sin(pi * x) * sympy.sin(pi * y)

@@ -82,10 +82,36 @@ def test_steps_match_reference(dd, name):
             got = b.download(cur)
             for v in VARS:
                 assert rel_err(got[v], z[f"step{n + 1}_{v}"]) <= TOL, f"step {n + 1} {v}"
-    if desc["integrator"] == "pc":
-        # last_residual of the reference: recompute for the last step through the class-level pieces
-        pass
     b.close()
+    if desc["integrator"] == "pc":
+        # last_residual of the reference's integrator (src/prob1base.py:3041-3043, 3076-3078, 3111-3113): the same
+        # steps through the reference-compatible classes, whose last_residual replays the last step's Newton pieces
+        p1 = dd["p1"]
+        variant = desc.get("variant", "regh")
+        fcls, Fcls, icls = {
+            "regh": (p1.ForcingTerms_RegHCsTriple, p1.SemiDiscreteField_RegHCsTriple,
+                     p1.P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_RegHCsTriple),
+            "cs": (p1.ForcingTerms_CsTriple, p1.SemiDiscreteField_CsTriple,
+                   p1.P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_CsTriple),
+            "h": (p1.ForcingTerms_HCsTriple, p1.SemiDiscreteField_HCsTriple,
+                  p1.P_ModifiedEuler_C_Trapezoidal_TimeIntegrator_HCsTriple)}[variant]
+        extra = dict(regularization_factor=desc["eta"]) if variant == "regh" else {}
+        if desc["case"] is not None:
+            forcing = fcls(mms_case=dd["CASES"][desc["case"]](grid=grid, model=model), model=model, **extra)
+        else:
+            forcing = p1.NoForcingTerms(grid)
+        field = Fcls(grid=grid, model=model, forcing_terms=forcing, **extra)
+        integ = icls(field, **extra, **desc["pc"])
+        st8 = p1.StateVars(*[z["init_" + v] for v in VARS], model=model, hh=grid.hh, kk=grid.kk)
+        t = desc["t0"]
+        for n in range(desc["nsteps"]):
+            st8 = integ.step(st8, t0=t, dt=dt)
+            t += dt
+        for v in VARS:
+            assert rel_err(getattr(st8, v), z[f"step{desc['nsteps']}_{v}"]) <= TOL, f"class API step {v}"
+        for v in ("T", "cl", "cd"):
+            scale = max(np.max(np.abs(z[f"step{desc['nsteps']}_{v}"])), 1e-300)
+            assert np.max(np.abs(integ.last_residual[v] - z["resid_" + v])) <= 1e-11 * scale, f"last_residual {v}"
 
 
 @pytest.mark.parametrize("name", fixture_names(kind="trial"))

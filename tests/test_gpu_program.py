@@ -5,7 +5,7 @@ Tolerance on the fields: 1e-12 relative to the field's maximum."""
 import numpy as np
 import pytest
 
-from golden_util import VARS
+from golden_util import VARS, fixture_names, load_fixture, rel_err
 from test_program_codegen import MODEL, nonseparable_exprs
 
 pytestmark = pytest.mark.gpu
@@ -187,3 +187,39 @@ def test_analytic_callable_case_steps_through_the_array_path(env):
         a, b = getattr(out[1], v), getattr(out[0], v)
         assert np.max(np.abs(a - b)) <= 2e-5 * max(np.max(np.abs(b)), 1e-3), v
         assert np.max(np.abs(a - b)) > 0 or v == "cp"      # (the two runs really used different sources)
+
+
+@pytest.mark.parametrize("name", fixture_names(kind="steps", program=True))
+def test_program_steps_match_the_reference(env, name):
+    """Pins the generated forcing programs to the REFERENCE (not to this package's own array mode): per-step fields
+    of the reference's MMSCaseSymbolic on the non-separable expressions, written by oracle/make_golden.py from the
+    live reference, against the class API here, which runs the case from an NVRTC-compiled program."""
+    import sympy
+    desc, z = load_fixture(name)
+    p1, ddcore = env["p1"], env["ddcore"]
+    # the fixture was generated from the same expressions the tests here use
+    plain = {p1.t_sym: sympy.Symbol("t"), p1.x_sym: sympy.Symbol("x"), p1.y_sym: sympy.Symbol("y")}
+    for k, v in nonseparable_exprs().items():
+        stored = sympy.sympify(desc["exprs"][k[:-9]])
+        assert sympy.simplify(v.subs(plain) - stored) == 0, k
+    model = env["product_model"](desc["model"])
+    grid = p1.Grid(z["x"], z["y"])
+    case = env["Case"](grid=grid, model=model)
+    integ, field = _integrator(env, grid, model, case, desc["eta"], False, "pc" if desc["integrator"] == "pc" else "fe")
+    t, dt = desc["t0"], desc["dt"]
+    s = p1.state_from_mms_when(mms_case=case, t=t, grid=grid)
+    for v in VARS:
+        assert rel_err(getattr(s, v), z["init_" + v]) <= 1e-13, v
+    for v, F in zip(VARS, (field.Fcp, field.FT, field.Fcl, field.Fcd, field.Fcs)):
+        assert rel_err(F(s, t), z["F0_" + v]) <= 1e-12, v
+    for n in range(desc["nsteps"]):
+        s = integ.step(s, t0=t, dt=dt)
+        t += dt
+        for v in VARS:
+            assert rel_err(getattr(s, v), z[f"step{n + 1}_{v}"]) <= 1e-12, (n, v)
+    assert field.binding().batch.mode == ddcore.MODE_PROGRAM
+    if desc["integrator"] == "pc":
+        assert integ.last_stats["cs_newton_iters"] == int(z["cs_newton_calls_per_step"][-1])
+        for v in ("T", "cl", "cd"):
+            scale = np.max(np.abs(z[f"step{desc['nsteps']}_{v}"]))
+            assert np.max(np.abs(integ.last_residual[v] - z["resid_" + v])) <= 1e-11 * scale

@@ -5,12 +5,15 @@ ensemble with per-member constants against the oracle.  Tolerance of the error n
 import functools
 import json
 
+import os
+
 import numpy as np
 import pytest
 
 from golden_util import VARS, load_fixture
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def close(a, b):
@@ -117,6 +120,46 @@ def test_ensemble_with_member_constants_matches_oracle(mods):
     e = ens.TrajectoryEnsemble(grid, mods["CASES"]["scp_fast1e1"], models[0], [etas[0]] * 3)
     res = e.run_for_errors(Tf, dt)
     assert close(res["overall"], [want[0, 0]] * 3)
+
+
+def test_ensemble_config3_spot_check_64_members(mods):
+    """SURVEY 8d config 3 as written: MMSCaseSlowlyChangingPeaks_Fast1e1, N = M = 32, dt = 5e-4, Tf = 0.01 (20 steps),
+    member parameters of the 10^5-member draw (rng 20250503: eta ~ logU[10, 1000]; K1..K4, DT, Kd each base * U[0.5,
+    1.5]) -- 64 of those members, picked at random, in one batched device run against the oracle member by member."""
+    import dataclasses
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import NOTEBOOK_CONSTS, OForcing, OGrid, make_case, run_trial
+    p1, ens = mods["p1"], mods["ens"]
+    n_all, n = 100000, 64
+    rng = np.random.default_rng(20250503)
+    etas_all = 10.0 ** rng.uniform(1.0, 3.0, n_all)
+    f_all = rng.uniform(0.5, 1.5, (n_all, 6))
+    # the bench draws its members the same way
+    bm, be = bench.ensemble_members(8)
+    assert np.allclose(be, 10.0 ** np.random.default_rng(20250503).uniform(1.0, 3.0, 8))
+    pick = np.sort(np.random.default_rng(64).choice(n_all, n, replace=False))
+    base = NOTEBOOK_CONSTS["pol"]
+    names = ("K1", "K2", "K3", "K4", "DT", "Kd")
+    omodels = [dataclasses.replace(base, **{k: getattr(base, k) * f_all[m, q] for q, k in enumerate(names)}) for m in pick]
+    etas = etas_all[pick]
+    models = [mods["product_model"](dict(K1=om.K1, K2=om.K2, K3=om.K3, K4=om.K4, DT=om.DT, Dl_max=om.Dl_max,
+                                         phi_l=om.phi_l, gamma_T=om.gamma_T, Kd=om.Kd, Sd=om.Sd, Dd_max=om.Dd_max,
+                                         phi_d=om.phi_d, r_sp=om.r_sp, T_ref=om.T_ref, kind=2)) for om in omodels]
+    grid = p1.make_uniform_grid(32, 32)
+    og = OGrid(np.array(grid.x), np.array(grid.y))
+    Tf, dt = 0.01, 5e-4
+    e = ens.TrajectoryEnsemble(grid, mods["CASES"]["scp_fast1e1"], models, etas, chunk=n)
+    res = e.run_for_errors(Tf, dt)
+    assert res["nsteps"] == 20
+    want = []
+    for om, eta in zip(omodels, etas):
+        oc = make_case("scp_fast1e1", om)
+        r = run_trial(oc, og, om, float(eta), OForcing(oc, om, float(eta), og), Tf=Tf, dt=dt)
+        want.append([r["overall"]] + [r["per_var"][v] for v in VARS])
+    got = np.column_stack([res["overall"], res["per_var"]])
+    assert close(got, np.array(want))
 
 
 # Published in the reference's notebooks (cell 9 outputs; BASELINE.md section 1.2): overall error per spatial level

@@ -27,7 +27,7 @@ def _setup(desc, z):
     return g, m, case, forcing, s
 
 
-@pytest.mark.parametrize("name", fixture_names(kind="steps"))
+@pytest.mark.parametrize("name", fixture_names(kind="steps") + fixture_names(kind="steps", program=True))
 def test_steps_match_reference(name):
     desc, z = load_fixture(name)
     g, m, case, forcing, s = _setup(desc, z)

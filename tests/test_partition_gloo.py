@@ -72,3 +72,14 @@ def test_halo_exchange_gloo(world):
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, 41, 7, 4, out), nprocs=world, join=True)
     assert all(out[r] for r in range(world))
+
+
+def test_slab_thinner_than_halo_is_refused():
+    import numpy as np
+    import pytest
+    """65 rows over 8 ranks with a halo of 24: rank 1 would expect 24 rows from rank 2, which owns 8.  The mesh
+    refuses such a partition up front (before any device work: the check precedes the batch creation)."""
+    import ddmesh
+    x = np.linspace(0.0, 1.0, 65)
+    with pytest.raises(ValueError, match="fewer than the halo"):
+        ddmesh.SlabMesh(x, x, world=8, rank=1, halo=24)
