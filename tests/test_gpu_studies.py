@@ -306,3 +306,33 @@ def test_device_combined_norms_equal_the_python_arithmetic_bit_for_bit(mods):
             if N == 32 and integrator == "pc":
                 assert np.isnan(norms).any() and got["overall"][0] == 0.0        # the blow-up really is in this run
         b.close()
+
+
+def _notebooks():
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import notebook_studies
+    return notebook_studies
+
+
+@pytest.mark.parametrize("name", ["MMSCaseSlowlyChangingPeaks_Fast1e1", "MMSCaseNonFullySmoothPol_cpcsH1_TclcdH2",
+                                  "MMSCaseNonFullySmoothPol_cpcsH2_TclcdH2", "MMSCaseNonFullySmoothPol_cpcsH2_TclcdH3"])
+def test_notebook_tables_of_the_long_studies(mods, name):
+    """The studies the notebooks run to Tf = 1 and Tf = 10 (up to 4096 steps at N = 256; 6 - 7 hours each on the
+    author's workstation): published overall errors and final observed orders -- SlowlyChangingPeaks_Fast1e1
+    2.092 (spatial) and 1.996 (temporal, including the two blown-up levels that print 0.0), NonFullySmoothPol
+    H1/H2 1.054 (the expected order breakdown), H2/H2 4.482 and 2.065, H2/H3 1.961."""
+    nbs = _notebooks()
+    nb = nbs.NOTEBOOKS[name]
+    res = nbs.run_notebook(name, which=("spatial", "temporal"))
+    for key in ("spatial", "temporal"):
+        r = res[key]
+        pub, got = np.array(r["published"]), np.array(r["reproduced"])
+        # error norms are differences of nearly equal O(1) fields: rounding of the fields (1e-13 after thousands
+        # of steps) on top of the printed digits
+        assert np.all(np.abs(got - pub) <= 2e-6 * pub + 2e-13), (key, got, pub)
+        want = r["published_final_rate"]
+        if want is None:
+            assert not np.isfinite(r["final_rate"]), (key, r["rates"])
+        else:
+            assert abs(r["final_rate"] - want) <= 2e-3, (key, r["rates"], want)

@@ -119,3 +119,57 @@ def test_marching_sizes_match_oracle(dd, solver, cid, case, consts, N, M, power,
     if cid == "scp_bigdt":
         assert max(st2["passes"]) >= 1 and max(st2["sweeps"]) >= 8, st2
     b.close()
+
+
+@pytest.fixture(scope="module")
+def oracle512():
+    """Two PC steps of MMSCasePol at N = M = 512 by the oracle (SuperLU on 261 121 unknowns: ~20 s per step)."""
+    from oracle import NOTEBOOK_CONSTS, OForcing, OGrid, PCStepper, exact_state, make_case
+    N = M = 512
+    om = NOTEBOOK_CONSTS["pol"]
+    eta, t0, dt = 50.0, 0.0, (1.0 / N) ** 1.5
+    x, y = np.linspace(0, 1, N + 1), np.linspace(0, 1, M + 1)
+    og = OGrid(x, y)
+    oc = make_case("pol", om)
+    stepper = PCStepper(og, om, eta, OForcing(oc, om, eta, og), keep_residuals=False)
+    ref = exact_state(oc, t0, og)
+    for k in range(2):
+        ref = stepper.step(ref, t0 + k * dt, dt)
+    return dict(N=N, M=M, om=om, eta=eta, t0=t0, dt=dt, x=x, y=y, ref=ref)
+
+
+def test_slab_mesh_512_world8_matches_oracle(dd, solver, oracle512):
+    """SURVEY 8d config 5 at its parity size: N = M = 512, row slabs over 8 ranks (all on one GPU, halo exchange by
+    device copies), marching kernels and a multi-tile / multi-strip solve on every slab.  Two PC steps against the
+    oracle (1e-12) and, at a fixed sweep plan, bit for bit against the undecomposed mesh."""
+    import ddmesh
+    ddcore, p1 = dd["ddcore"], dd["p1"]
+    o = oracle512
+    N, M, om, eta, t0, dt, x, y, ref = (o[k] for k in ("N", "M", "om", "eta", "t0", "dt", "x", "y", "ref"))
+    world = 8
+    model = dd["product_model"](_model_dict(om))
+    spec = dd["CASES"]["pol"](grid=p1.Grid(x, y), model=model).device_spec()
+
+    def run(world, opts):
+        meshes = ddmesh.SlabMesh.local_group(x, y, world) if world > 1 else [ddmesh.SlabMesh(x, y)]
+        for m in meshes:
+            m.batch.set_model(model, eta)
+            m.batch.forcing_spec(spec)
+            m.fill_exact(0, t0)
+        for k in range(2):
+            st = meshes[0].step_pc(k % 2, (k + 1) % 2, t0 + k * dt, dt, opts)
+        out = {v: np.concatenate([m.owned(0)[v] for m in meshes]) for v in VARS}
+        for m in meshes:
+            m.batch.close()
+        return out, st
+
+    got, st = run(world, ddcore.pc_options())
+    for v in VARS:
+        assert got[v].shape == (N + 1, M + 1)
+        assert rel_err(got[v], getattr(ref, v)) <= TOL, (v, st)
+    assert max(st["bound"]) <= 1e-13, st
+    fixed = ddcore.pc_options(fixed_sweeps=6)
+    many, _ = run(world, fixed)
+    one, _ = run(1, fixed)
+    for v in VARS:
+        assert np.array_equal(many[v], one[v]), v
