@@ -1335,8 +1335,8 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
     // on the physical boundary do not shrink.
     int v0 = b->asm0, v1 = b->asm1;
     const bool lo_edge = (b->row0 == 0), hi_edge = (b->row0 + b->nrows == b->N + 1);
-    // opt-in on wide grids: wavefront kernel (rows marched once per pass, no row halo); the previous step's
-    // increment as initial iterate is only known to the tile kernels
+    // wide grids, the variables DD_WAVE names (default: cl): wavefront kernel (rows marched once per pass, no row
+    // halo); the previous step's increment as initial iterate is only known to the tile kernels
     const bool wave = dd_wave_ok(b->g, L, var) && !vold;
     while (left > 0) {
         DDSolvePlan P;

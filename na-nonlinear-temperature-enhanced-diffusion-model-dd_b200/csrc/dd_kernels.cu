@@ -188,6 +188,50 @@ __global__ void __launch_bounds__(DD_BLOCK) k_eval_sources(DDGeom g, const DDMem
     out.v[DD_CS][o] = s.fcs;
 }
 
+// One-term, one-profile separable solutions (MMSCasePol and the other single-product cases): a thread owns a
+// column and walks down DD_SRC_ROWS rows.  The column's six table values stay in registers, the row's six are the
+// same address for the whole warp (one broadcast load each), and the node arithmetic is dd_sources itself, fed with
+// the sums dd_spatial_separable would have formed -- same operands, same order, same results as the generic kernel,
+// without its per-node table addressing and term loops.
+#define DD_SRC_ROWS 8
+__global__ void __launch_bounds__(DD_BLOCK) k_eval_sources_sep1(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
+                                                                DDState out, int slot, int own0, int own1) {
+    const int j = blockIdx.x * DD_BLOCK + threadIdx.x;
+    const int member = blockIdx.z;
+    const DDMember& mb = mem[member];
+    if (j > g.M || !mb.active) return;
+    const DDTables& tb = F.tab;
+    const double Y0 = __ldg(tb.Y[0][0] + j), Y1 = __ldg(tb.Y[0][1] + j), Y2 = __ldg(tb.Y[0][2] + j);
+    const bool jint = j > 0 && j < g.M;
+    const double QY1 = jint ? __ldg(tb.QY1 + j) : 0.0, QY2 = jint ? __ldg(tb.QY2 + j) : 0.0,
+                 QY3 = jint ? __ldg(tb.QY3 + j) : 0.0;
+    const int ra = own0 + blockIdx.y * DD_SRC_ROWS, rz = min(ra + DD_SRC_ROWS, own1);
+    long long o = member * g.mstride + (long long)ra * g.ld + j;
+    for (int r = ra; r < rz; ++r, o += g.ld) {
+        const int i = g.row0 + r;
+        const double X0 = __ldg(tb.X[0][0] + i), X1 = __ldg(tb.X[0][1] + i), X2 = __ldg(tb.X[0][2] + i);
+        const bool inter = jint && i > 0 && i < g.N;
+        DDSpatial sp;
+        const double sXY = 0.0 + X0 * Y0, sX1Y = 0.0 + X1 * Y0, sXY1 = 0.0 + X0 * Y1, sLap = 0.0 + (X2 * Y0 + X0 * Y2);
+#pragma unroll
+        for (int v = 0; v < DD_NVAR; ++v) {
+            sp.S[v] = sXY; sp.Sx[v] = sX1Y; sp.Sy[v] = sXY1; sp.Sl[v] = sLap;
+        }
+        sp.Q1 = sp.Q2 = sp.Q3 = 0.0;
+        if (inter) {
+            sp.Q1 = 0.0 + __ldg(tb.QX1 + i) * QY1;
+            sp.Q2 = 0.0 + __ldg(tb.QX2 + i) * QY2;
+            sp.Q3 = 0.0 + __ldg(tb.QX3 + i) * QY3;
+        }
+        const DDSrc q = dd_sources<DD_FORCING_SEPARABLE>(F, mb, sp, slot, i, j, o, inter, true);
+        out.v[DD_CP][o] = q.fcp;
+        out.v[DD_T][o] = q.fT;
+        out.v[DD_CL][o] = q.fcl;
+        out.v[DD_CD][o] = q.fcd;
+        out.v[DD_CS][o] = q.fcs;
+    }
+}
+
 #define DD_DISPATCH_MODE(mode, CALL)                               \
     switch (mode) {                                                \
         case DD_FORCING_NONE: { constexpr int MODE = DD_FORCING_NONE; CALL; } break;           \
@@ -234,6 +278,16 @@ cudaError_t dd_launch_fill_exact(const DDLaunch& L, int mode, const DDGeom& g, c
 cudaError_t dd_launch_eval_sources(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,
                                    const DDForcing& F, const DDState& out, int slot) {
     const int bpm = blocks_per_member(g, L);
+    static const bool no_fast = getenv("DD_NO_SRC_FAST") != nullptr;
+    if (mode == DD_FORCING_SEPARABLE && F.tab.nprof == 1 && F.tab.nterms == 1 && !no_fast && g.M + 1 >= 64 &&
+        L.nmembers <= 65535) {
+        const dim3 grid((unsigned)((g.M + 1 + DD_BLOCK - 1) / DD_BLOCK),
+                        (unsigned)((L.own1 - L.own0 + DD_SRC_ROWS - 1) / DD_SRC_ROWS), (unsigned)L.nmembers);
+        if (grid.y <= 65535u) {
+            k_eval_sources_sep1<<<grid, DD_BLOCK, 0, L.stream>>>(g, mem, F, out, slot, L.own0, L.own1);
+            return cudaGetLastError();
+        }
+    }
     if (mode == DD_FORCING_SEPARABLE)
         k_eval_sources<DD_FORCING_SEPARABLE><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(g, mem, F, out, slot, L.own0,
                                                                                           L.own1, bpm);

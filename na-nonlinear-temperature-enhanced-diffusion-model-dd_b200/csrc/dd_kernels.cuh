@@ -45,10 +45,10 @@ struct DDSolvePlan {
 
 cudaError_t dd_solver_configure();  // opt-in to large dynamic shared memory (once per process)
 
-// wavefront solver (dd_wave.cu): one pass of `sweeps` red-black SOR sweeps marching down column strips; wide grids,
-// opt-in (the register-tile kernels are as fast)
+// wavefront solver (dd_wave.cu): one pass of `sweeps` red-black SOR sweeps marching down column strips; wide grids;
+// used for the cl solve by default, the register-tile kernels for T and cd (as fast or faster there)
 cudaError_t dd_wave_configure();
-bool dd_wave_ok(const DDGeom& g, const DDLaunch& L, int var);  // opt-in: DD_WAVE=1 or DD_WAVE=T,cl,cd
+bool dd_wave_ok(const DDGeom& g, const DDLaunch& L, int var);  // DD_WAVE = 0 | 1 | list of T,cl,cd (default: cl)
 void dd_wave_max_sweeps(int const_band, int* any, int* wide);  // per pass: any variant / the widest one
 cudaError_t dd_launch_solve_wave(const DDLaunch& L, const DDGeom& g, const DDMember* mem, const DDRows& R,
                                  const double* xin, double* xout, const double* vstar, double* vnew,

@@ -47,8 +47,7 @@ def test_wave_solver_equals_tile_solver_bitwise(dd, N, M, sweeps):
     opts = dd["ddcore"].pc_options(fixed_sweeps=sweeps)
     out = {}
     for mode in ("wave", "tile"):
-        if mode == "wave":
-            os.environ["DD_WAVE"] = "1"
+        os.environ["DD_WAVE"] = "1" if mode == "wave" else "0"
         try:
             b = _batch(dd, "pol", om, x, y, 50.0)
             b.fill_exact(0, 0.1)
@@ -79,8 +78,7 @@ MARCH_CASES = [
 @pytest.fixture(params=["tile", "wave"])
 def solver(request):
     """Both solvers of the wide-grid regime: the register-tile kernels (default) and the wavefront kernel."""
-    if request.param == "wave":
-        os.environ["DD_WAVE"] = "1"
+    os.environ["DD_WAVE"] = "1" if request.param == "wave" else "0"
     yield request.param
     os.environ.pop("DD_WAVE", None)
 
