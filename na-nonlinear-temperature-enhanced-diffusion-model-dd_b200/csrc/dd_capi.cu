@@ -14,6 +14,7 @@
 
 #include "../../include/dd_b200.h"
 #include "dd_kernels.cuh"
+#include "dd_member.cuh"
 #include "dd_combine.cuh"
 #include "dd_tables_host.h"
 
@@ -63,6 +64,7 @@ struct dd_batch {
     double *d_norm_partial, *d_norm_out;
     int norm_bpm;
     double* d_combine_state = nullptr;  // dd_run_*_errors: running best / integral / last integrand, [B][18]
+    double* d_member_stats = nullptr;   // one-CTA-per-member runs: [B][16] solve statistics of the last step
     double* d_combined = nullptr;       // [B][6]
     // staged sources: the MMS sources of a time level are evaluated once (k_eval_sources) into one of two
     // sets of five arrays and the step kernels read them in ARRAYS mode; the t1 set of a step is the t0
@@ -421,7 +423,7 @@ extern "C" int dd_batch_destroy(dd_batch* b) {
     cudaFree(b->d_mem); cudaFree(b->d_t0); cudaFree(b->d_dt); cudaFree(b->d_stats); cudaFree(b->d_summary);
     cudaFree(b->d_itmax); cudaFree(b->d_itmin); cudaFree(b->d_used); cudaFree(b->d_norm_partial);
     cudaFree(b->d_norm_out);
-    cudaFree(b->d_combine_state); cudaFree(b->d_combined);
+    cudaFree(b->d_combine_state); cudaFree(b->d_combined); cudaFree(b->d_member_stats);
     cudaFree(b->d_flags);
     dd_ctx* ctx = b->ctx;
     delete b;
@@ -1795,6 +1797,81 @@ static int combine_async(dd_batch* b, double* combined_host) {
     return DD_OK;
 }
 
+// Small grids (the working set of a member fits in shared memory): whole trajectories on chip, one CTA per member
+// (dd_member.cu).  Possible when the forcing is evaluated on the device from tables, every member is a RegHCsTriple
+// one, the step is the default p = q = 1 one and no per-step norm series is asked for.  OPT-IN (DD_MEMBER_KERNEL=1):
+// measured on B200 (12 500 members of 33 x 33 nodes, profiles/README.md) it reaches 1.70e9 cell-steps/s against
+// 2.12e9 of the batched mesh kernels -- 16 warps per SM and the sources re-evaluated in every phase (there is no
+// room for staged source arrays next to the 19 work arrays) cost more than the HBM round trips it saves.
+static bool member_path_ok(const dd_batch* b, const dd_pc_options& opt, int nsteps, const double* norms_out) {
+    const char* on = getenv("DD_MEMBER_KERNEL");  // read per call: the tests compare the two paths in one process
+    if (!(on && *on && *on != '0') || norms_out || nsteps < 1 || b->is_slab || b->has_variants || b->fused_sources)
+        return false;
+    if (b->mode != DD_FORCING_SEPARABLE && b->mode != DD_FORCING_EXPSIN) return false;
+    if (opt.num_pc_steps != 1 || opt.num_newton_steps != 1 || opt.extrapolate_guess) return false;
+    if (opt.num_newton_iterations > 100000) return false;
+    for (int m = 0; m < b->B; ++m)
+        for (int v = 0; v < DD_NVAR; ++v)
+            if (b->mode == DD_FORCING_SEPARABLE && b->h_mem[m].phi_kind[v] == DD_PHI_HOST) return false;
+    return dd_member_fits(b->N, b->M);
+}
+
+static int run_member_kernel(dd_batch* b, int slot_a, int slot_b, int nsteps, const dd_pc_options& opt,
+                             double* combined_out, dd_step_stats* stats) {
+    dd_ctx* ctx = b->ctx;
+    int rc;
+    if (combined_out && (rc = ensure_combine(b)) != DD_OK) return rc;
+    if (!b->d_member_stats) CK(cudaMalloc((void**)&b->d_member_stats, sizeof(double) * 16 * b->B));
+    DDMemberArgs A;
+    memset(&A, 0, sizeof(A));
+    A.g = b->g;
+    A.mem = b->d_mem;
+    A.mem_rw = b->d_mem;
+    A.F = b->F;
+    A.in = cstate(b, slot_a);
+    A.out = mstate(b, nsteps % 2 == 0 ? slot_a : slot_b);
+    A.nmembers = b->B;
+    A.nsteps = nsteps;
+    A.cap = opt.num_newton_iterations;
+    A.rtol = (opt.consec_xs_rtol > 0.0 && opt.num_newton_iterations > 0) ? opt.consec_xs_rtol : 0.0;
+    A.cd_swap = opt.cd_band_swap;
+    A.fixed_sweeps = opt.fixed_sweeps;
+    A.max_sweeps = opt.max_sweeps;
+    A.solve_tol = opt.solve_tol;
+    A.combined = combined_out ? b->d_combined : nullptr;
+    A.stats = b->d_member_stats;
+    {
+        ProfScope ps_(ctx->stream, PC_OTHER, 1);
+        CK(dd_launch_member_run(ctx->stream, b->mode, A, ctx->sm_count));
+    }
+    std::vector<double> hs((size_t)16 * b->B);
+    CK(cudaMemcpyAsync(hs.data(), b->d_member_stats, sizeof(double) * hs.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    if (combined_out)
+        CK(cudaMemcpyAsync(combined_out, b->d_combined, sizeof(double) * 6 * b->B, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    b->prev_valid = false;
+    b->src_has[0] = b->src_has[1] = false;
+    dd_step_stats st;
+    memset(&st, 0, sizeof(st));
+    bool failed = false;
+    for (int m = 0; m < b->B; ++m) {
+        if (!b->h_mem[m].active) continue;
+        const double* q = hs.data() + (size_t)16 * m;
+        for (int k = 0; k < 3; ++k) {
+            if ((int)q[k] > st.sweeps[k]) st.sweeps[k] = (int)q[k];
+            st.passes[k] = 1;
+            if (q[3 + k] > st.rho[k] || q[3 + k] != q[3 + k]) st.rho[k] = q[3 + k];
+            if (q[6 + k] > st.resid[k]) st.resid[k] = q[6 + k];
+            if (q[9 + k] > st.bound[k]) st.bound[k] = q[9 + k];
+        }
+        if ((int)q[12] > st.cs_newton_iters) st.cs_newton_iters = (int)q[12];
+        if (q[13] != 0.0) failed = true;
+    }
+    if (stats) *stats = st;
+    if (failed) return fail(ctx, DD_ERR_NOT_CONVERGED, "linear solve of a member did not reach the residual bound");
+    return DD_OK;
+}
+
 static int run_pc_loop(dd_batch* b, int slot_a, int slot_b, const double* t0, const double* dt, int n_t, int nsteps,
                        const dd_pc_options* opt_in, double* norms_out, double* combined_out, dd_step_stats* stats) {
     if (!b || !slot_ok(b, slot_a) || !slot_ok(b, slot_b) || slot_a == slot_b || nsteps < 0) return DD_ERR_INVALID;
@@ -1806,6 +1883,7 @@ static int run_pc_loop(dd_batch* b, int slot_a, int slot_b, const double* t0, co
     int rc = check_opts(ctx, opt);
     if (rc != DD_OK) return rc;
     if ((rc = set_times(b, t0, dt, n_t)) != DD_OK) return rc;
+    if (member_path_ok(b, opt, nsteps, norms_out)) return run_member_kernel(b, slot_a, slot_b, nsteps, opt, combined_out, stats);
     int cur = slot_a, nxt = slot_b;
     const size_t nstride = (size_t)8 * b->B;
     if (combined_out && (rc = ensure_combine(b)) != DD_OK) return rc;

@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from golden_util import VARS, load_fixture
+from golden_util import VARS, load_fixture, rel_err
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -24,10 +24,11 @@ def close(a, b):
 @pytest.fixture(scope="module")
 def mods():
     import cvg_studies_base as cvg
+    import ddcore
     import ddensemble
     import prob1base as p1
     from test_hostsim import CASES, product_model
-    return dict(cvg=cvg, ens=ddensemble, p1=p1, CASES=CASES, product_model=product_model)
+    return dict(cvg=cvg, ens=ddensemble, p1=p1, ddcore=ddcore, CASES=CASES, product_model=product_model)
 
 
 def test_convergence_study_driver_matches_reference(mods):
@@ -348,3 +349,74 @@ def test_notebook_tables_of_the_long_studies(mods, name):
             assert not np.isfinite(r["final_rate"]), (key, r["rates"])
         else:
             assert abs(r["final_rate"] - want) <= 2e-3, (key, r["rates"], want)
+
+
+@pytest.mark.parametrize("case,N,M", [("scp_fast1e1", 32, 32), ("expsin", 20, 27), ("nfsp_h1h2", 16, 16)])
+def test_member_kernel_equals_batched_kernels(mods, case, N, M):
+    """Small grids run whole trajectories in one CTA per member (csrc/dd_member.cu: the time loop on chip); the same
+    members through the batched mesh kernels (the default) give the same final fields (1e-12), the same
+    combined error norms and the same cs-Newton iteration counts."""
+    p1, ddcore = mods["p1"], mods["ddcore"]
+    model = mods["product_model"](NOTEBOOK_MODEL["expsin" if case == "expsin" else "pol"])
+    grid = p1.Grid(np.linspace(0, 1, N + 1) ** 1.1, np.linspace(0, 1, M + 1))
+    spec = mods["CASES"][case](grid=grid, model=model).device_spec()
+    B, t0, dt, nsteps = 3, 0.05, 5e-4, 7
+    out = {}
+    for path in ("member", "batched"):
+        if path == "member":
+            os.environ["DD_MEMBER_KERNEL"] = "1"
+        try:
+            b = ddcore.Batch(grid.x, grid.y, B)
+            b.set_models([ddcore.model_struct(model, eta) for eta in (10.0, 50.0, 400.0)])
+            b.forcing_spec(spec)
+            b.fill_exact(0, t0)
+            res, st = b.run_errors(0, 1, t0, dt, nsteps)
+            final = 0 if nsteps % 2 == 0 else 1
+            out[path] = (res, st, [b.download(final, member=m) for m in range(B)])
+            b.close()
+        finally:
+            os.environ.pop("DD_MEMBER_KERNEL", None)
+    (ra, sa, fa), (rb, sb, fb) = out["member"], out["batched"]
+    assert sa["cs_newton_iters"] == sb["cs_newton_iters"]
+    assert max(sa["bound"]) <= 1e-13, sa
+    for m in range(B):
+        for v in VARS:
+            assert rel_err(fa[m][v], fb[m][v]) <= 1e-12, (m, v)
+    assert np.all(np.abs(ra["overall"] - rb["overall"]) <= 1e-9 * rb["overall"] + 1e-15)
+    assert np.all(np.abs(ra["per_var"] - rb["per_var"]) <= 1e-9 * rb["per_var"] + 1e-15)
+
+
+def test_member_kernel_cs_exit_test_fires(mods):
+    """A manufactured cs that is non-zero on every node, boundary included: the reference's global exit test of the
+    cs corrector (max |dx| < rtol |x| everywhere) can fire, and the one-CTA kernel stops at the same iteration as
+    the batched kernels' decide / redo pair."""
+    import prob1_mms_cases as p1mc
+    p1, ddcore = mods["p1"], mods["ddcore"]
+    t, x, y = p1.t_sym, p1.x_sym, p1.y_sym
+    model = mods["product_model"](NOTEBOOK_MODEL["pol"])
+    grid = p1.make_uniform_grid(14, 12)
+    case = p1mc._SeparableCase(grid, model, phi_exprs=[1 / (1 + t)] * 5, phi_specs=[p1mc.PhiSpec("inv1pt", (1.0,))] * 5,
+                               Xs=[x * (1 - x)] * 4 + [2 + x], Ys=[y * (1 - y)] * 4 + [2 + y])
+    spec = case.device_spec()
+    opt = ddcore.pc_options(num_newton_iterations=40, consec_xs_rtol=1e-6)
+    out = {}
+    for path in ("member", "batched"):
+        if path == "member":
+            os.environ["DD_MEMBER_KERNEL"] = "1"
+        try:
+            b = ddcore.Batch(grid.x, grid.y, 1)
+            b.set_model(model, 5.0)
+            b.forcing_spec(spec)
+            b.fill_exact(0, 0.0)
+            iters = []
+            for k in range(3):   # one-step runs: the count of every step
+                res, st = b.run_errors(k % 2, (k + 1) % 2, k * 1e-3, 1e-3, 1, opt)
+                iters.append(st["cs_newton_iters"])
+            out[path] = (iters, b.download(1))
+            b.close()
+        finally:
+            os.environ.pop("DD_MEMBER_KERNEL", None)
+    assert out["member"][0] == out["batched"][0], out
+    assert min(out["member"][0]) < 40, out["member"][0]   # the test really fired
+    for v in VARS:
+        assert rel_err(out["member"][1][v], out["batched"][1][v]) <= 1e-12, v
