@@ -221,6 +221,14 @@ int dd_batch_get_plan(dd_batch* b, int sweeps[3]);
 int dd_sweeps_for_rho(double rho, int max_sweeps); /* SOR sweeps the planner uses for a Gershgorin ratio rho */
 int dd_next_plan(int cur, double rho, double ratio, int max_sweeps); /* next step's sweeps from this step's verified ratio */
 
+/* One segment of a Newton solve of the phased step: `sweeps` red-black SOR sweeps of variable var (1 = T, 2 = cl,
+ * 3 = cd) continuing from the iterate of the previous segment (first = 1: from zero); unless last = 1 the iterate
+ * stays in the work array "x_cur" (dd_work_dev_ptr), whose halo rows a slab driver exchanges before the next
+ * segment.  Replaces the part of SuperLU's single direct solve (reference src/prob1base.py:2103, 2130) that a row
+ * slab cannot do alone when the matrix needs more sweeps than its halo supports between two exchanges. */
+int dd_pc_solve_segment(dd_batch* b, int var, int slot_in, int slot_out, const dd_pc_options* opt, int sweeps,
+                        int first, int last);
+
 /* ---- instrumentation (bench.py) ------------------------------------------ */
 long long dd_launch_count(void);                /* kernels launched by the library since it was loaded */
 int dd_profile_enable(int on);                  /* bracket every launch group with CUDA events */

@@ -124,6 +124,7 @@ SIGNATURES = {
     "dd_batch_set_relax_rho": (C.c_int, [_vp, _P(C.c_double * 3)]),
     "dd_sweeps_for_rho": (C.c_int, [C.c_double, C.c_int]),
     "dd_next_plan": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int]),
+    "dd_pc_solve_segment": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _P(dd_pc_options), C.c_int, C.c_int, C.c_int]),
     "dd_probe_math": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp]),
     "dd_probe_fp64": (C.c_int, [_vp, C.c_double, _dp]),
     "dd_solver_kernel_name": (C.c_char_p, [C.c_int]),

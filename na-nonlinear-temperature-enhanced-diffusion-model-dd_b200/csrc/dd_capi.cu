@@ -65,6 +65,7 @@ struct dd_batch {
     int norm_bpm;
     double* d_combine_state = nullptr;  // dd_run_*_errors: running best / integral / last integrand, [B][18]
     double* d_member_stats = nullptr;   // one-CTA-per-member runs: [B][16] solve statistics of the last step
+    const double* x_cur = nullptr;      // iterate left by an unfinished solve segment (dd_pc_solve_segment)
     double* d_combined = nullptr;       // [B][6]
     // staged sources: the MMS sources of a time level are evaluated once (k_eval_sources) into one of two
     // sets of five arrays and the step kernels read them in ARRAYS mode; the t1 set of a step is the t0
@@ -742,6 +743,12 @@ extern "C" int dd_work_dev_ptr(dd_batch* b, const char* name, void** ptr) {
         *ptr = b->d_summary;
         return DD_OK;
     }
+    if (!strcmp(name, "x_cur")) {
+        // the iterate a solve segment (dd_pc_solve_segment, last = 0) left behind: [member][nrows][even pitch]
+        if (!b->x_cur) return fail(b->ctx, DD_ERR_INVALID, "no solve segment is pending");
+        *ptr = const_cast<double*>(b->x_cur);
+        return DD_OK;
+    }
     if (!strcmp(name, "cs_used")) {
         // int[nmembers]: cs-Newton iterations used (phase 5 / 6)
         if (!b->d_used) return fail(b->ctx, DD_ERR_INVALID, "cs statistics not allocated yet");
@@ -1302,7 +1309,12 @@ static int launch_predictor(dd_batch* b, const DDStateC& s0, const DDPredictOut&
 
 static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const double* T1, const double* cl1,
                         const double* Y, double* vnew, const dd_pc_options& opt, int k, int* sweeps_used,
-                        int* passes_used, int what = 3, const double* vold = nullptr, bool summarise = true) {
+                        int* passes_used, int what = 3, const double* vold = nullptr, bool summarise = true,
+                        int seg_sweeps = 0, const double* seg_xin = nullptr, bool seg_finish = true,
+                        const double** seg_xlast = nullptr) {
+    // seg_*: one SEGMENT of a solve that the slab driver splits because the halo supports only so many sweeps
+    // between two exchanges of the iterate: seg_sweeps sweeps continuing from the iterate seg_xin (null: from zero);
+    // seg_finish = false leaves the iterate in a work array (*seg_xlast) instead of writing v_new and the statistics
     dd_ctx* ctx = b->ctx;
     DDRows R;
     int rc;
@@ -1317,7 +1329,7 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
             dd_launch_assemble(La, b->smode, var, b->g, b->d_mem, b->sF, ustar, T1, cl1, Y, opt.cd_band_swap, R, st));
     if (!(what & 2)) return DD_OK;
     const int vi = var - DD_T;
-    int sweeps = opt.fixed_sweeps > 0 ? opt.fixed_sweeps : b->ctl[b->cm].sweeps[vi];
+    int sweeps = seg_sweeps > 0 ? seg_sweeps : (opt.fixed_sweeps > 0 ? opt.fixed_sweeps : b->ctl[b->cm].sweeps[vi]);
     if (sweeps <= 0) {
         // first use: read the Gershgorin ratio back once to seed the plan
         CK(cudaMemsetAsync(b->d_summary + k, 0, sizeof(SolveSummary), ctx->stream));
@@ -1331,7 +1343,7 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
     const double* vstar = ustar.v[var];
     int left = sweeps, passes = 0;
     double *xa = nullptr, *xb = nullptr;
-    const double* xin = nullptr;  // nullptr = zero initial iterate, or vstar - vold on the first pass
+    const double* xin = seg_xin;  // nullptr = zero initial iterate, or vstar - vold on the first pass
     // rows on which the rows R and the iterate x are valid.  On a slab every pass consumes 2 rows per sweep
     // from each interior side (the halo rows are recomputed redundantly, never exchanged mid-solve); sides
     // on the physical boundary do not shrink.
@@ -1348,11 +1360,11 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
             int cap_all = 0, cap_wide = 0;
             dd_wave_max_sweeps(var == DD_T, &cap_all, &cap_wide);
             P.sweeps = left <= cap_all ? left : cap_wide;
-            P.last_pass = P.sweeps == left ? 1 : 0;
+            P.last_pass = (seg_finish && P.sweeps == left) ? 1 : 0;
             P.const_band = var == DD_T ? 1 : 0;
             P.halo = 2 * P.sweeps + 1;
         } else {
-            plan_pass(b, left, true, var == DD_T, &P);
+            plan_pass(b, left, seg_finish, var == DD_T, &P);
         }
         P.rho_fix = b->relax_rho[vi];
         if (P.sweeps <= 0) return fail(ctx, DD_ERR_INVALID, "no feasible solver tile");
@@ -1401,7 +1413,8 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
         }
         ++passes;
     }
-    if (summarise) {
+    if (seg_xlast) *seg_xlast = xin;
+    if (summarise && seg_finish) {
         ProfScope ps_(ctx->stream, PC_SUMMARISE, 1);
         k_summarise<<<1, 256, 0, ctx->stream>>>(st, b->B, b->d_mem, opt.solve_tol, b->d_summary + k);
     }
@@ -2230,6 +2243,45 @@ extern "C" int dd_step_pc_phase(dd_batch* b, int phase, int slot_in, int slot_ou
     }
 }
 
+
+// One segment of a Newton solve of the phased (slab) step: `sweeps` SOR sweeps of variable var (1 = T, 2 = cl,
+// 3 = cd) continuing from the iterate the previous segment left (first = 1: from zero).  Unless last = 1 the
+// iterate stays in a work array ("x_cur" of dd_work_dev_ptr), whose halo rows the slab driver exchanges before the
+// next segment: a halo of G rows supports (G - 3) / 2 sweeps between two exchanges, and with segments any number
+// of sweeps (weakly dominant matrices of large time steps) while the result stays the global red-black iteration,
+// bit for bit.  The system must have been assembled (phases 21 - 23).
+extern "C" int dd_pc_solve_segment(dd_batch* b, int var, int slot_in, int slot_out, const dd_pc_options* opt_in,
+                                   int sweeps, int first, int last) {
+    if (!b || !slot_ok(b, slot_in) || !slot_ok(b, slot_out) || slot_in == slot_out || var < DD_T || var > DD_CD ||
+        sweeps < 1)
+        return DD_ERR_INVALID;
+    dd_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    dd_pc_options opt;
+    if (opt_in) opt = *opt_in; else dd_pc_options_default(&opt);
+    int rc = check_opts(ctx, opt);
+    if (rc != DD_OK) return rc;
+    if (!first && !b->x_cur) return fail(ctx, DD_ERR_INVALID, "solve segment without a predecessor");
+    if ((rc = ensure_solve_slots(b, 4)) != DD_OK) return rc;
+    DDPredictOut po;
+    if ((rc = get_work(b, "cp1p", &po.cp1p)) != DD_OK) return rc;
+    if ((rc = get_work(b, "cs1p", &po.cs1p)) != DD_OK) return rc;
+    if ((rc = get_work(b, "YT", &po.YT)) != DD_OK) return rc;
+    if ((rc = get_work(b, "Ycl", &po.Ycl)) != DD_OK) return rc;
+    if ((rc = get_work(b, "Ycd", &po.Ycd)) != DD_OK) return rc;
+    const DDStateC s0 = cstate(b, slot_in);
+    const DDState sout = mstate(b, slot_out);
+    DDStateC u;
+    u.v[DD_CP] = po.cp1p; u.v[DD_T] = s0.v[DD_T]; u.v[DD_CL] = s0.v[DD_CL]; u.v[DD_CD] = s0.v[DD_CD];
+    u.v[DD_CS] = po.cs1p;
+    const double* Y = var == DD_T ? po.YT : (var == DD_CL ? po.Ycl : po.Ycd);
+    int sw = 0, pa = 0;
+    const double* xlast = nullptr;
+    rc = newton_solve(b, var, u, sout.v[DD_T], sout.v[DD_CL], Y, sout.v[var], opt, var - DD_T, &sw, &pa, 2, nullptr,
+                      true, sweeps, first ? nullptr : b->x_cur, last != 0, &xlast);
+    b->x_cur = last ? nullptr : xlast;
+    return rc;
+}
 
 // accuracy probe of the inline device exp / reciprocal (host arrays in, host arrays out)
 extern "C" int dd_probe_math(dd_ctx* ctx, int n, const double* in, double* out_exp, double* out_rcp) {

@@ -107,6 +107,12 @@ class _DistComm:
         with _Ordered(meshes, self.torch):
             exchange_halos([m.field(slot, v) for v in which], m.part, m.rank, m.world, m.G, self.dist)
 
+    def exchange_tensors(self, meshes, tensors):
+        """Halo rows of one arbitrary (local rows x pitch) tensor per mesh, e.g. the iterate of a solve segment."""
+        m = meshes[0]
+        with _Ordered(meshes, self.torch):
+            exchange_halos([tensors[0]], m.part, m.rank, m.world, m.G, self.dist)
+
     def allreduce(self, tensors, op, meshes=()):
         d = self.dist
         with _Ordered(meshes, self.torch):
@@ -138,6 +144,19 @@ class _LocalComm:
                     dn = meshes[m.rank + 1]
                     g = min(m.G, p["hi"])
                     t[p["own1"]:p["own1"] + g].copy_(dn.field(slot, v)[dn.part["own0"]:dn.part["own0"] + g])
+
+    def exchange_tensors(self, meshes, tensors):
+        with _Ordered(meshes, self.torch):
+            for m, t in zip(meshes, tensors):
+                p = m.part
+                if m.rank > 0:
+                    up, tu = meshes[m.rank - 1], tensors[m.rank - 1]
+                    g = min(m.G, p["lo"])
+                    t[p["own0"] - g:p["own0"]].copy_(tu[up.part["own1"] - g:up.part["own1"]])
+                if m.rank < m.world - 1:
+                    dn, td = meshes[m.rank + 1], tensors[m.rank + 1]
+                    g = min(m.G, p["hi"])
+                    t[p["own1"]:p["own1"] + g].copy_(td[dn.part["own0"]:dn.part["own0"] + g])
 
     def allreduce(self, tensors, op, meshes=()):
         torch = self.torch
@@ -317,12 +336,16 @@ class SlabMesh:
         arr = (C.c_double * 3)(*([float(r) for r in self._rho] if lag else [-1.0, -1.0, -1.0]))
         for m in group:
             m.batch.ctx.check(m.batch.lib.dd_batch_set_relax_rho(m.batch.handle, C.byref(arr)), "set_relax_rho")
+        limit = self.sweep_limit
         for k, var in ((1, "T"), (2, "cl"), (3, "cd")):
             phase(20 + k)  # assemble (T: done by the predictor on wide grids)
             if not lag:
                 comm.allreduce([m._tensor("stats", m.batch.work_dev_ptr("solve_stats"), (3, 5))[k - 1, 0:1]
                                 for m in group], "max", group)
-            phase(30 + k)
+            if plan[k - 1] <= limit:
+                phase(30 + k)
+            else:
+                self._solve_in_segments(k, slot_in, slot_out, opt, plan[k - 1], limit)
             comm.exchange(group, slot_out, (var,))
         phase(4)
         if track:
@@ -347,6 +370,31 @@ class SlabMesh:
             done.record()
         return dict(slot_in=slot_in, slot_out=slot_out, t0=t0, dt=dt, opt=opt, plan=plan, mode=mode, attempt=attempt,
                     host=host, done=done, track=track)
+
+    @property
+    def sweep_limit(self) -> int:
+        """SOR sweeps a halo of G rows supports between two exchanges of the iterate (every sweep consumes two
+        rows of valid data on each interior side, the assembled rows start one row in, the residual needs one more)."""
+        return max(1, (self.G - 3) // 2)
+
+    def _solve_in_segments(self, k, slot_in, slot_out, opt, sweeps, limit):
+        """A solve that needs more sweeps than the halo supports in one go (weakly dominant matrices of large time
+        steps): segments of at most `limit` sweeps, the iterate's halo rows exchanged in between.  Still the global
+        red-black iteration, bit for bit."""
+        comm, group = self._comm(), self.group
+        chunks = [limit] * (sweeps // limit) + ([sweeps % limit] if sweeps % limit else [])
+        for ci, c in enumerate(chunks):
+            last = ci == len(chunks) - 1
+            for m in group:
+                b = m.batch
+                b.ctx.check(b.lib.dd_pc_solve_segment(b.handle, k, slot_in, slot_out, C.byref(opt), c, int(ci == 0),
+                                                      int(last)), "pc_solve_segment")
+            if not last:
+                ts = []
+                for m in group:
+                    ncols = m.batch.shape[1]
+                    ts.append(m._tensor("x_cur", m.batch.work_dev_ptr("x_cur"), (m.batch.shape[0], ncols + (ncols & 1))))
+                comm.exchange_tensors(group, ts)
 
     def _host_buffers(self, attempt):
         """Two alternating sets of pinned read-back buffers (one step may be pending while the next is enqueued)."""
@@ -392,10 +440,9 @@ class SlabMesh:
         for m in self.group:
             m._ctl[mode]["plan"] = None
             m._prev = None
-        limit = (self.G - 3) // 2
-        if any(r > 1.0 and p >= limit for p, r in zip(plan, ratio)) or opt.fixed_sweeps > 0:
-            raise ddcore.DDNotConverged(f"slab step: {limit} SOR sweeps (all a halo of {self.G} rows supports) "
-                                        f"do not reach the residual bound; use a deeper halo. stats={stats}")
+        if any(r > 1.0 and p >= opt.max_sweeps for p, r in zip(plan, ratio)) or opt.fixed_sweeps > 0:
+            raise ddcore.DDNotConverged(f"slab step: {max(plan)} SOR sweeps do not reach the residual bound. "
+                                        f"stats={stats}")
         lib = self.batch.lib
         floor = [max(f, p + 1) if r > 1.0 else f for f, p, r in zip(ctl["floor"], plan, ratio)]
         theory = [lib.dd_sweeps_for_rho(float(x) * 1.02 + 1e-12, opt.max_sweeps) for x in rho]
@@ -408,19 +455,18 @@ class SlabMesh:
         """Same number of SOR sweeps on every rank, planned from the all-reduced Gershgorin ratios of the
         previous step (first step: as many sweeps as the halo supports)."""
         lib = self.batch.lib
-        limit = (self.G - 3) // 2
+        limit = self.sweep_limit
         if opt.fixed_sweeps > 0:
             plan = [opt.fixed_sweeps] * 3
         elif self._rho is None:
-            plan = [limit] * 3
+            plan = [limit] * 3  # first step: what one halo exchange supports; the verified residual takes it from there
         elif ctl["plan"] is not None:
-            plan = [min(p, limit) for p in ctl["plan"]]
+            plan = list(ctl["plan"])
         else:
             plan = [max(lib.dd_sweeps_for_rho(float(r) * 1.02 + 1e-12, opt.max_sweeps) + e, f)
                     for r, e, f in zip(self._rho, ctl["extra"], ctl["floor"])]
-        # never more than the halo supports; the residual bound is verified after every solve, so a clamped
-        # plan either passes or the step raises below
-        plan = [max(1, min(p, limit)) for p in plan]
+        # plans beyond `limit` sweeps are run in segments with the iterate's halo exchanged in between
+        plan = [max(1, min(int(p), opt.max_sweeps)) for p in plan]
         arr = (C.c_int * 3)(*plan)
         for m in self.group:
             m.batch.ctx.check(lib.dd_batch_set_plan(m.batch.handle, C.byref(arr)), "set_plan")

@@ -637,3 +637,61 @@ def test_pipelined_solver_on_slabs_equals_undecomposed_run(dd):
         got = np.concatenate([m.owned(0)[v] for m in meshes])
         assert np.array_equal(got, ref[v]), v
     one.close()
+
+
+@pytest.mark.parametrize("M", [40, 150])
+def test_slab_solves_in_segments_for_large_time_steps(dd, M):
+    """Matrices of a large time step (weak diagonal dominance: the constants of the steps_scp_10x10_pc_bigdt fixture)
+    need more SOR sweeps than a shallow halo supports between two exchanges.  The slab driver then runs the solve in
+    segments and exchanges the iterate's halo rows in between (dd_pc_solve_segment): three slabs with a halo of 7
+    rows (2 sweeps per segment) reproduce the oracle, and at a fixed plan of 9 sweeps the undecomposed run bit for
+    bit.  M = 40: tile kernels; M = 150: marching kernels and the wavefront kernel for cl."""
+    import ddmesh
+    from oracle import NOTEBOOK_CONSTS, OForcing, OGrid, PCStepper, exact_state, make_case
+    p1, ddcore = dd["p1"], dd["ddcore"]
+    N = 60
+    om = NOTEBOOK_CONSTS["pol"].with_changes(DT=0.5, Dl_max=0.3, Dd_max=0.2)
+    eta, t0, dt, world = 50.0, 0.0, 2e-3, 3
+    og = OGrid(np.linspace(0, 1, N + 1), np.linspace(0, 1, M + 1))
+    oc = make_case("scp_fast1e1", om)
+    model = dd["product_model"](dict(K1=om.K1, K2=om.K2, K3=om.K3, K4=om.K4, DT=om.DT, Dl_max=om.Dl_max,
+                                     phi_l=om.phi_l, gamma_T=om.gamma_T, Kd=om.Kd, Sd=om.Sd, Dd_max=om.Dd_max,
+                                     phi_d=om.phi_d, r_sp=om.r_sp, T_ref=om.T_ref, kind=2))
+    grid = p1.Grid(og.x, og.y)
+    spec = dd["CASES"]["scp_fast1e1"](grid=grid, model=model).device_spec()
+
+    def slabs():
+        meshes = ddmesh.SlabMesh.local_group(grid.x, grid.y, world, halo=7)
+        for m in meshes:
+            m.batch.set_model(model, eta)
+            m.batch.forcing_spec(spec)
+            m.fill_exact(0, t0)
+        return meshes
+
+    meshes = slabs()
+    assert meshes[0].sweep_limit == 2
+    nsteps = 3
+    for k in range(nsteps):
+        st = meshes[0].step_pc(k % 2, (k + 1) % 2, t0 + k * dt, dt)
+    assert max(st["sweeps"]) > meshes[0].sweep_limit, st     # the solves really ran in segments
+    got = {v: np.concatenate([m.owned(nsteps % 2)[v] for m in meshes]) for v in VARS}
+    s = exact_state(oc, t0, og)
+    stepper = PCStepper(og, om, eta, OForcing(oc, om, eta, og), keep_residuals=False)
+    for k in range(nsteps):
+        s = stepper.step(s, t0 + k * dt, dt)
+    for v in VARS:
+        assert rel_err(got[v], getattr(s, v)) <= TOL, (v, st)
+    fixed = ddcore.pc_options(fixed_sweeps=9)
+    meshes2 = slabs()
+    b = ddcore.Batch(grid.x, grid.y, 1)
+    b.set_model(model, eta)
+    b.forcing_spec(spec)
+    b.fill_exact(0, t0)
+    for k in range(2):
+        meshes2[0].step_pc(k % 2, (k + 1) % 2, t0 + k * dt, dt, fixed)
+        b.step_pc(k % 2, (k + 1) % 2, t0 + k * dt, dt, fixed)
+    one = b.download(0)
+    for v in VARS:
+        many = np.concatenate([m.owned(0)[v] for m in meshes2])
+        assert np.array_equal(many, one[v]), v
+    b.close()
