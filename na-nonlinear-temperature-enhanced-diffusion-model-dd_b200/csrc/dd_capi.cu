@@ -253,7 +253,8 @@ extern "C" int dd_ctx_create(int device, void* cuda_stream, dd_ctx** out) {
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     ctx->sm_count = prop.multiProcessorCount;
-    if (dd_solver_configure() != cudaSuccess || dd_wave_configure() != cudaSuccess) {
+    if (dd_solver_configure() != cudaSuccess || dd_wave_configure() != cudaSuccess ||
+        dd_lane_configure() != cudaSuccess) {
         cudaGetLastError();
         delete ctx;
         return DD_ERR_CUDA;
@@ -1351,11 +1352,18 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
     const bool lo_edge = (b->row0 == 0), hi_edge = (b->row0 + b->nrows == b->N + 1);
     // wide grids, the variables DD_WAVE names (default: cl): wavefront kernel (rows marched once per pass, no row
     // halo); the previous step's increment as initial iterate is only known to the tile kernels
-    const bool wave = dd_wave_ok(b->g, L, var) && !vold;
+    const bool lanek = dd_lane_ok(b->g, L, var) && !vold;
+    const bool wave = !lanek && dd_wave_ok(b->g, L, var) && !vold;
     while (left > 0) {
         DDSolvePlan P;
         memset(&P, 0, sizeof(P));
-        if (wave) {
+        if (lanek) {
+            // lane-private marching kernel: passes of nearly equal length, at most dd_lane_max_sweeps() sweeps each
+            P.sweeps = dd_lane_pass_sweeps(left);
+            P.last_pass = (seg_finish && P.sweeps == left) ? 1 : 0;
+            P.const_band = var == DD_T ? 1 : 0;
+            P.halo = 2 * P.sweeps + 1;
+        } else if (wave) {
             // as many sweeps per pass as the ring of the widest fitting kernel variant holds
             int cap_all = 0, cap_wide = 0;
             dd_wave_max_sweeps(var == DD_T, &cap_all, &cap_wide);
@@ -1397,7 +1405,11 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
             xin = x0;
             vo = nullptr;
         }
-        if (wave)
+        if (lanek)
+            CKP(PC_SOLVE_T + (var - DD_T), 1,
+                dd_launch_solve_lane(Lp, b->g, b->d_mem, R, xin, xout, vstar, vnew, var == DD_T ? 1 : 0, st,
+                                     P.const_band, P.sweeps, P.last_pass, P.rho_fix));
+        else if (wave)
             CKP(PC_SOLVE_T + (var - DD_T), 1,
                 dd_launch_solve_wave(Lp, b->g, b->d_mem, R, xin, xout, vstar, vnew, var == DD_T ? 1 : 0, st,
                                      P.const_band, P.sweeps, P.last_pass, P.rho_fix));

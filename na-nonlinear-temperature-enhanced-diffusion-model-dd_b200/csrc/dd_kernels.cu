@@ -23,6 +23,12 @@ __device__ __forceinline__ NodeIdx node_index(const DDGeom& g, int own0, int own
     const long long lin = (long long)chunk * blockDim.x + threadIdx.x;
     const long long total = (long long)(own1 - own0) * ncols;
     n.valid = lin < total;
+    if (total + DD_BLOCK <= 0x7fffffffLL) {  // (uniform) 32-bit division: a fifth of the 64-bit one's instructions
+        const unsigned rr = (unsigned)lin / (unsigned)ncols;
+        n.r = own0 + (int)rr;
+        n.j = (int)((unsigned)lin - rr * (unsigned)ncols);
+        return n;
+    }
     const long long rr = lin / ncols;
     n.r = own0 + (int)rr;
     n.j = (int)(lin - rr * ncols);
@@ -1013,7 +1019,7 @@ cudaError_t dd_launch_assemble_march(const DDLaunch& L, int mode, int var, const
 // ---------------------------------------------------------------------------
 // correctors
 // ---------------------------------------------------------------------------
-#define DD_CS_SMEM_CAP 1024  // per-iteration statistics staged in shared memory up to this many iterations
+#define DD_CS_STAGE 6  // iterations whose per-thread statistics are staged in shared memory (the rest: atomics)
 
 // VARIANTS = false: every member is a RegHCsTriple one (the iteration below); true: members may use the
 // closed-form cs correctors of CsTriple / HCsTriple (kept out of the common instantiation: it costs registers)
@@ -1025,21 +1031,15 @@ __global__ void __launch_bounds__(DD_BLOCK) k_correct(DDGeom g, const DDMember* 
                                                       double* __restrict__ cs_out, int cap, double rtol,
                                                       double* it_max, double* it_min, int* flags, int own0,
                                                       int own1, int bpm) {
-    // per-iteration block statistics of the reference's global exit test (max |dx|, min |x|):
-    // warp shuffles + shared-memory atomics, flushed to global memory once per block
-    __shared__ unsigned long long sh_max[DD_CS_SMEM_CAP], sh_min[DD_CS_SMEM_CAP];
+    // per-iteration statistics of the reference's global exit test (max |dx|, min |x|): every thread parks its
+    // two bit patterns per iteration in shared memory (two stores, no reduction inside the Newton loop); after
+    // the loop warp `it` reduces iteration `it` over the block and issues the two global atomics
+    __shared__ unsigned long long sh_dx[DD_CS_STAGE][DD_BLOCK], sh_ax[DD_CS_STAGE][DD_BLOCK];
     const NodeIdx n = node_index(g, own0, own1, bpm);
     const DDMember& mb = mem[n.member];
     if (!mb.active) return;
     const bool track = rtol > 0.0;
-    const int scap = cap < DD_CS_SMEM_CAP ? cap : DD_CS_SMEM_CAP;
-    if (track) {
-        for (int k = threadIdx.x; k < scap; k += blockDim.x) {
-            sh_max[k] = 0ull;
-            sh_min[k] = 0x7ff0000000000000ull;
-        }
-        __syncthreads();
-    }
+    const int scap = cap < DD_CS_STAGE ? cap : DD_CS_STAGE;
     double x = 0.0, y = 0.0, a = 0.0, cp1 = 0.0;
     long long o = 0;
     bool inter = false;
@@ -1075,15 +1075,15 @@ __global__ void __launch_bounds__(DD_BLOCK) k_correct(DDGeom g, const DDMember* 
         }
         if (track) {
             // global exit test of the reference: max_all |dx| < rtol |x| at every node
-            const double vmax = warp_max_bits(n.valid ? dx : 0.0);
             double ax = n.valid ? fabs(x) : __longlong_as_double(0x7ff0000000000000LL);
             if (ax != ax) ax = 0.0;  // NaN |x| fails the test exactly like 0 does
-            const double vmin = warp_min_bits(ax);
-            if (lane == 0) {
-                if (it < scap) {
-                    atomicMax(&sh_max[it], (unsigned long long)__double_as_longlong(vmax));
-                    atomicMin(&sh_min[it], (unsigned long long)__double_as_longlong(vmin));
-                } else {
+            if (it < DD_CS_STAGE) {
+                sh_dx[it][threadIdx.x] = (unsigned long long)__double_as_longlong(fabs(n.valid ? dx : 0.0));
+                sh_ax[it][threadIdx.x] = (unsigned long long)__double_as_longlong(ax);
+            } else {
+                const double vmax = warp_max_bits(n.valid ? dx : 0.0);
+                const double vmin = warp_min_bits(ax);
+                if (lane == 0) {
                     atomic_max_nonneg(&it_max[(long long)n.member * cap + it], vmax);
                     atomic_min_nonneg(&it_min[(long long)n.member * cap + it], vmin);
                 }
@@ -1093,9 +1093,20 @@ __global__ void __launch_bounds__(DD_BLOCK) k_correct(DDGeom g, const DDMember* 
     if (n.valid) cs_out[o] = x * (inter ? 1.0 : 0.0);
     if (track) {
         __syncthreads();
-        for (int k = threadIdx.x; k < scap; k += blockDim.x) {
-            atomicMax(reinterpret_cast<unsigned long long*>(&it_max[(long long)n.member * cap + k]), sh_max[k]);
-            atomicMin(reinterpret_cast<unsigned long long*>(&it_min[(long long)n.member * cap + k]), sh_min[k]);
+        for (int it = threadIdx.x >> 5; it < scap; it += DD_BLOCK / 32) {
+            unsigned long long vmax = 0ull, vmin = ~0ull;
+#pragma unroll
+            for (int k = 0; k < DD_BLOCK / 32; ++k) {
+                const unsigned long long a1 = sh_dx[it][lane + 32 * k], a2 = sh_ax[it][lane + 32 * k];
+                vmax = a1 > vmax ? a1 : vmax;
+                vmin = a2 < vmin ? a2 : vmin;
+            }
+            const double wmax = warp_max_bits(__longlong_as_double((long long)vmax));
+            const double wmin = warp_min_bits(__longlong_as_double((long long)vmin));
+            if (lane == 0) {
+                atomic_max_nonneg(&it_max[(long long)n.member * cap + it], wmax);
+                atomic_min_nonneg(&it_min[(long long)n.member * cap + it], wmin);
+            }
         }
     }
 }

@@ -47,6 +47,15 @@ cudaError_t dd_solver_configure();  // opt-in to large dynamic shared memory (on
 
 // wavefront solver (dd_wave.cu): one pass of `sweeps` red-black SOR sweeps marching down column strips; wide grids;
 // used for the cl solve by default, the register-tile kernels for T and cd (as fast or faster there)
+// lane-private marching solver (dd_lane.cu): DD_LANE = 0 | 1 | list of T,cl,cd
+cudaError_t dd_lane_configure();
+bool dd_lane_ok(const DDGeom& g, const DDLaunch& L, int var);
+int dd_lane_max_sweeps();
+int dd_lane_pass_sweeps(int left);
+cudaError_t dd_launch_solve_lane(const DDLaunch& L, const DDGeom& g, const DDMember* mem, const DDRows& R,
+                                 const double* xin, double* xout, const double* vstar, double* vnew,
+                                 int zero_boundary, DDSolveStats* stats, int const_band, int sweeps, int last_pass,
+                                 double rho_fix);
 cudaError_t dd_wave_configure();
 bool dd_wave_ok(const DDGeom& g, const DDLaunch& L, int var);  // DD_WAVE = 0 | 1 | list of T,cl,cd (default: cl)
 void dd_wave_max_sweeps(int const_band, int* any, int* wide);  // per pass: any variant / the widest one

@@ -11,6 +11,7 @@
 
 #include <vector>
 
+#include "dd_lane.cuh"
 #include "dd_wave.cuh"
 
 struct WSProblem {
@@ -119,6 +120,110 @@ extern "C" int ws_wave(WSProblem* P) {
 #define WS_CASE(CB_, C_) if (P->cb == CB_ && P->C == C_) { run<CB_, C_>(*P); return 0; }
     WS_CASE(1, 4) WS_CASE(1, 3) WS_CASE(1, 2) WS_CASE(1, 1) WS_CASE(0, 2) WS_CASE(0, 1)
 #undef WS_CASE
+    return 1;
+}
+
+// ---- lane-private marching kernel (csrc/dd_lane.cuh): the 32 lanes of a warp stepped one after the other; what a
+// lane receives by shuffle on the device is read here from its neighbour's registers BEFORE anybody's step ---------
+template <int CB, int S, int XIN, int U>
+static void lane_dispatch(int u, const WaveArgs& A, const WaveSeg& sg, std::vector<LaneRegs<CB, S, XIN>>& regs,
+                          const LaneSmem& sm, int tau, double omega, double fT, int order) {
+    if constexpr (U < 2 * S + 4) {
+        if (u != U) {
+            lane_dispatch<CB, S, XIN, U + 1>(u, A, sg, regs, sm, tau, omega, fT, order);
+            return;
+        }
+        constexpr int o = (U + 1) & 1;
+        double src[32][2 * S + 1], nb[32][2 * S + 1];
+        for (int l = 0; l < 32; ++l) dd_lane_offer<CB, S, XIN, U>(regs[l], src[l]);
+        for (int l = 0; l < 32; ++l) {
+            // __shfl_down / __shfl_up by one lane: the edge lane gets its own value back
+            const int from = o ? (l < 31 ? l + 1 : l) : (l > 0 ? l - 1 : l);
+            for (int k = 0; k <= 2 * S; ++k) nb[l][k] = src[from][k];
+        }
+        for (int ll = 0; ll < 32; ++ll) {
+            const int l = order ? 31 - ll : ll;
+            dd_lane_step<CB, S, XIN, U>(A, sg, regs[l], sm, tau, l, omega, fT, nb[l]);
+        }
+    }
+}
+
+template <int CB, int S, int XIN>
+static void run_lane(WSProblem& P) {
+    DDMember mb;
+    memset(&mb, 0, sizeof(mb));
+    mb.active = 1;
+    mb.dt = P.dt;
+    mb.m.DT = P.DT;
+    DDSolveStats st;
+    memset(&st, 0, sizeof(st));
+    st.rho = P.rho;
+    WaveArgs A;
+    memset(&A, 0, sizeof(A));
+    A.g.N = P.N; A.g.M = P.M; A.g.row0 = P.row0; A.g.nrows = P.nrows; A.g.ld = P.ld;
+    A.g.mstride = (long long)P.nrows * P.ld;
+    A.g.rh = P.rh; A.g.rhp = P.rhp; A.g.rk = P.rk; A.g.rkp = P.rkp;
+    A.mem = &mb;
+    A.bb = P.bb; A.aW = P.aW; A.aE = P.aE; A.aS = P.aS; A.aN = P.aN;
+    A.xin = P.xin; A.xout = P.xout; A.vstar = P.vstar; A.vnew = P.vnew;
+    A.stats = &st;
+    A.zero_boundary = P.zero_boundary;
+    A.ldR = P.ldR;
+    A.mstrideR = (long long)P.nrows * P.ldR;
+    A.own0 = P.own0; A.own1 = P.own1; A.vr0 = P.vr0; A.vr1 = P.vr1;
+    A.sweeps = S;
+    A.halo = dd_lane_halo(S, XIN);
+    A.last_pass = P.last_pass;
+    A.tj = 64 - 2 * A.halo;
+    A.nstrips = (P.M + 1 + A.tj - 1) / A.tj;
+    A.flat_total = (long long)A.nstrips * (P.own1 - P.own0);
+    A.flat_per_cta = (A.flat_total + P.nctas - 1) / P.nctas;
+    A.rho_fix = -1.0;
+    constexpr int PP = 2 * S + 4;
+    std::vector<double> ring(dd_lane_ring_doubles(CB, S, XIN));
+    std::vector<LaneRegs<CB, S, XIN>> regs(32);
+    unsigned hr = 0, hx = 0, hv = 0, hb = 0;
+    P.steps = 0;
+    const double fT = mb.dt * mb.m.DT;
+    double omega = 1.0;
+    if (P.rho < 1.0) omega = 2.0 / (1.0 + sqrt(1.0 - P.rho * P.rho));
+    for (int cta = 0; cta < P.nctas; ++cta) {
+        LaneSmem sm;
+        sm.base = ring.data();
+        long long f0 = (long long)cta * A.flat_per_cta;
+        const long long f1 = f0 + A.flat_per_cta < A.flat_total ? f0 + A.flat_per_cta : A.flat_total;
+        while (f0 < f1) {
+            const WaveSeg sg = dd_lane_segment(A, f0, f1, dd_lane_warmup(S, XIN));
+            f0 += sg.r1 - sg.r0;
+            for (double& v : ring) v = NAN;  // a march must not depend on what the previous one left behind
+            for (int l = 0; l < 32; ++l) dd_lane_init<CB, S, XIN>(A, sg, regs[l], sm, 0u, l, fT);
+            for (int q = 0; q < DD_LANE_LS; ++q)
+                for (int l = 0; l < 32; ++l) dd_lane_request<CB, S, XIN>(A, sg, regs[l], sm, q, l, q);
+            const int nsteps = dd_lane_steps(A, sg);
+            P.steps += nsteps;
+            for (int tau = 0; tau < nsteps; ++tau)
+                lane_dispatch<CB, S, XIN, 0>(tau % PP, A, sg, regs, sm, tau, omega, fT, P.order);
+            for (auto& r : regs) {
+                hr = r.hr > hr ? r.hr : hr;
+                hb = r.hb > hb ? r.hb : hb;
+                hx = r.hx > hx ? r.hx : hx;
+                hv = r.hv > hv ? r.hv : hv;
+            }
+        }
+    }
+    P.stats[0] = dd_wave_from_hi(hr, true); P.stats[1] = dd_wave_from_hi(hx, false);
+    P.stats[2] = dd_wave_from_hi(hv, false); P.stats[3] = dd_wave_from_hi(hb, false);
+}
+
+extern "C" int ws_lane(WSProblem* P) {
+#define WS_LANE(CB_, S_)                                                                  \
+    if (P->cb == CB_ && P->sweeps == S_) {                                                \
+        if (P->xin) run_lane<CB_, S_, 1>(*P); else run_lane<CB_, S_, 0>(*P);              \
+        return 0;                                                                         \
+    }
+    WS_LANE(1, 1) WS_LANE(1, 2) WS_LANE(1, 3) WS_LANE(1, 4) WS_LANE(1, 5)
+    WS_LANE(0, 1) WS_LANE(0, 2) WS_LANE(0, 3) WS_LANE(0, 4) WS_LANE(0, 5)
+#undef WS_LANE
     return 1;
 }
 

@@ -46,21 +46,26 @@ def test_wave_solver_equals_tile_solver_bitwise(dd, N, M, sweeps):
     x, y = np.linspace(0, 1, N + 1) ** 1.05, np.linspace(0, 1, M + 1)
     opts = dd["ddcore"].pc_options(fixed_sweeps=sweeps)
     out = {}
-    for mode in ("wave", "tile"):
+    for mode in ("wave", "lane", "tile"):
         os.environ["DD_WAVE"] = "1" if mode == "wave" else "0"
+        os.environ["DD_LANE"] = "1" if mode == "lane" else "0"
         try:
             b = _batch(dd, "pol", om, x, y, 50.0)
             b.fill_exact(0, 0.1)
             st = b.step_pc(0, 1, 0.1, 3e-4, opts)
-            out[mode] = (b.download(1), st)
+            out[mode] = (b.download(1), st, [b.lib.dd_solver_kernel_name(k).decode() for k in (1, 2, 3)])
             b.close()
         finally:
             os.environ.pop("DD_WAVE", None)
-    for v in VARS:
-        assert np.array_equal(out["wave"][0][v], out["tile"][0][v]), v
-    # the wavefront kernel keeps its statistics as high words (residual rounded up by at most 2^-20 relative)
-    for a, b in zip(out["wave"][1]["resid"], out["tile"][1]["resid"]):
-        assert b <= a <= b * (1 + 2e-6) + 1e-300, (a, b)
+            os.environ.pop("DD_LANE", None)
+    assert all(n.startswith("k_sor_wave") for n in out["wave"][2]), out["wave"][2]
+    assert all(n.startswith("k_sor_lane") for n in out["lane"][2]), out["lane"][2]
+    for mode in ("wave", "lane"):
+        for v in VARS:
+            assert np.array_equal(out[mode][0][v], out["tile"][0][v]), (mode, v)
+        # the marching kernels keep their statistics as high words (residual rounded up by at most 2^-20 relative)
+        for a, b in zip(out[mode][1]["resid"], out["tile"][1]["resid"]):
+            assert b <= a <= b * (1 + 2e-6) + 1e-300, (mode, a, b)
 
 
 MARCH_CASES = [
@@ -75,12 +80,14 @@ MARCH_CASES = [
 ]
 
 
-@pytest.fixture(params=["tile", "wave"])
+@pytest.fixture(params=["tile", "wave", "lane"])
 def solver(request):
-    """Both solvers of the wide-grid regime: the register-tile kernels (default) and the wavefront kernel."""
+    """The solvers of the wide-grid regime: register-tile kernels, wavefront kernel, lane-private marching kernel."""
     os.environ["DD_WAVE"] = "1" if request.param == "wave" else "0"
+    os.environ["DD_LANE"] = "1" if request.param == "lane" else "0"
     yield request.param
     os.environ.pop("DD_WAVE", None)
+    os.environ.pop("DD_LANE", None)
 
 
 @pytest.mark.parametrize("cid,case,consts,N,M,power,kind,P,Q,dt", MARCH_CASES, ids=[c[0] for c in MARCH_CASES])

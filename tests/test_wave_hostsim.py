@@ -27,13 +27,14 @@ class WSProblem(C.Structure):
 def _lib():
     os.makedirs(BUILD, exist_ok=True)
     src = os.path.join(HERE, "hostsim", "wavesim.cpp")
-    deps = [src] + [os.path.join(CSRC, f) for f in ("dd_wave.cuh", "dd_sor.cuh", "dd_nodeprog.cuh", "dd_physics.cuh",
+    deps = [src] + [os.path.join(CSRC, f) for f in ("dd_wave.cuh", "dd_lane.cuh", "dd_sor.cuh", "dd_nodeprog.cuh", "dd_physics.cuh",
                                                     "dd_types.h")]
     if not (os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps)):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-I", CSRC,
                                "-o", LIB, src])
     lib = C.CDLL(LIB)
     lib.ws_wave.restype = C.c_int
+    lib.ws_lane.restype = C.c_int
     lib.ws_reference.restype = C.c_int
     return lib
 
@@ -91,7 +92,7 @@ def _system(rng, N, M, cb, nonuniform):
 
 
 def _run(lib, N, M, arr, met, rho, dt, DT, ldR, *, cb, Cc, nwarps, nctas, sweeps, row0=0, nrows=None, own=None,
-         vr=None, last=1, xin=None, order=0, zero_boundary=0, vstar=None, reference=False):
+         vr=None, last=1, xin=None, order=0, zero_boundary=0, vstar=None, reference=False, kernel="wave"):
     nrows = N + 1 if nrows is None else nrows
     own = (0, nrows) if own is None else own
     vr = (0, nrows) if vr is None else vr
@@ -118,7 +119,7 @@ def _run(lib, N, M, arr, met, rho, dt, DT, ldR, *, cb, Cc, nwarps, nctas, sweeps
         x = np.zeros((nrows, ldR))
         assert lib.ws_reference(C.byref(P), _ptr(x)) == 0
         return x, vnew, list(P.stats), 0
-    rc = lib.ws_wave(C.byref(P))
+    rc = (lib.ws_lane if kernel == "lane" else lib.ws_wave)(C.byref(P))
     assert rc == 0, rc
     return xout, vnew, list(P.stats), P.steps
 
@@ -190,5 +191,72 @@ def test_wave_two_passes_continue_the_iteration():
     assert not np.isnan(x1[:, :M + 1]).any()
     x1[:, M + 1:] = 1e300
     _, v2, s2, _ = _run(lib, N, M, arr, met, rho, dt, DT, ldR, Cc=2, nwarps=12, nctas=3, sweeps=4, xin=x1, **kw)
+    assert np.array_equal(v2, vref)
+    assert s2 == sref
+
+
+# ---- the lane-private marching kernel (csrc/dd_lane.cuh) -------------------------------------------------------------
+LANE_CASES = [
+    # cb, sweeps, N, M, nctas
+    (1, 5, 70, 300, 3),
+    (1, 4, 45, 259, 1),
+    (1, 3, 90, 200, 4),
+    (1, 2, 60, 150, 2),
+    (1, 1, 33, 140, 5),
+    (0, 5, 80, 260, 3),
+    (0, 4, 64, 131, 2),
+    (0, 3, 50, 250, 7),
+    (0, 2, 70, 70, 2),
+    (0, 1, 20, 65, 1),
+]
+
+
+@pytest.mark.parametrize("cb,sweeps,N,M,nctas", LANE_CASES)
+@pytest.mark.parametrize("nonuniform", [False, True])
+def test_lane_equals_global_sor(cb, sweeps, N, M, nctas, nonuniform):
+    lib = _lib()
+    rng = np.random.default_rng(2000 * sweeps + N + M)
+    arr, met, rho, dt, DT, ldR = _system(rng, N, M, cb, nonuniform)
+    vstar = rng.normal(size=(N + 1, M + 1))
+    kw = dict(cb=cb, Cc=1, nwarps=1, nctas=nctas, sweeps=sweeps, vstar=vstar, zero_boundary=cb)
+    xr, vr_, sr, _ = _run(lib, N, M, arr, met, rho, dt, DT, ldR, reference=True, **kw)
+    for order in (0, 1):
+        _, vn, st, steps = _run(lib, N, M, arr, met, rho, dt, DT, ldR, order=order, kernel="lane", **kw)
+        assert np.array_equal(vn, vr_), (order, np.argwhere(vn != vr_)[:5])
+        assert st == sr
+
+
+@pytest.mark.parametrize("cb,sweeps", [(1, 5), (0, 5), (0, 3), (1, 2)])
+def test_lane_on_a_slab(cb, sweeps):
+    lib = _lib()
+    N, M = 140, 200
+    rng = np.random.default_rng(17 + sweeps)
+    arr, met, rho, dt, DT, ldR = _system(rng, N, M, cb, True)
+    vstar = rng.normal(size=(N + 1, M + 1))
+    kw = dict(cb=cb, Cc=1, nwarps=1, sweeps=sweeps, vstar=vstar, zero_boundary=cb)
+    _, vglob, _, _ = _run(lib, N, M, arr, met, rho, dt, DT, ldR, nctas=1, reference=True, **kw)
+    G = 2 * sweeps + 1
+    for (a, b) in ((0, 51), (51, 97), (97, N + 1)):
+        row0 = max(0, a - G - 2)
+        row1 = min(N + 1, b + G + 2)
+        own = (a - row0, b - row0)
+        vr = (0 if row0 == 0 else 1, row1 - row0 if row1 == N + 1 else row1 - row0 - 1)
+        _, vn, _, _ = _run(lib, N, M, arr, met, rho, dt, DT, ldR, nctas=3, row0=row0, nrows=row1 - row0, own=own, vr=vr,
+                           kernel="lane", **kw)
+        assert np.array_equal(vn[own[0]:own[1]], vglob[a:b])
+
+
+def test_lane_two_passes_continue_the_iteration():
+    lib = _lib()
+    N, M, cb = 60, 180, 0
+    rng = np.random.default_rng(199)
+    arr, met, rho, dt, DT, ldR = _system(rng, N, M, cb, False)
+    vstar = rng.normal(size=(N + 1, M + 1))
+    kw = dict(cb=cb, vstar=vstar, Cc=1, nwarps=1)
+    _, vref, sref, _ = _run(lib, N, M, arr, met, rho, dt, DT, ldR, nctas=1, sweeps=9, reference=True, **kw)
+    x1, _, _, _ = _run(lib, N, M, arr, met, rho, dt, DT, ldR, nctas=2, sweeps=5, last=0, kernel="lane", **kw)
+    assert not np.isnan(x1[:, :M + 1]).any()
+    x1[:, M + 1:] = 1e300
+    _, v2, s2, _ = _run(lib, N, M, arr, met, rho, dt, DT, ldR, nctas=3, sweeps=4, xin=x1, kernel="lane", **kw)
     assert np.array_equal(v2, vref)
     assert s2 == sref

@@ -1,2 +1,11 @@
-import json,sys
-d=json.loads(sys.stdin.read()); print(sys.argv[1], d["value"], d["ms_per_step"], d["config"]["solver"]["sweeps"], d["config"]["solver"]["passes"]); print({k:round(v["ms_per_step"],3) for k,v in d["roofline"]["kernels"].items()}); print(d.get("check"))
+"""One-screen digest of a bench.py JSON line: python tools/bench_brief.py FILE [FILE ...]"""
+import json
+import sys
+
+for path in sys.argv[1:]:
+    with open(path) as f:
+        d = json.loads(f.read().strip().splitlines()[-1])
+    sol = d["config"].get("solver", {})
+    print(path, d["value"], d["ms_per_step"], sol.get("sweeps"), sol.get("passes"), sol.get("kernels"))
+    print({k: round(v["ms_per_step"], 3) for k, v in d["roofline"]["kernels"].items()})
+    print(d.get("check"))

@@ -3,13 +3,16 @@
 look for it:
 
     ncu -i gpurun_out/<tag>_step.ncu-rep --page raw --csv > /tmp/raw.csv
-    python tools/ncu_step_summary.py /tmp/raw.csv <tag> [first_launch [launches_per_step]]
+    ncu -i gpurun_out/<tag>_step.ncu-rep --page source --csv > /tmp/src.csv      (optional: fp64 counts)
+    python tools/ncu_step_summary.py /tmp/raw.csv <tag> [first_launch [launches_per_step [/tmp/src.csv]]]
 
   profiles/<tag>_ncu_summary.json  duration, DRAM bytes, issue / fp64 / LSU utilisation, registers, occupancy, warp
                                    instructions, fp64 instruction counts of every captured launch
   profiles/<tag>_traffic.json      DRAM bytes per launch per kernel class (bench.py: roofline.traffic)
   profiles/<tag>_fp64.json         fp64 flops of the whole step = 2 DFMA + DADD + DMUL thread instructions
-                                   (predicated on), summed over the step's launches (bench.py: roofline.fp64)
+                                   (predicated on), summed over the step's launches (bench.py: roofline.fp64);
+                                   from the op-count metrics when the report has them, else from the per-instruction
+                                   counts of the source page (`--set full` carries those, not the op counters)
 
 The capture command is tools/prof_ncu_full.sh (a run under ncu is never a bench value: only counts and shares
 are taken from it)."""
@@ -44,6 +47,40 @@ UNIT_SCALE = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "ms": 1e3, 
               "msecond": 1e3, "usecond": 1.0, "nsecond": 1e-3}
 
 
+def source_page_fp64(path, launches):
+    """Fills dfma/dadd/dmul of every launch from the SASS view of the source page: predicated-on thread instructions
+    of the rows whose opcode is DFMA / DADD / DMUL.  (The page prints some launches twice; identical neighbours are
+    dropped, then the sections are matched to the raw page's launches in order and by name.)"""
+    secs, cur = [], None
+    for r in csv.reader(open(path)):
+        if r and r[0] == "Kernel Name":
+            cur = {"name": r[1], "rows": []}
+            secs.append(cur)
+        elif r and r[0] == "Address":
+            cur["hdr"] = r
+        elif cur is not None and r:
+            cur["rows"].append(r)
+    k = 0
+    for d in launches:
+        base = d["kernel"].split("(")[0].split("<")[0].replace("void ", "")
+        while k < len(secs) and base not in secs[k]["name"]:
+            k += 1
+        if k == len(secs):
+            raise SystemExit("source page has no section for " + d["kernel"])
+        s = secs[k]
+        k += 1
+        if k < len(secs) and secs[k]["name"] == s["name"] and secs[k]["rows"] == s["rows"]:
+            k += 1
+        h = s["hdr"]
+        isrc, ithr = h.index("Source"), h.index("Predicated-On Thread Instructions Executed")
+        cnt = {"DFMA": 0.0, "DADD": 0.0, "DMUL": 0.0}
+        for r in s["rows"]:
+            m = re.search(r"\b(DFMA|DADD|DMUL)\b", r[isrc])
+            if m:
+                cnt[m.group(1)] += float(r[ithr])
+        d["dfma"], d["dadd"], d["dmul"] = cnt["DFMA"], cnt["DADD"], cnt["DMUL"]
+
+
 def main():
     path, tag = sys.argv[1], sys.argv[2]
     first = int(sys.argv[3]) if len(sys.argv) > 3 else 0
@@ -63,8 +100,9 @@ def main():
                     continue
                 d[key] = v * UNIT_SCALE.get(units[i], 1.0)
         launches.append(d)
+    if len(sys.argv) > 5:
+        source_page_fp64(sys.argv[5], launches)
     launches = launches[first:first + per_step] if per_step else launches[first:]
-    solver_seen = 0
     for d in launches:
         k = d["kernel"]
         cls = None
