@@ -365,6 +365,28 @@ cudaError_t dd_launch_predict(const DDLaunch& L, int mode, const DDGeom& g, cons
 #define DD_PRAGMA(x) DD_PRAGMA_(x)
 #define DD_MARCH_LOOP DD_PRAGMA(unroll DD_MARCH_UNROLL)
 
+// Block-wide constants of a marching kernel, staged in shared memory: the member's model and the x metrics of the
+// block's rows.  Read through the member pointer / the 1-D arrays they are global loads whose lines the streaming
+// fields keep evicting from L1: every use then waits for L2 (the largest single stall of these kernels in the r02
+// profile, a fifth of all samples on the first use of m.Dl_max).  From shared memory they are 30-cycle loads.
+struct DDMarchShared {
+    DDModel m;
+    double rh[DD_MARCH_ROWS + 1];   // 1 / h_i,    i = i0 .. i0 + ROWS
+    double rhp[DD_MARCH_ROWS];      // 1 / hhat_i, i = i0 .. i0 + ROWS - 1
+};
+// (every thread of the block must call this: it ends in a barrier)
+__device__ __forceinline__ void dd_march_stage(DDMarchShared& sh, const DDGeom& g, const DDMember& mb, int ra) {
+    const int i0 = g.row0 + ra;
+    for (int k = threadIdx.x; k < (int)(sizeof(DDModel) / sizeof(double)); k += blockDim.x)
+        reinterpret_cast<double*>(&sh.m)[k] = reinterpret_cast<const double*>(&mb.m)[k];
+    for (int k = threadIdx.x; k <= DD_MARCH_ROWS; k += blockDim.x) {
+        const int i = i0 + k;
+        sh.rh[k] = (i >= 0 && i <= g.N) ? g.rh[i] : 0.0;
+        if (k < DD_MARCH_ROWS) sh.rhp[k] = (i >= 0 && i <= g.N) ? g.rhp[i] : 0.0;
+    }
+    __syncthreads();
+}
+
 struct DDMarchCell {
     double cp, T, cl, cd;
 };
@@ -423,12 +445,14 @@ k_predict_march(DDGeom g, const DDMember* __restrict__ mem, DDForcingArrays A, D
     const int rbk = bid / wcb, cbk = bid - rbk * wcb;
     const DDMember& mb = mem[member];
     if (!mb.active) return;
+    const int ra = r0 + rbk * DD_MARCH_ROWS, rz = min(ra + DD_MARCH_ROWS, r1);
+    __shared__ DDMarchShared sh;
+    dd_march_stage(sh, g, mb, ra);
     const int wc = cbk * (blockDim.x >> 5) + warp;
     if (wc >= nwc) return;  // whole warp
-    const DDModel& m = mb.m;
+    const DDModel& m = sh.m;
     const double dt = mb.dt;
     const int j = wc * 31 + lane - 1;
-    const int ra = r0 + rbk * DD_MARCH_ROWS, rz = min(ra + DD_MARCH_ROWS, r1);
     const bool col = j >= 0 && j <= g.M;
     const bool owner = lane >= 1 && col;
     const bool jint = j >= 1 && j <= g.M - 1;
@@ -456,7 +480,7 @@ k_predict_march(DDGeom g, const DDMember* __restrict__ mem, DDForcingArrays A, D
     {
         const int i = g.row0 + ra;
         if (jint && i >= 1 && i <= g.N - 1) {
-            W = dd_march_face(m, P, C, g.rh[i]);
+            W = dd_march_face(m, P, C, sh.rh[0]);
             wadv = 0.5 * (m.gamma_T * C.T * (C.cl + 1.0) + m.gamma_T * P.T * (P.cl + 1.0));
         }
     }
@@ -478,7 +502,7 @@ k_predict_march(DDGeom g, const DDMember* __restrict__ mem, DDForcingArrays A, D
         DDMarchFace E = {0.0, 0.0, 0.0};
         double eadv = 0.0;
         if (jint && i >= 0 && i <= g.N - 1 && r + 1 < g.nrows) {
-            E = dd_march_face(m, C, N, g.rh[i + 1]);
+            E = dd_march_face(m, C, N, sh.rh[r - ra + 1]);
             eadv = 0.5 * (m.gamma_T * N.T * (N.cl + 1.0) + m.gamma_T * C.T * (C.cl + 1.0));
         }
         // N face (columns j | j+1): used by this node and, as its S face, by lane + 1
@@ -492,7 +516,7 @@ k_predict_march(DDGeom g, const DDMember* __restrict__ mem, DDForcingArrays A, D
         if (owner) {
             const long long oR = moR + (long long)r * R.ld + j;
             if (inter) {
-                const double rhp = g.rhp[i];
+                const double rhp = sh.rhp[r - ra];
                 const double lap = rhp * (E.T - W.T) + rkp * (Nf.T - S.T);
                 const double FT0 = m.DT * lap - m.K3 * C.cp * C.T;
                 const double Fcl0 = (rhp * (E.cl - W.cl) + rkp * (Nf.cl - S.cl)) - rhp * (eadv - wadv) -
@@ -507,7 +531,7 @@ k_predict_march(DDGeom g, const DDMember* __restrict__ mem, DDForcingArrays A, D
                 out.cs1p[o] = dd_predict_cs_r(m, dt, csC, C.cl, C.cd, src.fcs0, src.fcs1, react0);
                 if (store_YT) out.YT[o] = YT;  // only later Newton steps / the class-level pieces read it
                 if (FUSE_T) {
-                    const double sumc = m.DT * (rhp * g.rh[i] + rhp * g.rh[i + 1] + cS + cN);
+                    const double sumc = m.DT * (rhp * sh.rh[r - ra] + rhp * sh.rh[r - ra + 1] + cS + cN);
                     const double d = 2.0 + dt * (sumc + m.K3 * cp1p);
                     const double FT1 = m.DT * lap - m.K3 * cp1p * C.T;
                     const double G0 = 2.0 * C.T - dt * (src.fT1 + FT1);
@@ -556,12 +580,14 @@ k_feuler_march(DDGeom g, const DDMember* __restrict__ mem, DDForcingArrays A, DD
     const int rbk = bid / wcb, cbk = bid - rbk * wcb;
     const DDMember& mb = mem[member];
     if (!mb.active) return;
+    const int ra = r0 + rbk * DD_MARCH_ROWS, rz = min(ra + DD_MARCH_ROWS, r1);
+    __shared__ DDMarchShared sh;
+    dd_march_stage(sh, g, mb, ra);
     const int wc = cbk * (blockDim.x >> 5) + warp;
     if (wc >= nwc) return;
-    const DDModel& m = mb.m;
+    const DDModel& m = sh.m;
     const double dt = mb.dt;
     const int j = wc * 31 + lane - 1;
-    const int ra = r0 + rbk * DD_MARCH_ROWS, rz = min(ra + DD_MARCH_ROWS, r1);
     const bool col = j >= 0 && j <= g.M;
     const bool owner = lane >= 1 && col;
     const bool jint = j >= 1 && j <= g.M - 1;
@@ -584,7 +610,7 @@ k_feuler_march(DDGeom g, const DDMember* __restrict__ mem, DDForcingArrays A, DD
     {
         const int i = g.row0 + ra;
         if (jint && i >= 1 && i <= g.N - 1) {
-            W = dd_march_face(m, P, C, g.rh[i]);
+            W = dd_march_face(m, P, C, sh.rh[0]);
             wadv = 0.5 * (m.gamma_T * C.T * (C.cl + 1.0) + m.gamma_T * P.T * (P.cl + 1.0));
         }
     }
@@ -603,7 +629,7 @@ k_feuler_march(DDGeom g, const DDMember* __restrict__ mem, DDForcingArrays A, DD
         DDMarchFace E = {0.0, 0.0, 0.0};
         double eadv = 0.0;
         if (jint && i >= 0 && i <= g.N - 1 && r + 1 < g.nrows) {
-            E = dd_march_face(m, C, N, g.rh[i + 1]);
+            E = dd_march_face(m, C, N, sh.rh[r - ra + 1]);
             eadv = 0.5 * (m.gamma_T * N.T * (N.cl + 1.0) + m.gamma_T * C.T * (C.cl + 1.0));
         }
         DDMarchFace Nf = {0.0, 0.0, 0.0};
@@ -615,7 +641,7 @@ k_feuler_march(DDGeom g, const DDMember* __restrict__ mem, DDForcingArrays A, DD
         if (owner) {
             double Fcp = f[DD_CP], FT = f[DD_T], Fcl = f[DD_CL], Fcd = f[DD_CD], Fcs = (f[DD_CS] - 0.0) * 0.0;
             if (irow && jint) {
-                const double rhp = g.rhp[i];
+                const double rhp = sh.rhp[r - ra];
                 const double react = dd_reaction(m, C.cl, C.cd, csC);
                 Fcp = f[DD_CP] + dd_Fcp_int(m, C.cp, C.T, C.cl);
                 FT = f[DD_T] + (m.DT * (rhp * (E.T - W.T) + rkp * (Nf.T - S.T)) - m.K3 * C.cp * C.T);
@@ -788,10 +814,10 @@ __device__ __forceinline__ bool dd_march_setup(const DDGeom& g, const DDRows& R,
     bid -= q->member * (wcb * nrb);
     const int rbk = bid / wcb, cbk = bid - rbk * wcb;
     q->wc = cbk * (blockDim.x >> 5) + warp;
-    if (q->wc >= nwc) return false;
-    q->j = q->wc * 31 + q->lane - 1;
     q->ra = r0 + rbk * DD_MARCH_ROWS;
     q->rz = min(q->ra + DD_MARCH_ROWS, r1);
+    if (q->wc >= nwc) return false;
+    q->j = q->wc * 31 + q->lane - 1;
     const int j = q->j;
     q->col = j >= 0 && j <= g.M;
     q->owner = q->lane >= 1 && q->col;
@@ -816,10 +842,13 @@ k_assemble_cl_march(DDGeom g, const DDMember* __restrict__ mem, const double* __
                     const double* __restrict__ T1, const double* __restrict__ Ycl, DDRows R, DDSolveStats* stats,
                     int r0, int r1, int nwc, int wcb, int nrb) {
     DDMarchGeom q;
-    if (!dd_march_setup(g, R, r0, r1, nwc, wcb, nrb, &q)) return;
+    const bool mine = dd_march_setup(g, R, r0, r1, nwc, wcb, nrb, &q);
     const DDMember& mb = mem[q.member];
     if (!mb.active) return;
-    const DDModel& m = mb.m;
+    __shared__ DDMarchShared sh;
+    dd_march_stage(sh, g, mb, q.ra);
+    if (!mine) return;
+    const DDModel& m = sh.m;
     const double dt = mb.dt;
     const int j = q.j;
     const double *cpA = u.v[DD_CP], *TA = u.v[DD_T], *clA = u.v[DD_CL];
@@ -842,7 +871,7 @@ k_assemble_cl_march(DDGeom g, const DDMember* __restrict__ mem, const double* __
         const int i = g.row0 + q.ra;
         if (q.jint && i >= 1 && i <= g.N - 1) {
             DlW = dd_Dl(m, 0.5 * (C.cp + P.cp));
-            flW = DlW * ((C.v - P.v) * g.rh[i]);
+            flW = DlW * ((C.v - P.v) * sh.rh[0]);
             advW = 0.5 * (m.gamma_T * C.T * (C.v + 1.0) + m.gamma_T * P.T * (P.v + 1.0));
         }
     }
@@ -863,7 +892,7 @@ k_assemble_cl_march(DDGeom g, const DDMember* __restrict__ mem, const double* __
         double DlE = 0.0, flE = 0.0, advE = 0.0;
         if (q.jint && i >= 0 && i <= g.N - 1 && r + 1 < g.nrows) {
             DlE = dd_Dl(m, 0.5 * (N.cp + C.cp));
-            flE = DlE * ((N.v - C.v) * g.rh[i + 1]);
+            flE = DlE * ((N.v - C.v) * sh.rh[r - q.ra + 1]);
             advE = 0.5 * (m.gamma_T * N.T * (N.v + 1.0) + m.gamma_T * C.T * (C.v + 1.0));
         }
         double DlN = 0.0, flN = 0.0;
@@ -876,8 +905,8 @@ k_assemble_cl_march(DDGeom g, const DDMember* __restrict__ mem, const double* __
         if (q.owner) {
             DDRow row = {0.0, 0.0, 0.0, 0.0, 0.0};
             if (inter) {
-                const double rhp = g.rhp[i];
-                const double dW = DlW * (rhp * g.rh[i]), dE = DlE * (rhp * g.rh[i + 1]);
+                const double rhp = sh.rhp[r - q.ra];
+                const double dW = DlW * (rhp * sh.rh[r - q.ra]), dE = DlE * (rhp * sh.rh[r - q.ra + 1]);
                 const double S = DlS * q.cS, Nn = DlN * q.cN;
                 const double W = dW + (m.gamma_T * P.T) * (0.5 * rhp);
                 const double E = dE - (m.gamma_T * N.T) * (0.5 * rhp);
@@ -907,10 +936,13 @@ k_assemble_cd_march(DDGeom g, const DDMember* __restrict__ mem, const double* __
                     const double* __restrict__ T1, const double* __restrict__ cl1, const double* __restrict__ Ycd,
                     int swap, DDRows R, DDSolveStats* stats, int r0, int r1, int nwc, int wcb, int nrb) {
     DDMarchGeom q;
-    if (!dd_march_setup(g, R, r0, r1, nwc, wcb, nrb, &q)) return;
+    const bool mine = dd_march_setup(g, R, r0, r1, nwc, wcb, nrb, &q);
     const DDMember& mb = mem[q.member];
     if (!mb.active) return;
-    const DDModel& m = mb.m;
+    __shared__ DDMarchShared sh;
+    dd_march_stage(sh, g, mb, q.ra);
+    if (!mine) return;
+    const DDModel& m = sh.m;
     const double dt = mb.dt;
     const int j = q.j;
     const double *cpA = u.v[DD_CP], *TA = u.v[DD_T], *clA = u.v[DD_CL], *cdA = u.v[DD_CD], *csA = u.v[DD_CS];
@@ -929,7 +961,7 @@ k_assemble_cd_march(DDGeom g, const DDMember* __restrict__ mem, const double* __
         if (q.jint && i >= 1 && i <= g.N - 1) {
             double dTf;
             DdW = dd_Dd_dT(m, 0.5 * (C.cp + P.cp), 0.5 * (C.T + P.T), &dTf);
-            const double gx = (C.v - P.v) * g.rh[i];
+            const double gx = (C.v - P.v) * sh.rh[0];
             flW = DdW * gx;
             jtW = (gx * dTf) * (0.5 * ((C.t1 - C.T) + (P.t1 - P.T)));
         }
@@ -953,7 +985,7 @@ k_assemble_cd_march(DDGeom g, const DDMember* __restrict__ mem, const double* __
         if (q.jint && i >= 0 && i <= g.N - 1 && r + 1 < g.nrows) {
             double dTf;
             DdE = dd_Dd_dT(m, 0.5 * (N.cp + C.cp), 0.5 * (N.T + C.T), &dTf);
-            const double gx = (N.v - C.v) * g.rh[i + 1];
+            const double gx = (N.v - C.v) * sh.rh[r - q.ra + 1];
             flE = DdE * gx;
             jtE = (gx * dTf) * (0.5 * ((N.t1 - N.T) + (C.t1 - C.T)));
         }
@@ -971,8 +1003,8 @@ k_assemble_cd_march(DDGeom g, const DDMember* __restrict__ mem, const double* __
         if (q.owner) {
             DDRow row = {0.0, 0.0, 0.0, 0.0, 0.0};
             if (inter) {
-                const double rhp = g.rhp[i];
-                const double W = DdW * (rhp * g.rh[i]), E = DdE * (rhp * g.rh[i + 1]);
+                const double rhp = sh.rhp[r - q.ra];
+                const double W = DdW * (rhp * sh.rh[r - q.ra]), E = DdE * (rhp * sh.rh[r - q.ra + 1]);
                 const double S = DdS * q.cS, Nn = DdN * q.cN;
                 const double KH = m.Kd * dd_F2(m, csc);
                 const double Cc = -(W + E + S + Nn) - KH * (clc + 1.0);

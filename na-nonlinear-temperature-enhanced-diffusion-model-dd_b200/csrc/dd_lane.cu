@@ -99,10 +99,12 @@ int dd_lane_pass_sweeps(int left) {
     return (left + passes - 1) / passes;
 }
 
-// Which solves run on the lane kernel: DD_LANE = 0 (none), 1 (all), or a list of variables "T,cl,cd"
+// Which solves run on the lane kernel: DD_LANE = 0 (none), 1 (all, the default), or a list of variables "T,cl,cd".
+// Measured on B200 at 8193 x 1025 nodes (profiles/README.md): T 0.23 ms against 0.35 ms with the register-tile
+// kernel, cl 0.24 against 0.31 (wavefront kernel), cd 0.14 against 0.21.
 bool dd_lane_ok(const DDGeom& g, const DDLaunch& L, int var) {
     const char* on = getenv("DD_LANE");  // read per call: the tests switch kernels inside one process
-    if (!on || !*on) on = "0";
+    if (!on || !*on) on = "1";
     if (*on == '0') return false;
     if (*on != '1') {
         static const char* names[3] = {"T", "cl", "cd"};

@@ -276,6 +276,7 @@ template <int CB, int S, int XIN, int U>
 DD_HD void dd_lane_step(const WaveArgs& A, const WaveSeg& sg, LaneRegs<CB, S, XIN>& R, const LaneSmem& sm, int tau, int lane,
                         double omega, double fT, const double* nb) {
     constexpr int P = 2 * S + 4, NC = CB ? 2 : 5, NA = DD_LANE_NA(CB, XIN), o = (U + 1) & 1;
+    (void)NA;
     // (1) row tau + LS is requested, row tau has arrived
     dd_lane_request<CB, S, XIN>(A, sg, R, sm, tau + DD_LANE_LS, lane, (U + DD_LANE_LS) % P);
     DD_LANE_WAIT();

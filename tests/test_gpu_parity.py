@@ -644,7 +644,7 @@ def test_slab_solves_in_segments_for_large_time_steps(dd, M):
     """Matrices of a large time step (weak diagonal dominance: the constants of the steps_scp_10x10_pc_bigdt fixture)
     need more SOR sweeps than a shallow halo supports between two exchanges.  The slab driver then runs the solve in
     segments and exchanges the iterate's halo rows in between (dd_pc_solve_segment): three slabs with a halo of 7
-    rows (2 sweeps per segment) reproduce the oracle, and at a fixed plan of 40 sweeps the undecomposed run bit for
+    rows (2 sweeps per segment) reproduce the oracle, and at a fixed plan of 9 sweeps the undecomposed run bit for
     bit.  M = 40: tile kernels; M = 150: marching kernels and the wavefront kernel for cl."""
     import ddmesh
     from oracle import NOTEBOOK_CONSTS, OForcing, OGrid, PCStepper, exact_state, make_case
@@ -681,7 +681,9 @@ def test_slab_solves_in_segments_for_large_time_steps(dd, M):
         s = stepper.step(s, t0 + k * dt, dt)
     for v in VARS:
         assert rel_err(got[v], getattr(s, v)) <= TOL, (v, st)
-    fixed = ddcore.pc_options(fixed_sweeps=40)  # (a fixed plan must converge, too: rho = 0.84 here)
+    # bit-for-bit equality does not need a converged solve: 9 sweeps (segments of 2, 2, 2, 2, 1), accepted at a
+    # loose tolerance (a fixed plan that fails the residual bound is an error in both drivers)
+    fixed = ddcore.pc_options(fixed_sweeps=9, solve_tol=1.0)
     meshes2 = slabs()
     b = ddcore.Batch(grid.x, grid.y, 1)
     b.set_model(model, eta)
