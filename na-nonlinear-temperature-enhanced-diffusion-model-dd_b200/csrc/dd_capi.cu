@@ -100,6 +100,7 @@ struct dd_batch {
     } rec[2];
     int rec_cur;
     double relax_rho[3];  // >= 0: ratio the solver derives omega from (slab meshes: the all-reduced one)
+    bool gs_only[3];      // the solve of this variable has fallen back to plain Gauss-Seidel (see gs_fallback)
     bool prev_valid, use_guess, phase_fused_T;
     int prev_in, prev_out;
     double prev_dt, cur_dt;  // first member's step size (the increment scales with it)
@@ -121,7 +122,10 @@ static void reset_ctl(dd_batch* b, bool all) {
                 b->ctl[m].floor[q] = 1;
             }
         }
-    if (all) b->cm = 0;
+    if (all) {
+        b->cm = 0;
+        b->gs_only[0] = b->gs_only[1] = b->gs_only[2] = false;
+    }
 }
 
 
@@ -343,6 +347,7 @@ extern "C" int dd_batch_create(dd_ctx* ctx, int N, int M, const double* x, const
     reset_ctl(b, true);
     b->prev_valid = b->use_guess = b->phase_fused_T = false;
     b->relax_rho[0] = b->relax_rho[1] = b->relax_rho[2] = -1.0;
+    b->gs_only[0] = b->gs_only[1] = b->gs_only[2] = false;
     b->prev_in = b->prev_out = -1;
     b->prev_dt = b->cur_dt = 0.0;
     b->rec_cur = 0;
@@ -1054,6 +1059,26 @@ static int next_plan(int cur, double rho, double ratio, int max_sweeps) {
     return want;
 }
 
+// The over-relaxation factor is the optimal one of a symmetric, consistently ordered matrix.  The cd system of a
+// very large time step is far from symmetric (its T-Jacobian term), and SOR can then DIVERGE although the matrix
+// is strictly diagonally dominant (seen at dt D / h^2 ~ 9).  Gauss-Seidel (omega = 1) converges for every strictly
+// diagonally dominant matrix, with an error factor <= rho per sweep: once three times the theoretical SOR count
+// has failed the residual bound, the variable's solves use it for the rest of the batch's life.
+static int sweeps_for_gs(double rho, int max_sweeps) {
+    if (!(rho >= 0.0) || rho >= 1.0) return max_sweeps;
+    if (rho < 1e-300) return 2;
+    int k = 2;
+    while (k < max_sweeps && pow(rho, k) > 1e-17) ++k;
+    return k;
+}
+static bool gs_fallback(dd_batch* b, int vi, int used, double rho, int max_sweeps, int* next) {
+    if (b->gs_only[vi] || !(rho < 1.0)) return false;
+    if (used < 3 * sweeps_for_rho(rho * 1.02 + 1e-12, max_sweeps) + 8) return false;
+    b->gs_only[vi] = true;
+    *next = sweeps_for_gs(rho * 1.02 + 1e-12, max_sweeps);
+    return true;
+}
+
 // choose tile shape and sweeps per pass
 static void plan_pass(const dd_batch* b, int sweeps_left, bool allow_last, bool const_band, DDSolvePlan* P) {
     const int rows = b->own1 - b->own0, cols = b->M + 1;
@@ -1374,7 +1399,7 @@ static int newton_solve(dd_batch* b, int var, const DDStateC& ustar, const doubl
         } else {
             plan_pass(b, left, seg_finish, var == DD_T, &P);
         }
-        P.rho_fix = b->relax_rho[vi];
+        P.rho_fix = b->gs_only[vi] ? 0.0 : b->relax_rho[vi];  // (ratio 0: omega = 1)
         if (P.sweeps <= 0) return fail(ctx, DD_ERR_INVALID, "no feasible solver tile");
         double* xout = nullptr;
         DDLaunch Lp = L;
@@ -1598,15 +1623,26 @@ static int pc_step_finish(dd_batch* b, dd_batch::StepRec& R, dd_step_stats* stat
             const int used = R.solve_sweeps[q];  // with deferred verification the plan may have moved on since
             if (!(sums[q].ratio <= 1.0)) {
                 // not enough sweeps: remember the failing count and go (at least) to the theoretical one
+                int gs_next = 0;
+                if (gs_fallback(b, vi, used, sums[q].rho, opt.max_sweeps, &gs_next)) {
+                    for (int m = 0; m < 2; ++m) {
+                        b->ctl[m].sweeps[vi] = gs_next;
+                        b->ctl[m].extra[vi] = 0;
+                        b->ctl[m].floor[vi] = 1;
+                    }
+                    continue;
+                }
                 if (c.floor[vi] < used + 1) c.floor[vi] = used + 1;
-                const int want = sweeps_for_rho(sums[q].rho * 1.02 + 1e-12, opt.max_sweeps);
+                const int want = b->gs_only[vi] ? sweeps_for_gs(sums[q].rho * 1.02 + 1e-12, opt.max_sweeps)
+                                                : sweeps_for_rho(sums[q].rho * 1.02 + 1e-12, opt.max_sweeps);
                 if (used >= want) c.extra[vi] += (used + 1) / 2 + 1;
                 int next = want + c.extra[vi];
                 if (next < c.floor[vi]) next = c.floor[vi];
                 if (next > opt.max_sweeps) next = opt.max_sweeps;
                 if (next > c.sweeps[vi]) c.sweeps[vi] = next;
             } else if (*converged && (q >= k - 3 || q < 3) && sums[q].ratio >= 0.0) {
-                int next = next_plan(used, sums[q].rho, sums[q].ratio, opt.max_sweeps);
+                // (Gauss-Seidel fallback: the plan only grows; its error factor is not the one next_plan assumes)
+                int next = b->gs_only[vi] ? used : next_plan(used, sums[q].rho, sums[q].ratio, opt.max_sweeps);
                 if (next < c.floor[vi]) next = c.floor[vi];
                 c.sweeps[vi] = next;
             }

@@ -223,23 +223,22 @@ DD_HD void dd_lane_offer(const LaneRegs<CB, S, XIN>& R, double* src) {
     for (int k = 0; k <= 2 * S; ++k) src[k] = R.X[1 - o][(U - 1 - k + 2 * P) % P];
 }
 
-// Gauss-Seidel value of cell (row slot SL, column o) -- c[]: bb, aW, aE, aS, aN | bb, dinv
+// Gauss-Seidel value minus x (the residual for iterate value x) of cell (row slot SL, column o) -- c[]: bb, aW, aE,
+// aS, aN | bb, dinv
 template <int CB, int S, int XIN, int SL, int O>
-DD_HD double dd_lane_gs(const LaneRegs<CB, S, XIN>& R, const double* c, double nb) {
+DD_HD double dd_lane_gs(const LaneRegs<CB, S, XIN>& R, const double* c, double nb, double x) {
     constexpr int P = 2 * S + 4;
     const double xw = R.X[O][(SL + P - 1) % P], xe = R.X[O][(SL + 1) % P];
     const double xs = O ? R.X[0][SL] : nb, xn = O ? nb : R.X[1][SL];
-    if (CB) return dd_sor_gsT(c[0], c[1], R.RW[CB ? SL : 0], R.RE[CB ? SL : 0], R.kS[O], R.kN[O], xw, xe, xs, xn);
-    return dd_sor_gs5(c[0], c[1], c[CB ? 0 : 2], c[CB ? 0 : 3], c[CB ? 0 : 4], xw, xe, xs, xn);
+    if (CB) return dd_sor_dT(c[0], c[1], R.RW[CB ? SL : 0], R.RE[CB ? SL : 0], R.kS[O], R.kN[O], xw, xe, xs, xn, x);
+    return dd_sor_d5(c[0], c[1], c[CB ? 0 : 2], c[CB ? 0 : 3], c[CB ? 0 : 4], xw, xe, xs, xn, x);
 }
 
-// one relaxation of cell (row slot SL, column O); returns gs - x_new (the cell's residual if its neighbours are final)
+// one relaxation of cell (row slot SL, column O)
 template <int CB, int S, int XIN, int SL, int O>
-DD_HD double dd_lane_relax(LaneRegs<CB, S, XIN>& R, const double* c, double nb, double omega) {
-    const double gs = dd_lane_gs<CB, S, XIN, SL, O>(R, c, nb);
-    const double xn = dd_sor_relax(R.X[O][SL], gs, omega);
-    R.X[O][SL] = xn;
-    return gs - xn;
+DD_HD void dd_lane_relax(LaneRegs<CB, S, XIN>& R, const double* c, double nb, double omega) {
+    const double x = R.X[O][SL];
+    R.X[O][SL] = dd_sor_relax(x, dd_lane_gs<CB, S, XIN, SL, O>(R, c, nb, x), omega);
 }
 
 // level pairs K .. S - 1 of step U: odd level 2 K + 1 on row tau - 2 K - 1 (coefficients from the ring, the other
@@ -262,8 +261,10 @@ DD_HD void dd_lane_pairs(LaneRegs<CB, S, XIN>& R, const LaneSmem& sm, const doub
             R.carry[K][a] = o ? p0 : p1;
         }
         dd_lane_relax<CB, S, XIN, s1, o>(R, use, nb[2 * K], omega);
-        const double res = dd_lane_relax<CB, S, XIN, s2, o>(R, old, nb[2 * K + 1], omega);
+        dd_lane_relax<CB, S, XIN, s2, o>(R, old, nb[2 * K + 1], omega);
         if (K == S - 1 && fin_row) {
+            // the neighbours of these cells are final: the residual of the new value
+            const double res = dd_lane_gs<CB, S, XIN, s2, o>(R, old, nb[2 * K + 1], R.X[o][s2]);
             const unsigned h = dd_wave_hi(res) & (0u - ((R.own >> o) & 1u));
             R.hr = h > R.hr ? h : R.hr;
         }
@@ -314,7 +315,7 @@ DD_HD void dd_lane_step(const WaveArgs& A, const WaveSeg& sg, LaneRegs<CB, S, XI
             c[0] = o ? b1 : b0;
 #pragma unroll
             for (int a = 1; a < NC; ++a) c[a] = dd_lane_lds(sm, R.ring + DD_LANE_OFF(CB, XIN, SO, a) + 8u * o);
-            const double res = dd_lane_gs<CB, S, XIN, SO, o>(R, c, nb[2 * S]) - R.X[o][SO];
+            const double res = dd_lane_gs<CB, S, XIN, SO, o>(R, c, nb[2 * S], R.X[o][SO]);
             const unsigned m0 = 0u - (R.own & 1u), m1 = 0u - ((R.own >> 1) & 1u);
             const unsigned h = dd_wave_hi(res) & (o ? m1 : m0);
             R.hr = h > R.hr ? h : R.hr;

@@ -116,8 +116,10 @@ __device__ MemberSolveOut member_solve(const DDGeom& g, const DDRows& R, double*
     const double* gS = geof + 2 * gstride;
     const double* gN = geof + 3 * gstride;
     auto gs_at = [&](int i, int j, int p) {
-        if (CB) return dd_sor_gsT(R.bb[p], R.aW[p], gW[i], gE[i], gS[j], gN[j], x[p - P], x[p + P], x[p - 1], x[p + 1]);
-        return dd_sor_gs5(R.bb[p], R.aW[p], R.aE[p], R.aS[p], R.aN[p], x[p - P], x[p + P], x[p - 1], x[p + 1]);
+        // gs - x: the cell's residual (dd_sor.cuh)
+        if (CB)
+            return dd_sor_dT(R.bb[p], R.aW[p], gW[i], gE[i], gS[j], gN[j], x[p - P], x[p + P], x[p - 1], x[p + 1], x[p]);
+        return dd_sor_d5(R.bb[p], R.aW[p], R.aE[p], R.aS[p], R.aN[p], x[p - P], x[p + P], x[p - 1], x[p + 1], x[p]);
     };
     auto sweep = [&]() {
         for (int c = 0; c < 2; ++c) {
@@ -146,7 +148,7 @@ __device__ MemberSolveOut member_solve(const DDGeom& g, const DDRows& R, double*
         for (int k = threadIdx.x; k < (N - 1) * (M - 1); k += DD_MEMBER_THREADS) {
             const int i = 1 + k / (M - 1), j = 1 + (k - (i - 1) * (M - 1));
             const int p = i * P + j;
-            rmax = dd_nn_max(rmax, gs_at(i, j, p) - x[p]);
+            rmax = dd_nn_max(rmax, gs_at(i, j, p));
             xmax = dd_nn_max(xmax, x[p]);
             vmax = dd_nn_max(vmax, vstar[p] + x[p]);
             bmax = dd_nn_max(bmax, R.bb[p]);

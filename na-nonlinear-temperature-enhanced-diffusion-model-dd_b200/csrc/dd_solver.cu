@@ -245,10 +245,10 @@ __global__ void __launch_bounds__(512) k_rbsor_tile(SolveArgs A) {
                     if (CONST_BAND) {
                         const int sj = 2 * pk + ((colour + par0 + si) & 1);
                         const int sic = on[u] ? si : 0, sjc = on[u] ? sj : 0;
-                        gs = dd_sor_gsT(bv[u], wv[u], rowW[sic], rowE[sic], colS[sjc], colN[sjc], xw[u], xe[u], xs[u],
-                                        xn[u]);
+                        gs = dd_sor_dT(bv[u], wv[u], rowW[sic], rowE[sic], colS[sjc], colN[sjc], xw[u], xe[u], xs[u],
+                                       xn[u], xv[u]);
                     } else {
-                        gs = dd_sor_gs5(bv[u], wv[u], ev[u], sv[u], nv[u], xw[u], xe[u], xs[u], xn[u]);
+                        gs = dd_sor_d5(bv[u], wv[u], ev[u], sv[u], nv[u], xw[u], xe[u], xs[u], xn[u], xv[u]);
                     }
                     if (on[u]) dd_smem[o_xc + si * PW + pk] = dd_sor_relax(xv[u], gs, omega);
                 }
@@ -291,11 +291,11 @@ __global__ void __launch_bounds__(512) k_rbsor_tile(SolveArgs A) {
                 const double bbv = Bb.c(col)[p];
                 double res;
                 if (CONST_BAND)
-                    res = dd_sor_gsT(bbv, AW.c(col)[p], rowW[si], rowE[si], colS[sj], colN[sj], xo[p - PW], xo[p + PW],
-                                     xo[p - 1 + o], xo[p + o]) - x;
+                    res = dd_sor_dT(bbv, AW.c(col)[p], rowW[si], rowE[si], colS[sj], colN[sj], xo[p - PW], xo[p + PW],
+                                    xo[p - 1 + o], xo[p + o], x);
                 else
-                    res = dd_sor_gs5(bbv, AW.c(col)[p], AE.c(col)[p], AS.c(col)[p], AN.c(col)[p], xo[p - PW], xo[p + PW],
-                                     xo[p - 1 + o], xo[p + o]) - x;
+                    res = dd_sor_d5(bbv, AW.c(col)[p], AE.c(col)[p], AS.c(col)[p], AN.c(col)[p], xo[p - PW], xo[p + PW],
+                                    xo[p - 1 + o], xo[p + o], x);
                 const bool inter = dd_is_interior(g, g.row0 + r, j);
                 const double vn = dd_newton_update(inter, vs[u], x, A.zero_boundary);
                 A.vnew[ogs[u]] = vn;
@@ -628,10 +628,10 @@ k_rbsor_reg(const __grid_constant__ SolveArgs A, const __grid_constant__ DDTileM
             const double xv = xc[p];
             double gs;
             if (CONST_BAND)
-                gs = dd_sor_gsT(cb[k][c], cw[k][c], rW[k], rE[k], (o ? cS2[1] : cS2[0]), (o ? cN2[1] : cN2[0]), xw, xe,
-                                xs, xn);
+                gs = dd_sor_dT(cb[k][c], cw[k][c], rW[k], rE[k], (o ? cS2[1] : cS2[0]), (o ? cN2[1] : cN2[0]), xw, xe,
+                               xs, xn, xv);
             else
-                gs = dd_sor_gs5(cb[k][c], cw[k][c], ce[k][c], cs[k][c], cn[k][c], xw, xe, xs, xn);
+                gs = dd_sor_d5(cb[k][c], cw[k][c], ce[k][c], cs[k][c], cn[k][c], xw, xe, xs, xn, xv);
             xnew[k] = dd_sor_relax(xv, gs, omega);
         }
 #pragma unroll
@@ -660,10 +660,10 @@ k_rbsor_reg(const __grid_constant__ SolveArgs A, const __grid_constant__ DDTileM
                 const double xw = xo[p - PW], xe = xo[p + PW], xs = xo[p + o - 1], xn = xo[p + o];
                 double res;
                 if (CONST_BAND)
-                    res = dd_sor_gsT(cb[k][c], cw[k][c], rW[k], rE[k], (o ? cS2[1] : cS2[0]), (o ? cN2[1] : cN2[0]), xw,
-                                     xe, xs, xn) - x;
+                    res = dd_sor_dT(cb[k][c], cw[k][c], rW[k], rE[k], (o ? cS2[1] : cS2[0]), (o ? cN2[1] : cN2[0]), xw,
+                                    xe, xs, xn, x);
                 else
-                    res = dd_sor_gs5(cb[k][c], cw[k][c], ce[k][c], cs[k][c], cn[k][c], xw, xe, xs, xn) - x;
+                    res = dd_sor_d5(cb[k][c], cw[k][c], ce[k][c], cs[k][c], cn[k][c], xw, xe, xs, xn, x);
                 rmax = nn_max(rmax, res);
                 xmax = nn_max(xmax, x);
                 bmax = nn_max(bmax, cb[k][c]);

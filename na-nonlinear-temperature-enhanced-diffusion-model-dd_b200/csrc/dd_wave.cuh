@@ -379,11 +379,12 @@ DD_HD void dd_wave_xinit(const WaveArgs& A, const WaveSeg& sg, WaveRegs<CB, C>& 
     }
 }
 
-// Gauss-Seidel value of the thread's cell (slot K, chunk c, colour CO) from the other colour's current iterate.
+// Gauss-Seidel value minus x (the residual for iterate value x) of the thread's cell (slot K, chunk c, colour CO)
+// from the other colour's current iterate.
 // In slot K the cells of colour CO sit on columns of parity O = CO ^ K: cell 2 p + O, neighbours 2 p + O -+ 1,
 // i.e. packed columns p + O - 1 and p + O of the other colour.
 template <int CB, int C, int K, int CO>
-DD_HD double dd_wave_gs(const WaveRegs<CB, C>& R, const WaveSmem& sm, int lane, int c) {
+DD_HD double dd_wave_gs(const WaveRegs<CB, C>& R, const WaveSmem& sm, int lane, int c, double x) {
     constexpr int PLB = (32 * C + 2) * 8, O = CO ^ K, W = 64 * C;
     const int off = (1 - CO) * PLB + c * 256;
     const double xw = dd_wave_lds(sm, R.axW[K] + (unsigned)off), xe = dd_wave_lds(sm, R.axE[K] + (unsigned)off);
@@ -391,11 +392,11 @@ DD_HD double dd_wave_gs(const WaveRegs<CB, C>& R, const WaveSmem& sm, int lane, 
     const double xn = dd_wave_lds(sm, (unsigned)((int)R.ax[K] + off + O * 8));
     if (CB) {
         const unsigned ka = sm.kaddr + (unsigned)((2 * lane + O + 64 * c) * 8);
-        return dd_sor_gsT(R.cb[K][c][CO], R.cw[K][c][CO], R.rW[K], R.rE[K], dd_wave_lds(sm, ka),
-                          dd_wave_lds(sm, ka + W * 8), xw, xe, xs, xn);
+        return dd_sor_dT(R.cb[K][c][CO], R.cw[K][c][CO], R.rW[K], R.rE[K], dd_wave_lds(sm, ka),
+                         dd_wave_lds(sm, ka + W * 8), xw, xe, xs, xn, x);
     }
-    return dd_sor_gs5(R.cb[K][c][CO], R.cw[K][c][CO], R.ce[CB ? 0 : K][CB ? 0 : c][CO], R.cs[CB ? 0 : K][CB ? 0 : c][CO],
-                      R.cn[CB ? 0 : K][CB ? 0 : c][CO], xw, xe, xs, xn);
+    return dd_sor_d5(R.cb[K][c][CO], R.cw[K][c][CO], R.ce[CB ? 0 : K][CB ? 0 : c][CO], R.cs[CB ? 0 : K][CB ? 0 : c][CO],
+                     R.cn[CB ? 0 : K][CB ? 0 : c][CO], xw, xe, xs, xn, x);
 }
 
 // ---- one half-sweep of the slot's row: colour CO ---------------------------------------------------------------
@@ -409,7 +410,7 @@ DD_HD void dd_wave_relax(const WaveArgs& A, const WaveSeg& sg, WaveRegs<CB, C>& 
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         const double xv = dd_wave_lds(sm, R.ax[K] + CO * PLB + c * 256);
-        gs[c] = dd_wave_gs<CB, C, K, CO>(R, sm, lane, c);
+        gs[c] = dd_wave_gs<CB, C, K, CO>(R, sm, lane, c, xv);
         xnew[c] = dd_sor_relax(xv, gs[c], omega);
     }
 #pragma unroll
@@ -420,7 +421,7 @@ DD_HD void dd_wave_relax(const WaveArgs& A, const WaveSeg& sg, WaveRegs<CB, C>& 
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const unsigned m = 0u - ((R.tmask >> (2 * c + O)) & 1u);
-                const unsigned h = dd_wave_hi(gs[c] - xnew[c]) & m;
+                const unsigned h = dd_wave_hi(dd_wave_gs<CB, C, K, CO>(R, sm, lane, c, xnew[c])) & m;
                 R.hr = h > R.hr ? h : R.hr;
             }
         }
@@ -437,7 +438,7 @@ DD_HD void dd_wave_resid0(const WaveArgs& A, const WaveSeg& sg, WaveRegs<CB, C>&
     for (int c = 0; c < C; ++c) {
         const unsigned m0 = 0u - ((R.tmask >> (2 * c + O)) & 1u), m1 = 0u - ((R.tmask >> (2 * c + 1 - O)) & 1u);
         const double x = dd_wave_lds(sm, R.ax[K] + c * 256);
-        const unsigned h = dd_wave_hi(dd_wave_gs<CB, C, K, 0>(R, sm, lane, c) - x) & m0;
+        const unsigned h = dd_wave_hi(dd_wave_gs<CB, C, K, 0>(R, sm, lane, c, x)) & m0;
         R.hr = h > R.hr ? h : R.hr;
         const unsigned b0 = dd_wave_hi(R.cb[K][c][0]) & m0, b1 = dd_wave_hi(R.cb[K][c][1]) & m1;
         R.hb = b0 > R.hb ? b0 : R.hb;

@@ -13,6 +13,7 @@ Two ways the path shards:
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -333,7 +334,10 @@ class SlabMesh:
         # which the host already holds (they move by O(dt) per step and convergence is verified anyway) --
         # three collectives less on the critical path.
         lag = opt.fixed_sweeps <= 0 and self._rho is not None and all(0.0 <= float(r) < 1.0 for r in self._rho)
-        arr = (C.c_double * 3)(*([float(r) for r in self._rho] if lag else [-1.0, -1.0, -1.0]))
+        rel = [float(r) for r in self._rho] if lag else [-1.0, -1.0, -1.0]
+        # a variable whose SOR solves diverged runs plain Gauss-Seidel from then on (ratio 0: omega = 1; _on_reject)
+        rel = [0.0 if g else r for r, g in zip(rel, self._gs_only())]
+        arr = (C.c_double * 3)(*rel)
         for m in group:
             m.batch.ctx.check(m.batch.lib.dd_batch_set_relax_rho(m.batch.handle, C.byref(arr)), "set_relax_rho")
         limit = self.sweep_limit
@@ -424,8 +428,9 @@ class SlabMesh:
             m._rho, m.last_stats = s[:, 0], stats
         if ok:
             # (a negative ratio marks a system that was NaN / Inf on entry: nothing to learn from it)
-            nxt = [max(self.batch.lib.dd_next_plan(int(p), float(r), float(q), opt.max_sweeps), f) if q >= 0.0 else p
-                   for p, r, q, f in zip(plan, s[:, 0], s[:, 1], ctl["floor"])]
+            nxt = [max(self.batch.lib.dd_next_plan(int(p), float(r), float(q), opt.max_sweeps), f)
+                   if (q >= 0.0 and not g) else p
+                   for p, r, q, f, g in zip(plan, s[:, 0], s[:, 1], ctl["floor"], self._gs_only())]
             for m in self.group:
                 m._ctl[mode]["plan"] = nxt
                 m._prev = (rec["slot_in"], rec["slot_out"], rec["dt"])
@@ -444,12 +449,41 @@ class SlabMesh:
             raise ddcore.DDNotConverged(f"slab step: {max(plan)} SOR sweeps do not reach the residual bound. "
                                         f"stats={stats}")
         lib = self.batch.lib
+        # Same fallback as the library (gs_fallback in dd_capi.cu): SOR with the over-relaxation of a symmetric
+        # matrix can diverge on the nonsymmetric cd system of very large time steps; once three times the
+        # theoretical count has failed, the variable is solved by Gauss-Seidel (error factor <= rho per sweep).
+        gs = self._gs_only()
+        for k, (p, r, x) in enumerate(zip(plan, ratio, rho)):
+            x = float(x)
+            if r > 1.0 and not gs[k] and 0.0 <= x < 1.0 and \
+                    p >= 3 * lib.dd_sweeps_for_rho(x * 1.02 + 1e-12, opt.max_sweeps) + 8:
+                gs[k] = True
+                for m in self.group:
+                    for md in (0, 1):
+                        m._ctl[md]["extra"][k], m._ctl[md]["floor"][k] = 0, 1
         floor = [max(f, p + 1) if r > 1.0 else f for f, p, r in zip(ctl["floor"], plan, ratio)]
-        theory = [lib.dd_sweeps_for_rho(float(x) * 1.02 + 1e-12, opt.max_sweeps) for x in rho]
+        theory = [self._gs_sweeps(float(x), opt.max_sweeps) if g else
+                  lib.dd_sweeps_for_rho(float(x) * 1.02 + 1e-12, opt.max_sweeps) for x, g in zip(rho, gs)]
         extra = [e + (p + 1) // 2 + 1 if (r > 1.0 and p >= th) else e
                  for e, p, r, th in zip(ctl["extra"], plan, ratio, theory)]
         for m in self.group:
             m._ctl[mode]["extra"], m._ctl[mode]["floor"] = extra, floor
+
+    def _gs_only(self) -> List[bool]:
+        """Per variable: its solves have fallen back to Gauss-Seidel (shared by the ranks of the group)."""
+        lead = self.group[0]
+        if not hasattr(lead, "_gs_flags"):
+            lead._gs_flags = [False, False, False]
+        return lead._gs_flags
+
+    @staticmethod
+    def _gs_sweeps(rho: float, max_sweeps: int) -> int:
+        rho = rho * 1.02 + 1e-12
+        if not (0.0 <= rho < 1.0):
+            return max_sweeps
+        if rho < 1e-300:
+            return 2
+        return int(min(max_sweeps, max(2, math.ceil(math.log(1e-17) / math.log(rho)))))
 
     def _common_plan(self, opt, ctl) -> List[int]:
         """Same number of SOR sweeps on every rank, planned from the all-reduced Gershgorin ratios of the
@@ -463,8 +497,9 @@ class SlabMesh:
         elif ctl["plan"] is not None:
             plan = list(ctl["plan"])
         else:
-            plan = [max(lib.dd_sweeps_for_rho(float(r) * 1.02 + 1e-12, opt.max_sweeps) + e, f)
-                    for r, e, f in zip(self._rho, ctl["extra"], ctl["floor"])]
+            plan = [max((self._gs_sweeps(float(r), opt.max_sweeps) if g else
+                         lib.dd_sweeps_for_rho(float(r) * 1.02 + 1e-12, opt.max_sweeps)) + e, f)
+                    for r, e, f, g in zip(self._rho, ctl["extra"], ctl["floor"], self._gs_only())]
         # plans beyond `limit` sweeps are run in segments with the iterate's halo exchanged in between
         plan = [max(1, min(int(p), opt.max_sweeps)) for p in plan]
         arr = (C.c_int * 3)(*plan)

@@ -246,10 +246,11 @@ extern "C" int ws_reference(WSProblem* P, double* x) {
             const bool ri = gi >= 1 && gi <= P->N - 1, cj = j >= 1 && j <= M - 1;
             const double rW = ri ? fT * P->rhp[gi] * P->rh[gi] : 0.0, rE = ri ? fT * P->rhp[gi] * P->rh[gi + 1] : 0.0;
             const double cS = cj ? fT * P->rkp[j] * P->rk[j] : 0.0, cN = cj ? fT * P->rkp[j] * P->rk[j + 1] : 0.0;
-            return dd_sor_gsT(P->bb[p], P->aW[p], rW, rE, cS, cN, nb(i - 1, j), nb(i + 1, j), nb(i, j - 1), nb(i, j + 1));
+            return dd_sor_dT(P->bb[p], P->aW[p], rW, rE, cS, cN, nb(i - 1, j), nb(i + 1, j), nb(i, j - 1), nb(i, j + 1),
+                             x[p]);
         }
-        return dd_sor_gs5(P->bb[p], P->aW[p], P->aE[p], P->aS[p], P->aN[p], nb(i - 1, j), nb(i + 1, j), nb(i, j - 1),
-                          nb(i, j + 1));
+        return dd_sor_d5(P->bb[p], P->aW[p], P->aE[p], P->aS[p], P->aN[p], nb(i - 1, j), nb(i + 1, j), nb(i, j - 1),
+                         nb(i, j + 1), x[p]);
     };
     for (int s = 0; s < P->sweeps; ++s)
         for (int colour = 0; colour < 2; ++colour)
@@ -269,7 +270,7 @@ extern "C" int ws_reference(WSProblem* P, double* x) {
                 const bool inter = gi > 0 && gi < P->N && j > 0 && j < M;
                 const double vn = dd_newton_update(inter, P->vstar[(size_t)i * P->ld + j], x[p], P->zero_boundary);
                 P->vnew[(size_t)i * P->ld + j] = vn;
-                up(hr, gs(i, j) - x[p]);
+                up(hr, gs(i, j));
                 up(hx, x[p]);
                 up(hv, vn);
                 up(hb, P->bb[p]);

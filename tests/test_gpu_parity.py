@@ -674,6 +674,9 @@ def test_slab_solves_in_segments_for_large_time_steps(dd, M):
     for k in range(nsteps):
         st = meshes[0].step_pc(k % 2, (k + 1) % 2, t0 + k * dt, dt)
     assert max(st["sweeps"]) > meshes[0].sweep_limit, st     # the solves really ran in segments
+    if M == 150:
+        # dt Dd / k^2 = 9: SOR diverges on the nonsymmetric cd system, the driver has fallen back to Gauss-Seidel
+        assert meshes[0]._gs_only()[2] and not meshes[0]._gs_only()[0], (meshes[0]._gs_only(), st)
     got = {v: np.concatenate([m.owned(nsteps % 2)[v] for m in meshes]) for v in VARS}
     s = exact_state(oc, t0, og)
     stepper = PCStepper(og, om, eta, OForcing(oc, om, eta, og), keep_residuals=False)
@@ -696,4 +699,38 @@ def test_slab_solves_in_segments_for_large_time_steps(dd, M):
     for v in VARS:
         many = np.concatenate([m.owned(0)[v] for m in meshes2])
         assert np.array_equal(many, one[v]), v
+    b.close()
+
+
+def test_sor_divergence_falls_back_to_gauss_seidel(dd):
+    """The over-relaxation factor is the optimal one of a symmetric matrix; on the cd system of a very large time
+    step (dt Dd / k^2 = 9, constants of the segment test at M = 150) SOR diverges although the matrix is strictly
+    diagonally dominant.  The step controller notices (three times the theoretical sweep count fails the residual
+    bound), switches that variable to Gauss-Seidel, which converges for every such matrix, and the step matches the
+    oracle's direct solve."""
+    from oracle import NOTEBOOK_CONSTS, OForcing, OGrid, PCStepper, exact_state, make_case
+    p1, ddcore = dd["p1"], dd["ddcore"]
+    N, M = 60, 150
+    om = NOTEBOOK_CONSTS["pol"].with_changes(DT=0.5, Dl_max=0.3, Dd_max=0.2)
+    eta, t0, dt = 50.0, 0.0, 2e-3
+    og = OGrid(np.linspace(0, 1, N + 1), np.linspace(0, 1, M + 1))
+    oc = make_case("scp_fast1e1", om)
+    model = dd["product_model"](dict(K1=om.K1, K2=om.K2, K3=om.K3, K4=om.K4, DT=om.DT, Dl_max=om.Dl_max,
+                                     phi_l=om.phi_l, gamma_T=om.gamma_T, Kd=om.Kd, Sd=om.Sd, Dd_max=om.Dd_max,
+                                     phi_d=om.phi_d, r_sp=om.r_sp, T_ref=om.T_ref, kind=2))
+    grid = p1.Grid(og.x, og.y)
+    b = ddcore.Batch(grid.x, grid.y, 1)
+    b.set_model(model, eta)
+    b.forcing_spec(dd["CASES"]["scp_fast1e1"](grid=grid, model=model).device_spec())
+    b.fill_exact(0, t0)
+    s = exact_state(oc, t0, og)
+    stepper = PCStepper(og, om, eta, OForcing(oc, om, eta, og), keep_residuals=False)
+    for k in range(2):
+        st = b.step_pc(k % 2, (k + 1) % 2, t0 + k * dt, dt)
+        s = stepper.step(s, t0 + k * dt, dt)
+    got = b.download(0)
+    for v in VARS:
+        assert rel_err(got[v], getattr(s, v)) <= TOL, (v, st)
+    # cd: far more sweeps than SOR's theoretical count for rho = 0.91 (about 50); T and cl stayed on SOR
+    assert st["sweeps"][2] > 150 and st["sweeps"][1] < 150, st
     b.close()
