@@ -59,18 +59,27 @@ DD_HD int dd_lane_halo(int S, int XIN) { return XIN ? 2 * S + 2 : 2 * S; }
 DD_HD int dd_lane_warmup(int S, int XIN) { return XIN ? 2 * S + 1 : 2 * S; }
 
 // one march (see dd_wave_segment): rows [r0, r1) of a strip, marched rows rs + q, q = 0 .. nq - 1, rs on an even
-// global row
+// global row.  The flat index runs over [member][row segment][strip][row of the segment] (A.nwo = rows per
+// segment; 0: one segment): warps with neighbouring flat ranges march the SAME rows of NEIGHBOURING strips at about
+// the same time, so the columns two strips share are read from HBM once and found in L2 the second time.
 DD_HD WaveSeg dd_lane_segment(const WaveArgs& A, long long f0, long long f1, int wu) {
     WaveSeg s;
     const int R = A.own1 - A.own0;
+    const int SR = A.nwo > 0 && A.nwo < R ? A.nwo : R;
+    const int nseg = (R + SR - 1) / SR;
     const long long per_member = (long long)A.nstrips * R;
     s.member = (int)(f0 / per_member);
     const long long rem = f0 - (long long)s.member * per_member;
-    const int strip = (int)(rem / R);
-    const int r = (int)(rem - (long long)strip * R);
+    const long long per_seg = (long long)SR * A.nstrips;
+    int g = (int)(rem / per_seg);
+    if (g > nseg - 1) g = nseg - 1;
+    const long long rem2 = rem - (long long)g * per_seg;
+    const int rows_g = g == nseg - 1 ? R - g * SR : SR;
+    const int strip = (int)(rem2 / rows_g);
+    const int r = (int)(rem2 - (long long)strip * rows_g);
     long long n = f1 - f0;
-    if (n > R - r) n = R - r;
-    s.r0 = A.own0 + r;
+    if (n > rows_g - r) n = rows_g - r;
+    s.r0 = A.own0 + g * SR + r;
     s.r1 = s.r0 + (int)n;
     s.c0 = strip * A.tj;
     s.tc = A.g.M + 1 - s.c0 < A.tj ? A.g.M + 1 - s.c0 : A.tj;

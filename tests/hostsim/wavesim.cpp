@@ -179,6 +179,7 @@ static void run_lane(WSProblem& P) {
     A.flat_total = (long long)A.nstrips * (P.own1 - P.own0);
     A.flat_per_cta = (A.flat_total + P.nctas - 1) / P.nctas;
     A.rho_fix = -1.0;
+    A.nwo = P.nwarps > 1 ? P.nwarps : 0;  // rows per segment of the flat order (0: strip-major)
     constexpr int PP = 2 * S + 4;
     std::vector<double> ring(dd_lane_ring_doubles(CB, S, XIN));
     std::vector<LaneRegs<CB, S, XIN>> regs(32);

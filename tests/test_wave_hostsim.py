@@ -197,8 +197,11 @@ def test_wave_two_passes_continue_the_iteration():
 
 # ---- the lane-private marching kernel (csrc/dd_lane.cuh) -------------------------------------------------------------
 LANE_CASES = [
-    # cb, sweeps, N, M, nctas
+    # cb, sweeps, N, M, nctas (a 6th entry: rows per segment of the [segment][strip][row] work order)
     (1, 5, 70, 300, 3),
+    (0, 3, 90, 200, 5, 31),
+    (1, 2, 77, 131, 4, 20),
+    (0, 5, 64, 260, 7, 33),
     (1, 4, 45, 259, 1),
     (1, 3, 90, 200, 4),
     (1, 2, 60, 150, 2),
@@ -211,14 +214,16 @@ LANE_CASES = [
 ]
 
 
-@pytest.mark.parametrize("cb,sweeps,N,M,nctas", LANE_CASES)
+@pytest.mark.parametrize("case", LANE_CASES, ids=[str(c) for c in LANE_CASES])
 @pytest.mark.parametrize("nonuniform", [False, True])
-def test_lane_equals_global_sor(cb, sweeps, N, M, nctas, nonuniform):
+def test_lane_equals_global_sor(case, nonuniform):
+    cb, sweeps, N, M, nctas = case[:5]
+    segrows = case[5] if len(case) > 5 else 1
     lib = _lib()
     rng = np.random.default_rng(2000 * sweeps + N + M)
     arr, met, rho, dt, DT, ldR = _system(rng, N, M, cb, nonuniform)
     vstar = rng.normal(size=(N + 1, M + 1))
-    kw = dict(cb=cb, Cc=1, nwarps=1, nctas=nctas, sweeps=sweeps, vstar=vstar, zero_boundary=cb)
+    kw = dict(cb=cb, Cc=1, nwarps=segrows, nctas=nctas, sweeps=sweeps, vstar=vstar, zero_boundary=cb)
     xr, vr_, sr, _ = _run(lib, N, M, arr, met, rho, dt, DT, ldR, reference=True, **kw)
     for order in (0, 1):
         _, vn, st, steps = _run(lib, N, M, arr, met, rho, dt, DT, ldR, order=order, kernel="lane", **kw)
