@@ -109,7 +109,7 @@ def main():
         for rx, c in CLASSES:
             if re.search(rx, k):
                 cls = c
-        if cls is None and re.search(r"k_rbsor|k_sor_wave", k):
+        if cls is None and re.search(r"k_rbsor|k_sor_wave|k_sor_lane", k):
             cls = "solver"
         d["class"] = cls or k
     # the solver launches of a step come in the order T (1 or 2 passes), cl, cd: split by the assemble kernels between
@@ -141,7 +141,9 @@ def main():
     dfma = sum(d.get("dfma", 0.0) for d in launches)
     dadd = sum(d.get("dadd", 0.0) for d in launches)
     dmul = sum(d.get("dmul", 0.0) for d in launches)
-    fj = {"source": src + "; smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul}_pred_on.sum over the step's launches",
+    how = ("predicated-on thread instructions of the DFMA / DADD / DMUL rows of the report's source page (SASS view)"
+           if len(sys.argv) > 5 else "smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul}_pred_on.sum")
+    fj = {"source": src + "; " + how + ", summed over the step's launches",
           "dfma_per_step": dfma, "dadd_per_step": dadd, "dmul_per_step": dmul,
           "flops_per_step": 2.0 * dfma + dadd + dmul,
           "per_class": {c: sum(2.0 * d.get("dfma", 0.0) + d.get("dadd", 0.0) + d.get("dmul", 0.0) for d in launches

@@ -1,4 +1,7 @@
-python bench.py --steps 10 --warmup 5 > gpurun_out/r01f_bench.json 2> gpurun_out/r01f_bench.err || exit 1
-python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > /dev/null 2>&1 || exit 1
-ncu --set full --clock-control none --import-source on -k 'regex:k_eval_sources|k_assemble_c._march|k_correct|k_predict_march|k_rbsor_reg' --launch-skip 10 -c 10 -f -o gpurun_out/r01f_step python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu2.log 2>&1
-tail -2 gpurun_out/ncu2.log
+# usage (on the GPU box): bash tools/prof_ncu_full.sh <tag>
+# One PC step of the default bench under `ncu --set full` (after the same command has run clean without ncu):
+# gpurun_out/<tag>_step.ncu-rep, summarised here with tools/ncu_step_summary.py.
+TAG="${1:-run}"
+timeout 200 python bench.py --steps 2 --warmup 12 --no-e2e --no-cpu-baseline --no-check > gpurun_out/${TAG}_plain.log 2>&1 || exit 1
+timeout 600 ncu --set full --clock-control none --import-source on --launch-skip 185 --launch-count 24 -f -o gpurun_out/${TAG}_step python bench.py --steps 2 --warmup 12 --no-e2e --no-cpu-baseline --no-check > gpurun_out/${TAG}_ncu2.log 2>&1
+tail -2 gpurun_out/${TAG}_ncu2.log
