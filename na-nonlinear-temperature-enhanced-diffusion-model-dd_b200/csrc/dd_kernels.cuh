@@ -57,7 +57,7 @@ cudaError_t dd_launch_solve_lane(const DDLaunch& L, const DDGeom& g, const DDMem
                                  int zero_boundary, DDSolveStats* stats, int const_band, int sweeps, int last_pass,
                                  double rho_fix);
 cudaError_t dd_wave_configure();
-bool dd_wave_ok(const DDGeom& g, const DDLaunch& L, int var);  // DD_WAVE = 0 | 1 | list of T,cl,cd (default: cl)
+bool dd_wave_ok(const DDGeom& g, const DDLaunch& L, int var);  // DD_WAVE = 0 | 1 | list of T,cl,cd (default: 0)
 void dd_wave_max_sweeps(int const_band, int* any, int* wide);  // per pass: any variant / the widest one
 cudaError_t dd_launch_solve_wave(const DDLaunch& L, const DDGeom& g, const DDMember* mem, const DDRows& R,
                                  const double* xin, double* xout, const double* vstar, double* vnew,

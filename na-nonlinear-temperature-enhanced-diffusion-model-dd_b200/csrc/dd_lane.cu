@@ -99,12 +99,19 @@ int dd_lane_pass_sweeps(int left) {
     return (left + passes - 1) / passes;
 }
 
-// Which solves run on the lane kernel: DD_LANE = 0 (none), 1 (all, the default), or a list of variables "T,cl,cd".
-// Measured on B200 at 8193 x 1025 nodes (profiles/README.md): T 0.23 ms against 0.35 ms with the register-tile
-// kernel, cl 0.24 against 0.31 (wavefront kernel), cd 0.14 against 0.21.
+// Which solves run on the lane kernel: DD_LANE unset = those with enough work to fill the GPU with independent
+// warps (a warp's march should be a few pipeline depths long: 2 x SMs x 80 rows of strips), 0 = none, 1 = every
+// solve the kernel can take, or a list of variables "T,cl,cd" (forced like 1).
+// Measured on B200 at 8193 x 1025 nodes (profiles/README.md): T 0.22 ms against 0.35 ms with the register-tile
+// kernel, cl 0.24 against 0.31 (wavefront kernel), cd 0.14 against 0.21; at 257 x 257 the tiles are faster (a
+// dozen warps cannot hide the march's latencies).
 bool dd_lane_ok(const DDGeom& g, const DDLaunch& L, int var) {
     const char* on = getenv("DD_LANE");  // read per call: the tests switch kernels inside one process
-    if (!on || !*on) on = "1";
+    const bool fits = g.M + 1 >= 4 * 31 && L.own1 - L.own0 >= 16;
+    if (!on || !*on) {
+        const long long strips = (g.M + 1 + 43) / 44;
+        return fits && (long long)L.nmembers * strips * (L.own1 - L.own0) >= 2LL * 148 * 80;
+    }
     if (*on == '0') return false;
     if (*on != '1') {
         static const char* names[3] = {"T", "cl", "cd"};
@@ -118,7 +125,7 @@ bool dd_lane_ok(const DDGeom& g, const DDLaunch& L, int var) {
         }
         if (!found) return false;
     }
-    return g.M + 1 >= 4 * 31 && L.own1 - L.own0 >= 16;
+    return fits;
 }
 
 cudaError_t dd_launch_solve_lane(const DDLaunch& L, const DDGeom& g, const DDMember* mem, const DDRows& R,

@@ -142,14 +142,14 @@ void dd_wave_max_sweeps(int const_band, int* any, int* wide) {
         }
 }
 
-// Which solves run on the wavefront kernel: DD_WAVE = 0 (none), 1 (all), or a list of variables "T,cl,cd"; default
-// "cl".  Measured on B200 at 8193 x 1025 nodes (profiles/README.md): cl 0.31 ms against 0.35 ms with the register-tile
+// Which solves run on the wavefront kernel (when the lane kernel does not take them): DD_WAVE = 0 (none, the
+// default), 1 (all), or a list of variables "T,cl,cd".  Measured on B200 at 8193 x 1025 nodes (profiles/README.md): cl 0.31 ms against 0.35 ms with the register-tile
 // kernel (five sweeps in one pass, one CTA per SM, no row halo), T 0.47 against 0.35 (two tile passes), cd 0.23
 // against 0.21 -- the wavefront's steps are lock-step sequences of a shared-memory phase, an fp64 phase and a
 // barrier that cannot overlap, so it only wins where the tile kernel's halo redundancy is largest.
 bool dd_wave_ok(const DDGeom& g, const DDLaunch& L, int var) {
     const char* on = getenv("DD_WAVE");  // read per call: the tests switch kernels inside one process
-    if (!on || !*on) on = "cl";
+    if (!on || !*on) on = "0";  // superseded by the lane kernel (dd_lane.cu); kept for comparison
     if (*on == '0') return false;
     if (*on != '1') {
         static const char* names[3] = {"T", "cl", "cd"};

@@ -645,7 +645,18 @@ def test_slab_solves_in_segments_for_large_time_steps(dd, M):
     need more SOR sweeps than a shallow halo supports between two exchanges.  The slab driver then runs the solve in
     segments and exchanges the iterate's halo rows in between (dd_pc_solve_segment): three slabs with a halo of 7
     rows (2 sweeps per segment) reproduce the oracle, and at a fixed plan of 9 sweeps the undecomposed run bit for
-    bit.  M = 40: tile kernels; M = 150: marching kernels and the wavefront kernel for cl."""
+    bit.  M = 40: tile kernels; M = 150: marching kernels and the lane-private marching solver (forced: grids this
+    small run the tile kernels by default)."""
+    import os
+    if M == 150:
+        os.environ["DD_LANE"] = "1"
+    try:
+        _segments_case(dd, M)
+    finally:
+        os.environ.pop("DD_LANE", None)
+
+
+def _segments_case(dd, M):
     import ddmesh
     from oracle import NOTEBOOK_CONSTS, OForcing, OGrid, PCStepper, exact_state, make_case
     p1, ddcore = dd["p1"], dd["ddcore"]
