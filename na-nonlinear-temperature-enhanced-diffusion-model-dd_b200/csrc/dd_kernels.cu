@@ -423,6 +423,53 @@ __device__ __forceinline__ DDMarchSrc dd_march_src(const DDForcingArrays& A, lon
     return q;
 }
 
+// ---- staged prefetch (DD_MARCH_STAGE): what an iteration of the marching predictor needs of the NEXT row comes
+// through a per-thread slot of a two-deep shared-memory ring, requested one iteration earlier by 8-byte cp.async
+// (zero-filled when the cell does not exist) instead of being held in registers across the iteration: 17 doubles
+// of registers less, and nothing is waited for before the shift at the end of the iteration.
+#ifndef DD_MARCH_STAGE
+#define DD_MARCH_STAGE 1
+#endif
+#define DD_PSTAGE_N 17  // cell (r+2, j): 4 | cell (r+1, j+1): 4 | cs (r+1, j) | sources (r+1, j): 8
+__device__ __forceinline__ void dd_stage_cp8(double* dst, const double* src, bool ok) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(ok ? 8 : 0) : "memory");
+}
+template <bool FUSE_T>
+__device__ __forceinline__ void dd_pstage_request(double (*st)[DD_MARCH_WARPS * 32], const DDStateC& s,
+                                                  const DDForcingArrays& A, long long o, long long ld, bool pNN,
+                                                  bool pNn, bool pcs, bool psrc) {
+    const int t = threadIdx.x;
+    const double* base = s.v[DD_CP];  // a valid address for the copies that read nothing
+    const long long oNN = pNN ? o + 2 * ld : 0, oNn = pNn ? o + ld + 1 : 0, oN = (pcs || psrc) ? o + ld : 0;
+    dd_stage_cp8(&st[0][t], s.v[DD_CP] + oNN, pNN);
+    dd_stage_cp8(&st[1][t], s.v[DD_T] + oNN, pNN);
+    dd_stage_cp8(&st[2][t], s.v[DD_CL] + oNN, pNN);
+    dd_stage_cp8(&st[3][t], s.v[DD_CD] + oNN, pNN);
+    dd_stage_cp8(&st[4][t], s.v[DD_CP] + oNn, pNn);
+    dd_stage_cp8(&st[5][t], s.v[DD_T] + oNn, pNn);
+    dd_stage_cp8(&st[6][t], s.v[DD_CL] + oNn, pNn);
+    dd_stage_cp8(&st[7][t], s.v[DD_CD] + oNn, pNn);
+    dd_stage_cp8(&st[8][t], s.v[DD_CS] + (pcs ? oN : 0), pcs);
+    const double* f[8] = {A.f[DD_CP][0], A.f[DD_CP][1], A.f[DD_CS][0], A.f[DD_CS][1],
+                          A.f[DD_T][0],  A.f[DD_CL][0], A.f[DD_CD][0], FUSE_T ? A.f[DD_T][1] : nullptr};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const bool ok = psrc && f[k] != nullptr;
+        dd_stage_cp8(&st[9 + k][t], ok ? f[k] + oN : base, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void dd_pstage_read(double (*st)[DD_MARCH_WARPS * 32], DDMarchCell* NN, DDMarchCell* Nn,
+                                               double* csN, DDMarchSrc* q) {
+    const int t = threadIdx.x;
+    NN->cp = st[0][t]; NN->T = st[1][t]; NN->cl = st[2][t]; NN->cd = st[3][t];
+    Nn->cp = st[4][t]; Nn->T = st[5][t]; Nn->cl = st[6][t]; Nn->cd = st[7][t];
+    *csN = st[8][t];
+    q->fcp0 = st[9][t]; q->fcp1 = st[10][t]; q->fcs0 = st[11][t]; q->fcs1 = st[12][t];
+    q->fT0 = st[13][t]; q->fcl0 = st[14][t]; q->fcd0 = st[15][t]; q->fT1 = st[16][t];
+}
+
 // fluxes through the face between cells a (lower index) and b, metric factor rm = 1 / spacing
 struct DDMarchFace {
     double T, cl, cd;
@@ -488,16 +535,32 @@ k_predict_march(DDGeom g, const DDMember* __restrict__ mem, DDForcingArrays A, D
         }
     }
     double rho = 0.0;
+#if DD_MARCH_STAGE
+    __shared__ double stage[2][DD_PSTAGE_N][DD_MARCH_WARPS * 32];
+    {
+        const bool nxt = ra + 1 < rz;
+        dd_pstage_request<FUSE_T>(stage[ra & 1], s, A, mo + (long long)ra * g.ld + j, g.ld,
+                                  col && nxt && ra + 2 < g.nrows, colN && nxt, col && nxt, owner && nxt);
+    }
+#endif
     DD_MARCH_LOOP
     for (int r = ra; r < rz; ++r) {
         const int i = g.row0 + r;
         const long long o = mo + (long long)r * g.ld + j;
         // requests for the next iteration
         const bool nxt = r + 1 < rz;
+#if DD_MARCH_STAGE
+        {
+            const bool nx2 = r + 2 < rz;  // what iteration r + 1 will need of row r + 2 (r + 3)
+            dd_pstage_request<FUSE_T>(stage[(r + 1) & 1], s, A, o + g.ld, g.ld, col && nx2 && r + 3 < g.nrows,
+                                      colN && nx2, col && nx2, owner && nx2);
+        }
+#else
         const DDMarchCell NN = dd_march_load(s, o + 2LL * g.ld, col && nxt && r + 2 < g.nrows);
         const DDMarchCell Nn = dd_march_load(s, o + g.ld + 1, colN && nxt);
         const double csN = (col && nxt) ? __ldg(s.v[DD_CS] + o + g.ld) : 0.0;
         const DDMarchSrc srcN = dd_march_src<FUSE_T>(A, o + g.ld, owner && nxt);
+#endif
 
         const bool irow = i >= 1 && i <= g.N - 1;
         const bool inter = irow && jint;
@@ -555,6 +618,14 @@ k_predict_march(DDGeom g, const DDMember* __restrict__ mem, DDForcingArrays A, D
                 }
             }
         }
+#if DD_MARCH_STAGE
+        DDMarchCell NN, Nn;
+        double csN;
+        DDMarchSrc srcN;
+        asm volatile("cp.async.wait_group 1;" ::: "memory");  // this iteration's set has landed, the next may be in flight
+        dd_pstage_read(stage[r & 1], &NN, &Nn, &csN, &srcN);
+        (void)nxt;
+#endif
         W = E;
         wadv = eadv;
         P = C;
@@ -564,6 +635,9 @@ k_predict_march(DDGeom g, const DDMember* __restrict__ mem, DDForcingArrays A, D
         csC = csN;
         src = srcN;
     }
+#if DD_MARCH_STAGE
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
     if (FUSE_T) {
         rho = warp_max_bits(rho);
         if (lane == 0) atomic_max_nonneg(&stats[member].rho, rho);
