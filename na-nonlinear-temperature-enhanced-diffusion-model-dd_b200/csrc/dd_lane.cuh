@@ -301,13 +301,15 @@ DD_HD void dd_lane_step(const WaveArgs& A, const WaveSeg& sg, LaneRegs<CB, S, XI
     } else {
         R.X[0][U] = R.X[1][U] = 0.0;
     }
+    // const band: the row's metrics are asked for now and multiplied up after the levels (4): they are global
+    // loads that mostly miss L1, and the row is first relaxed in the next step
+    double m_rp = 0.0, m_rh0 = 0.0, m_rh1 = 0.0;
     if (CB) {
         const int gi = A.g.row0 + i;
-        R.RW[CB ? U : 0] = R.RE[CB ? U : 0] = 0.0;
         if (tau < sg.nq && i >= A.vr0 && gi >= 1 && gi <= A.g.N - 1) {
-            const double rp = A.g.rhp[gi];
-            R.RW[CB ? U : 0] = fT * rp * A.g.rh[gi];
-            R.RE[CB ? U : 0] = fT * rp * A.g.rh[gi + 1];
+            m_rp = A.g.rhp[gi];
+            m_rh0 = A.g.rh[gi];
+            m_rh1 = A.g.rh[gi + 1];
         }
     }
     // (3) the 2 S levels, in pairs: odd level 2 k + 1 on row tau - 2 k - 1 (coefficients from the ring, the other
@@ -315,6 +317,11 @@ DD_HD void dd_lane_step(const WaveArgs& A, const WaveSeg& sg, LaneRegs<CB, S, XI
     //     previous step)
     const bool fin_row = A.last_pass && i - 2 * S >= sg.r0 && i - 2 * S < sg.r1;
     dd_lane_pairs<CB, S, XIN, U, 0>(R, sm, nb, omega, fin_row);
+    if (CB) {
+        // dt DT / (hhat_i h_i), dt DT / (hhat_i h_{i+1}): same products, in the same order, as in the tile kernels
+        R.RW[CB ? U : 0] = fT * m_rp * m_rh0;
+        R.RE[CB ? U : 0] = fT * m_rp * m_rh1;
+    }
     // (4) row tau - 2 S - 1 leaves: residual of its colour-0 cells (column o), |bb|, v_new = v* + x
     if (out) {
         const double x0 = R.X[0][SO], x1 = R.X[1][SO];
