@@ -1307,27 +1307,37 @@ __global__ void k_cs_decide(const DDMember* __restrict__ mem, int nmem, int cap,
     }
 }
 
+#define DD_REDO_CHUNKS 16
 template <int MODE>
 __global__ void __launch_bounds__(DD_BLOCK, DD_MINB) k_cs_redo(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
                                                       DDStateC s0, const double* __restrict__ cl1,
                                                       const double* __restrict__ cd1, double* __restrict__ cs_out,
                                                       int cap, const int* __restrict__ used, int own0, int own1,
                                                       int bpm) {
-    // the common case first: the cap-iteration result already stored is the answer (whole block, one load)
-    if (used[blockIdx.x / bpm] >= cap) return;
-    const NodeIdx n = node_index(g, own0, own1, bpm);
-    if (!n.valid) return;
-    const int u = used[n.member];
-    const DDMember& mb = mem[n.member];
+    // One block takes DD_REDO_CHUNKS consecutive 256-node chunks of a member (bpm = blocks per member of THIS
+    // launch).  The common case first: the cap-iteration result already stored is the answer (whole block, one
+    // load) -- the launch then costs a sixteenth of the blocks a node-per-thread grid would start for nothing.
+    const int member = blockIdx.x / bpm;
+    const int u = used[member];
+    const DDMember& mb = mem[member];
     if (u >= cap || !mb.active) return;
-    const long long mo = n.member * g.mstride;
-    const long long o = mo + (long long)n.r * g.ld + n.j;
-    double cp1, y, a;
-    // T1 is not needed for y, a: pass cl1 as a placeholder for the cp corrector inputs
-    dd_node_correct_prepare<MODE>(g, mb, F, s0, cl1, cl1, cd1, mo, n.r, n.j, &cp1, &y, &a);
-    double x = s0.v[DD_CS][o];
-    for (int it = 0; it < u; ++it) x = x + dd_cs_newton_dx(x, y, a, mb.m.eta);
-    cs_out[o] = x * (dd_is_interior(g, g.row0 + n.r, n.j) ? 1.0 : 0.0);
+    const int ncols = g.M + 1;
+    const long long total = (long long)(own1 - own0) * ncols;
+    const long long first = (long long)(blockIdx.x - member * bpm) * DD_REDO_CHUNKS * DD_BLOCK + threadIdx.x;
+    const long long mo = member * g.mstride;
+    for (int c = 0; c < DD_REDO_CHUNKS; ++c) {
+        const long long lin = first + (long long)c * DD_BLOCK;
+        if (lin >= total) return;
+        const long long rr = lin / ncols;
+        const int r = own0 + (int)rr, j = (int)(lin - rr * ncols);
+        const long long o = mo + (long long)r * g.ld + j;
+        double cp1, y, a;
+        // T1 is not needed for y, a: pass cl1 as a placeholder for the cp corrector inputs
+        dd_node_correct_prepare<MODE>(g, mb, F, s0, cl1, cl1, cd1, mo, r, j, &cp1, &y, &a);
+        double x = s0.v[DD_CS][o];
+        for (int it = 0; it < u; ++it) x = x + dd_cs_newton_dx(x, y, a, mb.m.eta);
+        cs_out[o] = x * (dd_is_interior(g, g.row0 + r, j) ? 1.0 : 0.0);
+    }
 }
 
 cudaError_t dd_launch_cs_finish(const DDLaunch& L, int mode, const DDGeom& g, const DDMember* mem,
@@ -1336,7 +1346,7 @@ cudaError_t dd_launch_cs_finish(const DDLaunch& L, int mode, const DDGeom& g, co
                                 int* used_out) {
     k_cs_decide<<<(L.nmembers + 127) / 128, 128, 0, L.stream>>>(mem, L.nmembers, cap, rtol, it_max, it_min,
                                                                 used_out);
-    const int bpm = blocks_per_member(g, L);
+    const int bpm = (blocks_per_member(g, L) + DD_REDO_CHUNKS - 1) / DD_REDO_CHUNKS;
     DD_DISPATCH_MODE(mode, (k_cs_redo<MODE><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(
                                g, mem, F, s0, cl1, cd1, cs_out, cap, used_out, L.own0, L.own1, bpm)));
     return cudaGetLastError();
