@@ -11,11 +11,11 @@ mkdir -p "$OBJ"
 FLAGS=(-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC
        -Xcompiler -fvisibility=default ${DD_PTXAS_V:+-Xptxas -v} ${DD_EXTRA_FLAGS:-})
 pids=()
-for u in dd_kernels dd_solver dd_wave dd_lane dd_member dd_capi; do
+for u in dd_kernels dd_solver dd_wave dd_lane dd_member dd_halo dd_capi; do
   "$NVCC" "${FLAGS[@]}" -c -o "$OBJ/$u.o" "$SRC/$u.cu" &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait "$p"; done
 "$NVCC" --shared -gencode arch=compute_100a,code=sm_100a -o "$OUT" "$OBJ"/dd_kernels.o "$OBJ"/dd_solver.o \
-  "$OBJ"/dd_wave.o "$OBJ"/dd_lane.o "$OBJ"/dd_member.o "$OBJ"/dd_capi.o -lcudart
+  "$OBJ"/dd_wave.o "$OBJ"/dd_lane.o "$OBJ"/dd_member.o "$OBJ"/dd_halo.o "$OBJ"/dd_capi.o -lcudart
 echo "built $OUT"

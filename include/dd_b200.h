@@ -229,6 +229,23 @@ int dd_next_plan(int cur, double rho, double ratio, int max_sweeps); /* next ste
 int dd_pc_solve_segment(dd_batch* b, int var, int slot_in, int slot_out, const dd_pc_options* opt, int sweeps,
                         int first, int last);
 
+/* ---- halo exchange of a row slab by direct NVLink stores ------------------------------------------------------
+ * One process per GPU on one node: each rank exports the allocations its neighbours write into (its state fields,
+ * its flag block) as 64-byte CUDA IPC handles, imports the neighbours' and from then on exchanges halo rows with ONE
+ * kernel per exchange: dd_halo_push copies the rank's first / last `count` doubles of owned rows (src_top, src_bot)
+ * into the up / down neighbour's halo rows (dst_up, dst_down: imported pointers + offsets) and handshakes through the
+ * flag blocks (ready-to-receive, delivered), exchange number `seq` strictly increasing and equal on all ranks; null
+ * src pointers on the mesh's first / last rank.  The reference has no counterpart (it is single-process); in the
+ * slab driver this replaces the NCCL send / recv pairs of ddmesh.exchange_halos. */
+int dd_ipc_export(dd_ctx* ctx, const void* dev_ptr, unsigned char* handle64); /* dev_ptr: base of a cudaMalloc'ed block */
+int dd_ipc_import(dd_ctx* ctx, const unsigned char* handle64, void** dev_ptr);
+int dd_ipc_close(dd_ctx* ctx, void* dev_ptr);
+int dd_halo_flags_create(dd_ctx* ctx, void** flags);
+int dd_halo_flags_destroy(dd_ctx* ctx, void* flags);
+int dd_halo_push(dd_ctx* ctx, const double* src_top, double* dst_up, const double* src_bot, double* dst_down,
+                 long long count, void* my_flags, void* up_flags, void* down_flags, unsigned seq);
+int dd_halo_status(dd_ctx* ctx, void* my_flags, int* status); /* 1: a handshake timed out */
+
 /* ---- instrumentation (bench.py) ------------------------------------------ */
 long long dd_launch_count(void);                /* kernels launched by the library since it was loaded */
 int dd_profile_enable(int on);                  /* bracket every launch group with CUDA events */

@@ -126,6 +126,13 @@ SIGNATURES = {
     "dd_next_plan": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int]),
     "dd_pc_solve_segment": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _P(dd_pc_options), C.c_int, C.c_int, C.c_int]),
     "dd_probe_math": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp]),
+    "dd_ipc_export": (C.c_int, [_vp, _vp, C.c_char_p]),
+    "dd_ipc_import": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
+    "dd_ipc_close": (C.c_int, [_vp, _vp]),
+    "dd_halo_flags_create": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "dd_halo_flags_destroy": (C.c_int, [_vp, _vp]),
+    "dd_halo_push": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_longlong, _vp, _vp, _vp, C.c_uint]),
+    "dd_halo_status": (C.c_int, [_vp, _vp, C.POINTER(C.c_int)]),
     "dd_probe_fp64": (C.c_int, [_vp, C.c_double, _dp]),
     "dd_solver_kernel_name": (C.c_char_p, [C.c_int]),
     "dd_launch_count": (C.c_longlong, []),

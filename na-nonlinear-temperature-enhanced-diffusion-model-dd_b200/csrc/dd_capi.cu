@@ -2331,6 +2331,67 @@ extern "C" int dd_pc_solve_segment(dd_batch* b, int var, int slot_in, int slot_o
     return rc;
 }
 
+// ---- halo exchange by direct peer stores (multi-process slab driver; see include/dd_b200.h) --------------------
+extern "C" int dd_ipc_export(dd_ctx* ctx, const void* dev_ptr, unsigned char* handle64) {
+    if (!ctx || !dev_ptr || !handle64) return DD_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles travel as 64 bytes");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)));
+    memcpy(handle64, &h, 64);
+    return DD_OK;
+}
+extern "C" int dd_ipc_import(dd_ctx* ctx, const unsigned char* handle64, void** dev_ptr) {
+    if (!ctx || !handle64 || !dev_ptr) return DD_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return DD_OK;
+}
+extern "C" int dd_ipc_close(dd_ctx* ctx, void* dev_ptr) {
+    if (!ctx || !dev_ptr) return DD_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaIpcCloseMemHandle(dev_ptr));
+    return DD_OK;
+}
+// flag block of a rank: 4 handshake words its neighbours write + the kernel's block counter + a status word
+extern "C" int dd_halo_flags_create(dd_ctx* ctx, void** flags) {
+    if (!ctx || !flags) return DD_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMalloc(flags, 64));
+    CK(cudaMemsetAsync(*flags, 0, 64, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DD_OK;
+}
+extern "C" int dd_halo_flags_destroy(dd_ctx* ctx, void* flags) {
+    if (!ctx) return DD_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (flags) CK(cudaFree(flags));
+    return DD_OK;
+}
+extern "C" int dd_halo_push(dd_ctx* ctx, const double* src_top, double* dst_up, const double* src_bot,
+                            double* dst_down, long long count, void* my_flags, void* up_flags, void* down_flags,
+                            unsigned seq) {
+    if (!ctx || !my_flags || count < 1 || (src_top && (!dst_up || !up_flags)) ||
+        (src_bot && (!dst_down || !down_flags)))
+        return DD_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    unsigned* f = static_cast<unsigned*>(my_flags);
+    g_prof.launches += 1;
+    CK(dd_launch_halo_push(ctx->stream, src_top, dst_up, src_bot, dst_down, count, f, static_cast<unsigned*>(up_flags),
+                           static_cast<unsigned*>(down_flags), seq, f + 4, reinterpret_cast<int*>(f + 5)));
+    return DD_OK;
+}
+// 0: every handshake so far completed; 1: a wait timed out (the neighbour never arrived)
+extern "C" int dd_halo_status(dd_ctx* ctx, void* my_flags, int* status) {
+    if (!ctx || !my_flags || !status) return DD_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(status, static_cast<unsigned*>(my_flags) + 5, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DD_OK;
+}
+
 // accuracy probe of the inline device exp / reciprocal (host arrays in, host arrays out)
 extern "C" int dd_probe_math(dd_ctx* ctx, int n, const double* in, double* out_exp, double* out_rcp) {
     if (!ctx || n < 1 || !in || !out_exp || !out_rcp) return DD_ERR_INVALID;

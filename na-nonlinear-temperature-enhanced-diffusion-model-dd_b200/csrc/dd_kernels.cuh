@@ -47,6 +47,10 @@ cudaError_t dd_solver_configure();  // opt-in to large dynamic shared memory (on
 
 // wavefront solver (dd_wave.cu): one pass of `sweeps` red-black SOR sweeps marching down column strips; wide grids;
 // used for the cl solve by default, the register-tile kernels for T and cd (as fast or faster there)
+// halo exchange by direct peer stores (dd_halo.cu)
+cudaError_t dd_launch_halo_push(cudaStream_t stream, const double* src_top, double* dst_up, const double* src_bot,
+                                double* dst_down, long long count, unsigned* my_flags, unsigned* up_flags,
+                                unsigned* down_flags, unsigned seq, unsigned* done_blocks, int* status);
 // lane-private marching solver (dd_lane.cu): DD_LANE = 0 | 1 | list of T,cl,cd
 cudaError_t dd_lane_configure();
 bool dd_lane_ok(const DDGeom& g, const DDLaunch& L, int var);

@@ -95,16 +95,122 @@ class _Ordered:
             self.torch.cuda.current_stream().synchronize()
 
 
+class _PeerHalo:
+    """Halo exchange of the state fields by direct NVLink stores (csrc/dd_halo.cu, include/dd_b200.h): every rank
+    exports its field allocations and a flag block as CUDA IPC handles once, imports its neighbours', and an
+    exchange is then ONE kernel on the library's stream (dd_halo_push) instead of NCCL send / recv pairs."""
+
+    def __init__(self, mesh, dist):
+        self.m, self.lib, self.ctx = mesh, mesh.batch.lib, mesh.batch.ctx
+        lib, ctx, b = self.lib, self.ctx, mesh.batch
+        self.flags = C.c_void_p()
+        ctx.check(lib.dd_halo_flags_create(ctx.handle, C.byref(self.flags)), "halo_flags_create")
+        self.seq = 0
+
+        def export(ptr):
+            h = C.create_string_buffer(64)
+            ctx.check(lib.dd_ipc_export(ctx.handle, C.c_void_p(int(ptr)), h), "ipc_export")
+            return h.raw
+
+        self.nslots = b.nslots
+        self.ptr = {(s, v): int(b.dev_ptr(s, v)[0]) for s in range(self.nslots) for v in VARS}
+        mine = dict(rank=mesh.rank, part=dict(mesh.part), flags=export(self.flags.value),
+                    fields={k: export(p) for k, p in self.ptr.items()})
+        everyone = [None] * mesh.world
+        dist.all_gather_object(everyone, mine)
+        self.nb = {}
+        self.opened = []
+        for side, r in (("up", mesh.rank - 1), ("down", mesh.rank + 1)):
+            if r < 0 or r >= mesh.world:
+                continue
+            info = everyone[r]
+
+            def imp(handle):
+                out = C.c_void_p()
+                ctx.check(lib.dd_ipc_import(ctx.handle, handle, C.byref(out)), "ipc_import")
+                self.opened.append(out.value)
+                return out.value
+
+            self.nb[side] = dict(part=info["part"], flags=imp(info["flags"]),
+                                 fields={k: imp(h) for k, h in info["fields"].items()})
+        dist.barrier()  # nobody pushes before every rank has zeroed its flags and imported the handles
+
+    def usable(self) -> bool:
+        p, G = self.m.part, self.m.G
+        return all(min(G, p[k]) == G for k, side in (("lo", "up"), ("hi", "down")) if side in self.nb)
+
+    def push(self, slot, var):
+        m, p, G = self.m, self.m.part, self.m.G
+        ld = m.batch.shape[1]
+        base = self.ptr[(slot, var)]
+        count = G * ld
+        self.seq += 1
+        src_top = dst_up = src_bot = dst_down = up_flags = down_flags = None
+        if "up" in self.nb:
+            nb = self.nb["up"]
+            src_top = base + p["own0"] * ld * 8
+            dst_up = nb["fields"][(slot, var)] + nb["part"]["own1"] * ld * 8
+            up_flags = nb["flags"]
+        if "down" in self.nb:
+            nb = self.nb["down"]
+            src_bot = base + (p["own1"] - G) * ld * 8
+            dst_down = nb["fields"][(slot, var)] + (nb["part"]["own0"] - G) * ld * 8
+            down_flags = nb["flags"]
+        self.ctx.check(self.lib.dd_halo_push(self.ctx.handle, src_top, dst_up, src_bot, dst_down, count, self.flags,
+                                             up_flags, down_flags, self.seq & 0xffffffff), "halo_push")
+
+    def check(self):
+        st = C.c_int(0)
+        self.ctx.check(self.lib.dd_halo_status(self.ctx.handle, self.flags, C.byref(st)), "halo_status")
+        if st.value:
+            raise RuntimeError("halo exchange: a neighbour never arrived (handshake timed out)")
+
+    def close(self):
+        for ptr in self.opened:
+            self.lib.dd_ipc_close(self.ctx.handle, C.c_void_p(ptr))
+        self.opened = []
+        if self.flags:
+            self.lib.dd_halo_flags_destroy(self.ctx.handle, self.flags)
+            self.flags = C.c_void_p()
+
+
 class _DistComm:
-    """Collectives of one rank per process (torch.distributed, NCCL on GPUs)."""
+    """Collectives of one rank per process (torch.distributed, NCCL on GPUs).  Halo rows of the state fields go by
+    direct peer stores (_PeerHalo) when the ranks share a node with peer access (DD_HALO=nccl turns it off); the
+    reductions and the odd exchange of a work array stay with NCCL."""
 
     def __init__(self):
+        import os
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
+        self.peer = None
+        self.peer_tried = os.environ.get("DD_HALO", "peer") == "nccl" or dist.get_backend() != "nccl"
+
+    def _peer(self, m):
+        if not self.peer_tried:
+            self.peer_tried = True
+            ok = 1
+            try:
+                peer = _PeerHalo(m, self.dist)
+                ok = 1 if peer.usable() else 0
+            except Exception:  # no IPC / peer access between these devices: every rank must agree on the fallback
+                peer, ok = None, 0
+            flag = self.torch.tensor([ok], device="cuda", dtype=self.torch.int32)
+            self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
+            if int(flag.item()) == 1:
+                self.peer = peer
+            elif peer is not None:
+                peer.close()
+        return self.peer
 
     def exchange(self, meshes, slot, which):
         m = meshes[0]
+        peer = self._peer(m)
+        if peer is not None:
+            for v in which:  # on the library's own stream: ordered with the kernels by construction
+                peer.push(slot, v)
+            return
         with _Ordered(meshes, self.torch):
             exchange_halos([m.field(slot, v) for v in which], m.part, m.rank, m.world, m.G, self.dist)
 
@@ -295,6 +401,9 @@ class SlabMesh:
         for m in self.group:
             m._pending = None
         ok, stats = self._finish(old)
+        peer = getattr(self.comm, "peer", None)
+        if peer is not None:
+            peer.check()
         if not ok:
             for m in self.group:
                 m.batch.ctx.synchronize()
