@@ -1,8 +1,8 @@
 # what the round-end driver does on a fresh box: GPU tests, smoke, default bench lines
-python -m pytest tests -x -q -m gpu 2>&1 | tail -2
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | cut -c1-120
-python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; echo "bench rc=$?"
-python bench.py --impl reference > gpurun_out/final_bench_reference.json 2>> gpurun_out/final_bench.err; echo "reference rc=$?"
+timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | cut -c1-120
+timeout 600 python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; echo "bench rc=$?"
+timeout 600 python bench.py --impl reference > gpurun_out/final_bench_reference.json 2>> gpurun_out/final_bench.err; echo "reference rc=$?"
 python - <<'PY'
 import json
 d = json.load(open("gpurun_out/final_bench.json"))
