@@ -1178,14 +1178,16 @@ cudaError_t dd_launch_assemble_march(const DDLaunch& L, int mode, int var, const
 
 // VARIANTS = false: every member is a RegHCsTriple one (the iteration below); true: members may use the
 // closed-form cs correctors of CsTriple / HCsTriple (kept out of the common instantiation: it costs registers)
-template <int MODE, bool VARIANTS>
+// CAPT > 0: the iteration cap as a compile-time constant (the reference's default of 5: the Newton loop unrolls)
+template <int MODE, bool VARIANTS, int CAPT>
 __global__ void __launch_bounds__(DD_BLOCK) k_correct(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
                                                       DDStateC s0, const double* __restrict__ T1,
                                                       const double* __restrict__ cl1,
                                                       const double* __restrict__ cd1, double* __restrict__ cp_out,
-                                                      double* __restrict__ cs_out, int cap, double rtol,
+                                                      double* __restrict__ cs_out, int cap_rt, double rtol,
                                                       double* it_max, double* it_min, int* flags, int own0,
                                                       int own1, int bpm) {
+    const int cap = CAPT > 0 ? CAPT : cap_rt;
     // per-iteration statistics of the reference's global exit test (max |dx|, min |x|): every thread parks its
     // two bit patterns per iteration in shared memory (two stores, no reduction inside the Newton loop); after
     // the loop warp `it` reduces iteration `it` over the block and issues the two global atomics
@@ -1222,6 +1224,7 @@ __global__ void __launch_bounds__(DD_BLOCK) k_correct(DDGeom g, const DDMember* 
     }
     const double eta = mb.m.eta;
     const int lane = threadIdx.x & 31;
+#pragma unroll
     for (int it = 0; it < cap; ++it) {
         double dx = 0.0;
         if (n.valid) {
@@ -1272,11 +1275,15 @@ cudaError_t dd_launch_correct(const DDLaunch& L, int mode, const DDGeom& g, cons
                               double* it_max, double* it_min, int* flags) {
     const int bpm = blocks_per_member(g, L);
     if (flags) {
-        DD_DISPATCH_MODE(mode, (k_correct<MODE, true><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(
+        DD_DISPATCH_MODE(mode, (k_correct<MODE, true, 0><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(
+                                   g, mem, F, s0, T1, cl1, cd1, cp_out, cs_out, cap, rtol, it_max, it_min, flags,
+                                   L.own0, L.own1, bpm)));
+    } else if (cap == 5) {
+        DD_DISPATCH_MODE(mode, (k_correct<MODE, false, 5><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(
                                    g, mem, F, s0, T1, cl1, cd1, cp_out, cs_out, cap, rtol, it_max, it_min, flags,
                                    L.own0, L.own1, bpm)));
     } else {
-        DD_DISPATCH_MODE(mode, (k_correct<MODE, false><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(
+        DD_DISPATCH_MODE(mode, (k_correct<MODE, false, 0><<<bpm * L.nmembers, DD_BLOCK, 0, L.stream>>>(
                                    g, mem, F, s0, T1, cl1, cd1, cp_out, cs_out, cap, rtol, it_max, it_min, flags,
                                    L.own0, L.own1, bpm)));
     }
