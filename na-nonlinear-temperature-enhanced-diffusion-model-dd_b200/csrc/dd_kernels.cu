@@ -199,7 +199,9 @@ __global__ void __launch_bounds__(DD_BLOCK) k_eval_sources(DDGeom g, const DDMem
 // same address for the whole warp (one broadcast load each), and the node arithmetic is dd_sources itself, fed with
 // the sums dd_spatial_separable would have formed -- same operands, same order, same results as the generic kernel,
 // without its per-node table addressing and term loops.
+#ifndef DD_SRC_ROWS
 #define DD_SRC_ROWS 8
+#endif
 __global__ void __launch_bounds__(DD_BLOCK) k_eval_sources_sep1(DDGeom g, const DDMember* __restrict__ mem, DDForcing F,
                                                                 DDState out, int slot, int own0, int own1) {
     const int j = blockIdx.x * DD_BLOCK + threadIdx.x;

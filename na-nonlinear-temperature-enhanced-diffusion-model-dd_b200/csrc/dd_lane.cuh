@@ -28,7 +28,13 @@
 #include "dd_wave.cuh"
 
 #define DD_LANE_LS 2  // a row's coefficients are requested this many steps before the row enters
-#define DD_LANE_PF 6  // ... and prefetched into L2 this many rows before that
+// ... and prefetched into L2 this many rows before that.  Measured on B200 (T / cl / cd solves of the bench mesh, ms):
+// no prefetch 0.217 / 0.230 / 0.171, 1 row 0.183 / 0.235 / 0.141, 2 rows 0.184 / 0.234 / 0.137, 3 rows 0.188 / 0.231 /
+// 0.137, 6 rows 0.199 / 0.233 / 0.145, 12 rows 0.235 / 0.247 / 0.200: the lines must arrive shortly before the
+// cp.async asks for them, earlier ones are evicted again by the stream of the other arrays.
+#ifndef DD_LANE_PF
+#define DD_LANE_PF ((S) >= 4 ? 3 : 2)
+#endif
 
 #define DD_LANE_NA(CB, XIN) (((CB) ? 2 : 5) + (XIN))  // staged arrays: bb, dinv | bb, aW, aE, aS, aN; + x of the previous pass
 #define DD_LANE_VS 4  // slots of the v* ring (power of two > LS)
@@ -208,7 +214,7 @@ DD_HD void dd_lane_request(const WaveArgs& A, const WaveSeg& sg, const LaneRegs<
     DD_LANE_COMMIT();
     // a few rows further down: into L2
     const int qp = q + DD_LANE_PF;
-    if (qp < sg.nq && j0 >= 0 && j0 < A.g.M) {
+    if (DD_LANE_PF > 0 && qp < sg.nq && j0 >= 0 && j0 < A.g.M) {
         const long long op = sg.moR + (long long)(sg.rs + qp) * A.ldR + j0;
         dd_lane_prefetch(A.bb + op);
         dd_lane_prefetch(A.aW + op);
