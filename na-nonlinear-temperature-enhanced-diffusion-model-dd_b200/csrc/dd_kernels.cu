@@ -366,6 +366,9 @@ cudaError_t dd_launch_predict(const DDLaunch& L, int mode, const DDGeom& g, cons
 #ifndef DD_ASMCD_MINB
 #define DD_ASMCD_MINB 5  // with its next-row data staged in shared memory the kernel fits 96 registers: five CTAs per SM, 0.217 -> 0.211 ms
 #endif
+#ifndef DD_ASMCL_MINB
+#define DD_ASMCL_MINB 5
+#endif
 #ifndef DD_MARCH_UNROLL
 #define DD_MARCH_UNROLL 1
 #endif
@@ -919,7 +922,7 @@ __device__ __forceinline__ bool dd_march_setup(const DDGeom& g, const DDRows& R,
     return true;
 }
 
-__global__ void __launch_bounds__(DD_MARCH_WARPS * 32, DD_MARCH_MINB)
+__global__ void __launch_bounds__(DD_MARCH_WARPS * 32, DD_ASMCL_MINB)
 k_assemble_cl_march(DDGeom g, const DDMember* __restrict__ mem, const double* __restrict__ f1, DDStateC u,
                     const double* __restrict__ T1, const double* __restrict__ Ycl, DDRows R, DDSolveStats* stats,
                     int r0, int r1, int nwc, int wcb, int nrb) {
@@ -938,6 +941,30 @@ k_assemble_cl_march(DDGeom g, const DDMember* __restrict__ mem, const double* __
     DDMarchA P = dd_marchA_load(cpA, TA, clA, T1, oa - g.ld, q.col && q.ra - 1 >= 0);
     DDMarchA C = dd_marchA_load(cpA, TA, clA, T1, oa, q.col);
     DDMarchA N = dd_marchA_load(cpA, TA, clA, T1, oa + g.ld, q.col && q.ra + 1 < g.nrows);
+#if DD_MARCH_STAGE
+    // next-row data through a per-thread slot of a two-deep shared-memory ring (see dd_pstage_request): cell
+    // (r+2, j): cp, T, cl, T1 | cp, cl of (r+1, j+1) | Ycl, f1 of (r+1, j)
+    double cpn = q.colN ? __ldg(cpA + oa + 1) : 0.0, cln = q.colN ? __ldg(clA + oa + 1) : 0.0;
+    double yc = q.owner ? __ldg(Ycl + oa) : 0.0, fc = q.owner ? dd_ldg0(f1, oa) : 0.0;
+    __shared__ double stage[2][8][DD_MARCH_WARPS * 32];
+    auto request = [&](int rr, double (*st)[DD_MARCH_WARPS * 32]) {
+        const int t = threadIdx.x;
+        const long long o = q.mo + (long long)rr * g.ld + j;
+        const bool nxt = rr + 1 < q.rz;
+        const bool pNN = q.col && nxt && rr + 2 < g.nrows, pCn = q.colN && nxt, pn = q.owner && nxt;
+        const long long oNN = pNN ? o + 2LL * g.ld : 0, oCn = pCn ? o + g.ld + 1 : 0, oN = pn ? o + g.ld : 0;
+        dd_stage_cp8(&st[0][t], cpA + oNN, pNN);
+        dd_stage_cp8(&st[1][t], TA + oNN, pNN);
+        dd_stage_cp8(&st[2][t], clA + oNN, pNN);
+        dd_stage_cp8(&st[3][t], T1 + oNN, pNN);
+        dd_stage_cp8(&st[4][t], cpA + oCn, pCn);
+        dd_stage_cp8(&st[5][t], clA + oCn, pCn);
+        dd_stage_cp8(&st[6][t], Ycl + oN, pn);
+        dd_stage_cp8(&st[7][t], f1 ? f1 + oN : cpA, pn && f1 != nullptr);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    request(q.ra, stage[q.ra & 1]);
+#else
     // two rows of requests in flight: row r+3 of the rolling fields and row r+2 of everything else are
     // asked for while row r is computed
     DDMarchA N2 = dd_marchA_load(cpA, TA, clA, T1, oa + 2LL * g.ld, q.col && q.ra + 1 < q.rz && q.ra + 2 < g.nrows);
@@ -947,6 +974,7 @@ k_assemble_cl_march(DDGeom g, const DDMember* __restrict__ mem, const double* __
     double cpn1 = (q.colN && has1) ? __ldg(cpA + oa + g.ld + 1) : 0.0;
     double cln1 = (q.colN && has1) ? __ldg(clA + oa + g.ld + 1) : 0.0;
     double yc1 = (q.owner && has1) ? __ldg(Ycl + oa + g.ld) : 0.0, fc1 = (q.owner && has1) ? dd_ldg0(f1, oa + g.ld) : 0.0;
+#endif
     // W face of the first row
     double DlW = 0.0, flW = 0.0, advW = 0.0;
     {
@@ -962,6 +990,9 @@ k_assemble_cl_march(DDGeom g, const DDMember* __restrict__ mem, const double* __
     for (int r = q.ra; r < q.rz; ++r) {
         const int i = g.row0 + r;
         const long long o = q.mo + (long long)r * g.ld + j;
+#if DD_MARCH_STAGE
+        request(r + 1, stage[(r + 1) & 1]);
+#else
         const bool nx2 = r + 2 < q.rz;
         const DDMarchA NN = dd_marchA_load(cpA, TA, clA, T1, o + 3LL * g.ld, q.col && nx2 && r + 3 < g.nrows);
         const double cpnN = (q.colN && nx2) ? __ldg(cpA + o + 2LL * g.ld + 1) : 0.0;
@@ -969,6 +1000,7 @@ k_assemble_cl_march(DDGeom g, const DDMember* __restrict__ mem, const double* __
         const double ycN = (q.owner && nx2) ? __ldg(Ycl + o + 2LL * g.ld) : 0.0;
         const double fcN = (q.owner && nx2) ? dd_ldg0(f1, o + 2LL * g.ld) : 0.0;
 
+#endif
         const bool irow = i >= 1 && i <= g.N - 1;
         const bool inter = irow && q.jint;
         double DlE = 0.0, flE = 0.0, advE = 0.0;
@@ -1005,10 +1037,24 @@ k_assemble_cl_march(DDGeom g, const DDMember* __restrict__ mem, const double* __
             dd_store_row(R, q.moR + (long long)r * R.ld + j, row);
         }
         DlW = DlE; flW = flE; advW = advE;
+#if DD_MARCH_STAGE
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        {
+            const double(*st)[DD_MARCH_WARPS * 32] = stage[r & 1];
+            const int tt = threadIdx.x;
+            const DDMarchA NN = {st[0][tt], st[1][tt], st[2][tt], st[3][tt]};
+            P = C; C = N; N = NN;
+            cpn = st[4][tt]; cln = st[5][tt]; yc = st[6][tt]; fc = st[7][tt];
+        }
+#else
         P = C; C = N; N = N2; N2 = NN;
         cpn = cpn1; cln = cln1; yc = yc1; fc = fc1;
         cpn1 = cpnN; cln1 = clnN; yc1 = ycN; fc1 = fcN;
+#endif
     }
+#if DD_MARCH_STAGE
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
     rho = warp_max_bits(rho);
     if (q.lane == 0) atomic_max_nonneg(&stats[q.member].rho, rho);
 }
