@@ -989,10 +989,10 @@ k_assemble_cl_march(DDGeom g, const DDMember* __restrict__ mem, const double* __
     DD_MARCH_LOOP
     for (int r = q.ra; r < q.rz; ++r) {
         const int i = g.row0 + r;
-        const long long o = q.mo + (long long)r * g.ld + j;
 #if DD_MARCH_STAGE
         request(r + 1, stage[(r + 1) & 1]);
 #else
+        const long long o = q.mo + (long long)r * g.ld + j;
         const bool nx2 = r + 2 < q.rz;
         const DDMarchA NN = dd_marchA_load(cpA, TA, clA, T1, o + 3LL * g.ld, q.col && nx2 && r + 3 < g.nrows);
         const double cpnN = (q.colN && nx2) ? __ldg(cpA + o + 2LL * g.ld + 1) : 0.0;

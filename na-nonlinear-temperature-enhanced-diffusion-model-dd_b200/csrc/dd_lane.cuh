@@ -264,6 +264,7 @@ template <int CB, int S, int XIN, int U, int K>
 DD_HD void dd_lane_pairs(LaneRegs<CB, S, XIN>& R, const LaneSmem& sm, const double* nb, double omega, bool fin_row) {
     if constexpr (K < S) {
         constexpr int P = 2 * S + 4, NC = CB ? 2 : 5, NA = DD_LANE_NA(CB, XIN), o = (U + 1) & 1;
+        (void)NA;
         constexpr int s1 = (U + 2 * P - 2 * K - 1) % P, s2 = (U + 2 * P - 2 * K - 2) % P;
         double old[NC], use[NC];
 #pragma unroll
