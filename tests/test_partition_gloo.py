@@ -83,3 +83,22 @@ def test_slab_thinner_than_halo_is_refused():
     x = np.linspace(0.0, 1.0, 65)
     with pytest.raises(ValueError, match="fewer than the halo"):
         ddmesh.SlabMesh(x, x, world=8, rank=1, halo=24)
+
+
+def test_gauss_seidel_fallback_sweep_count():
+    """Sweeps the slab driver plans for a variable that has fallen back to Gauss-Seidel (ddmesh._on_reject): error
+    factor <= rho per sweep down to 1e-17, monotone in rho, capped by max_sweeps, defined at the ends of the range."""
+    import math
+    gs = ddmesh.SlabMesh._gs_sweeps
+    prev = 0
+    for rho in (0.0, 1e-6, 0.1, 0.5, 0.9, 0.97):
+        n = gs(rho, 20000)
+        assert n >= max(2, prev), (rho, n)
+        r = rho * 1.02 + 1e-12
+        assert r ** n <= 1e-17 * 1.0000001 or n == 2, (rho, n)
+        if n > 2:
+            assert r ** (n - 1) > 1e-17 * 0.999, (rho, n)
+        prev = n
+    assert gs(0.9126, 20000) == math.ceil(math.log(1e-17) / math.log(0.9126 * 1.02 + 1e-12))
+    assert gs(0.999, 100) == 100          # capped
+    assert gs(1.0, 500) == 500 and gs(float("nan"), 500) == 500 and gs(-0.1, 500) == 500  # not dominant: the cap
