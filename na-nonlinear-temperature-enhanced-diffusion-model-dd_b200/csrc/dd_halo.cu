@@ -13,7 +13,7 @@
 //   E  that block waits for F_r[2] >= seq (up has delivered) and F_r[3] >= seq; kernels launched after this one see
 //      the neighbours' rows.
 // Every rank runs its kernel on its own GPU, so the spin loops cannot starve each other; a wait that lasts longer
-// than about two seconds gives up and reports it (status word), which the driver turns into an error.
+// than about a minute gives up and reports it (status word), which the driver turns into an error.
 #include <string.h>
 
 #include "dd_kernels.cuh"
@@ -43,7 +43,8 @@ __device__ __forceinline__ unsigned halo_load_flag(const unsigned* p) {
 __device__ __forceinline__ bool halo_wait(const unsigned* p, unsigned seq, int* status) {
     const long long t0 = clock64();
     while ((int)(halo_load_flag(p) - seq) < 0) {
-        if (clock64() - t0 > 4000000000LL) {
+        if (clock64() - t0 > 120000000000LL) {  // about a minute: a neighbour may be busy with a one-off (a compile, a
+                                                // check run on one rank); NCCL would wait for ever
             *status = 1;
             return false;
         }
